@@ -1,0 +1,425 @@
+"""CPU oracle for the fusion / ME-MHACL / contrastive hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product package
+(`multimodal-sentiment-aanalysis_b200/`) may import this file; only `tests/`,
+`__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference` legs of
+`bench.py` use it, and only as the checker / CPU baseline.
+
+It is a plain-PyTorch (CPU, fp32 or fp64) functional restatement of the
+reference arithmetic, parametrised in (E, H, L, R, input widths, wiring) so
+that it also runs at BASELINE.json's text/image sizes where the reference's
+own `CrossModalTransformer.forward` cannot (its gate concatenates on dim=1,
+MultimodalModel.py:147, which is the feature axis only when Lq == 1).
+
+Parity pin: the reference holds no golden vectors or tests for this path
+(SURVEY.md section 4), so the oracle is pinned against the *imported reference itself*
+at the reference's native sizes (tests/test_oracle_vs_reference.py, run where
+/root/reference is mounted) and against committed fixtures generated from the
+imported reference by oracle/make_goldens.py (tests/golden/native_*.pt).
+
+Every function cites the reference lines it follows
+(paths relative to /root/reference/MML_ZYC/).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+Params = Dict[str, Tensor]
+
+
+# --------------------------------------------------------------------------
+# torch.nn.MultiheadAttention, need_weights=True branch
+# (third-party: torch/nn/functional.py multi_head_attention_forward, reached from
+#  MultimodalModel.py:139-143 and ME-MHACL/model.py:71 / MultimodalModel.py:397)
+# --------------------------------------------------------------------------
+def mha_core(q: Tensor, k: Tensor, v: Tensor, num_heads: int) -> Tensor:
+    """q:[Lq,B,E] k,v:[Lk,B,E] (already projected, seq-first) -> [Lq*B, E] pre-out-proj."""
+    Lq, B, E = q.shape
+    Lk = k.shape[0]
+    d = E // num_heads
+    qh = q.reshape(Lq, B * num_heads, d).transpose(0, 1)
+    kh = k.reshape(Lk, B * num_heads, d).transpose(0, 1)
+    vh = v.reshape(Lk, B * num_heads, d).transpose(0, 1)
+    # scale is applied to q *before* the bmm (functional.py need_weights branch)
+    q_scaled = qh * math.sqrt(1.0 / float(d))
+    w = torch.bmm(q_scaled, kh.transpose(-2, -1))
+    w = torch.softmax(w, dim=-1)
+    o = torch.bmm(w, vh)
+    return o.transpose(0, 1).contiguous().view(Lq * B, E)
+
+
+def mha_cross(query: Tensor, key: Tensor, value: Tensor, in_w: Tensor, in_b: Tensor,
+              out_w: Tensor, out_b: Tensor, num_heads: int) -> Tensor:
+    """batch_first cross attention as nn.MultiheadAttention(E,H,batch_first=True) runs it
+    when called from CrossModalTransformer.forward (MultimodalModel.py:139-143): key and
+    value are distinct tensor objects after the unsqueeze at :134-137, so torch takes the
+    three-way `w.chunk(3)` in-projection."""
+    B, Lq, E = query.shape
+    q = query.transpose(1, 0)
+    k = key.transpose(1, 0)
+    v = value.transpose(1, 0)
+    w_q, w_k, w_v = in_w.chunk(3)
+    b_q, b_k, b_v = in_b.chunk(3)
+    qp = F.linear(q, w_q, b_q)
+    kp = F.linear(k, w_k, b_k)
+    vp = F.linear(v, w_v, b_v)
+    o = mha_core(qp, kp, vp, num_heads)
+    o = F.linear(o, out_w, out_b).view(Lq, B, E)
+    return o.transpose(1, 0)
+
+
+def mha_self_seq_first(x: Tensor, in_w: Tensor, in_b: Tensor, out_w: Tensor, out_b: Tensor,
+                       num_heads: int) -> Tensor:
+    """self attention, seq-first [L,B,E] (ME-MHACL/model.py:71, MultimodalModel.py:397):
+    packed in-projection `linear(x, W, b)` then split in q,k,v order."""
+    L, B, E = x.shape
+    proj = F.linear(x, in_w, in_b)
+    proj = proj.unflatten(-1, (3, E)).unsqueeze(0).transpose(0, -2).squeeze(-2).contiguous()
+    o = mha_core(proj[0], proj[1], proj[2], num_heads)
+    return F.linear(o, out_w, out_b).view(L, B, E)
+
+
+# --------------------------------------------------------------------------
+# CrossModalTransformer (MultimodalModel.py:108-149)
+# --------------------------------------------------------------------------
+def cross_block(query: Tensor, kv: Tensor, p: Params, prefix: str, num_heads: int) -> Tensor:
+    """query:[B,Lq,E] kv:[B,Lk,E] -> [B,Lq,E].
+    MHA (:139-143) -> gate = sigmoid(Linear(2E,E)(cat[q, attn])) (:147, restated with the
+    concat on the LAST dim so Lq > 1 works; identical when Lq == 1) ->
+    g*q + (1-g)*attn (:148) -> LayerNorm(E) (:149)."""
+    attn = mha_cross(query, kv, kv,
+                     p[prefix + "multihead_attn.in_proj_weight"], p[prefix + "multihead_attn.in_proj_bias"],
+                     p[prefix + "multihead_attn.out_proj.weight"], p[prefix + "multihead_attn.out_proj.bias"],
+                     num_heads)
+    gate = torch.sigmoid(F.linear(torch.cat([query, attn], dim=-1),
+                                  p[prefix + "gate.0.weight"], p[prefix + "gate.0.bias"]))
+    out = gate * query + (1 - gate) * attn
+    E = query.shape[-1]
+    return F.layer_norm(out, (E,), p[prefix + "norm.weight"], p[prefix + "norm.bias"], 1e-5)
+
+
+# --------------------------------------------------------------------------
+# Linear -> BatchNorm1d -> GELU -> Dropout chains
+# (fusion :179-189, arousal_head :192-199, valence_head :200-225)
+# and Linear -> ReLU -> BatchNorm1d -> Dropout chains (ProjectionHead, ME-MHACL/model.py:82-97)
+# --------------------------------------------------------------------------
+def batchnorm1d(x: Tensor, p: Params, prefix: str, training: bool, eps: float = 1e-5,
+                momentum: float = 0.1, buffers: Optional[Dict[str, Tensor]] = None) -> Tensor:
+    """nn.BatchNorm1d on [B,N] through the same third-party op the reference reaches
+    (torch.nn.functional.batch_norm): train mode = batch mean / biased variance
+    y = (x-mean)/sqrt(var+eps)*w+b; running stats (when `buffers` is given) updated with the
+    UNBIASED variance and momentum 0.1; eval mode = running stats."""
+    w, b = p[prefix + "weight"], p[prefix + "bias"]
+    src = buffers if buffers is not None else p
+    rm = src.get(prefix + "running_mean")
+    rv = src.get(prefix + "running_var")
+    if training:
+        if buffers is not None:
+            buffers[prefix + "num_batches_tracked"] += 1
+            return F.batch_norm(x, rm, rv, w, b, True, momentum, eps)
+        return F.batch_norm(x, None, None, w, b, True, momentum, eps)
+    return F.batch_norm(x, rm, rv, w, b, False, momentum, eps)
+
+
+def mlp_chain(x: Tensor, p: Params, prefix: str, plan: Sequence[Tuple[str, int]], training: bool,
+              dropout_masks: Optional[List[Tensor]] = None,
+              buffers: Optional[Dict[str, Tensor]] = None) -> Tensor:
+    """Run an nn.Sequential restated as a plan of (kind, index) steps, kind in
+    {linear, bn, gelu, relu, dropout}.  GELU is the exact-erf form (nn.GELU() default).
+    Dropout: identity unless `dropout_masks` supplies pre-scaled keep masks (one per dropout)."""
+    mi = 0
+    for kind, idx in plan:
+        key = f"{prefix}{idx}."
+        if kind == "linear":
+            x = F.linear(x, p[key + "weight"], p[key + "bias"])
+        elif kind == "bn":
+            x = batchnorm1d(x, p, key, training, buffers=buffers)
+        elif kind == "gelu":
+            x = F.gelu(x)
+        elif kind == "relu":
+            x = F.relu(x)
+        elif kind == "dropout":
+            if dropout_masks is not None and training:
+                x = x * dropout_masks[mi]
+            mi += 1
+        else:
+            raise ValueError(kind)
+    return x
+
+
+FUSION_PLAN = [("linear", 0), ("bn", 1), ("gelu", 2), ("dropout", 3),
+               ("linear", 4), ("bn", 5), ("gelu", 6), ("dropout", 7)]
+AROUSAL_PLAN = [("linear", 0), ("bn", 1), ("gelu", 2), ("dropout", 3), ("linear", 4)]
+VALENCE_PLAN = [("linear", 0), ("bn", 1), ("gelu", 2), ("dropout", 3),
+                ("linear", 4), ("bn", 5), ("gelu", 6), ("dropout", 7),
+                ("linear", 8), ("bn", 9), ("gelu", 10), ("dropout", 11),
+                ("linear", 12), ("bn", 13), ("gelu", 14), ("dropout", 15),
+                ("linear", 16)]
+PROJECTION_PLAN = [("linear", 0), ("relu", 1), ("bn", 2), ("dropout", 3),
+                   ("linear", 4), ("relu", 5), ("bn", 6), ("dropout", 7), ("linear", 8)]
+
+
+# --------------------------------------------------------------------------
+# Contrastive losses
+# --------------------------------------------------------------------------
+def infonce(feat1: Tensor, feat2: Tensor, labels: Tensor, temperature: Tensor,
+            labels2: Optional[Tensor] = None, row_offset: int = 0) -> Tensor:
+    """MultimodalTransformerModel.compute_contrastive_loss (MultimodalModel.py:232-260).
+    `labels2` / `row_offset` generalise it to a row block of a batch-sharded similarity
+    matrix: rows are local samples (global index row_offset+i), columns the gathered
+    global batch; the reference's fill_diagonal_(0) (:241) then clears the GLOBAL diagonal."""
+    f1 = F.normalize(feat1, dim=1)                                   # :234
+    f2 = F.normalize(feat2, dim=1)                                   # :235
+    sim = torch.mm(f1, f2.t()) / temperature                         # :237
+    l2 = labels if labels2 is None else labels2
+    pos_mask = torch.eq(labels.unsqueeze(1), l2.unsqueeze(0)).to(sim.dtype)   # :240
+    n_rows = pos_mask.shape[0]
+    idx = torch.arange(n_rows)
+    cols = idx + row_offset
+    ok = cols < pos_mask.shape[1]
+    pos_mask[idx[ok], cols[ok]] = 0                                  # :241 fill_diagonal_(0)
+    sim = sim - torch.max(sim, dim=1, keepdim=True)[0]               # :245 (grad flows through max)
+    exp_sim = torch.exp(sim)                                         # :248
+    pos_sim = (exp_sim * pos_mask).sum(1)                            # :251
+    all_sim = exp_sim.sum(1)                                         # :254
+    loss = -torch.log((pos_sim + 1e-12) / (all_sim + 1e-12))         # :257
+    return loss.mean()                                               # :260
+
+
+def supcon(z1: Tensor, z2: Tensor, labels: Tensor, temperature: float = 0.1) -> Tensor:
+    """train.py:16-40 contrastive_loss (SupCon over the 2B stacked views, no max subtraction)."""
+    z1 = F.normalize(z1, dim=1)
+    z2 = F.normalize(z2, dim=1)
+    z = torch.cat([z1, z2], dim=0)
+    sim = torch.matmul(z, z.T) / temperature
+    lab = labels.view(-1, 1)
+    lab = torch.cat([lab, lab], dim=0)
+    mask = torch.eq(lab, lab.T).to(sim.dtype)
+    self_mask = torch.eye(mask.size(0), dtype=torch.bool)
+    mask = mask.masked_fill(self_mask, 0)
+    sim_exp = torch.exp(sim)
+    sim_exp = sim_exp.masked_fill(self_mask, 0)
+    sim_sum = sim_exp.sum(dim=1, keepdim=True)
+    log_prob = sim - torch.log(sim_sum + 1e-8)
+    loss = -(mask * log_prob).sum(dim=1) / (mask.sum(dim=1) + 1e-8)
+    return loss.mean()
+
+
+def ntxent(z1: Tensor, z2: Tensor, temperature: float = 0.5) -> Tensor:
+    """ME-MHACL/train.py:47-66 contrastive_loss (SimCLR NT-Xent)."""
+    n = z1.size(0)
+    z = torch.cat([z1, z2], dim=0)
+    z = F.normalize(z, dim=1)
+    sim = torch.matmul(z, z.T)
+    mask = torch.eye(2 * n, dtype=torch.bool)
+    sim = sim.masked_fill(mask, -9e15)
+    sim = sim / temperature
+    targets = torch.cat([torch.arange(n, 2 * n), torch.arange(0, n)], dim=0)
+    return F.cross_entropy(sim, targets)
+
+
+# --------------------------------------------------------------------------
+# MultimodalTransformerModel.forward hot path (MultimodalModel.py:262-322)
+# --------------------------------------------------------------------------
+@dataclass
+class FusionConfig:
+    """Shape/wiring description of one instance of the hot path.
+
+    wiring == "native":  the reference's own wiring (three modality feature vectors [B,E];
+        query is always modality 0, :287-297; three self-contrast losses, :271-284).
+    wiring == "bidirectional": BASELINE.json's text+image re-skin (SURVEY.md section 8(d) canonical
+        composition): text tokens [B,L,D_t] and image regions [B,R,D_i] are projected to E
+        (Subnetwork.proj pattern, :86), block e2p is query=text/kv=image, block p2e is
+        query=image/kv=text, token mean-pool (:76 pattern) feeds the three fused slots,
+        modality weights read the RAW pooled features (:299-301), InfoNCE(f1,f2,labels)."""
+    embed_dim: int = 256
+    num_heads: int = 4
+    num_classes: int = 3
+    wiring: str = "native"
+    text_dim: int = 768
+    image_dim: int = 2048
+    contract: str = "multitask"      # "multitask" = 5-tuple (MultiTaskTrainer.py:199), "single" = Trainer.py:60
+    valence: bool = True
+
+
+@dataclass
+class FusionOutputs:
+    arousal: Tensor
+    valence: Optional[Tensor]
+    contrastive: List[Tensor]
+    feats: Dict[str, Tensor] = field(default_factory=dict)
+
+
+def fusion_forward(cfg: FusionConfig, p: Params, inputs: Sequence[Tensor],
+                   labels: Optional[Tensor] = None, training: bool = True,
+                   dropout_masks: Optional[Dict[str, List[Tensor]]] = None,
+                   buffers: Optional[Dict[str, Tensor]] = None,
+                   gathered: Optional[Tuple[Tensor, Tensor, int]] = None) -> FusionOutputs:
+    """The hot path of MultimodalTransformerModel.forward, starting from per-modality FEATURES
+    (the modality encoders eeg_net/eye_net/pps_net, :264-266, are out of scope).
+
+    native:        inputs = (f_eeg[B,E], f_eye[B,E], f_pps[B,E])
+    bidirectional: inputs = (text[B,L,D_t], image[B,R,D_i])
+    labels: arousal labels [B] int64 (the reference contrasts on labels[0], :273).
+    gathered: optional (f2_global, labels_global, row_offset) for the batch-sharded InfoNCE."""
+    H = cfg.num_heads
+    dm = dropout_masks or {}
+    out_feats: Dict[str, Tensor] = {}
+    contrastive: List[Tensor] = []
+    cw = p["contrastive_weight"]
+    T = p["temperature"]
+
+    if cfg.wiring == "native":
+        f0, f1r, f2r = [x if x.ndim == 2 else x.squeeze(1) for x in inputs]
+        if labels is not None:                                       # :271-284
+            for f in (f0, f1r, f2r):
+                contrastive.append(infonce(f, f, labels, T))
+        e1 = cross_block(f0.unsqueeze(1), f1r.unsqueeze(1), p, "cross_attn_e2p.", H).squeeze(1)   # :287
+        e2 = cross_block(f0.unsqueeze(1), f2r.unsqueeze(1), p, "cross_attn_p2e.", H).squeeze(1)   # :293
+        raw = torch.cat([f0, f1r, f2r], dim=1)                       # :300
+        slots = (f0, e1, e2)
+    elif cfg.wiring == "bidirectional":
+        text, image = inputs[0], inputs[1]
+        t = F.linear(text, p["eeg_net.proj.weight"], p["eeg_net.proj.bias"])      # :86 pattern
+        v = F.linear(image, p["eye_net.proj.weight"], p["eye_net.proj.bias"])
+        t2 = cross_block(t, v, p, "cross_attn_e2p.", H)              # text <- image
+        v2 = cross_block(v, t, p, "cross_attn_p2e.", H)              # image <- text
+        f0, fv = t.mean(1), v.mean(1)                                # :76 pooling pattern
+        e1, e2 = t2.mean(1), v2.mean(1)
+        raw = torch.cat([f0, fv], dim=1)
+        slots = (f0, e1, e2)
+        if labels is not None:
+            if gathered is None:
+                contrastive.append(infonce(e1, e2, labels, T))
+            else:
+                g2, gl, off = gathered
+                contrastive.append(infonce(e1, g2, labels, T, labels2=gl, row_offset=off))
+    else:
+        raise ValueError(cfg.wiring)
+    out_feats["slot0"], out_feats["slot1"], out_feats["slot2"] = slots
+
+    h = F.gelu(F.linear(raw, p["attention_weights.0.weight"], p["attention_weights.0.bias"]))     # :171-176
+    w = torch.softmax(F.linear(h, p["attention_weights.2.weight"], p["attention_weights.2.bias"]), dim=1)
+    fused = torch.cat([slots[0] * w[:, 0:1], slots[1] * w[:, 1:2], slots[2] * w[:, 2:3]], dim=1)  # :302-306
+    out_feats["weights"] = w
+    fused = mlp_chain(fused, p, "fusion.", FUSION_PLAN, training, dm.get("fusion"), buffers)      # :309
+    out_feats["fused"] = fused
+    arousal = mlp_chain(fused, p, "arousal_head.", AROUSAL_PLAN, training, dm.get("arousal_head"), buffers)  # :312
+    valence = None
+    if cfg.valence:
+        valence = mlp_chain(fused, p, "valence_head.", VALENCE_PLAN, training, dm.get("valence_head"), buffers)  # :313
+    contrastive = [cw * c for c in contrastive]                      # :315-317 -> shape (1,)
+    return FusionOutputs(arousal, valence, contrastive, out_feats)
+
+
+def trainer_loss(cfg: FusionConfig, p: Params, inputs, labels, **kw) -> Tuple[Tensor, FusionOutputs]:
+    """Trainer.py:60-71 step loss for the single-task contract, with the trainer-owned weight
+    folded to 1: CE(arousal_logits, labels) + sum(contrastive terms)."""
+    out = fusion_forward(cfg, p, inputs, labels, **kw)
+    ce = F.cross_entropy(out.arousal, labels)                        # Trainer.py:17,68
+    loss = ce
+    for c in out.contrastive:
+        loss = loss + c.sum()
+    return loss, out
+
+
+# --------------------------------------------------------------------------
+# ME-MHACL pieces (rows J, K, M of SURVEY.md section 8a)
+# --------------------------------------------------------------------------
+def memhacl_fusion(feats: Sequence[Tensor], p: Params, num_heads: int = 8, variant: str = "mean",
+                   training: bool = True, buffers=None) -> Tensor:
+    """MultiModalEncoder.forward fusion tail.
+    variant "mean": ME-MHACL/model.py:68-74 (stack dim 0 -> self-MHA -> mean over modalities).
+    variant "max":  MultimodalModel.py:388-406 (L2-normalise inputs, self-MHA, max over
+                    modalities, fusion_mlp = Linear-ReLU-BN)."""
+    if variant == "max":
+        feats = [F.normalize(f, dim=-1) for f in feats]
+    x = torch.stack(list(feats), dim=0)
+    a = mha_self_seq_first(x, p["multihead_attn.in_proj_weight"], p["multihead_attn.in_proj_bias"],
+                           p["multihead_attn.out_proj.weight"], p["multihead_attn.out_proj.bias"], num_heads)
+    if variant == "mean":
+        return a.mean(dim=0)
+    fused = a.max(dim=0)[0]
+    return mlp_chain(fused, p, "fusion_mlp.", [("linear", 0), ("relu", 1), ("bn", 2)], training, None, buffers)
+
+
+def projection_head(x: Tensor, p: Params, training: bool = True, dropout_masks=None, buffers=None) -> Tensor:
+    """ProjectionHead.forward (ME-MHACL/model.py:82-97; MultimodalModel.py:414-429)."""
+    return mlp_chain(x, p, "net.", PROJECTION_PLAN, training, dropout_masks, buffers)
+
+
+def classifier(x: Tensor, p: Params, training: bool = True, dropout_mask: Optional[Tensor] = None):
+    """Classifier.forward (ME-MHACL/model.py:105-119; MultimodalModel.py:437-451)."""
+    h = F.relu(F.linear(x, p["shared.0.weight"], p["shared.0.bias"]))
+    if dropout_mask is not None and training:
+        h = h * dropout_mask
+    return (F.linear(h, p["fc_arousal.weight"], p["fc_arousal.bias"]),
+            F.linear(h, p["fc_valence.weight"], p["fc_valence.bias"]))
+
+
+# --------------------------------------------------------------------------
+# Parameter construction with the reference initialisers (for sizes the reference cannot build)
+# --------------------------------------------------------------------------
+def init_params(cfg: FusionConfig, seed: int = 0, dtype=torch.float32) -> Tuple[Params, Dict[str, Tensor]]:
+    """Parameters + BN buffers with the reference's key names and initialisers
+    (nn.MultiheadAttention xavier-uniform in_proj / zero biases; nn.Linear default
+    kaiming-uniform(a=sqrt 5); LN/BN weight 1 bias 0; temperature 0.01; contrastive_weight 1)."""
+    import torch.nn as nn
+    g = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    E, H, C = cfg.embed_dim, cfg.num_heads, cfg.num_classes
+    mods: Dict[str, nn.Module] = {}
+    if cfg.wiring == "bidirectional":
+        mods["eeg_net.proj"] = nn.Linear(cfg.text_dim, E)
+        mods["eye_net.proj"] = nn.Linear(cfg.image_dim, E)
+        raw_w = 2 * E
+    else:
+        raw_w = 3 * E
+    for name in ("cross_attn_e2p", "cross_attn_p2e"):
+        mods[name + ".multihead_attn"] = nn.MultiheadAttention(E, H, batch_first=True)
+        mods[name + ".gate.0"] = nn.Linear(2 * E, E)
+        mods[name + ".norm"] = nn.LayerNorm(E)
+    mods["attention_weights.0"] = nn.Linear(raw_w, 64)
+    mods["attention_weights.2"] = nn.Linear(64, 3)
+    mods["fusion.0"] = nn.Linear(3 * E, 256); mods["fusion.1"] = nn.BatchNorm1d(256)
+    mods["fusion.4"] = nn.Linear(256, 128); mods["fusion.5"] = nn.BatchNorm1d(128)
+    mods["arousal_head.0"] = nn.Linear(128, 128); mods["arousal_head.1"] = nn.BatchNorm1d(128)
+    mods["arousal_head.4"] = nn.Linear(128, C)
+    if cfg.valence:
+        dims = [(128, 256), (256, 256), (256, 128), (128, 64)]
+        for i, (a, b) in enumerate(dims):
+            mods[f"valence_head.{4 * i}"] = nn.Linear(a, b)
+            mods[f"valence_head.{4 * i + 1}"] = nn.BatchNorm1d(b)
+        mods["valence_head.16"] = nn.Linear(64, C)
+    params: Params = {}
+    buffers: Dict[str, Tensor] = {}
+    for mname, m in mods.items():
+        for k, v in m.state_dict().items():
+            full = f"{mname}.{k}"
+            if "running_" in k or "num_batches" in k:
+                buffers[full] = v.clone()
+            else:
+                params[full] = v.detach().clone().to(dtype)
+    params["contrastive_weight"] = torch.ones(1, dtype=dtype)
+    params["temperature"] = torch.tensor(0.01, dtype=dtype)
+    torch.random.set_rng_state(g)
+    return params, buffers
+
+
+def synth_inputs(cfg: FusionConfig, batch: int, L: int = 64, R: int = 49, seed: int = 1234,
+                 dtype=torch.float32):
+    """Seeded synthetic inputs of SURVEY.md section 8(d): N(0,1) features, labels randint(0,3)."""
+    g = torch.Generator().manual_seed(seed)
+    if cfg.wiring == "bidirectional":
+        xs = (torch.randn(batch, L, cfg.text_dim, generator=g, dtype=dtype),
+              torch.randn(batch, R, cfg.image_dim, generator=g, dtype=dtype))
+    else:
+        xs = tuple(torch.randn(batch, cfg.embed_dim, generator=g, dtype=dtype) for _ in range(3))
+    labels = torch.randint(0, cfg.num_classes, (batch,), generator=g)
+    return xs, labels
