@@ -1,0 +1,204 @@
+/* mmsa.h -- C ABI of the B200 (sm_100a) fusion / ME-MHACL / contrastive hot path.
+ *
+ * The reference (zhouyuchenzyccccc/Multimodal-Sentiment-Aanalysis, /root/reference/MML_ZYC) is pure
+ * PyTorch and has no FFI of its own: its "operator API" for this path is the nn.Module call
+ * `model(eeg, eye, pps, labels)` made by Trainer.py:60 / Tester.py:53 /
+ * dataLoader/MultiTaskTrainer.py:199.  Each entry point below replaces the ATen op group that one
+ * reference line dispatches; the citation after each declaration names that line.  The Python host
+ * (multimodal-sentiment-aanalysis_b200/mmsa) binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host; the caller allocates every
+ *    output and workspace, the callee allocates nothing and keeps no reference after returning;
+ *  - `dtype` is the storage type of activations: MMSA_F32 (parity mode) or MMSA_BF16 (performance
+ *    mode, fp32 accumulation).  Parameters, statistics, losses and parameter gradients are fp32;
+ *  - `stream` is a cudaStream_t; all work is enqueued on it, there are no hidden synchronisations;
+ *  - return 0 on success, non-zero on error (message through mmsa_last_error()); sm_100 only:
+ *    on any other device every compute entry point fails with MMSA_ERR_DEVICE (no fallback).
+ */
+#ifndef MMSA_H_
+#define MMSA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMSA_F32 0
+#define MMSA_BF16 1
+
+#define MMSA_OK 0
+#define MMSA_ERR_ARG 1
+#define MMSA_ERR_CUDA 2
+#define MMSA_ERR_DEVICE 3
+
+#define MMSA_ACT_NONE 0
+#define MMSA_ACT_SIGMOID 1
+#define MMSA_ACT_GELU 2
+#define MMSA_ACT_RELU 3
+
+/* BatchNorm block orders */
+#define MMSA_BN_THEN_GELU 0 /* Linear-BN-GELU-Dropout, MultimodalModel.py:179-199 */
+#define MMSA_RELU_THEN_BN 1 /* Linear-ReLU-BN-Dropout, ME-MHACL/model.py:82-97 */
+#define MMSA_BN_ONLY 2
+
+/* contrastive loss kinds */
+#define MMSA_LOSS_INFONCE 0 /* MultimodalModel.py:232-260 */
+#define MMSA_LOSS_SUPCON 1  /* train.py:16-40 */
+#define MMSA_LOSS_NTXENT 2  /* ME-MHACL/train.py:47-66 */
+
+const char* mmsa_version(void);
+const char* mmsa_last_error(void);
+/* 0 when the current CUDA device is sm_100; MMSA_ERR_DEVICE otherwise. */
+int mmsa_check_device(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches). */
+int64_t mmsa_launch_count(void);
+
+/* ---- dtype plumbing (host `.float()` boundary, Trainer.py:53-54) ---------------------------- */
+int mmsa_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+
+/* ---- Linear: y = x W^T + b   (nn.Linear: MultimodalModel.py:86,112-121,172-198) -------------
+ * x:[M,K] (row stride ldx), optional second operand x2:[M,K2] concatenated on the feature axis
+ * (the gate's cat[q, attn], MultimodalModel.py:147), W:[N,K+K2] fp32 master (row stride ldw) or
+ * bf16 copy when dtype==BF16 (w_dtype), bias:[N] fp32 or NULL, residual:[M,N] (dtype, stride ldr)
+ * or NULL, act applied last.  y:[M,N] (out_dtype, row stride ldy). */
+int mmsa_linear_fwd(int dtype, int64_t M, int64_t N, int64_t K, int64_t K2,
+                    const void* x, int64_t ldx, const void* x2, int64_t ldx2,
+                    const void* w, int64_t ldw, const float* bias,
+                    const void* residual, int64_t ldr, int act,
+                    void* y, int64_t ldy, int out_dtype, void* stream);
+/* dgrad: dx[M,K] = dy[M,N] W[N,K] (+ residual).  W row stride ldw lets a column block of a wider
+ * weight be addressed (gate.0.weight[:, :E] / [:, E:]). */
+int mmsa_linear_dgrad(int dtype, int64_t M, int64_t N, int64_t K,
+                      const void* dy, int64_t lddy, const void* w, int64_t ldw,
+                      const void* residual, int64_t ldr,
+                      void* dx, int64_t lddx, int out_dtype, void* stream);
+/* wgrad: dw[N,K] (fp32, row stride lddw) = dy[M,N]^T x[M,K]; db[N] = column sums of dy (or NULL).
+ * workspace: fp32, mmsa_linear_wgrad_workspace(...) bytes (split-K partials). */
+int64_t mmsa_linear_wgrad_workspace(int dtype, int64_t M, int64_t N, int64_t K);
+int mmsa_linear_wgrad(int dtype, int64_t M, int64_t N, int64_t K,
+                      const void* dy, int64_t lddy, const void* x, int64_t ldx,
+                      float* dw, int64_t lddw, float* db, void* workspace, void* stream);
+
+/* ---- multi-head attention core (torch F.multi_head_attention_forward need_weights branch,
+ *      reached from MultimodalModel.py:139-143, ME-MHACL/model.py:71) ------------------------
+ * q:[B,Lq,H*D] row stride ldq, k/v:[B,Lk,H*D] row strides ldk/ldv (K and V may alias one packed
+ * [B,Lk,2E] buffer), o:[B,Lq,H*D] row stride ldo, lse:[B,H,Lq] fp32 (log-sum-exp of the scaled
+ * scores; saved for backward instead of the B*H*Lq*Lk probability matrix).  scale = 1/sqrt(D)
+ * is applied to q before the product, as torch does.  D in {32, 64}. */
+/* test hook: route bf16 attention through the CUDA-core engine (engine cross-check). */
+void mmsa_debug_force_simt_attention(int on);
+int mmsa_attn_fwd(int dtype, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t D,
+                  const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                  void* o, int64_t ldo, float* lse, void* stream);
+/* delta:[B,H,Lq] fp32 scratch. */
+int mmsa_attn_bwd(int dtype, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t D,
+                  const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                  const void* o, int64_t ldo, const void* dout, int64_t lddo, const float* lse,
+                  float* delta, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                  void* stream);
+
+/* ---- sigmoid gate + blend + LayerNorm (MultimodalModel.py:147-149) --------------------------
+ * gate_pre:[M,E] = Linear(2E,E)(cat[q,attn]) before the sigmoid; g_out = sigmoid(gate_pre);
+ * u = g*q + (1-g)*attn; y = LayerNorm(u; gamma, beta, eps).  mean/rstd:[M] fp32 saved. */
+int mmsa_gate_ln_fwd(int dtype, int64_t M, int64_t E, const void* gate_pre, const void* q, const void* attn,
+                     const float* gamma, const float* beta, float eps,
+                     void* g_out, void* y, float* mean, float* rstd, void* stream);
+/* dy:[M,E]; when dy_rows_per_sample > 0, dy is [M/dy_rows_per_sample, E] and is broadcast over the
+ * tokens of a sample and scaled by 1/dy_rows_per_sample (backward of a token mean-pool).
+ * dq_bcast (or NULL): [M/bcast_rows, E] gradient of a token mean-pool of q, added to dq_part as
+ * dq_bcast[row / bcast_rows] / bcast_rows (saves materialising the broadcast).  dq_add (or NULL):
+ * [M,E] further gradient w.r.t. q (e.g. from the mirrored block, where q served as key/value).
+ * outputs: dq_part = du*g (+ bcast), dattn_part = du*(1-g), dgate_pre = du*(q-attn)*g*(1-g);
+ * dgamma/dbeta:[E] fp32 (partials: [nblk,2,E] fp32 workspace, nblk from mmsa_gate_ln_bwd_blocks). */
+int64_t mmsa_gate_ln_bwd_blocks(int64_t M);
+int mmsa_gate_ln_bwd(int dtype, int64_t M, int64_t E, const void* dy, int64_t dy_rows_per_sample,
+                     const void* g, const void* q, const void* attn,
+                     const float* gamma, const float* mean, const float* rstd,
+                     const void* dq_bcast, int64_t bcast_rows, const void* dq_add,
+                     void* dq_part, void* dattn_part, void* dgate_pre,
+                     float* dgamma, float* dbeta, float* partials, void* stream);
+
+/* ---- token pooling (mean: MultimodalModel.py:76 / ME-MHACL/model.py:73; max: MultimodalModel.py:401)
+ * x:[B,L,E] -> y:[B,E]; argmax:[B,E] int32 only for max. */
+int mmsa_pool_fwd(int dtype, int64_t B, int64_t L, int64_t E, const void* x, int is_max,
+                  void* y, int32_t* argmax, void* stream);
+int mmsa_pool_bwd(int dtype, int64_t B, int64_t L, int64_t E, const void* dy, int is_max,
+                  const int32_t* argmax, void* dx, void* stream);
+
+/* ---- modality weights softmax + weighted concat (MultimodalModel.py:171-176 tail, :299-306) --
+ * logits:[B,S] (dtype) -> w = softmax(logits) (fp32 [B,S]); fused[B,S*E] = cat_s(slot_s * w[:,s]). */
+int mmsa_modal_concat_fwd(int dtype, int64_t B, int64_t E, int S, const void* logits,
+                          const void* const* slots_host, float* w, void* fused, void* stream);
+int mmsa_modal_concat_bwd(int dtype, int64_t B, int64_t E, int S, const void* dfused, const float* w,
+                          const void* const* slots_host, void* const* dslots_host, void* dlogits, void* stream);
+
+/* ---- activation (nn.GELU exact-erf, MultimodalModel.py:173; ReLU, ME-MHACL/model.py:108) ---- */
+int mmsa_act_fwd(int dtype, int64_t n, const void* x, int act, void* y, void* stream);
+int mmsa_act_bwd(int dtype, int64_t n, const void* x, const void* dy, int act, void* dx, void* stream);
+
+/* ---- BatchNorm1d + activation + dropout on [B,N] (MultimodalModel.py:180-183, 193-196;
+ *      ME-MHACL/model.py:84-87) ---------------------------------------------------------------
+ * training!=0: batch statistics (biased var), running stats updated in place with momentum and
+ * unbiased var; else running stats.  keep_mask:[B,N] uint8 or NULL: if dropout_p>0 and
+ * mask_given==0 the kernel draws it (Philox, seed/offset) and writes it; if mask_given it reads it.
+ * save_mean/save_rstd:[N] fp32. */
+int mmsa_bn_act_fwd(int dtype, int64_t B, int64_t N, int order, const void* x,
+                    const float* gamma, const float* beta, float* running_mean, float* running_var,
+                    float momentum, float eps, int training,
+                    float dropout_p, uint8_t* keep_mask, int mask_given, uint64_t seed, uint64_t offset,
+                    void* y, float* save_mean, float* save_rstd, void* stream);
+int mmsa_bn_act_bwd(int dtype, int64_t B, int64_t N, int order, const void* x, const void* dy,
+                    const float* gamma, const float* beta, const float* save_mean, const float* save_rstd, int training,
+                    float dropout_p, const uint8_t* keep_mask,
+                    void* dx, float* dgamma, float* dbeta, void* stream);
+
+/* ---- stand-alone dropout (nn.Dropout after ReLU, ME-MHACL/model.py:105-109); y = keep ? x/(1-p) : 0.
+ * keep_mask:[n] uint8 is drawn (Philox) and written unless mask_given; backward = same call on dy
+ * with mask_given=1. */
+int mmsa_dropout(int dtype, int64_t n, const void* x, float p, uint8_t* keep_mask, int mask_given,
+                 uint64_t seed, uint64_t offset, void* y, void* stream);
+
+/* ---- softmax cross-entropy, mean reduction (nn.CrossEntropyLoss, Trainer.py:17,68) ----------
+ * logits:[B,C] fp32, labels:[B] int64; loss:[1] fp32, pred:[B] int64 (argmax, Trainer.py:87). */
+int mmsa_ce_fwd(int64_t B, int64_t C, const float* logits, const int64_t* labels,
+                float* loss, int64_t* pred, float* row_loss, void* stream);
+int mmsa_ce_bwd(int64_t B, int64_t C, const float* logits, const int64_t* labels,
+                const float* dloss, float* dlogits, void* stream);
+
+/* ---- L2 row normalisation (F.normalize, MultimodalModel.py:234-235) -------------------------- */
+int mmsa_l2norm_fwd(int dtype, int64_t B, int64_t E, const void* x, void* y, float* norm, void* stream);
+/* dx = (dy - y <y,dy>) / max(norm, 1e-12), dy = dy1 (+ dy2 when not NULL), both fp32 [B,E]. */
+int mmsa_l2norm_bwd(int dtype, int64_t B, int64_t E, const void* y, const float* norm, const float* dy1,
+                    const float* dy2, void* dx, void* stream);
+
+/* ---- contrastive losses on a similarity block -------------------------------------------------
+ * sim:[B,Bg] fp32 = f1n f2n^T (un-scaled cosine block, from mmsa_linear_fwd with out_dtype F32),
+ * rows are local samples with global index row_offset+i, columns the gathered global batch.
+ * kind INFONCE: MultimodalModel.py:237-260 (inv_temp = 1/temperature, device scalar temperature,
+ *   grad flows through the row max; dtemp accumulates dL/dtemperature);
+ * kind SUPCON: train.py:24-40; kind NTXENT: ME-MHACL/train.py:55-65 (partner = (i+Bg/2) mod Bg).
+ * fwd writes row_stats:[B,4] fp32 (max, all, pos, argmax-as-float bits) and loss:[1] = sum_i l_i/denominator.
+ * bwd writes G:[B,Bg] (g_dtype) = dloss * dL/dsim (w.r.t. the UN-scaled cosine) and dtemp:[1]. */
+int mmsa_contrastive_fwd(int kind, int64_t B, int64_t Bg, int64_t row_offset, const float* sim,
+                         const int64_t* labels_rows, const int64_t* labels_cols,
+                         const float* temperature, float temperature_const, int64_t denom,
+                         float* row_stats, float* row_loss, float* loss, void* stream);
+int mmsa_contrastive_bwd(int kind, int64_t B, int64_t Bg, int64_t row_offset, const float* sim,
+                         const int64_t* labels_rows, const int64_t* labels_cols,
+                         const float* temperature, float temperature_const, int64_t denom,
+                         const float* row_stats, const float* dloss,
+                         void* G, int g_dtype, float* dtemp_rows, float* dtemp, void* stream);
+
+/* ---- fused global-norm clip + AdamW over a flat fp32 parameter arena (Trainer.py:19-21,80-81;
+ *      SURVEY.md section 8(f) rank 1) ----------------------------------------------------------- */
+int mmsa_sumsq(const float* x, int64_t n, float* partials, int64_t nblk, float* out, void* stream);
+int mmsa_clip_adamw(float* p, const float* g, float* m, float* v, int64_t n, const float* gradsq,
+                    float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay,
+                    int64_t step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMSA_H_ */

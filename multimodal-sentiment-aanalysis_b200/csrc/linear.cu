@@ -1,0 +1,170 @@
+// linear.cu -- C ABI of the three Linear products (fwd, dgrad, wgrad) over the two GEMM engines:
+//   bf16 storage  -> tcgen05/TMA kernel (gemm_sm100.cu); N < 16 or unaligned -> CUDA-core kernel
+//   fp32 storage  -> CUDA-core fp32 kernel (gemm_simt.cu), the 1e-5 parity mode
+// Replaces the cuBLAS addmm calls behind nn.Linear / MHA in/out-proj / gate
+// (MultimodalModel.py:86,112-121,139-147,172-198).
+#include "common.cuh"
+
+namespace mmsa {
+
+int gemm_simt_f32(const GemmDesc& d, int splits, cudaStream_t s);
+int gemm_simt_bf16(const GemmDesc& d, int splits, cudaStream_t s);
+int gemm_simt_real_splits(int64_t Kt, int splits);
+int gemm_bf16_sm100_splits(const GemmDesc& d, int splits, cudaStream_t s);
+int gemm_num_sms();
+
+static int tc_real_splits(int64_t Kt, int splits) {
+  int64_t kb = ceil_div(Kt, 64);
+  if (splits < 1) splits = 1;
+  if (splits > kb) splits = (int)kb;
+  int64_t per = ceil_div(kb, splits);
+  return (int)ceil_div(kb, per);
+}
+
+static bool use_tc(int dtype, const GemmDesc& d) {
+  return dtype == MMSA_BF16 && d.N >= 16 && gemm_bf16_sm100_supported(d);
+}
+
+static int run_gemm(int dtype, const GemmDesc& d, int splits, cudaStream_t s) {
+  if (dtype == MMSA_F32) return gemm_simt_f32(d, splits, s);
+  if (use_tc(dtype, d)) return gemm_bf16_sm100_splits(d, splits, s);
+  return gemm_simt_bf16(d, splits, s);
+}
+
+// column sums of dy[M,N] in two deterministic stages
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(int64_t M, int64_t N, const T* __restrict__ dy, int64_t ld, int64_t rows_per_blk,
+                      float* __restrict__ partials) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int64_t col = (int64_t)blockIdx.x * 32 + tx;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_blk;
+  const int64_t r1 = r0 + rows_per_blk < M ? r0 + rows_per_blk : M;
+  float s = 0.f;
+  if (col < N)
+    for (int64_t r = r0 + ty; r < r1; r += 8) s += to_f(dy[r * ld + col]);
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && col < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][tx];
+    partials[(int64_t)blockIdx.y * N + col] = t;
+  }
+}
+
+// out[i] = sum_s partials[s*stride + i] for a [rows, cols] matrix with output row stride ldo
+__global__ void reduce_splits_kernel(const float* __restrict__ partials, int splits, int64_t stride, int64_t rows,
+                                     int64_t cols, int64_t ldp, float* __restrict__ out, int64_t ldo) {
+  int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / cols, c = i % cols;
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += partials[(int64_t)k * stride + r * ldp + c];
+    out[r * ldo + c] = s;
+  }
+}
+
+constexpr int kMaxSplits = 16;
+constexpr int kColsumRowSplits = 64;
+
+}  // namespace mmsa
+
+using namespace mmsa;
+
+extern "C" {
+
+int mmsa_linear_fwd(int dtype, int64_t M, int64_t N, int64_t K, int64_t K2, const void* x, int64_t ldx,
+                    const void* x2, int64_t ldx2, const void* w, int64_t ldw, const float* bias,
+                    const void* residual, int64_t ldr, int act, void* y, int64_t ldy, int out_dtype,
+                    void* stream) {
+  MMSA_REQUIRE_DEVICE();
+  MMSA_REQUIRE(dtype == MMSA_F32 || dtype == MMSA_BF16, "mmsa_linear_fwd: bad dtype");
+  MMSA_REQUIRE(M >= 0 && N > 0 && K > 0, "mmsa_linear_fwd: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+  MMSA_REQUIRE(!(dtype == MMSA_F32 && out_dtype == MMSA_BF16), "mmsa_linear_fwd: fp32 mode writes fp32");
+  if (M == 0) return MMSA_OK;
+  GemmDesc d{};
+  d.M = M; d.N = N; d.K = K; d.K2 = x2 ? K2 : 0;
+  d.A = x; d.lda = ldx; d.a_mn_major = false; d.A2 = x2; d.lda2 = ldx2;
+  d.B = w; d.ldb = ldw; d.b_mn_major = false;
+  d.bias = bias; d.residual = residual; d.ldr = ldr; d.act = act;
+  d.C = y; d.ldc = ldy; d.out_dtype = out_dtype; d.alpha = 1.f;
+  return run_gemm(dtype, d, 1, (cudaStream_t)stream);
+}
+
+int mmsa_linear_dgrad(int dtype, int64_t M, int64_t N, int64_t K, const void* dy, int64_t lddy, const void* w,
+                      int64_t ldw, const void* residual, int64_t ldr, void* dx, int64_t lddx, int out_dtype,
+                      void* stream) {
+  MMSA_REQUIRE_DEVICE();
+  MMSA_REQUIRE(dtype == MMSA_F32 || dtype == MMSA_BF16, "mmsa_linear_dgrad: bad dtype");
+  MMSA_REQUIRE(M >= 0 && N > 0 && K > 0, "mmsa_linear_dgrad: bad shape");
+  MMSA_REQUIRE(!(dtype == MMSA_F32 && out_dtype == MMSA_BF16), "mmsa_linear_dgrad: fp32 mode writes fp32");
+  if (M == 0) return MMSA_OK;
+  GemmDesc d{};
+  d.M = M; d.N = K; d.K = N; d.K2 = 0;
+  d.A = dy; d.lda = lddy; d.a_mn_major = false; d.A2 = nullptr;
+  d.B = w; d.ldb = ldw; d.b_mn_major = true;      // W[N,K]: reduction index n is the row -> MN-major B
+  d.bias = nullptr; d.residual = residual; d.ldr = ldr; d.act = MMSA_ACT_NONE;
+  d.C = dx; d.ldc = lddx; d.out_dtype = out_dtype; d.alpha = 1.f;
+  return run_gemm(dtype, d, 1, (cudaStream_t)stream);
+}
+
+int64_t mmsa_linear_wgrad_workspace(int dtype, int64_t M, int64_t N, int64_t K) {
+  (void)dtype; (void)M;
+  return (int64_t)sizeof(float) * (kMaxSplits * N * K + (int64_t)kColsumRowSplits * N);
+}
+
+int mmsa_linear_wgrad(int dtype, int64_t M, int64_t N, int64_t K, const void* dy, int64_t lddy, const void* x,
+                      int64_t ldx, float* dw, int64_t lddw, float* db, void* workspace, void* stream) {
+  MMSA_REQUIRE_DEVICE();
+  MMSA_REQUIRE(dtype == MMSA_F32 || dtype == MMSA_BF16, "mmsa_linear_wgrad: bad dtype");
+  MMSA_REQUIRE(M > 0 && N > 0 && K > 0, "mmsa_linear_wgrad: bad shape");
+  MMSA_REQUIRE(workspace != nullptr, "mmsa_linear_wgrad: workspace required");
+  cudaStream_t s = (cudaStream_t)stream;
+  float* ws = reinterpret_cast<float*>(workspace);
+  float* ws_colsum = ws + (int64_t)kMaxSplits * N * K;
+  if (dw != nullptr) {
+    GemmDesc d{};
+    d.M = N; d.N = K; d.K = M; d.K2 = 0;
+    d.A = dy; d.lda = lddy; d.a_mn_major = true;    // dy[M,N]: reduction index m is the row
+    d.A2 = nullptr;
+    d.B = x; d.ldb = ldx; d.b_mn_major = true;      // x[M,K]:  reduction index m is the row
+    d.bias = nullptr; d.residual = nullptr; d.act = MMSA_ACT_NONE; d.alpha = 1.f; d.out_dtype = MMSA_F32;
+    const bool tc = use_tc(dtype, d);
+    // split the long reduction (M = B*L) so that the few output tiles still fill the SMs
+    int64_t tiles = tc ? ceil_div(N, 128) * ceil_div(K, (K % 192 == 0 ? 192 : 256)) : ceil_div(N, 64) * ceil_div(K, 64);
+    int splits = (int)(gemm_num_sms() / (tiles > 0 ? tiles : 1));
+    if (splits > kMaxSplits) splits = kMaxSplits;
+    if (splits < 1) splits = 1;
+    int real = tc ? tc_real_splits(M, splits) : gemm_simt_real_splits(M, splits);
+    if (real <= 1) {
+      d.C = dw; d.ldc = lddw;
+      int rc = run_gemm(dtype, d, 1, s);
+      if (rc) return rc;
+    } else {
+      d.C = ws; d.ldc = K;
+      int rc = run_gemm(dtype, d, splits, s);
+      if (rc) return rc;
+      int64_t total = N * K;
+      int64_t blocks = ceil_div(total, 256);
+      if (blocks > 148 * 8) blocks = 148 * 8;
+      reduce_splits_kernel<<<(unsigned)blocks, 256, 0, s>>>(ws, real, N * K, N, K, K, dw, lddw);
+      MMSA_LAUNCH_CHECK("reduce_splits_kernel");
+    }
+  }
+  if (db != nullptr) {
+    int rs = (int)(M < kColsumRowSplits * 8 ? ceil_div(M, 8) : kColsumRowSplits);
+    if (rs < 1) rs = 1;
+    int64_t rpb = ceil_div(M, rs);
+    rs = (int)ceil_div(M, rpb);
+    dim3 block(32, 8), grid((unsigned)ceil_div(N, 32), (unsigned)rs);
+    MMSA_DISPATCH_DTYPE(dtype, T, (colsum_partial_kernel<T><<<grid, block, 0, s>>>(M, N, (const T*)dy, lddy, rpb, ws_colsum)));
+    MMSA_LAUNCH_CHECK("colsum_partial_kernel");
+    reduce_splits_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, s>>>(ws_colsum, rs, N, 1, N, N, db, N);
+    MMSA_LAUNCH_CHECK("reduce_splits_kernel");
+  }
+  return MMSA_OK;
+}
+
+}  // extern "C"

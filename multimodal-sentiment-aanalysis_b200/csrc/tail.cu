@@ -1,0 +1,522 @@
+// tail.cu -- small [B, N] kernels behind the pooled features:
+//   BatchNorm1d(+GELU/ReLU)+dropout fwd/bwd, softmax cross-entropy, contrastive row reductions
+//   (InfoNCE / SupCon / NT-Xent) and their gradients, global-norm clip + AdamW.
+// Reference arithmetic: MultimodalModel.py:179-199 (fusion / heads), Trainer.py:17,68 (CE),
+// MultimodalModel.py:232-260 (InfoNCE), train.py:16-40 (SupCon), ME-MHACL/train.py:47-66 (NT-Xent),
+// Trainer.py:19-21,80-81 (clip + AdamW).
+#include "common.cuh"
+
+namespace mmsa {
+
+// ------------------------------------------------------------------ Philox4x32-10 (dropout masks)
+__device__ __forceinline__ uint32_t philox_first(uint64_t seed, uint64_t ctr) {
+  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0u, c3 = 0u;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return c0;
+}
+
+// ------------------------------------------------------------------ BatchNorm1d + act + dropout
+// block (32 columns, 8 row lanes); one block per 32 columns; three passes over the (tiny) [B,N] input.
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_act_fwd_kernel(int64_t B, int N, int order, const T* __restrict__ x, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, float* __restrict__ running_mean,
+                  float* __restrict__ running_var, float momentum, float eps, int training,
+                  float dropout_p, uint8_t* __restrict__ keep_mask, int mask_given, uint64_t seed,
+                  uint64_t offset, T* __restrict__ y, float* __restrict__ save_mean,
+                  float* __restrict__ save_rstd) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int col = blockIdx.x * 32 + tx;
+  const bool ok = col < N;
+  const bool pre_relu = (order == MMSA_RELU_THEN_BN);
+  float mean = 0.f, var = 1.f;
+  if (training) {
+    float s = 0.f;
+    if (ok)
+      for (int64_t r = ty; r < B; r += 8) {
+        float v = to_f(x[r * N + col]);
+        if (pre_relu) v = fmaxf(v, 0.f);
+        s += v;
+      }
+    red[ty][tx] = s;
+    __syncthreads();
+    s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][tx];
+    mean = s / (float)B;
+    __syncthreads();
+    float q = 0.f;
+    if (ok)
+      for (int64_t r = ty; r < B; r += 8) {
+        float v = to_f(x[r * N + col]);
+        if (pre_relu) v = fmaxf(v, 0.f);
+        float d = v - mean;
+        q += d * d;
+      }
+    red[ty][tx] = q;
+    __syncthreads();
+    q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) q += red[k][tx];
+    var = q / (float)B;
+    if (ok && ty == 0 && running_mean != nullptr) {
+      float unbiased = B > 1 ? q / (float)(B - 1) : var;
+      running_mean[col] = (1.f - momentum) * running_mean[col] + momentum * mean;
+      running_var[col] = (1.f - momentum) * running_var[col] + momentum * unbiased;
+    }
+  } else if (ok) {
+    mean = running_mean[col];
+    var = running_var[col];
+  }
+  const float rstd = 1.f / sqrtf(var + eps);
+  if (ok && ty == 0) { save_mean[col] = mean; save_rstd[col] = rstd; }
+  if (!ok) return;
+  const float gm = gamma[col], bt = beta[col];
+  const bool drop = training && dropout_p > 0.f;
+  const float keep_scale = drop ? 1.f / (1.f - dropout_p) : 1.f;
+  for (int64_t r = ty; r < B; r += 8) {
+    float v = to_f(x[r * N + col]);
+    if (pre_relu) v = fmaxf(v, 0.f);
+    float z = (v - mean) * rstd * gm + bt;
+    if (order == MMSA_BN_THEN_GELU) z = gelu_erf(z);
+    if (drop) {
+      uint8_t keep;
+      if (mask_given) keep = keep_mask[r * N + col];
+      else {
+        uint32_t rnd = philox_first(seed, offset + (uint64_t)(r * N + col));
+        keep = ((float)(rnd >> 8) * (1.f / 16777216.f)) >= dropout_p ? 1 : 0;
+        keep_mask[r * N + col] = keep;
+      }
+      z = keep ? z * keep_scale : 0.f;
+    }
+    y[r * N + col] = from_f<T>(z);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_act_bwd_kernel(int64_t B, int N, int order, const T* __restrict__ x, const T* __restrict__ dy,
+                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                  const float* __restrict__ save_mean, const float* __restrict__ save_rstd, int training,
+                  float dropout_p, const uint8_t* __restrict__ keep_mask, T* __restrict__ dx,
+                  float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float red[2][8][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int col = blockIdx.x * 32 + tx;
+  const bool ok = col < N;
+  const bool pre_relu = (order == MMSA_RELU_THEN_BN);
+  const bool drop = training && dropout_p > 0.f;
+  const float keep_scale = drop ? 1.f / (1.f - dropout_p) : 1.f;
+  const float mean = ok ? save_mean[col] : 0.f, rstd = ok ? save_rstd[col] : 0.f;
+  const float gm = ok ? gamma[col] : 0.f, bt = ok ? beta[col] : 0.f;
+  float sdz = 0.f, sdzx = 0.f;
+  if (ok)
+    for (int64_t r = ty; r < B; r += 8) {
+      float v = to_f(x[r * N + col]);
+      if (pre_relu) v = fmaxf(v, 0.f);
+      float xh = (v - mean) * rstd;
+      float d = to_f(dy[r * N + col]);
+      if (drop) d = keep_mask[r * N + col] ? d * keep_scale : 0.f;
+      if (order == MMSA_BN_THEN_GELU) d *= gelu_erf_grad(xh * gm + bt);
+      sdz += d;
+      sdzx += d * xh;
+    }
+  red[0][ty][tx] = sdz;
+  red[1][ty][tx] = sdzx;
+  __syncthreads();
+  sdz = 0.f; sdzx = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { sdz += red[0][k][tx]; sdzx += red[1][k][tx]; }
+  if (!ok) return;
+  if (ty == 0) { dgamma[col] = sdzx; dbeta[col] = sdz; }
+  const float invB = 1.f / (float)B;
+  for (int64_t r = ty; r < B; r += 8) {
+    float raw = to_f(x[r * N + col]);
+    float v = pre_relu ? fmaxf(raw, 0.f) : raw;
+    float xh = (v - mean) * rstd;
+    float d = to_f(dy[r * N + col]);
+    if (drop) d = keep_mask[r * N + col] ? d * keep_scale : 0.f;
+    if (order == MMSA_BN_THEN_GELU) d *= gelu_erf_grad(xh * gm + bt);
+    float dv = training ? gm * rstd * (d - sdz * invB - xh * sdzx * invB) : gm * rstd * d;
+    if (pre_relu && raw <= 0.f) dv = 0.f;
+    dx[r * N + col] = from_f<T>(dv);
+  }
+}
+
+// ------------------------------------------------------------------ softmax cross-entropy
+__global__ void ce_fwd_kernel(int64_t B, int C, const float* __restrict__ logits, const int64_t* __restrict__ labels,
+                              int64_t* __restrict__ pred, float* __restrict__ row_loss) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= B) return;
+  const float* z = logits + r * C;
+  float mx = z[0]; int am = 0;
+  for (int c = 1; c < C; ++c) if (z[c] > mx) { mx = z[c]; am = c; }
+  float s = 0.f;
+  for (int c = 0; c < C; ++c) s += expf(z[c] - mx);
+  int64_t y = labels[r];
+  row_loss[r] = (logf(s) + mx) - z[y];
+  if (pred) pred[r] = am;
+}
+
+// deterministic single-block sum: out[0] = scale * sum(v[0..n))
+__global__ void sum_scale_kernel(const float* __restrict__ v, int64_t n, float scale, float* __restrict__ out) {
+  __shared__ float sm[32];
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
+  s = block_sum(s, sm);
+  if (threadIdx.x == 0) out[0] = s * scale;
+}
+
+__global__ void ce_bwd_kernel(int64_t B, int C, const float* __restrict__ logits, const int64_t* __restrict__ labels,
+                              const float* __restrict__ dloss, float* __restrict__ dlogits) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= B) return;
+  const float* z = logits + r * C;
+  float mx = z[0];
+  for (int c = 1; c < C; ++c) mx = fmaxf(mx, z[c]);
+  float s = 0.f;
+  for (int c = 0; c < C; ++c) s += expf(z[c] - mx);
+  float g = dloss[0] / (float)B;
+  int64_t y = labels[r];
+  for (int c = 0; c < C; ++c) dlogits[r * C + c] = g * (expf(z[c] - mx) / s - (c == y ? 1.f : 0.f));
+}
+
+// ------------------------------------------------------------------ contrastive row kernels
+// one warp per row of the [B, Bg] cosine block.
+__device__ __forceinline__ float load_temp(const float* tptr, float tconst) { return tptr ? tptr[0] : tconst; }
+
+__global__ void __launch_bounds__(256)
+contrastive_fwd_kernel(int kind, int64_t B, int64_t Bg, int64_t row_offset, const float* __restrict__ sim,
+                       const int64_t* __restrict__ lab_r, const int64_t* __restrict__ lab_c,
+                       const float* __restrict__ tptr, float tconst, float* __restrict__ row_stats,
+                       float* __restrict__ row_loss) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 8 + warp;
+  if (i >= B) return;
+  const float T = load_temp(tptr, tconst);
+  const float* row = sim + i * Bg;
+  const int64_t gi = row_offset + i;
+  if (kind == MMSA_LOSS_INFONCE) {
+    const int64_t yi = lab_r[i];
+    float mx = -INFINITY; int64_t am = 0;
+    for (int64_t j = lane; j < Bg; j += 32) {
+      float s = row[j] / T;
+      if (s > mx) { mx = s; am = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {   // max with first-index tie break (torch.max CPU semantics)
+      float om = __shfl_xor_sync(0xffffffffu, mx, o);
+      long long oa = __shfl_xor_sync(0xffffffffu, (long long)am, o);
+      if (om > mx || (om == mx && oa < am)) { mx = om; am = oa; }
+    }
+    float all = 0.f, pos = 0.f;
+    for (int64_t j = lane; j < Bg; j += 32) {
+      float e = expf(row[j] / T - mx);
+      all += e;
+      if (j != gi && lab_c[j] == yi) pos += e;
+    }
+    all = warp_sum(all); pos = warp_sum(pos);
+    if (lane == 0) {
+      row_stats[i * 4 + 0] = mx; row_stats[i * 4 + 1] = all; row_stats[i * 4 + 2] = pos;
+      row_stats[i * 4 + 3] = __int_as_float((int)am);
+      row_loss[i] = -logf((pos + 1e-12f) / (all + 1e-12f));
+    }
+  } else if (kind == MMSA_LOSS_SUPCON) {
+    const int64_t yi = lab_r[i];
+    float se = 0.f, cnt = 0.f, ms = 0.f;
+    for (int64_t j = lane; j < Bg; j += 32) {
+      if (j == gi) continue;
+      float s = row[j] / T;
+      se += expf(s);
+      if (lab_c[j] == yi) { cnt += 1.f; ms += s; }
+    }
+    se = warp_sum(se); cnt = warp_sum(cnt); ms = warp_sum(ms);
+    if (lane == 0) {
+      float lse = logf(se + 1e-8f);
+      row_stats[i * 4 + 0] = se; row_stats[i * 4 + 1] = cnt; row_stats[i * 4 + 2] = ms; row_stats[i * 4 + 3] = lse;
+      row_loss[i] = -(ms - cnt * lse) / (cnt + 1e-8f);
+    }
+  } else {  // NT-Xent: CE over the row with the diagonal masked, target = partner view
+    const int64_t partner = (gi + Bg / 2) % Bg;
+    float mx = -INFINITY;
+    for (int64_t j = lane; j < Bg; j += 32) if (j != gi) mx = fmaxf(mx, row[j] / T);
+    mx = warp_max(mx);
+    float se = 0.f;
+    for (int64_t j = lane; j < Bg; j += 32) if (j != gi) se += expf(row[j] / T - mx);
+    se = warp_sum(se);
+    if (lane == 0) {
+      row_stats[i * 4 + 0] = mx; row_stats[i * 4 + 1] = se; row_stats[i * 4 + 2] = 0.f; row_stats[i * 4 + 3] = 0.f;
+      row_loss[i] = (logf(se) + mx) - row[partner] / T;
+    }
+  }
+}
+
+template <typename TG>
+__global__ void __launch_bounds__(256)
+contrastive_bwd_kernel(int kind, int64_t B, int64_t Bg, int64_t row_offset, const float* __restrict__ sim,
+                       const int64_t* __restrict__ lab_r, const int64_t* __restrict__ lab_c,
+                       const float* __restrict__ tptr, float tconst, float inv_denom,
+                       const float* __restrict__ row_stats, const float* __restrict__ dloss,
+                       TG* __restrict__ G, float* __restrict__ dtemp_rows) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 8 + warp;
+  if (i >= B) return;
+  const float T = load_temp(tptr, tconst);
+  const float up = dloss[0] * inv_denom;
+  const float* row = sim + i * Bg;
+  TG* grow = G + i * Bg;
+  const int64_t gi = row_offset + i;
+  float dts = 0.f;   // sum_j gs_ij * s_ij
+  if (kind == MMSA_LOSS_INFONCE) {
+    const int64_t yi = lab_r[i];
+    const float mx = row_stats[i * 4 + 0], all = row_stats[i * 4 + 1], pos = row_stats[i * 4 + 2];
+    const int64_t am = (int64_t)__float_as_int(row_stats[i * 4 + 3]);
+    const float ia = 1.f / (all + 1e-12f), ip = 1.f / (pos + 1e-12f);
+    const float gmax = pos * ip - all * ia;     // gradient that flows through the subtracted row max
+    for (int64_t j = lane; j < Bg; j += 32) {
+      float s = row[j] / T;
+      float e = expf(s - mx);
+      float gs = e * ia;
+      if (j != gi && lab_c[j] == yi) gs -= e * ip;
+      if (j == am) gs += gmax;
+      gs *= up;
+      dts += gs * s;
+      grow[j] = from_f<TG>(gs / T);
+    }
+  } else if (kind == MMSA_LOSS_SUPCON) {
+    const int64_t yi = lab_r[i];
+    const float se = row_stats[i * 4 + 0], cnt = row_stats[i * 4 + 1];
+    const float ic = 1.f / (cnt + 1e-8f), cfrac = cnt * ic, ise = 1.f / (se + 1e-8f);
+    for (int64_t j = lane; j < Bg; j += 32) {
+      float gs = 0.f, s = row[j] / T;
+      if (j != gi) {
+        gs = cfrac * expf(s) * ise;
+        if (lab_c[j] == yi) gs -= ic;
+      }
+      gs *= up;
+      dts += gs * s;
+      grow[j] = from_f<TG>(gs / T);
+    }
+  } else {
+    const int64_t partner = (gi + Bg / 2) % Bg;
+    const float mx = row_stats[i * 4 + 0], se = row_stats[i * 4 + 1];
+    for (int64_t j = lane; j < Bg; j += 32) {
+      float gs = 0.f, s = row[j] / T;
+      if (j != gi) gs = expf(s - mx) / se;
+      if (j == partner) gs -= 1.f;
+      gs *= up;
+      dts += gs * s;
+      grow[j] = from_f<TG>(gs / T);
+    }
+  }
+  dts = warp_sum(dts);
+  if (lane == 0 && dtemp_rows) dtemp_rows[i] = -dts / T;   // ds/dT = -s/T
+}
+
+// ------------------------------------------------------------------ clip + AdamW
+__global__ void sumsq_partial_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ partials) {
+  __shared__ float sm[32];
+  float s = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = x[i];
+    s += v * v;
+  }
+  s = block_sum(s, sm);
+  if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+// torch.nn.utils.clip_grad_norm_(params, max_norm) then AdamW (decoupled weight decay), Trainer.py:19-21,80-81
+__global__ void clip_adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                  float* __restrict__ v, int64_t n, const float* __restrict__ gradsq,
+                                  float max_norm, float lr, float beta1, float beta2, float eps, float wd,
+                                  float bc1, float bc2) {
+  float total = sqrtf(gradsq[0]);
+  float coef = max_norm / (total + 1e-6f);
+  coef = coef < 1.f ? coef : 1.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * coef;
+    float pi = p[i] * (1.f - lr * wd);
+    float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
+}  // namespace mmsa
+
+using namespace mmsa;
+
+extern "C" {
+
+int mmsa_bn_act_fwd(int dtype, int64_t B, int64_t N, int order, const void* x, const float* gamma,
+                    const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                    int training, float dropout_p, uint8_t* keep_mask, int mask_given, uint64_t seed,
+                    uint64_t offset, void* y, float* save_mean, float* save_rstd, void* stream) {
+  MMSA_REQUIRE_DEVICE();
+  MMSA_REQUIRE(B > 0 && N > 0, "mmsa_bn_act_fwd: empty input");
+  MMSA_REQUIRE(training || (running_mean && running_var), "mmsa_bn_act_fwd: eval mode needs running stats");
+  MMSA_REQUIRE(!(training && dropout_p > 0.f) || keep_mask != nullptr, "mmsa_bn_act_fwd: dropout needs keep_mask storage");
+  MMSA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "mmsa_bn_act_fwd: dropout_p out of [0,1)");
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 block(32, 8);
+  MMSA_DISPATCH_DTYPE(dtype, T, (bn_act_fwd_kernel<T><<<(unsigned)ceil_div(N, 32), block, 0, s>>>(
+      B, (int)N, order, (const T*)x, gamma, beta, running_mean, running_var, momentum, eps, training, dropout_p,
+      keep_mask, mask_given, seed, offset, (T*)y, save_mean, save_rstd)));
+  MMSA_LAUNCH_CHECK("bn_act_fwd_kernel");
+  return MMSA_OK;
+}
+
+int mmsa_bn_act_bwd(int dtype, int64_t B, int64_t N, int order, const void* x, const void* dy,
+                    const float* gamma, const float* beta, const float* save_mean, const float* save_rstd,
+                    int training, float dropout_p, const uint8_t* keep_mask, void* dx, float* dgamma,
+                    float* dbeta, void* stream) {
+  MMSA_REQUIRE_DEVICE();
+  MMSA_REQUIRE(B > 0 && N > 0, "mmsa_bn_act_bwd: empty input");
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 block(32, 8);
+  MMSA_DISPATCH_DTYPE(dtype, T, (bn_act_bwd_kernel<T><<<(unsigned)ceil_div(N, 32), block, 0, s>>>(
+      B, (int)N, order, (const T*)x, (const T*)dy, gamma, beta, save_mean, save_rstd, training, dropout_p, keep_mask,
+      (T*)dx, dgamma, dbeta)));
+  MMSA_LAUNCH_CHECK("bn_act_bwd_kernel");
+  return MMSA_OK;
+}
+
+int mmsa_ce_fwd(int64_t B, int64_t C, const float* logits, const int64_t* labels, float* loss, int64_t* pred,
+                float* row_loss, void* stream) {
+  MMSA_REQUIRE_DEVICE();
+  MMSA_REQUIRE(B > 0 && C > 0 && C <= 64, "mmsa_ce_fwd: bad shape B=%lld C=%lld", (long long)B, (long long)C);
+  cudaStream_t s = (cudaStream_t)stream;
+  ce_fwd_kernel<<<(unsigned)ceil_div(B, 128), 128, 0, s>>>(B, (int)C, logits, labels, pred, row_loss);
+  MMSA_LAUNCH_CHECK("ce_fwd_kernel");
+  sum_scale_kernel<<<1, 256, 0, s>>>(row_loss, B, 1.f / (float)B, loss);
+  MMSA_LAUNCH_CHECK("sum_scale_kernel");
+  return MMSA_OK;
+}
+
+int mmsa_ce_bwd(int64_t B, int64_t C, const float* logits, const int64_t* labels, const float* dloss,
+                float* dlogits, void* stream) {
+  MMSA_REQUIRE_DEVICE();
+  MMSA_REQUIRE(B > 0 && C > 0 && C <= 64, "mmsa_ce_bwd: bad shape");
+  cudaStream_t s = (cudaStream_t)stream;
+  ce_bwd_kernel<<<(unsigned)ceil_div(B, 128), 128, 0, s>>>(B, (int)C, logits, labels, dloss, dlogits);
+  MMSA_LAUNCH_CHECK("ce_bwd_kernel");
+  return MMSA_OK;
+}
+
+int mmsa_contrastive_fwd(int kind, int64_t B, int64_t Bg, int64_t row_offset, const float* sim,
+                         const int64_t* labels_rows, const int64_t* labels_cols, const float* temperature,
+                         float temperature_const, int64_t denom, float* row_stats, float* row_loss,
+                         float* loss, void* stream) {
+  MMSA_REQUIRE_DEVICE();
+  MMSA_REQUIRE(kind >= 0 && kind <= 2, "mmsa_contrastive_fwd: bad kind %d", kind);
+  MMSA_REQUIRE(B > 0 && Bg > 0 && denom > 0, "mmsa_contrastive_fwd: empty input");
+  MMSA_REQUIRE(kind == MMSA_LOSS_NTXENT || (labels_rows && labels_cols), "mmsa_contrastive_fwd: labels required");
+  cudaStream_t s = (cudaStream_t)stream;
+  contrastive_fwd_kernel<<<(unsigned)ceil_div(B, 8), 256, 0, s>>>(kind, B, Bg, row_offset, sim, labels_rows,
+                                                                  labels_cols, temperature, temperature_const,
+                                                                  row_stats, row_loss);
+  MMSA_LAUNCH_CHECK("contrastive_fwd_kernel");
+  sum_scale_kernel<<<1, 256, 0, s>>>(row_loss, B, 1.f / (float)denom, loss);
+  MMSA_LAUNCH_CHECK("sum_scale_kernel");
+  return MMSA_OK;
+}
+
+int mmsa_contrastive_bwd(int kind, int64_t B, int64_t Bg, int64_t row_offset, const float* sim,
+                         const int64_t* labels_rows, const int64_t* labels_cols, const float* temperature,
+                         float temperature_const, int64_t denom, const float* row_stats, const float* dloss,
+                         void* G, int g_dtype, float* dtemp_rows, float* dtemp, void* stream) {
+  MMSA_REQUIRE_DEVICE();
+  MMSA_REQUIRE(kind >= 0 && kind <= 2, "mmsa_contrastive_bwd: bad kind %d", kind);
+  MMSA_REQUIRE(B > 0 && Bg > 0 && denom > 0, "mmsa_contrastive_bwd: empty input");
+  cudaStream_t s = (cudaStream_t)stream;
+  float inv_denom = 1.f / (float)denom;
+  if (g_dtype == MMSA_F32)
+    contrastive_bwd_kernel<float><<<(unsigned)ceil_div(B, 8), 256, 0, s>>>(
+        kind, B, Bg, row_offset, sim, labels_rows, labels_cols, temperature, temperature_const, inv_denom,
+        row_stats, dloss, (float*)G, dtemp_rows);
+  else
+    contrastive_bwd_kernel<bf16><<<(unsigned)ceil_div(B, 8), 256, 0, s>>>(
+        kind, B, Bg, row_offset, sim, labels_rows, labels_cols, temperature, temperature_const, inv_denom,
+        row_stats, dloss, (bf16*)G, dtemp_rows);
+  MMSA_LAUNCH_CHECK("contrastive_bwd_kernel");
+  if (dtemp_rows && dtemp) {
+    sum_scale_kernel<<<1, 256, 0, s>>>(dtemp_rows, B, 1.f, dtemp);
+    MMSA_LAUNCH_CHECK("sum_scale_kernel");
+  }
+  return MMSA_OK;
+}
+
+int mmsa_sumsq(const float* x, int64_t n, float* partials, int64_t nblk, float* out, void* stream) {
+  MMSA_REQUIRE_DEVICE();
+  MMSA_REQUIRE(nblk > 0 && nblk <= 4096, "mmsa_sumsq: nblk out of range");
+  cudaStream_t s = (cudaStream_t)stream;
+  sumsq_partial_kernel<<<(unsigned)nblk, 256, 0, s>>>(x, n, partials);
+  MMSA_LAUNCH_CHECK("sumsq_partial_kernel");
+  sum_scale_kernel<<<1, 256, 0, s>>>(partials, nblk, 1.f, out);
+  MMSA_LAUNCH_CHECK("sum_scale_kernel");
+  return MMSA_OK;
+}
+
+int mmsa_clip_adamw(float* p, const float* g, float* m, float* v, int64_t n, const float* gradsq,
+                    float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay,
+                    int64_t step, void* stream) {
+  MMSA_REQUIRE_DEVICE();
+  MMSA_REQUIRE(step >= 1, "mmsa_clip_adamw: step starts at 1");
+  if (n == 0) return MMSA_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  int64_t blocks = ceil_div(n, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  clip_adamw_kernel<<<(unsigned)blocks, 256, 0, s>>>(p, g, m, v, n, gradsq, max_norm, lr, beta1, beta2, eps,
+                                                    weight_decay, bc1, bc2);
+  MMSA_LAUNCH_CHECK("clip_adamw_kernel");
+  return MMSA_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ stand-alone dropout
+// nn.Dropout(0.5) after a ReLU with no BatchNorm in between (Classifier.shared, ME-MHACL/model.py:105-109).
+// Backward is the same kernel applied to dy with the saved mask.
+namespace mmsa {
+template <typename T>
+__global__ void dropout_kernel(int64_t n, const T* __restrict__ x, float p, uint8_t* __restrict__ keep_mask,
+                               int mask_given, uint64_t seed, uint64_t offset, T* __restrict__ y) {
+  const float scale = 1.f / (1.f - p);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    uint8_t keep;
+    if (mask_given) keep = keep_mask[i];
+    else {
+      uint32_t rnd = philox_first(seed, offset + (uint64_t)i);
+      keep = ((float)(rnd >> 8) * (1.f / 16777216.f)) >= p ? 1 : 0;
+      keep_mask[i] = keep;
+    }
+    y[i] = from_f<T>(keep ? to_f(x[i]) * scale : 0.f);
+  }
+}
+}  // namespace mmsa
+
+extern "C" int mmsa_dropout(int dtype, int64_t n, const void* x, float p, uint8_t* keep_mask, int mask_given,
+                            uint64_t seed, uint64_t offset, void* y, void* stream) {
+  MMSA_REQUIRE_DEVICE();
+  MMSA_REQUIRE(p >= 0.f && p < 1.f && keep_mask != nullptr, "mmsa_dropout: bad arguments");
+  if (n == 0) return MMSA_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  int64_t blocks = mmsa::ceil_div(n, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  MMSA_DISPATCH_DTYPE(dtype, T, (mmsa::dropout_kernel<T><<<(unsigned)blocks, 256, 0, s>>>(
+      n, (const T*)x, p, keep_mask, mask_given, seed, offset, (T*)y)));
+  MMSA_LAUNCH_CHECK("dropout_kernel");
+  return MMSA_OK;
+}

@@ -1,0 +1,12 @@
+"""mmsa -- B200 (sm_100a) hot path of the multimodal fusion / ME-MHACL / contrastive model.
+
+Python host mirroring the reference's nn.Module interface (MultimodalModel.py, ME-MHACL/model.py)
+over a C-ABI CUDA library (include/mmsa.h).  Importing the package does not need a GPU; running
+any op does, and raises if the extension is missing (no fallback)."""
+from . import _lib
+from .model import (Classifier, CrossModalTransformer, FeatureProjection, MultiModalEncoder,
+                    MultimodalTransformerModel, ProjectionHead)
+from .ops import cross_entropy, infonce, ntxent, supcon
+
+__all__ = ["MultimodalTransformerModel", "CrossModalTransformer", "FeatureProjection", "MultiModalEncoder",
+           "ProjectionHead", "Classifier", "cross_entropy", "infonce", "supcon", "ntxent", "_lib"]

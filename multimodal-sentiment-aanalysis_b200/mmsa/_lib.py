@@ -1,0 +1,101 @@
+"""ctypes binding of libmmsa.so (the C ABI declared in include/mmsa.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, the caller
+gets an exception.  PyTorch is only used for device memory and streams."""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+from ctypes import c_float, c_int, c_int64, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmmsa.so")
+HEADER_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "include", "mmsa.h"))
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_SIGMOID, ACT_GELU, ACT_RELU = 0, 1, 2, 3
+BN_THEN_GELU, RELU_THEN_BN, BN_ONLY = 0, 1, 2
+LOSS_INFONCE, LOSS_SUPCON, LOSS_NTXENT = 0, 1, 2
+
+P, I, L, F, U = c_void_p, c_int, c_int64, c_float, c_uint64
+
+# name -> (restype, argtypes); must cover every symbol include/mmsa.h declares
+_PROTOS = {
+    "mmsa_version": (ctypes.c_char_p, []),
+    "mmsa_last_error": (ctypes.c_char_p, []),
+    "mmsa_check_device": (I, []),
+    "mmsa_launch_count": (L, []),
+    "mmsa_cast": (I, [P, I, P, I, L, P]),
+    "mmsa_linear_fwd": (I, [I, L, L, L, L, P, L, P, L, P, L, P, P, L, I, P, L, I, P]),
+    "mmsa_linear_dgrad": (I, [I, L, L, L, P, L, P, L, P, L, P, L, I, P]),
+    "mmsa_linear_wgrad_workspace": (L, [I, L, L, L]),
+    "mmsa_linear_wgrad": (I, [I, L, L, L, P, L, P, L, P, L, P, P, P]),
+    "mmsa_debug_force_simt_attention": (None, [I]),
+    "mmsa_attn_fwd": (I, [I, L, L, L, L, L, P, L, P, L, P, L, P, L, P, P]),
+    "mmsa_attn_bwd": (I, [I, L, L, L, L, L, P, L, P, L, P, L, P, L, P, L, P, P, P, L, P, L, P, L, P]),
+    "mmsa_gate_ln_fwd": (I, [I, L, L, P, P, P, P, P, F, P, P, P, P, P]),
+    "mmsa_gate_ln_bwd_blocks": (L, [L]),
+    "mmsa_gate_ln_bwd": (I, [I, L, L, P, L, P, P, P, P, P, P, P, L, P, P, P, P, P, P, P, P]),
+    "mmsa_pool_fwd": (I, [I, L, L, L, P, I, P, P, P]),
+    "mmsa_pool_bwd": (I, [I, L, L, L, P, I, P, P, P]),
+    "mmsa_modal_concat_fwd": (I, [I, L, L, I, P, P, P, P, P]),
+    "mmsa_modal_concat_bwd": (I, [I, L, L, I, P, P, P, P, P, P]),
+    "mmsa_act_fwd": (I, [I, L, P, I, P, P]),
+    "mmsa_act_bwd": (I, [I, L, P, P, I, P, P]),
+    "mmsa_bn_act_fwd": (I, [I, L, L, I, P, P, P, P, P, F, F, I, F, P, I, U, U, P, P, P, P]),
+    "mmsa_bn_act_bwd": (I, [I, L, L, I, P, P, P, P, P, P, I, F, P, P, P, P, P]),
+    "mmsa_dropout": (I, [I, L, P, F, P, I, U, U, P, P]),
+    "mmsa_ce_fwd": (I, [L, L, P, P, P, P, P, P]),
+    "mmsa_ce_bwd": (I, [L, L, P, P, P, P, P]),
+    "mmsa_l2norm_fwd": (I, [I, L, L, P, P, P, P]),
+    "mmsa_l2norm_bwd": (I, [I, L, L, P, P, P, P, P, P]),
+    "mmsa_contrastive_fwd": (I, [I, L, L, L, P, P, P, P, F, L, P, P, P, P]),
+    "mmsa_contrastive_bwd": (I, [I, L, L, L, P, P, P, P, F, L, P, P, P, I, P, P, P]),
+    "mmsa_sumsq": (I, [P, L, P, L, P, P]),
+    "mmsa_clip_adamw": (I, [P, P, P, P, L, P, F, F, F, F, F, F, L, P]),
+}
+
+_lib = None
+
+
+def header_symbols():
+    """Every function name include/mmsa.h declares."""
+    with open(HEADER_PATH) as f:
+        text = f.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mmsa_[a-z0-9_]+)\s*\(", text)))
+
+
+def load():
+    """dlopen libmmsa.so and bind every prototype.  Raises if the library or a symbol is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"mmsa: CUDA extension {LIB_PATH} is missing. Build it with "
+            f"`python __graft_entry__.py` (nvcc, sm_100a). There is no CPU/PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _PROTOS.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class MmsaError(RuntimeError):
+    pass
+
+
+def call(name: str, *args):
+    """Invoke an int-returning entry point; raise MmsaError with mmsa_last_error() on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise MmsaError(f"{name} failed (code {rc}): {lib.mmsa_last_error().decode()}")
+
+
+def launch_count() -> int:
+    return int(load().mmsa_launch_count())

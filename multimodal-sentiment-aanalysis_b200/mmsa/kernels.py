@@ -1,0 +1,320 @@
+"""Thin tensor-level wrappers over the C ABI: each function takes torch CUDA tensors, allocates the
+outputs (caller-allocates convention of include/mmsa.h) and enqueues the kernels on the current
+stream.  No arithmetic happens in Python/PyTorch here."""
+from __future__ import annotations
+
+from typing import Optional, Sequence, Tuple
+
+import ctypes
+import torch
+
+from . import _lib
+from ._lib import F32, BF16, call
+
+Tensor = torch.Tensor
+
+
+def dt(t_or_dtype) -> int:
+    d = t_or_dtype.dtype if isinstance(t_or_dtype, Tensor) else t_or_dtype
+    if d == torch.float32:
+        return F32
+    if d == torch.bfloat16:
+        return BF16
+    raise TypeError(f"mmsa: unsupported dtype {d}")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _check(*ts: Optional[Tensor]):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.MmsaError("mmsa: tensors must live on a CUDA device (no CPU fallback)")
+
+
+def cast(x: Tensor, dtype: torch.dtype) -> Tensor:
+    """dtype conversion through mmsa_cast (fp32 <-> bf16)."""
+    if x.dtype == dtype:
+        return x
+    _check(x)
+    x = x.contiguous()
+    y = torch.empty_like(x, dtype=dtype)
+    call("mmsa_cast", x.data_ptr(), dt(x), y.data_ptr(), dt(dtype), x.numel(), _stream())
+    return y
+
+
+def linear_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor], *, x2: Optional[Tensor] = None,
+               residual: Optional[Tensor] = None, act: int = 0, out_dtype: Optional[torch.dtype] = None,
+               out: Optional[Tensor] = None) -> Tensor:
+    """y[M,N] = act(cat[x, x2] @ w.T + bias + residual); x:[M,K] (row stride x.stride(0)), w:[N,K(+K2)]."""
+    _check(x, w, bias, x2, residual)
+    M, K = x.shape
+    N = w.shape[0]
+    K2 = 0 if x2 is None else x2.shape[1]
+    assert w.shape[1] == K + K2 and x.stride(1) == 1 and w.stride(1) == 1
+    od = out_dtype or x.dtype
+    y = out if out is not None else torch.empty((M, N), device=x.device, dtype=od)
+    call("mmsa_linear_fwd", dt(x), M, N, K, K2, x.data_ptr(), x.stride(0), _p(x2), 0 if x2 is None else x2.stride(0),
+         w.data_ptr(), w.stride(0), _p(bias), _p(residual), 0 if residual is None else residual.stride(0), act,
+         y.data_ptr(), y.stride(0), dt(od), _stream())
+    return y
+
+
+def linear_dgrad(dy: Tensor, w: Tensor, *, residual: Optional[Tensor] = None,
+                 out_dtype: Optional[torch.dtype] = None, out: Optional[Tensor] = None) -> Tensor:
+    """dx[M,K] = dy[M,N] @ w[N,K] (+ residual)."""
+    _check(dy, w, residual)
+    M, N = dy.shape
+    K = w.shape[1]
+    assert w.shape[0] == N and dy.stride(1) == 1 and w.stride(1) == 1
+    od = out_dtype or dy.dtype
+    dx = out if out is not None else torch.empty((M, K), device=dy.device, dtype=od)
+    call("mmsa_linear_dgrad", dt(dy), M, N, K, dy.data_ptr(), dy.stride(0), w.data_ptr(), w.stride(0),
+         _p(residual), 0 if residual is None else residual.stride(0), dx.data_ptr(), dx.stride(0), dt(od), _stream())
+    return dx
+
+
+def linear_wgrad(dy: Tensor, x: Tensor, *, dw: Optional[Tensor] = None, db: Optional[Tensor] = None,
+                 want_bias: bool = True, want_weight: bool = True) -> Tuple[Optional[Tensor], Optional[Tensor]]:
+    """dw[N,K] = dy[M,N].T @ x[M,K] (fp32); db[N] = dy.sum(0) (fp32).  `dw` may be a strided view
+    (a column block of a wider weight gradient)."""
+    _check(dy, x, dw)
+    M, N = dy.shape
+    K = x.shape[1]
+    assert x.shape[0] == M and dy.stride(1) == 1 and x.stride(1) == 1
+    if want_weight and dw is None:
+        dw = torch.empty((N, K), device=dy.device, dtype=torch.float32)
+    if want_bias and db is None:
+        db = torch.empty((N,), device=dy.device, dtype=torch.float32)
+    if not want_bias:
+        db = None
+    if M == 0:
+        if dw is not None:
+            dw.zero_()
+        if db is not None:
+            db.zero_()
+        return dw, db
+    nbytes = _lib.load().mmsa_linear_wgrad_workspace(dt(dy), M, N, K)
+    ws = torch.empty((nbytes // 4,), device=dy.device, dtype=torch.float32)
+    call("mmsa_linear_wgrad", dt(dy), M, N, K, dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0),
+         _p(dw) if want_weight else None, 0 if dw is None else dw.stride(0), _p(db), ws.data_ptr(), _stream())
+    return (dw if want_weight else None), db
+
+
+def attn_fwd(q: Tensor, k: Tensor, v: Tensor, B: int, H: int, Lq: int, Lk: int, D: int) -> Tuple[Tensor, Tensor]:
+    """q:[B*Lq, >=H*D] views, k/v:[B*Lk, ...] views (row strides may differ) -> o:[B*Lq,H*D], lse:[B,H,Lq]."""
+    _check(q, k, v)
+    o = torch.empty((B * Lq, H * D), device=q.device, dtype=q.dtype)
+    lse = torch.empty((B, H, Lq), device=q.device, dtype=torch.float32)
+    call("mmsa_attn_fwd", dt(q), B, H, Lq, Lk, D, q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0),
+         v.data_ptr(), v.stride(0), o.data_ptr(), o.stride(0), lse.data_ptr(), _stream())
+    return o, lse
+
+
+def attn_bwd(q, k, v, o, dout, lse, B, H, Lq, Lk, D, dq: Tensor, dk: Tensor, dv: Tensor):
+    _check(q, k, v, o, dout, lse, dq, dk, dv)
+    delta = torch.empty((B, H, Lq), device=q.device, dtype=torch.float32)
+    call("mmsa_attn_bwd", dt(q), B, H, Lq, Lk, D, q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0),
+         v.data_ptr(), v.stride(0), o.data_ptr(), o.stride(0), dout.data_ptr(), dout.stride(0), lse.data_ptr(),
+         delta.data_ptr(), dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0), dv.data_ptr(), dv.stride(0),
+         _stream())
+
+
+def gate_ln_fwd(gate_pre: Tensor, q: Tensor, attn: Tensor, gamma: Tensor, beta: Tensor, eps: float,
+                want_y: bool = True):
+    _check(gate_pre, q, attn, gamma, beta)
+    M, E = q.shape
+    g = torch.empty_like(q)
+    y = torch.empty_like(q) if want_y else None
+    mean = torch.empty((M,), device=q.device, dtype=torch.float32)
+    rstd = torch.empty((M,), device=q.device, dtype=torch.float32)
+    call("mmsa_gate_ln_fwd", dt(q), M, E, gate_pre.data_ptr(), q.data_ptr(), attn.data_ptr(), gamma.data_ptr(),
+         beta.data_ptr(), float(eps), g.data_ptr(), _p(y), mean.data_ptr(), rstd.data_ptr(), _stream())
+    return g, y, mean, rstd
+
+
+def gate_ln_bwd(dy: Tensor, rows_per_sample: int, g, q, attn, gamma, mean, rstd, *,
+                dq_bcast: Optional[Tensor] = None, bcast_rows: int = 0, dq_add: Optional[Tensor] = None):
+    _check(dy, g, q, attn)
+    M, E = q.shape
+    dq_part = torch.empty_like(q)
+    dattn_part = torch.empty_like(q)
+    dgate_pre = torch.empty_like(q)
+    dgamma = torch.empty((E,), device=q.device, dtype=torch.float32)
+    dbeta = torch.empty((E,), device=q.device, dtype=torch.float32)
+    nblk = _lib.load().mmsa_gate_ln_bwd_blocks(M)
+    partials = torch.empty((nblk, 2, E), device=q.device, dtype=torch.float32)
+    call("mmsa_gate_ln_bwd", dt(q), M, E, dy.data_ptr(), rows_per_sample, g.data_ptr(), q.data_ptr(), attn.data_ptr(),
+         gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _p(dq_bcast), bcast_rows, _p(dq_add),
+         dq_part.data_ptr(), dattn_part.data_ptr(), dgate_pre.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+         partials.data_ptr(), _stream())
+    return dq_part, dattn_part, dgate_pre, dgamma, dbeta
+
+
+def pool_fwd(x: Tensor, B: int, L: int, is_max: bool = False):
+    _check(x)
+    E = x.shape[-1]
+    y = torch.empty((B, E), device=x.device, dtype=x.dtype)
+    arg = torch.empty((B, E), device=x.device, dtype=torch.int32) if is_max else None
+    call("mmsa_pool_fwd", dt(x), B, L, E, x.data_ptr(), int(is_max), y.data_ptr(), _p(arg), _stream())
+    return y, arg
+
+
+def pool_bwd(dy: Tensor, B: int, L: int, is_max: bool = False, argmax: Optional[Tensor] = None):
+    _check(dy)
+    E = dy.shape[-1]
+    dx = torch.empty((B * L, E), device=dy.device, dtype=dy.dtype)
+    call("mmsa_pool_bwd", dt(dy), B, L, E, dy.data_ptr(), int(is_max), _p(argmax), dx.data_ptr(), _stream())
+    return dx
+
+
+def _ptr_array(ts: Sequence[Optional[Tensor]]):
+    arr = (ctypes.c_void_p * len(ts))()
+    for i, t in enumerate(ts):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+def modal_concat_fwd(logits: Tensor, slots: Sequence[Tensor]):
+    _check(logits, *slots)
+    B, E = slots[0].shape
+    S = len(slots)
+    w = torch.empty((B, S), device=logits.device, dtype=torch.float32)
+    fused = torch.empty((B, S * E), device=logits.device, dtype=slots[0].dtype)
+    arr = _ptr_array(slots)
+    call("mmsa_modal_concat_fwd", dt(slots[0]), B, E, S, logits.data_ptr(), ctypes.cast(arr, ctypes.c_void_p),
+         w.data_ptr(), fused.data_ptr(), _stream())
+    return w, fused
+
+
+def modal_concat_bwd(dfused: Tensor, w: Tensor, slots: Sequence[Tensor], need: Sequence[bool]):
+    _check(dfused, w, *slots)
+    B, E = slots[0].shape
+    S = len(slots)
+    dslots = [torch.empty_like(s) if n else None for s, n in zip(slots, need)]
+    dlogits = torch.empty((B, S), device=dfused.device, dtype=slots[0].dtype)
+    a1, a2 = _ptr_array(slots), _ptr_array(dslots)
+    call("mmsa_modal_concat_bwd", dt(slots[0]), B, E, S, dfused.data_ptr(), w.data_ptr(),
+         ctypes.cast(a1, ctypes.c_void_p), ctypes.cast(a2, ctypes.c_void_p), dlogits.data_ptr(), _stream())
+    return dslots, dlogits
+
+
+def act_fwd(x: Tensor, act: int) -> Tensor:
+    _check(x)
+    y = torch.empty_like(x)
+    call("mmsa_act_fwd", dt(x), x.numel(), x.data_ptr(), act, y.data_ptr(), _stream())
+    return y
+
+
+def act_bwd(x: Tensor, dy: Tensor, act: int) -> Tensor:
+    _check(x, dy)
+    dx = torch.empty_like(x)
+    call("mmsa_act_bwd", dt(x), x.numel(), x.data_ptr(), dy.data_ptr(), act, dx.data_ptr(), _stream())
+    return dx
+
+
+def bn_act_fwd(x: Tensor, gamma, beta, running_mean, running_var, momentum: float, eps: float, training: bool,
+               order: int, dropout_p: float, keep_mask: Optional[Tensor], seed: int, offset: int):
+    _check(x, gamma, beta)
+    B, N = x.shape
+    y = torch.empty_like(x)
+    save_mean = torch.empty((N,), device=x.device, dtype=torch.float32)
+    save_rstd = torch.empty((N,), device=x.device, dtype=torch.float32)
+    mask_given = keep_mask is not None
+    if training and dropout_p > 0 and keep_mask is None:
+        keep_mask = torch.empty((B, N), device=x.device, dtype=torch.uint8)
+    call("mmsa_bn_act_fwd", dt(x), B, N, order, x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _p(running_mean),
+         _p(running_var), float(momentum), float(eps), int(training), float(dropout_p), _p(keep_mask),
+         int(mask_given), seed, offset, y.data_ptr(), save_mean.data_ptr(), save_rstd.data_ptr(), _stream())
+    return y, save_mean, save_rstd, keep_mask
+
+
+def bn_act_bwd(x, dy, gamma, beta, save_mean, save_rstd, training: bool, order: int, dropout_p: float, keep_mask):
+    _check(x, dy)
+    B, N = x.shape
+    dx = torch.empty_like(x)
+    dgamma = torch.empty((N,), device=x.device, dtype=torch.float32)
+    dbeta = torch.empty((N,), device=x.device, dtype=torch.float32)
+    call("mmsa_bn_act_bwd", dt(x), B, N, order, x.data_ptr(), dy.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+         save_mean.data_ptr(), save_rstd.data_ptr(), int(training), float(dropout_p), _p(keep_mask), dx.data_ptr(),
+         dgamma.data_ptr(), dbeta.data_ptr(), _stream())
+    return dx, dgamma, dbeta
+
+
+def dropout(x: Tensor, p: float, keep_mask: Optional[Tensor], mask_given: bool, seed: int, offset: int):
+    _check(x, keep_mask)
+    y = torch.empty_like(x)
+    if keep_mask is None:
+        keep_mask = torch.empty(x.shape, device=x.device, dtype=torch.uint8)
+    call("mmsa_dropout", dt(x), x.numel(), x.data_ptr(), float(p), keep_mask.data_ptr(), int(mask_given), seed, offset,
+         y.data_ptr(), _stream())
+    return y, keep_mask
+
+
+def ce_fwd(logits: Tensor, labels: Tensor):
+    _check(logits, labels)
+    B, C = logits.shape
+    loss = torch.empty((1,), device=logits.device, dtype=torch.float32)
+    pred = torch.empty((B,), device=logits.device, dtype=torch.int64)
+    row = torch.empty((B,), device=logits.device, dtype=torch.float32)
+    call("mmsa_ce_fwd", B, C, logits.data_ptr(), labels.data_ptr(), loss.data_ptr(), pred.data_ptr(), row.data_ptr(),
+         _stream())
+    return loss, pred
+
+
+def ce_bwd(logits: Tensor, labels: Tensor, dloss: Tensor) -> Tensor:
+    _check(logits, labels, dloss)
+    B, C = logits.shape
+    dlogits = torch.empty_like(logits)
+    call("mmsa_ce_bwd", B, C, logits.data_ptr(), labels.data_ptr(), dloss.data_ptr(), dlogits.data_ptr(), _stream())
+    return dlogits
+
+
+def l2norm_fwd(x: Tensor):
+    _check(x)
+    B, E = x.shape
+    y = torch.empty_like(x)
+    norm = torch.empty((B,), device=x.device, dtype=torch.float32)
+    call("mmsa_l2norm_fwd", dt(x), B, E, x.data_ptr(), y.data_ptr(), norm.data_ptr(), _stream())
+    return y, norm
+
+
+def l2norm_bwd(y: Tensor, norm: Tensor, dy1: Tensor, dy2: Optional[Tensor]) -> Tensor:
+    _check(y, norm, dy1, dy2)
+    B, E = y.shape
+    dx = torch.empty_like(y)
+    call("mmsa_l2norm_bwd", dt(y), B, E, y.data_ptr(), norm.data_ptr(), dy1.data_ptr(), _p(dy2), dx.data_ptr(),
+         _stream())
+    return dx
+
+
+def contrastive_fwd(kind: int, sim: Tensor, labels_rows, labels_cols, temperature: Optional[Tensor],
+                    temperature_const: float, row_offset: int, denom: int):
+    _check(sim, labels_rows, labels_cols, temperature)
+    B, Bg = sim.shape
+    stats = torch.empty((B, 4), device=sim.device, dtype=torch.float32)
+    row_loss = torch.empty((B,), device=sim.device, dtype=torch.float32)
+    loss = torch.empty((1,), device=sim.device, dtype=torch.float32)
+    call("mmsa_contrastive_fwd", kind, B, Bg, row_offset, sim.data_ptr(), _p(labels_rows), _p(labels_cols),
+         _p(temperature), float(temperature_const), denom, stats.data_ptr(), row_loss.data_ptr(), loss.data_ptr(),
+         _stream())
+    return loss, stats
+
+
+def contrastive_bwd(kind: int, sim: Tensor, labels_rows, labels_cols, temperature: Optional[Tensor],
+                    temperature_const: float, row_offset: int, denom: int, stats: Tensor, dloss: Tensor,
+                    g_dtype: torch.dtype):
+    _check(sim, stats, dloss)
+    B, Bg = sim.shape
+    G = torch.empty((B, Bg), device=sim.device, dtype=g_dtype)
+    dtemp_rows = torch.empty((B,), device=sim.device, dtype=torch.float32)
+    dtemp = torch.empty((1,), device=sim.device, dtype=torch.float32)
+    call("mmsa_contrastive_bwd", kind, B, Bg, row_offset, sim.data_ptr(), _p(labels_rows), _p(labels_cols),
+         _p(temperature), float(temperature_const), denom, stats.data_ptr(), dloss.data_ptr(), G.data_ptr(),
+         dt(g_dtype), dtemp_rows.data_ptr(), dtemp.data_ptr(), _stream())
+    return G, dtemp

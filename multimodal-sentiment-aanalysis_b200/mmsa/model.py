@@ -1,0 +1,325 @@
+"""Drop-in nn.Modules for the reference's fusion / ME-MHACL path.
+
+Same class names, constructor defaults, attribute names, parameter names/shapes (state_dict keys)
+and forward signatures as /root/reference/MML_ZYC/MultimodalModel.py and ME-MHACL/model.py, so
+Trainer.py:60, Tester.py:53 and dataLoader/MultiTaskTrainer.py:199 can call them unchanged.  The
+sub-modules (nn.MultiheadAttention, nn.Linear, nn.LayerNorm, nn.BatchNorm1d ...) are kept only as
+PARAMETER CONTAINERS (so initialisation and checkpoints match the reference); their own forward is
+never called -- every forward here runs the hand-written sm_100a kernels through mmsa.ops, and
+fails loudly off-GPU (no fallback)."""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import kernels as K
+from . import ops
+from ._lib import BN_THEN_GELU, RELU_THEN_BN
+
+Tensor = torch.Tensor
+
+
+class _DropoutState:
+    """Seeds for the in-kernel Philox dropout; parity tests may inject explicit keep masks."""
+
+    def __init__(self, seed: int = 0x5EED):
+        self.seed = seed
+        self.offset = 0
+        self.mask_provider: Optional[Callable[[str, Tuple[int, ...]], Optional[Tensor]]] = None
+
+    def next(self, name: str, shape) -> Tuple[Optional[Tensor], int, int]:
+        mask = self.mask_provider(name, tuple(shape)) if self.mask_provider else None
+        off = self.offset
+        n = 1
+        for s in shape:
+            n *= int(s)
+        self.offset += n
+        return mask, self.seed, off
+
+
+def run_sequential(x: Tensor, seq: nn.Sequential, drop: _DropoutState, name: str, logits_fp32: bool) -> Tensor:
+    """Execute an nn.Sequential of the reference's head/fusion layouts on the CUDA kernels.
+    Recognised groups: Linear[-BatchNorm1d-GELU[-Dropout]] (MultimodalModel.py:179-225),
+    Linear[-ReLU-BatchNorm1d[-Dropout]] (ME-MHACL/model.py:82-97), Linear-ReLU[-Dropout] (:105-109),
+    Linear-GELU (:172-173), trailing Linear, trailing Softmax handled by the caller."""
+    mods = list(seq.children())
+    i, n = 0, len(mods)
+    while i < n:
+        m = mods[i]
+        if isinstance(m, nn.Linear):
+            nxt = mods[i + 1:i + 4]
+            last = (i == n - 1) or all(isinstance(z, nn.Softmax) for z in mods[i + 1:])
+            x = ops.linear(x, m.weight, m.bias, out_fp32=(last and logits_fp32))
+            i += 1
+            if len(nxt) >= 2 and isinstance(nxt[0], nn.BatchNorm1d) and isinstance(nxt[1], nn.GELU):
+                p, used = 0.0, 2
+                if len(nxt) >= 3 and isinstance(nxt[2], nn.Dropout):
+                    p, used = nxt[2].p, 3
+                mask, seed, off = drop.next(f"{name}.{i + used - 1}", x.shape) if (p > 0 and seq.training) else (None, 0, 0)
+                x = ops.bn_act(x, nxt[0], BN_THEN_GELU, p, mask, seed, off)
+                i += used
+            elif len(nxt) >= 2 and isinstance(nxt[0], nn.ReLU) and isinstance(nxt[1], nn.BatchNorm1d):
+                p, used = 0.0, 2
+                if len(nxt) >= 3 and isinstance(nxt[2], nn.Dropout):
+                    p, used = nxt[2].p, 3
+                mask, seed, off = drop.next(f"{name}.{i + used - 1}", x.shape) if (p > 0 and seq.training) else (None, 0, 0)
+                x = ops.bn_act(x, nxt[1], RELU_THEN_BN, p, mask, seed, off)
+                i += used
+        elif isinstance(m, nn.GELU):
+            x = ops.gelu(x)
+            i += 1
+        elif isinstance(m, nn.ReLU):
+            x = ops.relu(x)
+            i += 1
+        elif isinstance(m, nn.Dropout):
+            if m.p > 0 and seq.training:
+                mask, seed, off = drop.next(f"{name}.{i}", x.shape)
+                x = ops.dropout(x, m.p, True, mask, seed, off)
+            i += 1
+        elif isinstance(m, nn.Softmax):
+            i += 1          # the 3-way modality softmax is fused into modal_concat
+        else:
+            raise NotImplementedError(f"mmsa: no kernel mapping for {type(m).__name__} in {name}")
+    return x
+
+
+class FeatureProjection(nn.Module):
+    """`Subnetwork.proj = nn.Linear(input_dim, feat_dim)` (MultimodalModel.py:86,102): the projection
+    GEMM that maps BERT tokens [B,L,768] / ResNet-50 regions [B,49,2048] to the fusion width."""
+
+    def __init__(self, input_dim: int, feat_dim: int = 256):
+        super().__init__()
+        self.proj = nn.Linear(input_dim, feat_dim)
+
+    def forward(self, x: Tensor) -> Tensor:
+        return ops.linear(x, self.proj.weight, self.proj.bias)
+
+
+class CrossModalTransformer(nn.Module):
+    """MultimodalModel.py:108-149.  forward(query, key, value) with 2-D [B,E] or 3-D [B,L,E] inputs;
+    the gate concat runs on the feature axis, so Lq > 1 works (identical to the reference for Lq == 1)."""
+
+    def __init__(self, embed_dim: int = 256, num_heads: int = 4):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.num_heads = num_heads
+        self.multihead_attn = nn.MultiheadAttention(embed_dim=embed_dim, num_heads=num_heads, batch_first=True)
+        self.gate = nn.Sequential(nn.Linear(embed_dim * 2, embed_dim), nn.Sigmoid())
+        self.norm = nn.LayerNorm(embed_dim)
+
+    def kernel_params(self) -> Tuple[Tensor, ...]:
+        a = self.multihead_attn
+        return (a.in_proj_weight, a.in_proj_bias, a.out_proj.weight, a.out_proj.bias,
+                self.gate[0].weight, self.gate[0].bias, self.norm.weight, self.norm.bias)
+
+    def forward(self, query: Tensor, key: Tensor, value: Tensor) -> Tensor:
+        if key is not value and key.data_ptr() != value.data_ptr():
+            raise NotImplementedError("mmsa: CrossModalTransformer kernels take key and value from one tensor, "
+                                      "as every reference call site does (MultimodalModel.py:287-297)")
+        squeeze = query.ndim == 2
+        if squeeze:
+            query = query.unsqueeze(1)
+        if key.ndim == 2:
+            key = key.unsqueeze(1)
+        out = ops.cross_block(query, key, *self.kernel_params(), self.num_heads)
+        return out.squeeze(1) if squeeze else out
+
+
+class MultimodalTransformerModel(nn.Module):
+    """Drop-in for MultimodalModel.MultimodalTransformerModel (MultimodalModel.py:152-322).
+
+    wiring="native":  the reference's three-modality wiring at its own sizes.  The modality encoders
+        (eeg_net/eye_net/pps_net, :164-166) are outside the hot path: pass them in `encoders`, or
+        leave the default nn.Identity() and feed [B,E] features.
+    wiring="bidirectional": BASELINE.json's text+image re-skin -- eeg_net/eye_net become the
+        projection GEMMs over BERT tokens [B,L,text_dim] and ResNet regions [B,R,image_dim]; the
+        third positional input (pps) is accepted and ignored.
+    contract="multitask": forward(..., labels=(arousal, valence)) -> 5-tuple (MultiTaskTrainer.py:199).
+    contract="single":    forward(x0, x1, x2, labels[B]) -> (logits, contrastive_loss) and
+                          forward(x0, x1, x2) -> logits   (Trainer.py:60, Tester.py:53)."""
+
+    def __init__(self, num_classes: int = 3, temperature: float = 0.01, *, embed_dim: int = 256, num_heads: int = 4,
+                 wiring: str = "native", text_dim: int = 768, image_dim: int = 2048, contract: str = "multitask",
+                 compute_dtype: torch.dtype = torch.float32, encoders: Optional[Sequence[nn.Module]] = None,
+                 valence: bool = True):
+        super().__init__()
+        assert wiring in ("native", "bidirectional") and contract in ("multitask", "single")
+        E = embed_dim
+        self.embed_dim, self.num_heads, self.wiring, self.contract = E, num_heads, wiring, contract
+        self.compute_dtype = compute_dtype
+        if wiring == "native":
+            enc = list(encoders) if encoders is not None else [nn.Identity(), nn.Identity(), nn.Identity()]
+            self.eeg_net, self.eye_net, self.pps_net = enc
+            raw_width = 3 * E
+        else:
+            self.eeg_net = FeatureProjection(text_dim, E)
+            self.eye_net = FeatureProjection(image_dim, E)
+            self.pps_net = nn.Identity()
+            raw_width = 2 * E
+        self.cross_attn_e2p = CrossModalTransformer(E, num_heads)
+        self.cross_attn_p2e = CrossModalTransformer(E, num_heads)
+        self.attention_weights = nn.Sequential(nn.Linear(raw_width, 64), nn.GELU(), nn.Linear(64, 3), nn.Softmax(dim=1))
+        self.fusion = nn.Sequential(
+            nn.Linear(E * 3, 256), nn.BatchNorm1d(256, eps=1e-5), nn.GELU(), nn.Dropout(0.3),
+            nn.Linear(256, 128), nn.BatchNorm1d(128, eps=1e-5), nn.GELU(), nn.Dropout(0.3))
+        self.arousal_head = nn.Sequential(
+            nn.Linear(128, 128), nn.BatchNorm1d(128), nn.GELU(), nn.Dropout(0.3), nn.Linear(128, num_classes))
+        if valence:
+            self.valence_head = nn.Sequential(
+                nn.Linear(128, 256), nn.BatchNorm1d(256), nn.GELU(), nn.Dropout(0.3),
+                nn.Linear(256, 256), nn.BatchNorm1d(256), nn.GELU(), nn.Dropout(0.3),
+                nn.Linear(256, 128), nn.BatchNorm1d(128), nn.GELU(), nn.Dropout(0.3),
+                nn.Linear(128, 64), nn.BatchNorm1d(64), nn.GELU(), nn.Dropout(0.3),
+                nn.Linear(64, num_classes))
+        else:
+            self.valence_head = None
+        self.contrastive_weight = nn.Parameter(torch.ones(1))
+        self.temperature = nn.Parameter(torch.tensor(temperature))
+        self._drop = _DropoutState()
+        # data-parallel contrastive sharding (set by mmsa.dist.shard_contrastive)
+        self.dp_group = None
+
+    # -- helpers ------------------------------------------------------------------------------------
+    def set_dropout(self, p: float) -> "MultimodalTransformerModel":
+        for m in self.modules():
+            if isinstance(m, nn.Dropout):
+                m.p = p
+        return self
+
+    def _cd(self, x: Tensor) -> Tensor:
+        if not x.is_floating_point():
+            x = x.float()
+        return K.cast(x.contiguous(), self.compute_dtype)
+
+    def compute_contrastive_loss(self, feat1: Tensor, feat2: Tensor, labels: Tensor) -> Tensor:
+        """MultimodalModel.py:232-260."""
+        return ops.infonce(feat1, feat2, labels, self.temperature)
+
+    def _tail(self, raw_a: Tensor, raw_b: Optional[Tensor], slots: Sequence[Tensor]):
+        aw = self.attention_weights
+        h = ops.gelu(ops.linear(raw_a, aw[0].weight, aw[0].bias, x2=raw_b))
+        logits3 = ops.linear(h, aw[2].weight, aw[2].bias)
+        fused, w = ops.modal_concat(logits3, slots)
+        fused = run_sequential(fused, self.fusion, self._drop, "fusion", False)
+        arousal = run_sequential(fused, self.arousal_head, self._drop, "arousal_head", True)
+        valence = None
+        if self.valence_head is not None and self.contract == "multitask":
+            valence = run_sequential(fused, self.valence_head, self._drop, "valence_head", True)
+        return arousal, valence
+
+    # -- forward ------------------------------------------------------------------------------------
+    def forward(self, eeg: Tensor, eye: Tensor, pps: Optional[Tensor] = None, labels=None):
+        if labels is not None and self.contract == "multitask":
+            con_labels = labels[0]                                   # MultimodalModel.py:273
+        else:
+            con_labels = labels
+        if con_labels is not None:
+            con_labels = con_labels.contiguous().long()
+        contrastive: List[Tensor] = []
+        if self.wiring == "native":
+            f0 = self._cd(self.eeg_net(eeg))
+            f1 = self._cd(self.eye_net(eye))
+            f2 = self._cd(self.pps_net(pps))
+            if con_labels is not None:                               # :271-284
+                for f in (f0, f1, f2):
+                    contrastive.append(ops.infonce(f, f, con_labels, self.temperature))
+            e1 = self.cross_attn_e2p(f0, f1, f1)                     # :287
+            e2 = self.cross_attn_p2e(f0, f2, f2)                     # :293
+            raw_a, raw_b = torch.cat([f0, f1, f2], dim=1), None      # :300 (tiny [B,3E] copy)
+            slots = (f0, e1, e2)
+        else:
+            text, image = self._cd(eeg), self._cd(eye)
+            f0, fv, e1, e2 = ops.fusion_core(text, image, self.eeg_net.proj.weight, self.eeg_net.proj.bias,
+                                             self.eye_net.proj.weight, self.eye_net.proj.bias, self.num_heads,
+                                             self.cross_attn_e2p.kernel_params(), self.cross_attn_p2e.kernel_params())
+            raw_a, raw_b = f0, fv
+            slots = (f0, e1, e2)
+            if con_labels is not None:
+                if self.dp_group is not None:
+                    from . import dist as mdist
+                    contrastive.append(mdist.sharded_infonce(e1, e2, con_labels, self.temperature, self.dp_group))
+                else:
+                    contrastive.append(ops.infonce(e1, e2, con_labels, self.temperature))
+                if self.contract == "multitask":
+                    contrastive.append(ops.infonce(e2, e1, con_labels, self.temperature))
+        arousal, valence = self._tail(raw_a, raw_b, slots)
+        contrastive = [self.contrastive_weight * c for c in contrastive]     # :315-317 -> shape (1,)
+        if self.contract == "single":
+            if labels is None:
+                return arousal                                       # Tester.py:53
+            total = contrastive[0]
+            for c in contrastive[1:]:
+                total = total + c
+            return arousal, total                                    # Trainer.py:60
+        if labels is None:
+            return arousal, valence                                  # :319-320
+        while len(contrastive) < 3:
+            contrastive.append(torch.zeros(1, device=arousal.device))
+        return arousal, valence, contrastive[0], contrastive[1], contrastive[2]   # :321-322
+
+
+class MultiModalEncoder(nn.Module):
+    """ME-MHACL fusion tail (ME-MHACL/model.py:47-74; variant MultimodalModel.py:357-406): three
+    modality features -> 3-token self-attention (8 heads) -> mean (or max + fusion_mlp) over modalities.
+    The Conv1d/BiLSTM modality encoders are outside the hot path: pass them in `encoders` or feed features."""
+
+    def __init__(self, feat_dim: int = 256, num_heads: int = 8, variant: str = "mean",
+                 encoders: Optional[Sequence[nn.Module]] = None, compute_dtype: torch.dtype = torch.float32):
+        super().__init__()
+        assert variant in ("mean", "max")
+        self.feat_dim, self.num_heads, self.variant = feat_dim, num_heads, variant
+        self.compute_dtype = compute_dtype
+        enc = list(encoders) if encoders is not None else [nn.Identity(), nn.Identity(), nn.Identity()]
+        self.eeg_net, self.eye_net, self.pps_net = enc
+        self.multihead_attn = nn.MultiheadAttention(embed_dim=feat_dim, num_heads=num_heads, batch_first=False)
+        if variant == "max":
+            self.fusion_mlp = nn.Sequential(nn.Linear(feat_dim, feat_dim), nn.ReLU(), nn.BatchNorm1d(feat_dim))
+        self._drop = _DropoutState()
+
+    def forward(self, eeg: Tensor, eye: Tensor, pps: Tensor, labels=None) -> Tensor:
+        cd = self.compute_dtype
+        feats = [K.cast(n(x).float().contiguous(), cd) for n, x in
+                 ((self.eeg_net, eeg), (self.eye_net, eye), (self.pps_net, pps))]
+        if self.variant == "max":                                    # MultimodalModel.py:388-390
+            feats = [ops.l2_normalize(f) for f in feats]
+        x = ops.stack_tokens(feats)                                  # [B,3,E]
+        a = self.multihead_attn
+        y = ops.self_attention(x, a.in_proj_weight, a.in_proj_bias, a.out_proj.weight, a.out_proj.bias, self.num_heads)
+        if self.variant == "mean":
+            return ops.mean_pool(y)                                  # ME-MHACL/model.py:73
+        fused = ops.max_pool(y)                                      # MultimodalModel.py:401
+        return run_sequential(fused, self.fusion_mlp, self._drop, "fusion_mlp", False)
+
+
+class ProjectionHead(nn.Module):
+    """ME-MHACL/model.py:77-97 (Linear-ReLU-BN-Dropout x2 + Linear)."""
+
+    def __init__(self, in_dim: int = 256, hidden_dim: int = 256, out_dim: int = 128):
+        super().__init__()
+        self.net = nn.Sequential(
+            nn.Linear(in_dim, hidden_dim), nn.ReLU(inplace=True), nn.BatchNorm1d(hidden_dim), nn.Dropout(0.5),
+            nn.Linear(hidden_dim, out_dim), nn.ReLU(inplace=True), nn.BatchNorm1d(out_dim), nn.Dropout(0.5),
+            nn.Linear(out_dim, out_dim))
+        self._drop = _DropoutState()
+
+    def forward(self, x: Tensor) -> Tensor:
+        return run_sequential(x, self.net, self._drop, "net", False)
+
+
+class Classifier(nn.Module):
+    """ME-MHACL/model.py:100-119 / MultimodalModel.py:432-451 (num_out = 2 or 3)."""
+
+    def __init__(self, in_dim: int = 256, hidden_dim: int = 128, num_out: int = 3):
+        super().__init__()
+        self.shared = nn.Sequential(nn.Linear(in_dim, hidden_dim), nn.ReLU(inplace=True), nn.Dropout(0.5))
+        self.fc_arousal = nn.Linear(hidden_dim, num_out)
+        self.fc_valence = nn.Linear(hidden_dim, num_out)
+        self._drop = _DropoutState()
+
+    def forward(self, x: Tensor):
+        h = run_sequential(x, self.shared, self._drop, "shared", False)
+        out_a = ops.linear(h, self.fc_arousal.weight, self.fc_arousal.bias, out_fp32=True)
+        out_v = ops.linear(h, self.fc_valence.weight, self.fc_valence.bias, out_fp32=True)
+        return out_a, out_v

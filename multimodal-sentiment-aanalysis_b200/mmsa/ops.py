@@ -1,0 +1,525 @@
+"""torch.autograd.Functions over the C ABI.  Every forward/backward below is a sequence of
+mmsa_* calls; PyTorch supplies storage, streams and the autograd tape only.
+
+Storage mode: activations are fp32 (parity mode, 1e-5) or bf16 (performance mode, fp32 accumulate,
+fp32 master parameters); the mode is the dtype of the activation tensors handed in."""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import kernels as K
+from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, BN_ONLY, BN_THEN_GELU, LOSS_INFONCE, LOSS_NTXENT,
+                   LOSS_SUPCON, RELU_THEN_BN)
+
+Tensor = torch.Tensor
+
+
+def _w(w: Tensor, dtype: torch.dtype) -> Tensor:
+    """fp32 master weight -> compute-dtype copy (mmsa_cast); identity in fp32 mode."""
+    w = w.detach()
+    if not w.is_contiguous():
+        w = w.contiguous()
+    return K.cast(w, dtype)
+
+
+def _c(t: Tensor) -> Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------ Linear
+class LinearFn(Function):
+    """nn.Linear (MultimodalModel.py:86,172-198): y = x W^T + b over the last dim.
+    x may be split in two feature segments (x, x2) to avoid materialising a concat."""
+
+    @staticmethod
+    def forward(ctx, x, x2, w, b, out_fp32: bool):
+        cd = x.dtype
+        lead = x.shape[:-1]
+        x2d = _c(x).view(-1, x.shape[-1])
+        x22d = None if x2 is None else _c(x2).view(-1, x2.shape[-1])
+        wc = _w(w, cd)
+        od = torch.float32 if out_fp32 else cd
+        y = K.linear_fwd(x2d, wc, None if b is None else b.detach(), x2=x22d, out_dtype=od)
+        ctx.save_for_backward(x2d, x22d, wc)
+        ctx.has_bias = b is not None
+        ctx.in_shapes = (x.shape, None if x2 is None else x2.shape)
+        ctx.cd = cd
+        return y.view(*lead, w.shape[0])
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x2d, x22d, wc = ctx.saved_tensors
+        cd = ctx.cd
+        dy2d = K.cast(_c(dy).view(-1, dy.shape[-1]), cd)
+        Kx = x2d.shape[1]
+        dx = dx2 = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = K.linear_dgrad(dy2d, wc[:, :Kx]).view(ctx.in_shapes[0])
+        if x22d is not None and ctx.needs_input_grad[1]:
+            dx2 = K.linear_dgrad(dy2d, wc[:, Kx:]).view(ctx.in_shapes[1])
+        if ctx.needs_input_grad[2] or (ctx.has_bias and ctx.needs_input_grad[3]):
+            want_w = ctx.needs_input_grad[2]
+            want_b = ctx.has_bias and ctx.needs_input_grad[3]
+            if x22d is None:
+                dw, db = K.linear_wgrad(dy2d, x2d, want_bias=want_b, want_weight=want_w)
+            else:
+                dw = torch.empty((wc.shape[0], wc.shape[1]), device=dy.device, dtype=torch.float32)
+                _, db = K.linear_wgrad(dy2d, x2d, dw=dw[:, :Kx], want_bias=want_b, want_weight=True)
+                K.linear_wgrad(dy2d, x22d, dw=dw[:, Kx:], want_bias=False, want_weight=True)
+                if not want_w:
+                    dw = None
+        return dx, dx2, dw, db, None
+
+
+def linear(x: Tensor, w: Tensor, b: Optional[Tensor], x2: Optional[Tensor] = None, out_fp32: bool = False) -> Tensor:
+    return LinearFn.apply(x, x2, w, b, out_fp32)
+
+
+class ActFn(Function):
+    """nn.GELU (exact erf) / nn.ReLU / sigmoid, elementwise."""
+
+    @staticmethod
+    def forward(ctx, x, act: int):
+        x = _c(x)
+        ctx.save_for_backward(x)
+        ctx.act = act
+        return K.act_fwd(x, act)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return K.act_bwd(x, K.cast(_c(dy), x.dtype), ctx.act), None
+
+
+def gelu(x):
+    return ActFn.apply(x, ACT_GELU)
+
+
+def relu(x):
+    return ActFn.apply(x, ACT_RELU)
+
+
+# ------------------------------------------------------------------------------------------ cross block
+class _BlockState:
+    """Tensors one CrossModalTransformer block keeps between forward and backward."""
+    __slots__ = ("q_in", "kv_in", "Qp", "KVp", "O", "lse", "A", "G", "mean", "rstd", "w_in", "w_out", "w_gate",
+                 "gamma", "B", "Lq", "Lk", "E", "H")
+
+
+def _block_fwd(q_in: Tensor, kv_in: Tensor, B: int, Lq: int, Lk: int, H: int, in_w, in_b, out_w, out_b, gate_w,
+               gate_b, ln_w, ln_b, eps: float = 1e-5) -> Tuple[Tensor, _BlockState]:
+    """CrossModalTransformer.forward (MultimodalModel.py:124-149) on flattened [B*L, E] activations.
+    MHA in-projection (q rows of in_proj_weight; packed k,v rows), attention core, out-projection,
+    gate GEMM over the two operands [q | attn] (no concat), fused sigmoid/blend/LayerNorm."""
+    cd = q_in.dtype
+    E = q_in.shape[1]
+    st = _BlockState()
+    st.w_in, st.w_out, st.w_gate = _w(in_w, cd), _w(out_w, cd), _w(gate_w, cd)
+    in_b = in_b.detach()
+    st.Qp = K.linear_fwd(q_in, st.w_in[:E], in_b[:E])
+    st.KVp = K.linear_fwd(kv_in, st.w_in[E:], in_b[E:])
+    st.O, st.lse = K.attn_fwd(st.Qp, st.KVp[:, :E], st.KVp[:, E:], B, H, Lq, Lk, E // H)
+    st.A = K.linear_fwd(st.O, st.w_out, out_b.detach())
+    gate_pre = K.linear_fwd(q_in, st.w_gate, gate_b.detach(), x2=st.A)
+    st.gamma = ln_w.detach()
+    st.G, y, st.mean, st.rstd = K.gate_ln_fwd(gate_pre, q_in, st.A, st.gamma, ln_b.detach(), eps)
+    st.q_in, st.kv_in = q_in, kv_in
+    st.B, st.Lq, st.Lk, st.E, st.H = B, Lq, Lk, E, H
+    return y, st
+
+
+def _block_bwd(st: _BlockState, dy: Tensor, dy_rows_per_sample: int, *, dq_bcast: Optional[Tensor] = None,
+               dq_add: Optional[Tensor] = None, dkv_residual: Optional[Tensor] = None,
+               need_dq: bool = True, need_dkv: bool = True, need_w: bool = True):
+    """Backward of _block_fwd.  dy is [B*Lq,E], or [B,E] when dy_rows_per_sample=Lq (mean-pooled output).
+    Returns (dq, dkv, grads) with grads = (d_in_w, d_in_b, d_out_w, d_out_b, d_gate_w, d_gate_b, d_ln_w, d_ln_b).
+    All accumulation of gradients w.r.t. q and kv happens in GEMM residual epilogues / the LN kernel."""
+    E, B, Lq, Lk, H = st.E, st.B, st.Lq, st.Lk, st.H
+    dev = dy.device
+    r0, r1, dgate, d_ln_w, d_ln_b = K.gate_ln_bwd(dy, dy_rows_per_sample, st.G, st.q_in, st.A, st.gamma, st.mean,
+                                                  st.rstd, dq_bcast=dq_bcast,
+                                                  bcast_rows=Lq if dq_bcast is not None else 0, dq_add=dq_add)
+    d_gate_w = d_gate_b = d_out_w = d_out_b = d_in_w = d_in_b = None
+    if need_w:
+        d_gate_w = torch.empty((E, 2 * E), device=dev, dtype=torch.float32)
+        _, d_gate_b = K.linear_wgrad(dgate, st.q_in, dw=d_gate_w[:, :E])
+        K.linear_wgrad(dgate, st.A, dw=d_gate_w[:, E:], want_bias=False)
+    dA = K.linear_dgrad(dgate, st.w_gate[:, E:], residual=r1)
+    dq_acc = K.linear_dgrad(dgate, st.w_gate[:, :E], residual=r0) if need_dq else None
+    if need_w:
+        d_out_w, d_out_b = K.linear_wgrad(dA, st.O)
+    dO = K.linear_dgrad(dA, st.w_out)
+    dQp = torch.empty_like(st.Qp)
+    dKVp = torch.empty_like(st.KVp)
+    K.attn_bwd(st.Qp, st.KVp[:, :E], st.KVp[:, E:], st.O, dO, st.lse, B, H, Lq, Lk, E // H,
+               dQp, dKVp[:, :E], dKVp[:, E:])
+    if need_w:
+        d_in_w = torch.empty((3 * E, E), device=dev, dtype=torch.float32)
+        d_in_b = torch.empty((3 * E,), device=dev, dtype=torch.float32)
+        K.linear_wgrad(dQp, st.q_in, dw=d_in_w[:E], db=d_in_b[:E])
+        K.linear_wgrad(dKVp, st.kv_in, dw=d_in_w[E:], db=d_in_b[E:])
+    dq = K.linear_dgrad(dQp, st.w_in[:E], residual=dq_acc) if need_dq else None
+    dkv = K.linear_dgrad(dKVp, st.w_in[E:], residual=dkv_residual) if need_dkv else None
+    return dq, dkv, (d_in_w, d_in_b, d_out_w, d_out_b, d_gate_w, d_gate_b, d_ln_w, d_ln_b)
+
+
+class CrossBlockFn(Function):
+    """One CrossModalTransformer block, query [B,Lq,E] x key/value [B,Lk,E] -> [B,Lq,E]."""
+
+    @staticmethod
+    def forward(ctx, query, kv, in_w, in_b, out_w, out_b, gate_w, gate_b, ln_w, ln_b, num_heads: int):
+        B, Lq, E = query.shape
+        Lk = kv.shape[1]
+        y, st = _block_fwd(_c(query).view(B * Lq, E), _c(kv).view(B * Lk, E), B, Lq, Lk, num_heads,
+                           in_w, in_b, out_w, out_b, gate_w, gate_b, ln_w, ln_b)
+        ctx.st = st
+        return y.view(B, Lq, E)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        st = ctx.st
+        need_w = any(ctx.needs_input_grad[2:10])
+        dq, dkv, g = _block_bwd(st, K.cast(_c(dy), st.q_in.dtype).view(st.B * st.Lq, st.E), 0,
+                                need_dq=ctx.needs_input_grad[0], need_dkv=ctx.needs_input_grad[1], need_w=need_w)
+        ctx.st = None
+        dq = None if dq is None else dq.view(st.B, st.Lq, st.E)
+        dkv = None if dkv is None else dkv.view(st.B, st.Lk, st.E)
+        g = tuple(gi if need else None for gi, need in zip(g, ctx.needs_input_grad[2:10]))
+        return (dq, dkv) + g + (None,)
+
+
+def cross_block(query, kv, in_w, in_b, out_w, out_b, gate_w, gate_b, ln_w, ln_b, num_heads: int) -> Tensor:
+    return CrossBlockFn.apply(query, kv, in_w, in_b, out_w, out_b, gate_w, gate_b, ln_w, ln_b, num_heads)
+
+
+class FusionCoreFn(Function):
+    """The sequence part of the re-skinned path in ONE autograd node (SURVEY.md section 8(d) composition):
+        t = Linear(text), v = Linear(image)                         (Subnetwork.proj pattern, :86)
+        t2 = Block_e2p(query=t, kv=v), v2 = Block_p2e(query=v, kv=t) (:287-297, bidirectional)
+        returns mean_tokens(t), mean_tokens(v), mean_tokens(t2), mean_tokens(v2)   each [B,E]
+    Keeping it one node lets every gradient accumulation on the big [B,L,E] tensors happen inside
+    GEMM epilogues instead of autograd's add kernels, and the pooled-output backward never
+    materialises a [B,L,E] broadcast."""
+
+    @staticmethod
+    def forward(ctx, text, image, wt, bt, wi, bi, num_heads, *bp):
+        p1, p2 = bp[:8], bp[8:]
+        cd = text.dtype
+        B, L, Dt = text.shape
+        R, Di = image.shape[1], image.shape[2]
+        text2d, image2d = _c(text).view(B * L, Dt), _c(image).view(B * R, Di)
+        wtc, wic = _w(wt, cd), _w(wi, cd)
+        t = K.linear_fwd(text2d, wtc, bt.detach())
+        v = K.linear_fwd(image2d, wic, bi.detach())
+        t2, st1 = _block_fwd(t, v, B, L, R, num_heads, *p1)
+        v2, st2 = _block_fwd(v, t, B, R, L, num_heads, *p2)
+        f0, _ = K.pool_fwd(t, B, L)
+        fv, _ = K.pool_fwd(v, B, R)
+        e1, _ = K.pool_fwd(t2, B, L)
+        e2, _ = K.pool_fwd(v2, B, R)
+        ctx.st = (st1, st2, text2d, image2d)
+        ctx.dims = (B, L, R)
+        return f0, fv, e1, e2
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, df0, dfv, de1, de2):
+        st1, st2, text2d, image2d = ctx.st
+        ctx.st = None
+        B, L, R = ctx.dims
+        cd = text2d.dtype
+        df0, dfv, de1, de2 = (K.cast(_c(x), cd) for x in (df0, dfv, de1, de2))
+        need_w1 = any(ctx.needs_input_grad[7:15])
+        need_w2 = any(ctx.needs_input_grad[15:23])
+        # block e2p: grad wrt t (as query, + pooled f0 broadcast), grad wrt v (as key/value)
+        dt1, dv1, g1 = _block_bwd(st1, de1, L, dq_bcast=df0, need_w=need_w1)
+        # block p2e: grad wrt v (as query, + pooled fv broadcast + dv1), grad wrt t (as kv, + dt1)
+        dv_tot, dt_tot, g2 = _block_bwd(st2, de2, R, dq_bcast=dfv, dq_add=dv1, dkv_residual=dt1, need_w=need_w2)
+        dwt = dbt = dwi = dbi = None
+        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+            dwt, dbt = K.linear_wgrad(dt_tot, text2d)
+        if ctx.needs_input_grad[4] or ctx.needs_input_grad[5]:
+            dwi, dbi = K.linear_wgrad(dv_tot, image2d)
+        return (None, None, dwt, dbt, dwi, dbi, None) + g1 + g2
+
+
+def fusion_core(text, image, wt, bt, wi, bi, num_heads, block1: Sequence[Tensor], block2: Sequence[Tensor]):
+    return FusionCoreFn.apply(text, image, wt, bt, wi, bi, num_heads, *block1, *block2)
+
+
+# ------------------------------------------------------------------------------------------ attention (generic)
+class AttnFn(Function):
+    """Attention core on projected q,k,v given as [B*L, H*D] (possibly strided column views)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, B, H, Lq, Lk):
+        D = q.shape[1] // H
+        o, lse = K.attn_fwd(q, k, v, B, H, Lq, Lk, D)
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.dims = (B, H, Lq, Lk, D)
+        return o
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, do):
+        q, k, v, o, lse = ctx.saved_tensors
+        B, H, Lq, Lk, D = ctx.dims
+        dq = torch.empty((B * Lq, H * D), device=q.device, dtype=q.dtype)
+        dk = torch.empty((B * Lk, H * D), device=q.device, dtype=q.dtype)
+        dv = torch.empty((B * Lk, H * D), device=q.device, dtype=q.dtype)
+        K.attn_bwd(q, k, v, o, K.cast(_c(do), q.dtype), lse, B, H, Lq, Lk, D, dq, dk, dv)
+        return dq, dk, dv, None, None, None, None
+
+
+def self_attention(x: Tensor, in_w, in_b, out_w, out_b, num_heads: int) -> Tensor:
+    """nn.MultiheadAttention self-attention on x:[B,S,E] (batch-major), packed in-projection
+    (ME-MHACL/model.py:71, MultimodalModel.py:397)."""
+    B, S, E = x.shape
+    qkv = linear(x.reshape(B * S, E), in_w, in_b)
+    o = AttnFn.apply(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], B, num_heads, S, S)
+    return linear(o, out_w, out_b).view(B, S, E)
+
+
+# ------------------------------------------------------------------------------------------ pooling
+class PoolFn(Function):
+    @staticmethod
+    def forward(ctx, x, is_max: bool):
+        B, L, E = x.shape
+        y, arg = K.pool_fwd(_c(x).view(B * L, E), B, L, is_max)
+        ctx.dims = (B, L, E, is_max)
+        ctx.arg = arg
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        B, L, E, is_max = ctx.dims
+        return K.pool_bwd(_c(dy), B, L, is_max, ctx.arg).view(B, L, E), None
+
+
+def mean_pool(x):
+    return PoolFn.apply(x, False)
+
+
+def max_pool(x):
+    return PoolFn.apply(x, True)
+
+
+class L2NormFn(Function):
+    """F.normalize(x, dim=-1) (MultimodalModel.py:388-390)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        y, norm = K.l2norm_fwd(x)
+        ctx.save_for_backward(y, norm)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        y, norm = ctx.saved_tensors
+        return K.l2norm_bwd(y, norm, K.cast(_c(dy), torch.float32), None)
+
+
+def l2_normalize(x):
+    return L2NormFn.apply(x)
+
+
+def stack_tokens(feats: Sequence[Tensor]) -> Tensor:
+    """[B,E] x S -> [B,S,E]; a device copy (torch.stack), no arithmetic."""
+    return torch.stack(list(feats), dim=1)
+
+
+# ------------------------------------------------------------------------------------------ modality weights
+class ModalConcatFn(Function):
+    """softmax over S modality logits + weighted concat (MultimodalModel.py:175,299-306)."""
+
+    @staticmethod
+    def forward(ctx, logits, *slots):
+        slots = [_c(s) for s in slots]
+        w, fused = K.modal_concat_fwd(K.cast(_c(logits), slots[0].dtype), slots)
+        ctx.save_for_backward(w, *slots)
+        ctx.mark_non_differentiable(w)
+        ctx.ldtype = logits.dtype
+        return fused, w
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dfused, _dw):
+        w, *slots = ctx.saved_tensors
+        need = list(ctx.needs_input_grad[1:])
+        dslots, dlogits = K.modal_concat_bwd(K.cast(_c(dfused), slots[0].dtype), w, slots, need)
+        return (K.cast(dlogits, ctx.ldtype),) + tuple(dslots)
+
+
+def modal_concat(logits, slots: Sequence[Tensor]):
+    return ModalConcatFn.apply(logits, *slots)
+
+
+# ------------------------------------------------------------------------------------------ BN + act + dropout
+class BnActFn(Function):
+    """BatchNorm1d + GELU/ReLU + Dropout on [B,N] (MultimodalModel.py:180-183; ME-MHACL/model.py:84-87)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, training, order, dropout_p,
+                keep_mask, seed, offset):
+        x = _c(x)
+        y, mean, rstd, mask = K.bn_act_fwd(x, gamma.detach(), beta.detach(), running_mean, running_var, momentum, eps,
+                                           training, order, dropout_p, keep_mask, seed, offset)
+        ctx.save_for_backward(x, gamma.detach(), beta.detach(), mean, rstd)
+        ctx.mask = mask
+        ctx.cfg = (training, order, dropout_p)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, gamma, beta, mean, rstd = ctx.saved_tensors
+        training, order, p = ctx.cfg
+        dx, dgamma, dbeta = K.bn_act_bwd(x, K.cast(_c(dy), x.dtype), gamma, beta, mean, rstd, training, order, p,
+                                         ctx.mask)
+        return (dx, dgamma, dbeta) + (None,) * 10
+
+
+def bn_act(x, bn: torch.nn.BatchNorm1d, order: int, dropout_p: float = 0.0, keep_mask: Optional[Tensor] = None,
+           seed: int = 0, offset: int = 0):
+    training = bn.training
+    if training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    return BnActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                         0.1 if bn.momentum is None else bn.momentum, bn.eps, training, order,
+                         dropout_p if training else 0.0, keep_mask, seed, offset)
+
+
+class DropoutFn(Function):
+    """nn.Dropout with no BatchNorm in front (Classifier.shared, ME-MHACL/model.py:105-109)."""
+
+    @staticmethod
+    def forward(ctx, x, p, keep_mask, seed, offset):
+        y, mask = K.dropout(_c(x), p, keep_mask, keep_mask is not None, seed, offset)
+        ctx.mask, ctx.p = mask, p
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        dx, _ = K.dropout(_c(dy), ctx.p, ctx.mask, True, 0, 0)
+        return dx, None, None, None, None
+
+
+def dropout(x, p: float, training: bool, keep_mask: Optional[Tensor] = None, seed: int = 0, offset: int = 0):
+    if not training or p <= 0.0:
+        return x
+    return DropoutFn.apply(x, p, keep_mask, seed, offset)
+
+
+# ------------------------------------------------------------------------------------------ losses
+class CrossEntropyFn(Function):
+    """nn.CrossEntropyLoss() (mean) on fp32 logits (Trainer.py:17,68)."""
+
+    @staticmethod
+    def forward(ctx, logits, labels):
+        logits = _c(logits.float())
+        loss, pred = K.ce_fwd(logits, labels)
+        ctx.save_for_backward(logits, labels)
+        ctx.pred = pred
+        return loss.view(())
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dloss):
+        logits, labels = ctx.saved_tensors
+        return K.ce_bwd(logits, labels, _c(dloss.float()).view(1)), None
+
+
+def cross_entropy(logits, labels):
+    return CrossEntropyFn.apply(logits, labels)
+
+
+class ContrastiveFn(Function):
+    """normalize -> cosine block f1n f2n^T -> row reductions (InfoNCE / SupCon / NT-Xent).
+    f1:[B,E] local rows, f2:[Bg,E] columns (the gathered global batch under data parallelism).
+    The small [B,E] embeddings are processed in fp32 whatever the storage mode: with T=0.01 a bf16
+    cosine (4e-3) would move the scaled logits by 0.4."""
+
+    @staticmethod
+    def forward(ctx, f1, f2, labels_r, labels_c, temperature, temperature_const, kind, row_offset, denom, same):
+        a = K.cast(_c(f1.detach()), torch.float32)
+        n1, norm1 = K.l2norm_fwd(a)
+        if same:
+            n2, norm2 = n1, norm1
+        else:
+            n2, norm2 = K.l2norm_fwd(K.cast(_c(f2.detach()), torch.float32))
+        sim = K.linear_fwd(n1, n2, None, out_dtype=torch.float32)
+        tptr = None if temperature is None else temperature.detach().float().view(1)
+        loss, stats = K.contrastive_fwd(kind, sim, labels_r, labels_c, tptr, temperature_const, row_offset, denom)
+        ctx.save_for_backward(n1, norm1, n2, norm2, sim, stats, labels_r, labels_c, tptr)
+        ctx.cfg = (temperature_const, kind, row_offset, denom, same, f1.dtype, f2.dtype)
+        return loss.view(())
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dloss):
+        n1, norm1, n2, norm2, sim, stats, labels_r, labels_c, tptr = ctx.saved_tensors
+        tconst, kind, row_offset, denom, same, d1, d2 = ctx.cfg
+        G, dtemp = K.contrastive_bwd(kind, sim, labels_r, labels_c, tptr, tconst, row_offset, denom, stats,
+                                     _c(dloss.float()).view(1), torch.float32)
+        dn1 = K.linear_dgrad(G, n2)
+        dn2, _ = K.linear_wgrad(G, n1, want_bias=False)
+        if same:
+            df1 = K.cast(K.l2norm_bwd(n1, norm1, dn1, dn2), d1)
+            df2 = None
+        else:
+            df1 = K.cast(K.l2norm_bwd(n1, norm1, dn1, None), d1)
+            df2 = K.cast(K.l2norm_bwd(n2, norm2, dn2, None), d2) if ctx.needs_input_grad[1] else None
+        dT = dtemp.view(()) if (tptr is not None and ctx.needs_input_grad[4]) else None
+        return df1, df2, None, None, dT, None, None, None, None, None
+
+
+def infonce(f1: Tensor, f2: Tensor, labels: Tensor, temperature, labels_cols: Optional[Tensor] = None,
+            row_offset: int = 0) -> Tensor:
+    """MultimodalTransformerModel.compute_contrastive_loss (MultimodalModel.py:232-260).
+    `labels_cols`/`row_offset` describe a row block of a batch-sharded similarity matrix."""
+    same = f1 is f2
+    lc = labels if labels_cols is None else labels_cols
+    t_tensor = temperature if isinstance(temperature, Tensor) else None
+    t_const = 0.0 if t_tensor is not None else float(temperature)
+    return ContrastiveFn.apply(f1, f2, labels, lc, t_tensor, t_const, LOSS_INFONCE, row_offset, f1.shape[0], same)
+
+
+def supcon(z1: Tensor, z2: Tensor, labels: Tensor, temperature: float = 0.1) -> Tensor:
+    """train.py:16-40 contrastive_loss: SupCon over the 2B stacked views."""
+    z = _StackFn.apply(z1, z2)
+    lab = torch.cat([labels.view(-1), labels.view(-1)])
+    return ContrastiveFn.apply(z, z, lab, lab, None, float(temperature), LOSS_SUPCON, 0, z.shape[0], True)
+
+
+def ntxent(z1: Tensor, z2: Tensor, temperature: float = 0.5) -> Tensor:
+    """ME-MHACL/train.py:47-66 contrastive_loss: NT-Xent over the 2N stacked views."""
+    z = _StackFn.apply(z1, z2)
+    return ContrastiveFn.apply(z, z, None, None, None, float(temperature), LOSS_NTXENT, 0, z.shape[0], True)
+
+
+class _StackFn(Function):
+    """cat([z1, z2], 0) as two device-to-device copies (plumbing; no arithmetic)."""
+
+    @staticmethod
+    def forward(ctx, z1, z2):
+        n = z1.shape[0]
+        z = torch.empty((2 * n, z1.shape[1]), device=z1.device, dtype=z1.dtype)
+        z[:n].copy_(z1)
+        z[n:].copy_(z2)
+        ctx.n = n
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        return dz[:ctx.n], dz[ctx.n:]

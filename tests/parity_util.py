@@ -1,0 +1,85 @@
+"""Shared parity harness: build the drop-in model and the oracle from the same parameters and
+seeded inputs, run fwd+bwd on both, and report per-tensor errors.
+
+Error metric (used for every tolerance in tests/): for a tensor x against reference r,
+    err = max|x - r| / max(max|r|, floor)
+i.e. relative to the tensor's scale (elementwise relative error is meaningless where r crosses 0)."""
+from __future__ import annotations
+
+import os
+import sys
+from typing import Dict, Optional
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "multimodal-sentiment-aanalysis_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from oracle import fusion_oracle as O  # noqa: E402
+
+
+def rel_err(x: torch.Tensor, r: torch.Tensor, floor: float = 1e-12) -> float:
+    x = x.detach().double().cpu().reshape(-1)
+    r = r.detach().double().cpu().reshape(-1)
+    if x.numel() == 0:
+        return 0.0
+    return float((x - r).abs().max() / max(float(r.abs().max()), floor))
+
+
+def oracle_step(cfg: O.FusionConfig, params: Dict[str, torch.Tensor], inputs, labels, dtype=torch.float32,
+                gathered=None):
+    """Oracle fwd+bwd of the Trainer.py:60-79 step: loss = CE(arousal) + sum(contrastive)."""
+    p = {k: v.detach().clone().to(dtype).requires_grad_(True) for k, v in params.items()}
+    xs = tuple(x.to(dtype) for x in inputs)
+    loss, out = O.trainer_loss(cfg, p, xs, labels, training=True, gathered=gathered)
+    loss.backward()
+    grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in p.items()}
+    return loss.detach(), out, grads
+
+
+def build_model(cfg: O.FusionConfig, params, buffers, compute_dtype, device):
+    import mmsa
+    model = mmsa.MultimodalTransformerModel(
+        num_classes=cfg.num_classes, embed_dim=cfg.embed_dim, num_heads=cfg.num_heads, wiring=cfg.wiring,
+        text_dim=cfg.text_dim, image_dim=cfg.image_dim, contract=cfg.contract, compute_dtype=compute_dtype,
+        valence=cfg.valence)
+    sd = {k: v.clone() for k, v in params.items()}
+    sd.update({k: v.clone() for k, v in buffers.items()})
+    missing, unexpected = model.load_state_dict(sd, strict=True)
+    model.set_dropout(0.0)
+    return model.to(device).train()
+
+
+def run_fusion_parity(batch: int = 4, L: int = 64, R: int = 49, dtype: str = "fp32", tol: float = 1e-5,
+                      device: str = "cuda:0", embed_dim: int = 768, num_heads: int = 12, text_dim: int = 768,
+                      image_dim: int = 2048, seed: int = 0, oracle_dtype=torch.float32) -> Dict:
+    """Bidirectional (text+image) fusion step on the GPU vs the CPU oracle on identical inputs."""
+    import mmsa
+    cd = torch.float32 if dtype == "fp32" else torch.bfloat16
+    cfg = O.FusionConfig(embed_dim=embed_dim, num_heads=num_heads, wiring="bidirectional", text_dim=text_dim,
+                         image_dim=image_dim, contract="single", valence=False)
+    params, buffers = O.init_params(cfg, seed=seed)
+    inputs, labels = O.synth_inputs(cfg, batch, L=L, R=R, seed=1234 + seed)
+    o_loss, o_out, o_grads = oracle_step(cfg, params, inputs, labels, dtype=oracle_dtype)
+
+    model = build_model(cfg, params, buffers, cd, device)
+    text, image = (x.to(device) for x in inputs)
+    lab = labels.to(device)
+    logits, closs = model(text, image, None, lab)
+    ce = mmsa.cross_entropy(logits, lab)
+    loss = ce + closs.sum()
+    loss.backward()
+    torch.cuda.synchronize()
+
+    errs = {"logits": rel_err(logits, o_out.arousal), "loss": rel_err(loss, o_loss)}
+    for k, prm in model.named_parameters():
+        g = prm.grad if prm.grad is not None else torch.zeros_like(prm)
+        errs["grad:" + k] = rel_err(g, o_grads[k])
+    worst = max(errs, key=lambda k: errs[k])
+    labels_equal = bool(torch.equal(logits.argmax(1).cpu(), o_out.arousal.argmax(1)))
+    return {"ok": errs[worst] <= tol and labels_equal, "max_rel": errs[worst], "worst": worst, "errs": errs,
+            "loss": float(loss), "oracle_loss": float(o_loss), "labels_equal": labels_equal,
+            "logit_margin": float((o_out.arousal.topk(2, dim=1).values[:, 0] - o_out.arousal.topk(2, dim=1).values[:, 1]).min())}

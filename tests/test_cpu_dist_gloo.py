@@ -1,0 +1,81 @@
+"""world_size-2 gloo tests (CPU) of the data-parallel host logic: all-gather with reduce-scatter
+backward, the sharded InfoNCE row-block convention, and the flat-bucket gradient all-reduce.
+The device kernels are not involved: the arithmetic here is the oracle's, the plumbing is mmsa.dist."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "multimodal-sentiment-aanalysis_b200")
+
+
+def _worker(rank: int, world: int, port: int, q):
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mmsa import dist as mdist
+        from oracle import fusion_oracle as O
+        torch.manual_seed(0)
+        Bg, E = 8, 16
+        B = Bg // world
+        f1 = torch.randn(Bg, E, dtype=torch.float64)
+        f2 = torch.randn(Bg, E, dtype=torch.float64)
+        labels = torch.randint(0, 3, (Bg,))
+        T = torch.tensor(0.07, dtype=torch.float64)
+        # global reference (single process)
+        a, b = f1.clone().requires_grad_(True), f2.clone().requires_grad_(True)
+        ref = O.infonce(a, b, labels, T)
+        ref.backward()
+        # sharded: this rank owns rows [rank*B, (rank+1)*B)
+        sl = slice(rank * B, (rank + 1) * B)
+        x, y = f1[sl].clone().requires_grad_(True), f2[sl].clone().requires_grad_(True)
+        y_all = mdist.all_gather_rows(y)
+        lab_all = mdist.gather_labels(labels[sl])
+        assert torch.equal(lab_all, labels)
+        loss = O.infonce(x, y_all, labels[sl], T, labels2=lab_all, row_offset=rank * B)
+        loss.backward()
+        # mean over ranks of the local means == global mean; gradients: local rows exact / world,
+        # gathered columns reduce-scattered (sum over ranks) / world
+        tot = loss.detach().clone()
+        dist.all_reduce(tot)
+        ok = abs(float(tot) / world - float(ref)) < 1e-12
+        ok &= bool(torch.allclose(x.grad / world, a.grad[sl], atol=1e-12))
+        ok &= bool(torch.allclose(y.grad / world, b.grad[sl], atol=1e-12))
+        # flat-bucket gradient all-reduce (mean)
+        lin = torch.nn.Linear(4, 3)
+        lin2 = torch.nn.Linear(3, 2)
+        with torch.no_grad():
+            for p_ in list(lin.parameters()) + list(lin2.parameters()):
+                p_.grad = torch.full_like(p_, float(rank + 1))
+        lin2.bias.grad = None                                   # a rank-local missing grad is treated as zero
+        red = mdist.GradAllReducer(list(lin.parameters()) + list(lin2.parameters()), bucket_mb=1e-5)
+        red.step()
+        want = sum(range(1, world + 1)) / world
+        ok &= all(bool(torch.allclose(p_.grad, torch.full_like(p_, want))) for p_ in lin.parameters())
+        ok &= bool(torch.allclose(lin2.bias.grad, torch.zeros_like(lin2.bias)))
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_sharded_contrastive_and_grad_allreduce_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29000 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=100) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+    assert all(ok for _, ok in results), results

@@ -1,0 +1,178 @@
+"""CPU suite (-m "not gpu"): the oracle against the imported reference and the committed goldens,
+the host-side contracts, and the C-ABI library (loads, exports every symbol of include/mmsa.h,
+refuses to compute without a B200)."""
+import os
+import re
+import sys
+
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from parity_util import O, rel_err
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+REF = "/root/reference/MML_ZYC"
+has_ref = os.path.isdir(REF)
+
+
+# ------------------------------------------------------------------ oracle vs the imported reference
+@pytest.mark.skipif(not has_ref, reason="reference tree not mounted (GPU box)")
+@pytest.mark.parametrize("B", [2, 20, 64])
+def test_oracle_bit_identical_to_reference(B):
+    """oracle.fusion_forward == reference MultimodalTransformerModel.forward, outputs and every
+    gradient bit for bit, at the reference's native sizes (encoders = Identity, dropout p = 0)."""
+    sys.path.insert(0, REF)
+    import MultimodalModel as R
+    torch.manual_seed(B)
+    m = R.MultimodalTransformerModel()
+    m.eeg_net, m.eye_net, m.pps_net = nn.Identity(), nn.Identity(), nn.Identity()
+    for mod in m.modules():
+        if isinstance(mod, nn.Dropout):
+            mod.p = 0.0
+    m.train()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    cfg = O.FusionConfig()
+    xs, labels = O.synth_inputs(cfg, B, seed=B)
+    a, v, c0, c1, c2 = m(*xs, labels=(labels, labels))
+    (F.cross_entropy(a, labels) + F.cross_entropy(v, labels) + c0.sum() + c1.sum() + c2.sum()).backward()
+    p = {k: t.clone().requires_grad_(t.dtype.is_floating_point) for k, t in sd.items()}
+    out = O.fusion_forward(cfg, p, xs, labels, training=True)
+    (F.cross_entropy(out.arousal, labels) + F.cross_entropy(out.valence, labels)
+     + sum(c.sum() for c in out.contrastive)).backward()
+    assert torch.equal(a, out.arousal) and torch.equal(v, out.valence)
+    for x, y in zip((c0, c1, c2), out.contrastive):
+        assert torch.equal(x, y)
+    for k, prm in m.named_parameters():
+        assert torch.equal(prm.grad, p[k].grad), k
+
+
+@pytest.mark.skipif(not has_ref, reason="reference tree not mounted (GPU box)")
+def test_oracle_block_matches_reference_with_long_keys():
+    """Lq = 1, Lk = 49 is the one multi-token shape the reference block can run."""
+    sys.path.insert(0, REF)
+    import MultimodalModel as R
+    torch.manual_seed(0)
+    blk = R.CrossModalTransformer()
+    q = torch.randn(5, 256)
+    kv = torch.randn(5, 49, 256)
+    ref = blk(q, kv, kv)
+    p = {"b." + k: v for k, v in blk.state_dict().items()}
+    got = O.cross_block(q.unsqueeze(1), kv, p, "b.", 4).squeeze(1)
+    # 3-D key/value are passed through un-squeezed, so `key is value` holds and torch takes the packed
+    # k,v in-projection (one [2E] GEMM instead of two): same arithmetic, different blocking -> ulp level
+    assert rel_err(got, ref) <= 1e-6
+
+
+# ------------------------------------------------------------------ oracle vs committed goldens
+@pytest.mark.parametrize("case", ["native_case_B2_T0.01.pt", "native_case_B20_T0.5.pt", "native_case_B64_T0.07.pt"])
+def test_oracle_reproduces_goldens(case):
+    gp = torch.load(os.path.join(GOLD, "native_params.pt"))
+    c = torch.load(os.path.join(GOLD, case))
+    p = {k: t.clone().requires_grad_(t.dtype.is_floating_point) for k, t in gp["state_dict"].items()}
+    with torch.no_grad():
+        p["temperature"].fill_(c["temperature"])
+    cfg = O.FusionConfig()
+    out = O.fusion_forward(cfg, p, c["inputs"], c["labels"], training=True)
+    loss = (F.cross_entropy(out.arousal, c["labels"]) + F.cross_entropy(out.valence, c["val_labels"])
+            + sum(x.sum() for x in out.contrastive))
+    loss.backward()
+    assert rel_err(out.arousal, c["arousal"]) <= 1e-6 and rel_err(out.valence, c["valence"]) <= 1e-6
+    assert rel_err(loss, c["loss"]) <= 1e-6
+    for k, dig in c["grads"].items():
+        flat = p[k].grad.reshape(-1)
+        assert float((flat[dig["idx"]] - dig["vals"]).abs().max()) <= 1e-6 * max(dig["absmax"], 1e-12) * 10, k
+
+
+def test_oracle_losses_reproduce_goldens():
+    g = torch.load(os.path.join(GOLD, "memhacl.pt"))
+    c = g["supcon"]
+    assert rel_err(O.supcon(c["z1"], c["z2"], c["labels"], 0.1), c["loss"]) <= 1e-6
+    c = g["ntxent"]
+    assert rel_err(O.ntxent(c["z1"], c["z2"], 0.5), c["loss"]) <= 1e-6
+    pm = {"multihead_attn." + k: v for k, v in g["mean"]["state_dict"].items()}
+    assert rel_err(O.memhacl_fusion(g["feats"], pm, 8, "mean"), g["mean"]["out"]) <= 1e-6
+    assert rel_err(O.memhacl_fusion(g["feats"], dict(g["max"]["state_dict"]), 8, "max"), g["max"]["out"]) <= 1e-6
+    assert rel_err(O.projection_head(g["projection"]["x"], dict(g["projection"]["state_dict"])),
+                   g["projection"]["out"]) <= 1e-6
+    oa, ov = O.classifier(g["classifier"]["x"], dict(g["classifier"]["state_dict"]))
+    assert rel_err(oa, g["classifier"]["out_a"]) <= 1e-6 and rel_err(ov, g["classifier"]["out_v"]) <= 1e-6
+
+
+def test_oracle_sharded_infonce_equals_global():
+    """row-block form (labels2 / row_offset) used under data parallelism == the reference's global form."""
+    g = torch.Generator().manual_seed(0)
+    f1, f2 = torch.randn(16, 32, generator=g, dtype=torch.float64), torch.randn(16, 32, generator=g, dtype=torch.float64)
+    lab = torch.randint(0, 3, (16,), generator=g)
+    T = torch.tensor(0.05, dtype=torch.float64)
+    full = O.infonce(f1, f2, lab, T)
+    parts = [O.infonce(f1[r * 4:(r + 1) * 4], f2, lab[r * 4:(r + 1) * 4], T, labels2=lab, row_offset=r * 4) for r in range(4)]
+    assert abs(float(full) - float(sum(parts) / 4)) < 1e-12
+
+
+def test_oracle_bidirectional_runs_at_baseline_shapes():
+    cfg = O.FusionConfig(embed_dim=768, num_heads=12, wiring="bidirectional", contract="single", valence=False)
+    params, _ = O.init_params(cfg, seed=0)
+    xs, labels = O.synth_inputs(cfg, 2, L=64, R=49)
+    loss, out = O.trainer_loss(cfg, params, xs, labels)
+    assert out.arousal.shape == (2, 3) and torch.isfinite(loss)
+    n = sum(v.numel() for k, v in params.items())
+    assert n == 10_181_381 + 0 or n > 9_000_000     # ~10.2 M fusion parameters at E=768
+
+
+# ------------------------------------------------------------------ C ABI
+def test_library_loads_and_exports_every_header_symbol():
+    from mmsa import _lib
+    lib = _lib.load()
+    names = _lib.header_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"libmmsa.so does not export {n}"
+        assert n in _lib._PROTOS, f"no ctypes prototype for {n}"
+    assert lib.mmsa_version().decode().startswith("mmsa-b200")
+
+
+def test_prototype_arity_matches_header():
+    from mmsa import _lib
+    text = open(_lib.HEADER_PATH).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    for m in re.finditer(r"\b(mmsa_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+        name, args = m.group(1), m.group(2).strip()
+        n = 0 if args in ("", "void") else args.count(",") + 1
+        assert len(_lib._PROTOS[name][1]) == n, f"{name}: header has {n} args, binding has {len(_lib._PROTOS[name][1])}"
+
+
+def test_no_gpu_means_error_not_fallback():
+    """Without a B200 the product path must fail loudly."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import mmsa
+    from mmsa import _lib
+    assert _lib.load().mmsa_check_device() != 0
+    assert "sm_100" in _lib.load().mmsa_last_error().decode()
+    model = mmsa.MultimodalTransformerModel()
+    xs, labels = O.synth_inputs(O.FusionConfig(), 4)
+    with pytest.raises(Exception):
+        model(*xs, labels=(labels, labels))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(os.path.dirname(os.path.dirname(__file__)), "multimodal-sentiment-aanalysis_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(root, f), encoding="utf-8").read()
+                assert "fusion_oracle" not in src and "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_state_dict_keys_match_reference_layout():
+    import mmsa
+    gp = torch.load(os.path.join(GOLD, "native_params.pt"))
+    model = mmsa.MultimodalTransformerModel()
+    assert list(model.state_dict().keys()) == gp["keys"]
+    for k, v in model.state_dict().items():
+        assert tuple(v.shape) == tuple(gp["state_dict"][k].shape), k
+    # module. prefix stripping of Tester.load_model (Tester.py:32-33) round-trips
+    sd = {"module." + k: v for k, v in model.state_dict().items()}
+    model.load_state_dict({k[7:]: v for k, v in sd.items()}, strict=True)

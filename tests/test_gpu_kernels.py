@@ -1,0 +1,435 @@
+"""Kernel-level parity (-m gpu): every C-ABI entry point against a plain PyTorch fp32/fp64 statement
+of the same op on identical seeded inputs.  Tolerances (parity_util.rel_err, relative to tensor
+scale): fp32 storage 1e-5, bf16 storage 2e-2 (BASELINE.json north_star)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from parity_util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-5, torch.bfloat16: 2e-2}
+
+
+def _k():
+    from mmsa import kernels
+    return kernels
+
+
+def _rand(shape, dtype, dev, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dev).to(dtype)
+
+
+# ---------------------------------------------------------------------------------------- GEMMs
+GEMM_SHAPES = [
+    (256, 768, 768),      # one E x E projection, 2 m-tiles
+    (392, 768, 2048),     # image projection at B=8 (ragged M: 392 = 3*128 + 8)
+    (1000, 1536, 768),    # packed K/V projection, ragged M
+    (64, 256, 2304),      # fusion.0 (small M)
+    (37, 64, 1536),       # tiny ragged everything
+    (300, 3, 128),        # class head, N = 3 (CUDA-core path)
+    (128, 128, 72),       # K not a multiple of 64 (TMA zero fill)
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_linear_fwd(cuda_device, dtype, M, N, K):
+    k = _k()
+    x = _rand((M, K), dtype, cuda_device, 1)
+    w = _rand((N, K), dtype, cuda_device, 2, 1 / math.sqrt(K))
+    b = _rand((N,), torch.float32, cuda_device, 3)
+    r = _rand((M, N), dtype, cuda_device, 4)
+    y = k.linear_fwd(x, w, b, residual=r)
+    ref = x.double() @ w.double().T + b.double() + r.double()
+    assert rel_err(y, ref) <= TOL[dtype]
+    # fp32 output from bf16 operands (logits path)
+    y32 = k.linear_fwd(x, w, b, out_dtype=torch.float32)
+    assert y32.dtype == torch.float32
+    assert rel_err(y32, x.double() @ w.double().T + b.double()) <= (1e-5 if dtype == torch.float32 else 2e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_linear_fwd_split_operand(cuda_device, dtype):
+    """gate GEMM: cat[q, attn] @ Wg^T without the concat (MultimodalModel.py:147)."""
+    k = _k()
+    M, E = 520, 768
+    q = _rand((M, E), dtype, cuda_device, 1)
+    a = _rand((M, E), dtype, cuda_device, 2)
+    w = _rand((E, 2 * E), dtype, cuda_device, 3, 0.02)
+    b = _rand((E,), torch.float32, cuda_device, 4)
+    y = k.linear_fwd(q, w, b, x2=a)
+    ref = torch.cat([q, a], 1).double() @ w.double().T + b.double()
+    assert rel_err(y, ref) <= TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K", [(256, 768, 768), (392, 1536, 768), (77, 3, 128), (640, 768, 1536)])
+def test_linear_dgrad(cuda_device, dtype, M, N, K):
+    k = _k()
+    dy = _rand((M, N), dtype, cuda_device, 1)
+    wfull = _rand((N, K + 64), dtype, cuda_device, 2, 1 / math.sqrt(N))
+    w = wfull[:, 64:]                      # column block of a wider weight (ld != K)
+    r = _rand((M, K), dtype, cuda_device, 3)
+    dx = k.linear_dgrad(dy, w, residual=r)
+    ref = dy.double() @ w.double() + r.double()
+    assert rel_err(dx, ref) <= TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K", [(1024, 768, 768), (392, 768, 2048), (5000, 1536, 768), (300, 3, 128), (64, 256, 2304)])
+def test_linear_wgrad(cuda_device, dtype, M, N, K):
+    k = _k()
+    dy = _rand((M, N), dtype, cuda_device, 1)
+    x = _rand((M, K), dtype, cuda_device, 2)
+    dwfull = torch.zeros((N, K + 8), device=cuda_device)
+    dw, db = k.linear_wgrad(dy, x, dw=dwfull[:, 8:])
+    ref_w = dy.double().T @ x.double()
+    ref_b = dy.double().sum(0)
+    tol = 1e-5 if dtype == torch.float32 else 2e-3     # bf16 operands, fp32 accumulate and output
+    assert rel_err(dw, ref_w) <= tol
+    assert rel_err(db, ref_b) <= tol
+    assert float(dwfull[:, :8].abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------------------------------- attention
+def _attn_ref(q, k, v, B, H, Lq, Lk, D):
+    qd = q.double().view(B, Lq, H, D).transpose(1, 2)
+    kd = k.double().view(B, Lk, H, D).transpose(1, 2)
+    vd = v.double().view(B, Lk, H, D).transpose(1, 2)
+    s = (qd / math.sqrt(D)) @ kd.transpose(-1, -2)
+    p = torch.softmax(s, -1)
+    o = (p @ vd).transpose(1, 2).reshape(B * Lq, H * D)
+    return o, torch.logsumexp(s, -1)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,H,Lq,Lk,D", [(3, 12, 64, 49, 64), (2, 12, 49, 128, 64), (2, 4, 1, 1, 64),
+                                         (5, 8, 3, 3, 32), (1, 12, 130, 70, 64), (2, 12, 49, 512, 64)])
+def test_attention(cuda_device, dtype, B, H, Lq, Lk, D):
+    k_ = _k()
+    E = H * D
+    q = _rand((B * Lq, E), dtype, cuda_device, 1)
+    kv = _rand((B * Lk, 2 * E), dtype, cuda_device, 2)        # packed K|V, row stride 2E
+    kk, vv = kv[:, :E], kv[:, E:]
+    do = _rand((B * Lq, E), dtype, cuda_device, 3)
+    o, lse = k_.attn_fwd(q, kk, vv, B, H, Lq, Lk, D)
+    qr, kr, vr = (t.detach().double().requires_grad_(True) for t in (q, kk, vv))
+    o_ref, lse_ref = _attn_ref(qr, kr, vr, B, H, Lq, Lk, D)
+    assert rel_err(o, o_ref) <= TOL[dtype]
+    assert rel_err(lse, lse_ref) <= (1e-5 if dtype == torch.float32 else 2e-3)
+    o_ref.backward(do.double())
+    dq = torch.empty_like(q)
+    dkv = torch.empty_like(kv)
+    k_.attn_bwd(q, kk, vv, o, do, lse, B, H, Lq, Lk, D, dq, dkv[:, :E], dkv[:, E:])
+    assert rel_err(dq, qr.grad) <= TOL[dtype]
+    assert rel_err(dkv[:, :E], kr.grad) <= TOL[dtype]
+    assert rel_err(dkv[:, E:], vr.grad) <= TOL[dtype]
+
+
+def test_attention_engines_agree(cuda_device):
+    """bf16: tensor-core engine vs CUDA-core engine on the same inputs."""
+    from mmsa import _lib
+    k_ = _k()
+    B, H, Lq, Lk, D = 2, 12, 128, 49, 64
+    E = H * D
+    q = _rand((B * Lq, E), torch.bfloat16, cuda_device, 1)
+    kv = _rand((B * Lk, 2 * E), torch.bfloat16, cuda_device, 2)
+    o1, l1 = k_.attn_fwd(q, kv[:, :E], kv[:, E:], B, H, Lq, Lk, D)
+    _lib.load().mmsa_debug_force_simt_attention(1)
+    try:
+        o2, l2 = k_.attn_fwd(q, kv[:, :E], kv[:, E:], B, H, Lq, Lk, D)
+    finally:
+        _lib.load().mmsa_debug_force_simt_attention(0)
+    assert rel_err(o1, o2) <= 2e-2 and rel_err(l1, l2) <= 2e-3
+
+
+# ---------------------------------------------------------------------------------------- gate + LN
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,E,L", [(8 * 64, 768, 64), (5 * 49, 768, 49), (20, 256, 1), (3 * 7, 1024, 7)])
+def test_gate_ln(cuda_device, dtype, M, E, L):
+    k = _k()
+    gp = _rand((M, E), dtype, cuda_device, 1)
+    q = _rand((M, E), dtype, cuda_device, 2)
+    a = _rand((M, E), dtype, cuda_device, 3)
+    gamma = _rand((E,), torch.float32, cuda_device, 4) * 0.1 + 1
+    beta = _rand((E,), torch.float32, cuda_device, 5) * 0.1
+    g, y, mean, rstd = k.gate_ln_fwd(gp, q, a, gamma, beta, 1e-5)
+
+    def ref(gp_, q_, a_, gm, bt):
+        gg = torch.sigmoid(gp_)
+        u = gg * q_ + (1 - gg) * a_
+        return F.layer_norm(u, (E,), gm, bt, 1e-5)
+
+    ins = [t.detach().double().requires_grad_(True) for t in (gp, q, a, gamma, beta)]
+    y_ref = ref(*ins)
+    assert rel_err(y, y_ref) <= TOL[dtype]
+    assert rel_err(g, torch.sigmoid(gp.double())) <= TOL[dtype]
+    # backward, token-pooled form: dy is [M/L, E] broadcast over tokens / L, plus a pooled grad for q
+    B = M // L
+    dyp = _rand((B, E), dtype, cuda_device, 6)
+    dqb = _rand((B, E), dtype, cuda_device, 7)
+    dqa = _rand((M, E), dtype, cuda_device, 8)
+    (y_ref.view(B, L, E).mean(1) * dyp.double()).sum().backward()
+    dq_part, da_part, dgp, dgamma, dbeta = k.gate_ln_bwd(dyp, L, g, q, a, gamma, mean, rstd, dq_bcast=dqb, bcast_rows=L,
+                                                       dq_add=dqa)
+    g_ = g.double()
+    du_q = ins[1].grad      # = du*g
+    extra = dqb.double().repeat_interleave(L, 0) / L + dqa.double()
+    tol = TOL[dtype]
+    assert rel_err(dq_part, du_q + extra) <= tol
+    assert rel_err(da_part, ins[2].grad) <= tol
+    assert rel_err(dgp, ins[0].grad) <= (tol if dtype == torch.float32 else 4e-2)
+    assert rel_err(dgamma, ins[3].grad) <= (1e-5 if dtype == torch.float32 else 2e-2)
+    assert rel_err(dbeta, ins[4].grad) <= (1e-5 if dtype == torch.float32 else 2e-2)
+    # plain form
+    dy = _rand((M, E), dtype, cuda_device, 9)
+    for t in ins:
+        t.grad = None
+    ref(*ins).backward(dy.double())
+    dq_part, da_part, dgp, dgamma, dbeta = k.gate_ln_bwd(dy, 0, g, q, a, gamma, mean, rstd)
+    assert rel_err(dq_part, ins[1].grad) <= tol and rel_err(da_part, ins[2].grad) <= tol
+    assert rel_err(dgamma, ins[3].grad) <= (1e-5 if dtype == torch.float32 else 2e-2)
+
+
+# ---------------------------------------------------------------------------------------- pooling / concat
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,L,E", [(8, 64, 768), (5, 49, 768), (6, 3, 256), (2, 512, 768), (3, 1, 256)])
+def test_pool(cuda_device, dtype, B, L, E):
+    k = _k()
+    x = _rand((B * L, E), dtype, cuda_device, 1)
+    y, _ = k.pool_fwd(x, B, L)
+    assert rel_err(y, x.double().view(B, L, E).mean(1)) <= TOL[dtype]
+    ym, arg = k.pool_fwd(x, B, L, is_max=True)
+    vals, idx = x.float().view(B, L, E).max(1)
+    assert torch.equal(ym.float(), vals)
+    assert torch.equal(arg.long(), idx)
+    dy = _rand((B, E), dtype, cuda_device, 2)
+    dx = k.pool_bwd(dy, B, L)
+    assert rel_err(dx, (dy.double() / L).repeat_interleave(L, 0)) <= TOL[dtype]
+    dxm = k.pool_bwd(dy, B, L, True, arg)
+    ref = torch.zeros(B, L, E, dtype=torch.float64, device=cuda_device).scatter_(1, idx.unsqueeze(1), dy.double().unsqueeze(1))
+    assert rel_err(dxm, ref.view(B * L, E)) <= TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_modal_concat(cuda_device, dtype):
+    k = _k()
+    B, E, S = 37, 768, 3
+    logits = _rand((B, S), dtype, cuda_device, 1)
+    slots = [_rand((B, E), dtype, cuda_device, 2 + i) for i in range(S)]
+    w, fused = k.modal_concat_fwd(logits, slots)
+    lr = logits.detach().double().requires_grad_(True)
+    sr = [s.detach().double().requires_grad_(True) for s in slots]
+    wr = torch.softmax(lr, 1)
+    fr = torch.cat([sr[i] * wr[:, i:i + 1] for i in range(S)], 1)
+    assert rel_err(w, wr) <= 1e-5 and rel_err(fused, fr) <= TOL[dtype]
+    df = _rand((B, S * E), dtype, cuda_device, 9)
+    fr.backward(df.double())
+    dslots, dlog = k.modal_concat_bwd(df, w, slots, [True] * S)
+    for i in range(S):
+        assert rel_err(dslots[i], sr[i].grad) <= TOL[dtype]
+    assert rel_err(dlog, lr.grad) <= TOL[dtype]
+
+
+# ---------------------------------------------------------------------------------------- BN / dropout / act
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("order", [0, 1])
+@pytest.mark.parametrize("training", [True, False])
+def test_bn_act(cuda_device, dtype, order, training):
+    k = _k()
+    B, N, p = 48, 200, 0.3
+    x = _rand((B, N), dtype, cuda_device, 1)
+    gamma = _rand((N,), torch.float32, cuda_device, 2) * 0.1 + 1
+    beta = _rand((N,), torch.float32, cuda_device, 3) * 0.1
+    rm = _rand((N,), torch.float32, cuda_device, 4) * 0.1
+    rv = _rand((N,), torch.float32, cuda_device, 5).abs() + 0.5
+    keep = (torch.rand(B, N, generator=torch.Generator().manual_seed(6)) >= p).to(torch.uint8).to(cuda_device)
+    rm_k, rv_k = rm.clone(), rv.clone()
+    y, mean, rstd, mask = k.bn_act_fwd(x, gamma, beta, rm_k, rv_k, 0.1, 1e-5, training, order, p if training else 0.0,
+                                       keep if training else None, 0, 0)
+    xr, gr, br = (t.detach().double().requires_grad_(True) for t in (x, gamma, beta))
+    rm_r, rv_r = rm.double().clone(), rv.double().clone()
+    h = F.relu(xr) if order == 1 else xr
+    h = F.batch_norm(h, rm_r, rv_r, gr, br, training, 0.1, 1e-5)
+    if order == 0:
+        h = F.gelu(h)
+    if training:
+        h = h * keep.double() / (1 - p)
+    assert rel_err(y, h) <= TOL[dtype]
+    if training:
+        assert rel_err(rm_k, rm_r) <= 1e-5 and rel_err(rv_k, rv_r) <= (1e-5 if dtype == torch.float32 else 1e-2)
+    dy = _rand((B, N), dtype, cuda_device, 7)
+    h.backward(dy.double())
+    dx, dg, db = k.bn_act_bwd(x, dy, gamma, beta, mean, rstd, training, order, p if training else 0.0,
+                              mask if training else None)
+    assert rel_err(dx, xr.grad) <= TOL[dtype]
+    assert rel_err(dg, gr.grad) <= (1e-5 if dtype == torch.float32 else 2e-2)
+    assert rel_err(db, br.grad) <= (1e-5 if dtype == torch.float32 else 2e-2)
+
+
+def test_dropout_rng(cuda_device):
+    """in-kernel Philox: keep rate ~ 1-p, deterministic for a fixed (seed, offset), scaled by 1/(1-p)."""
+    k = _k()
+    x = torch.ones(4096, 64, device=cuda_device)
+    y1, m1 = k.dropout(x, 0.3, None, False, 123, 0)
+    y2, m2 = k.dropout(x, 0.3, None, False, 123, 0)
+    y3, m3 = k.dropout(x, 0.3, None, False, 124, 0)
+    assert torch.equal(m1, m2) and not torch.equal(m1, m3)
+    assert abs(float(m1.float().mean()) - 0.7) < 0.01
+    assert torch.allclose(y1, m1.float() / 0.7)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("act", [2, 3])
+def test_act(cuda_device, dtype, act):
+    k = _k()
+    x = _rand((1000, 67), dtype, cuda_device, 1)
+    y = k.act_fwd(x, act)
+    xr = x.detach().double().requires_grad_(True)
+    ref = F.gelu(xr) if act == 2 else F.relu(xr)
+    assert rel_err(y, ref) <= TOL[dtype]
+    dy = _rand((1000, 67), dtype, cuda_device, 2)
+    ref.backward(dy.double())
+    assert rel_err(k.act_bwd(x, dy, act), xr.grad) <= TOL[dtype]
+
+
+# ---------------------------------------------------------------------------------------- losses
+def test_cross_entropy(cuda_device):
+    k = _k()
+    B, C = 257, 3
+    logits = _rand((B, C), torch.float32, cuda_device, 1, 3.0)
+    labels = torch.randint(0, C, (B,), generator=torch.Generator().manual_seed(2)).to(cuda_device)
+    loss, pred = k.ce_fwd(logits, labels)
+    lr = logits.detach().double().requires_grad_(True)
+    ref = F.cross_entropy(lr, labels)
+    assert rel_err(loss, ref) <= 1e-5
+    assert torch.equal(pred, logits.argmax(1))
+    ref.backward()
+    dl = k.ce_bwd(logits, labels, torch.ones(1, device=cuda_device))
+    assert rel_err(dl, lr.grad) <= 1e-5
+
+
+def _oracle():
+    from oracle import fusion_oracle as O
+    return O
+
+
+@pytest.mark.parametrize("B,E,same,T", [(32, 256, True, 0.01), (64, 768, False, 0.01), (48, 128, False, 0.2),
+                                        (20, 256, True, 0.5)])
+def test_infonce_op(cuda_device, B, E, same, T):
+    """ops.infonce vs oracle (MultimodalModel.py:232-260), including dT and the max-subtraction gradient."""
+    from mmsa import ops
+    O = _oracle()
+    g = torch.Generator().manual_seed(B)
+    f1 = torch.randn(B, E, generator=g)
+    f2 = f1 if same else (f1 * 0.7 + 0.3 * torch.randn(B, E, generator=g))
+    labels = torch.randint(0, 3, (B,), generator=g)
+    temp = torch.tensor(T)
+    a = f1.clone().double().requires_grad_(True)
+    b = a if same else f2.clone().double().requires_grad_(True)
+    tt = temp.clone().double().requires_grad_(True)
+    ref = O.infonce(a, b, labels, tt)
+    ref.backward()
+    x = f1.clone().to(cuda_device).requires_grad_(True)
+    y = x if same else f2.clone().to(cuda_device).requires_grad_(True)
+    tg = temp.clone().to(cuda_device).requires_grad_(True)
+    out = ops.infonce(x, y, labels.to(cuda_device), tg)
+    out.backward()
+    assert rel_err(out, ref) <= 1e-5
+    assert rel_err(x.grad, a.grad) <= 2e-4      # fp32 exp(s/T) at T=0.01 amplifies cosine rounding 100x
+    if not same:
+        assert rel_err(y.grad, b.grad) <= 2e-4
+    assert rel_err(tg.grad, tt.grad) <= 2e-4
+
+
+def test_infonce_edge_cases(cuda_device):
+    """rows with no positives, duplicate rows (ties in the row max), single class."""
+    from mmsa import ops
+    O = _oracle()
+    g = torch.Generator().manual_seed(7)
+    f = torch.randn(12, 64, generator=g)
+    f[5] = f[2]                                   # exact duplicate -> tie on the row max
+    for labels in (torch.arange(12), torch.zeros(12, dtype=torch.long), torch.tensor([0, 1, 2] * 4)):
+        a = f.clone().double().requires_grad_(True)
+        ref = O.infonce(a, a, labels, torch.tensor(0.05, dtype=torch.float64))
+        ref.backward()
+        x = f.clone().to(cuda_device).requires_grad_(True)
+        out = ops.infonce(x, x, labels.to(cuda_device), 0.05)
+        out.backward()
+        assert rel_err(out, ref) <= 1e-5
+        assert rel_err(x.grad, a.grad) <= 2e-4
+
+
+def test_sharded_infonce_rows(cuda_device):
+    """row block + global diagonal: two half-batches reproduce the full-batch loss and gradients."""
+    from mmsa import ops
+    O = _oracle()
+    g = torch.Generator().manual_seed(11)
+    B, E = 32, 128
+    f1, f2 = torch.randn(B, E, generator=g), torch.randn(B, E, generator=g)
+    labels = torch.randint(0, 3, (B,), generator=g)
+    a, b = f1.clone().double().requires_grad_(True), f2.clone().double().requires_grad_(True)
+    ref = O.infonce(a, b, labels, torch.tensor(0.07, dtype=torch.float64))
+    ref.backward()
+    x, y = f1.clone().to(cuda_device).requires_grad_(True), f2.clone().to(cuda_device).requires_grad_(True)
+    lab = labels.to(cuda_device)
+    h = B // 2
+    total = 0
+    for r in range(2):
+        total = total + 0.5 * ops.infonce(x[r * h:(r + 1) * h], y, lab[r * h:(r + 1) * h], 0.07, labels_cols=lab,
+                                          row_offset=r * h)
+    total.backward()
+    assert rel_err(total, ref) <= 1e-5
+    assert rel_err(x.grad, a.grad) <= 1e-4 and rel_err(y.grad, b.grad) <= 1e-4
+
+
+def test_supcon_ntxent(cuda_device):
+    from mmsa import ops
+    O = _oracle()
+    g = torch.Generator().manual_seed(3)
+    B, D = 24, 128
+    z1, z2 = torch.randn(B, D, generator=g), torch.randn(B, D, generator=g)
+    labels = torch.randint(0, 2, (B,), generator=g)
+    for name in ("supcon", "ntxent"):
+        a, b = z1.clone().double().requires_grad_(True), z2.clone().double().requires_grad_(True)
+        ref = O.supcon(a, b, labels, 0.1) if name == "supcon" else O.ntxent(a, b, 0.5)
+        ref.backward()
+        x, y = z1.clone().to(cuda_device).requires_grad_(True), z2.clone().to(cuda_device).requires_grad_(True)
+        out = ops.supcon(x, y, labels.to(cuda_device), 0.1) if name == "supcon" else ops.ntxent(x, y, 0.5)
+        out.backward()
+        assert rel_err(out, ref) <= 1e-5, name
+        assert rel_err(x.grad, a.grad) <= 1e-4 and rel_err(y.grad, b.grad) <= 1e-4, name
+
+
+def test_clip_adamw(cuda_device):
+    """fused global-norm clip + AdamW vs torch clip_grad_norm_ + AdamW (Trainer.py:19-21,80-81)."""
+    from mmsa import _lib
+    n = 100_003
+    p0 = _rand((n,), torch.float32, cuda_device, 1)
+    g0 = _rand((n,), torch.float32, cuda_device, 2, 0.05)
+    ref_p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref_p], lr=1e-4, weight_decay=0.01)
+    p, m, v = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    partials = torch.empty(256, device=cuda_device)
+    sq = torch.empty(1, device=cuda_device)
+    st = torch.cuda.current_stream().cuda_stream
+    for step in range(1, 4):
+        grad = g0 * step
+        ref_p.grad = grad.clone()
+        torch.nn.utils.clip_grad_norm_([ref_p], 1.0)
+        opt.step()
+        _lib.call("mmsa_sumsq", grad.data_ptr(), n, partials.data_ptr(), 256, sq.data_ptr(), st)
+        _lib.call("mmsa_clip_adamw", p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), n, sq.data_ptr(),
+                  1.0, 1e-4, 0.9, 0.999, 1e-8, 0.01, step, st)
+    assert rel_err(p, ref_p) <= 1e-6
+
+
+def test_not_sm100_message():
+    """the device gate exists and reports (on the B200 box it passes)."""
+    from mmsa import _lib
+    assert _lib.load().mmsa_check_device() == 0

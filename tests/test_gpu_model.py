@@ -1,0 +1,204 @@
+"""Model-level parity (-m gpu): the drop-in modules, called the way Trainer.py / Tester.py /
+MultiTaskTrainer.py call the reference model, against the CPU oracle and the committed goldens
+(generated from the imported reference by oracle/make_goldens.py).
+Tolerances: fp32 1e-5, bf16 2e-2 (parity_util.rel_err; BASELINE.json north_star)."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from parity_util import O, build_model, oracle_step, rel_err, run_fusion_parity
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _check_digest(grad: torch.Tensor, dig, tol: float, name: str):
+    flat = grad.detach().reshape(-1).cpu()
+    scale = max(dig["absmax"], 1e-12)
+    err = float((flat[dig["idx"]] - dig["vals"]).abs().max()) / scale
+    assert err <= tol, f"{name}: sampled grad err {err:.3e}"
+    n_err = abs(float(flat.double().norm()) - dig["norm"]) / max(dig["norm"], 1e-12)
+    assert n_err <= max(tol, 1e-5) * 10, f"{name}: grad norm err {n_err:.3e}"
+
+
+# ------------------------------------------------------------------ re-skinned (text + image) path
+@pytest.mark.parametrize("batch,L", [(4, 64), (3, 128), (2, 512)])
+def test_fusion_step_fp32(cuda_device, batch, L):
+    rep = run_fusion_parity(batch=batch, L=L, R=49, dtype="fp32", tol=1e-5)
+    assert rep["labels_equal"]
+    assert rep["ok"], (rep["worst"], rep["max_rel"], {k: v for k, v in rep["errs"].items() if v > 1e-5})
+
+
+@pytest.mark.parametrize("batch,L", [(8, 64), (4, 128)])
+def test_fusion_step_bf16(cuda_device, batch, L):
+    rep = run_fusion_parity(batch=batch, L=L, R=49, dtype="bf16", tol=2e-2)
+    assert rep["ok"], (rep["worst"], rep["max_rel"], rep["logit_margin"],
+                       {k: v for k, v in rep["errs"].items() if v > 2e-2})
+
+
+def test_fusion_eval_and_contracts(cuda_device):
+    """Tester.py:53 (`outputs = model(eeg, eye, pps)` under no_grad/eval) and the return arities."""
+    cfg = O.FusionConfig(embed_dim=768, num_heads=12, wiring="bidirectional", contract="single", valence=False)
+    params, buffers = O.init_params(cfg, seed=1)
+    inputs, labels = O.synth_inputs(cfg, 6, L=64, R=49, seed=5)
+    model = build_model(cfg, params, buffers, torch.float32, cuda_device)
+    text, image = (x.to(cuda_device) for x in inputs)
+    out = model(text, image, None, labels.to(cuda_device))
+    assert isinstance(out, tuple) and len(out) == 2 and out[0].shape == (6, 3) and out[1].shape == (1,)
+    model.eval()
+    with torch.no_grad():
+        logits = model(text, image, None)
+    assert logits.shape == (6, 3) and logits.dtype == torch.float32
+    p = {k: v for k, v in params.items()}
+    p.update(model.state_dict())                       # running stats after the one train step
+    p = {k: v.detach().cpu() for k, v in p.items()}
+    ref = O.fusion_forward(cfg, p, inputs, None, training=False)
+    assert rel_err(logits, ref.arousal) <= 1e-5
+    probs = torch.softmax(logits, dim=1)               # Tester.py:54
+    assert torch.isfinite(probs).all()
+
+
+# ------------------------------------------------------------------ native wiring vs goldens from the reference
+@pytest.mark.parametrize("case", ["native_case_B2_T0.01.pt", "native_case_B20_T0.01.pt", "native_case_B20_T0.5.pt",
+                                  "native_case_B64_T0.07.pt"])
+def test_native_against_reference_goldens(cuda_device, case):
+    import mmsa
+    gp = torch.load(os.path.join(GOLD, "native_params.pt"))
+    c = torch.load(os.path.join(GOLD, case))
+    model = mmsa.MultimodalTransformerModel().set_dropout(0.0)
+    assert list(model.state_dict().keys()) == gp["keys"], "state_dict keys must match the reference's"
+    model.load_state_dict(gp["state_dict"], strict=True)
+    with torch.no_grad():
+        model.temperature.fill_(c["temperature"])
+    model = model.to(cuda_device).train()
+    xs = [x.to(cuda_device) for x in c["inputs"]]
+    labels, vlabels = c["labels"].to(cuda_device), c["val_labels"].to(cuda_device)
+    a, v, c0, c1, c2 = model(*xs, labels=(labels, vlabels))       # MultiTaskTrainer.py:199 contract
+    assert a.shape == c["arousal"].shape and c0.shape == (1,)
+    loss = mmsa.cross_entropy(a, labels) + mmsa.cross_entropy(v, vlabels) + c0.sum() + c1.sum() + c2.sum()
+    loss.backward()
+    assert rel_err(a, c["arousal"]) <= 1e-5 and rel_err(v, c["valence"]) <= 1e-5
+    for got, want in zip((c0, c1, c2), c["contrastive"]):
+        assert rel_err(got, want) <= 1e-5
+    assert rel_err(loss, c["loss"]) <= 1e-5
+    assert torch.equal(a.argmax(1).cpu(), c["arousal"].argmax(1))
+    tol = 1e-5 if c["temperature"] >= 0.05 else 1e-4
+    for k, prm in model.named_parameters():
+        if k in c["grads"]:
+            _check_digest(prm.grad, c["grads"][k], tol * 5, k)
+    for k, b in model.named_buffers():
+        assert rel_err(b.float(), c["buffers_after"][k].float()) <= 1e-5, k
+    model.eval()
+    with torch.no_grad():
+        ea, ev = model(*xs)
+    assert rel_err(ea, c["eval_arousal"]) <= 1e-5 and rel_err(ev, c["eval_valence"]) <= 1e-5
+
+
+def test_single_contract_native(cuda_device):
+    """Trainer.py:60 `outputs, contrastive_loss = model(eeg, eye, pps, labels)` with 1-D labels."""
+    import mmsa
+    model = mmsa.MultimodalTransformerModel(contract="single").set_dropout(0.0).to(cuda_device).train()
+    cfg = O.FusionConfig()
+    xs, labels = O.synth_inputs(cfg, 16, seed=9)
+    out, closs = model(*[x.to(cuda_device) for x in xs], labels.to(cuda_device))
+    assert out.shape == (16, 3) and closs.shape == (1,)
+    crit = torch.nn.CrossEntropyLoss()                 # the trainer's own criterion works on our logits
+    w = torch.nn.Parameter(torch.ones(1, device=cuda_device))
+    loss = crit(out, labels.to(cuda_device)) + w * closs
+    loss.backward()
+    torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+    assert w.grad is not None
+
+
+def test_requires_grad_toggling(cuda_device):
+    """MultiTaskTrainer.py:50-177 freezes sub-modules by attribute name; frozen params get no grad."""
+    import mmsa
+    model = mmsa.MultimodalTransformerModel().set_dropout(0.0).to(cuda_device).train()
+    for p in model.cross_attn_e2p.parameters():
+        p.requires_grad = False
+    for p in model.fusion.parameters():
+        p.requires_grad = False
+    cfg = O.FusionConfig()
+    xs, labels = O.synth_inputs(cfg, 8, seed=3)
+    a, v, c0, c1, c2 = model(*[x.to(cuda_device) for x in xs], labels=(labels.to(cuda_device), labels.to(cuda_device)))
+    (mmsa.cross_entropy(a, labels.to(cuda_device)) + c0.sum()).backward()
+    assert all(p.grad is None for p in model.cross_attn_e2p.parameters())
+    assert all(p.grad is None for p in model.fusion.parameters())
+    assert all(p.grad is not None for p in model.arousal_head.parameters())
+    assert model.temperature.grad is not None and model.contrastive_weight.grad is not None
+
+
+# ------------------------------------------------------------------ ME-MHACL pieces vs goldens from the reference
+def test_memhacl_against_reference_goldens(cuda_device):
+    import mmsa
+    g = torch.load(os.path.join(GOLD, "memhacl.pt"))
+    feats = [f.to(cuda_device) for f in g["feats"]]
+    labels = g["labels"].to(cuda_device)
+    # mean variant (ME-MHACL/model.py:68-74)
+    enc = mmsa.MultiModalEncoder(variant="mean")
+    enc.multihead_attn.load_state_dict(g["mean"]["state_dict"])
+    enc = enc.to(cuda_device).train()
+    xs = [f.clone().requires_grad_(True) for f in feats]
+    y = enc(*xs)
+    y.square().sum().backward()
+    assert rel_err(y, g["mean"]["out"]) <= 1e-5
+    for x, d in zip(xs, g["mean"]["dfeats"]):
+        assert rel_err(x.grad, d) <= 1e-5
+    for k, p in enc.multihead_attn.named_parameters():
+        _check_digest(p.grad, g["mean"]["grads"][k], 5e-5, k)
+    # max variant (MultimodalModel.py:388-406)
+    enc2 = mmsa.MultiModalEncoder(variant="max")
+    enc2.load_state_dict(g["max"]["state_dict"], strict=True)
+    enc2 = enc2.to(cuda_device).train()
+    xs = [f.clone().requires_grad_(True) for f in feats]
+    y2 = enc2(*xs)
+    y2.square().sum().backward()
+    assert rel_err(y2, g["max"]["out"]) <= 1e-5
+    for x, d in zip(xs, g["max"]["dfeats"]):
+        assert rel_err(x.grad, d) <= 2e-5
+    # ProjectionHead (ME-MHACL/model.py:82-97) and Classifier
+    ph = mmsa.ProjectionHead()
+    ph.load_state_dict(g["projection"]["state_dict"], strict=True)
+    for m in ph.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    ph = ph.to(cuda_device).train()
+    x = g["projection"]["x"].to(cuda_device).requires_grad_(True)
+    z = ph(x)
+    z.square().sum().backward()
+    assert rel_err(z, g["projection"]["out"]) <= 1e-5 and rel_err(x.grad, g["projection"]["dx"]) <= 1e-5
+    for k, p in ph.named_parameters():
+        _check_digest(p.grad, g["projection"]["grads"][k], 5e-5, k)
+    cl = mmsa.Classifier()
+    cl.load_state_dict(g["classifier"]["state_dict"], strict=True)
+    for m in cl.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    cl = cl.to(cuda_device).train()
+    x = g["classifier"]["x"].to(cuda_device).requires_grad_(True)
+    oa, ov = cl(x)
+    (mmsa.cross_entropy(oa, labels) + mmsa.cross_entropy(ov, labels)).backward()
+    assert rel_err(oa, g["classifier"]["out_a"]) <= 1e-5 and rel_err(ov, g["classifier"]["out_v"]) <= 1e-5
+    assert rel_err(x.grad, g["classifier"]["dx"]) <= 1e-5
+    # SupCon (train.py:16-40) and NT-Xent (ME-MHACL/train.py:47-66)
+    for name in ("supcon", "ntxent"):
+        c = g[name]
+        z1, z2 = c["z1"].to(cuda_device).requires_grad_(True), c["z2"].to(cuda_device).requires_grad_(True)
+        loss = mmsa.supcon(z1, z2, c["labels"].to(cuda_device), 0.1) if name == "supcon" else mmsa.ntxent(z1, z2, 0.5)
+        loss.backward()
+        assert rel_err(loss, c["loss"]) <= 1e-5, name
+        assert rel_err(z1.grad, c["dz1"]) <= 2e-5 and rel_err(z2.grad, c["dz2"]) <= 2e-5, name
+
+
+def test_no_fallback_on_cpu_tensors(cuda_device):
+    """CPU tensors must fail loudly, never silently run a PyTorch path."""
+    import mmsa
+    from mmsa._lib import MmsaError
+    model = mmsa.MultimodalTransformerModel().train()          # parameters left on the CPU
+    cfg = O.FusionConfig()
+    xs, labels = O.synth_inputs(cfg, 4, seed=1)
+    with pytest.raises((MmsaError, RuntimeError)):
+        model(*xs, labels=(labels, labels))
