@@ -54,6 +54,15 @@ const char* mmsa_last_error(void);
 int mmsa_check_device(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 int64_t mmsa_launch_count(void);
+/* Per-launch device timing for bench.py's roofline leg.  mmsa_prof_enable(1) clears and starts
+ * recording: every kernel launch is bracketed by CUDA events on its own stream and booked, with its
+ * algorithmic work (FLOPs for contraction kernels, bytes for memory-bound ones), under the kernel's
+ * name; mmsa_prof_enable(0) stops.  mmsa_prof_collect synchronises the device and returns the
+ * number of entries written: names[i*name_stride], counts[i] launches, ms[i] summed device time,
+ * work[i] summed algorithmic work.  Not usable while a CUDA graph is being captured. */
+void mmsa_prof_enable(int on);
+int mmsa_prof_collect(char* names_host, int name_stride, int64_t* counts_host, double* ms_host,
+                      double* work_host, int max_entries);
 
 /* ---- dtype plumbing (host `.float()` boundary, Trainer.py:53-54) ---------------------------- */
 int mmsa_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);

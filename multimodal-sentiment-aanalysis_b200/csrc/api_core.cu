@@ -1,6 +1,9 @@
 // api_core.cu -- error reporting, device gate, launch accounting, dtype casts.
 #include <stdarg.h>
 #include <atomic>
+#include <mutex>
+#include <vector>
+#include <string.h>
 #include "common.cuh"
 
 namespace mmsa {
@@ -15,6 +18,41 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- per-launch timing (bench.py roofline leg) ----
+int g_prof_on = 0;
+struct ProfRec { int entry; cudaEvent_t a, b; };
+struct ProfEntry { char name[48]; int64_t count; double ms; double work; };
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<ProfEntry> g_prof_entries;
+static std::mutex g_prof_mu;
+static thread_local int g_prof_open = -1;
+
+void prof_begin(const char* name, cudaStream_t s, double work) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  int e = -1;
+  for (size_t i = 0; i < g_prof_entries.size(); ++i)
+    if (strncmp(g_prof_entries[i].name, name, sizeof(g_prof_entries[i].name) - 1) == 0) { e = (int)i; break; }
+  if (e < 0) {
+    ProfEntry pe{};
+    strncpy(pe.name, name, sizeof(pe.name) - 1);
+    g_prof_entries.push_back(pe);
+    e = (int)g_prof_entries.size() - 1;
+  }
+  g_prof_entries[e].count += 1;
+  g_prof_entries[e].work += work;
+  ProfRec r{e, nullptr, nullptr};
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, s);
+  g_prof_recs.push_back(r);
+  g_prof_open = (int)g_prof_recs.size() - 1;
+}
+void prof_end(cudaStream_t s) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (g_prof_open >= 0 && g_prof_open < (int)g_prof_recs.size()) cudaEventRecord(g_prof_recs[g_prof_open].b, s);
+  g_prof_open = -1;
+}
 
 bool device_ok() {
   static int cached_dev = -1;
@@ -69,6 +107,41 @@ int mmsa_check_device(void) {
 }
 int64_t mmsa_launch_count(void) { return g_launches.load(); }
 
+void mmsa_prof_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (on) {
+    for (auto& r : g_prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof_recs.clear();
+    g_prof_entries.clear();
+  }
+  g_prof_on = on ? 1 : 0;
+}
+
+int mmsa_prof_collect(char* names, int name_stride, int64_t* counts, double* ms, double* work, int max_entries) {
+  cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& e : g_prof_entries) e.ms = 0.0;
+  for (auto& r : g_prof_recs) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) g_prof_entries[r.entry].ms += (double)t;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  (void)cudaGetLastError();
+  g_prof_recs.clear();
+  int n = (int)g_prof_entries.size() < max_entries ? (int)g_prof_entries.size() : max_entries;
+  for (int i = 0; i < n; ++i) {
+    if (names && name_stride > 0) {
+      strncpy(names + (size_t)i * name_stride, g_prof_entries[i].name, (size_t)name_stride - 1);
+      names[(size_t)i * name_stride + name_stride - 1] = 0;
+    }
+    counts[i] = g_prof_entries[i].count;
+    ms[i] = g_prof_entries[i].ms;
+    work[i] = g_prof_entries[i].work;
+  }
+  return n;
+}
+
 int mmsa_cast(const void* src, int sdt, void* dst, int ddt, int64_t n, void* stream) {
   MMSA_REQUIRE_DEVICE();
   if (n == 0) return MMSA_OK;
@@ -78,6 +151,7 @@ int mmsa_cast(const void* src, int sdt, void* dst, int ddt, int64_t n, void* str
   int64_t blocks = ceil_div(ceil_div(n, 8), threads);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
+  ProfScope prof("cast", s, (double)n * ((sdt == MMSA_F32 ? 4 : 2) + (ddt == MMSA_F32 ? 4 : 2)));
   if (sdt == MMSA_F32 && ddt == MMSA_BF16)
     cast_kernel<float, bf16><<<(unsigned)blocks, threads, 0, s>>>((const float*)src, (bf16*)dst, n);
   else if (sdt == MMSA_BF16 && ddt == MMSA_F32)

@@ -328,6 +328,7 @@ bool attn_mma_supported(int64_t D, int64_t ldq, int64_t ldk, int64_t ldv, int64_
 int attn_fwd_mma_bf16(int64_t B, int64_t H, int64_t Lq, int64_t Lk, const void* q, int64_t ldq, const void* k, int64_t ldk,
                       const void* v, int64_t ldv, void* o, int64_t ldo, float* lse, cudaStream_t s) {
   dim3 grid((unsigned)ceil_div(Lq, AT), (unsigned)(B * H));
+  ProfScope prof("attn_fwd_mma", s, 2.0 * 64 * (double)B * H * (2.0 * Lq + 2.0 * Lk));
   attn_fwd_mma_kernel<<<grid, 128, 0, s>>>((int)H, (int)Lq, (int)Lk, (const bf16*)q, ldq, (const bf16*)k, ldk,
                                           (const bf16*)v, ldv, (bf16*)o, ldo, lse, 0.125f);
   MMSA_LAUNCH_CHECK("attn_fwd_mma_kernel");
@@ -341,11 +342,15 @@ int attn_bwd_mma_bf16(int64_t B, int64_t H, int64_t Lq, int64_t Lk, const void* 
   int rc = attn_delta<bf16, 64>(B, H, Lq, o, ldo, dout, lddo, delta, s);
   if (rc) return rc;
   dim3 g1((unsigned)ceil_div(Lq, AT), (unsigned)(B * H));
+  {
+  ProfScope prof("attn_bwd_dq_mma", s, 2.0 * 64 * (double)B * H * (3.0 * Lq + 2.0 * Lk));
   attn_bwd_dq_mma_kernel<<<g1, 128, 0, s>>>((int)H, (int)Lq, (int)Lk, (const bf16*)q, ldq, (const bf16*)k, ldk,
                                            (const bf16*)v, ldv, (const bf16*)dout, lddo, lse, delta, (bf16*)dq, lddq,
                                            0.125f);
+  }
   MMSA_LAUNCH_CHECK("attn_bwd_dq_mma_kernel");
   dim3 g2((unsigned)ceil_div(Lk, AT), (unsigned)(B * H));
+  ProfScope prof("attn_bwd_dkv_mma", s, 2.0 * 64 * (double)B * H * (2.0 * Lq + 4.0 * Lk));
   attn_bwd_dkv_mma_kernel<<<g2, 128, 0, s>>>((int)H, (int)Lq, (int)Lk, (const bf16*)q, ldq, (const bf16*)k, ldk,
                                             (const bf16*)v, ldv, (const bf16*)dout, lddo, lse, delta, (bf16*)dk, lddk,
                                             (bf16*)dv, lddv, 0.125f);

@@ -235,6 +235,7 @@ template <typename T, int D>
 int attn_fwd_simt(int64_t B, int64_t H, int64_t Lq, int64_t Lk, const void* q, int64_t ldq, const void* k, int64_t ldk,
                   const void* v, int64_t ldv, void* o, int64_t ldo, float* lse, cudaStream_t s) {
   dim3 grid((unsigned)ceil_div(Lq, kAttnWarps), (unsigned)(B * H));
+  ProfScope prof("attn_fwd_simt", s, (double)sizeof(T) * D * (double)B * H * (2.0 * Lq + 2.0 * Lk));
   attn_fwd_simt_kernel<T, D><<<grid, kAttnWarps * 32, 0, s>>>((int)H, (int)Lq, (int)Lk, (const T*)q, ldq, (const T*)k, ldk,
                                                              (const T*)v, ldv, (T*)o, ldo, lse, 1.f / sqrtf((float)D));
   MMSA_LAUNCH_CHECK("attn_fwd_simt_kernel");
@@ -245,6 +246,7 @@ template <typename T, int D>
 int attn_delta(int64_t B, int64_t H, int64_t Lq, const void* o, int64_t ldo, const void* dout, int64_t lddo, float* delta,
                cudaStream_t s) {
   int64_t warps = B * Lq * H;
+  ProfScope prof("attn_delta", s, (double)sizeof(T) * D * (double)B * H * 2.0 * Lq);
   attn_delta_kernel<T, D><<<(unsigned)ceil_div(warps * 32, 256), 256, 0, s>>>(B * Lq, (int)H, (int)Lq, (const T*)o, ldo,
                                                                            (const T*)dout, lddo, delta);
   MMSA_LAUNCH_CHECK("attn_delta_kernel");
@@ -259,11 +261,15 @@ int attn_bwd_simt(int64_t B, int64_t H, int64_t Lq, int64_t Lk, const void* q, i
   if (rc) return rc;
   const float scale = 1.f / sqrtf((float)D);
   dim3 g1((unsigned)ceil_div(Lq, kAttnWarps), (unsigned)(B * H));
+  {
+  ProfScope prof("attn_bwd_dq_simt", s, (double)sizeof(T) * D * (double)B * H * (3.0 * Lq + 2.0 * Lk));
   attn_bwd_dq_simt_kernel<T, D><<<g1, kAttnWarps * 32, 0, s>>>((int)H, (int)Lq, (int)Lk, (const T*)q, ldq, (const T*)k, ldk,
                                                               (const T*)v, ldv, (const T*)dout, lddo, lse, delta, (T*)dq,
                                                               lddq, scale);
+  }
   MMSA_LAUNCH_CHECK("attn_bwd_dq_simt_kernel");
   dim3 g2((unsigned)ceil_div(Lk, kAttnWarps), (unsigned)(B * H));
+  ProfScope prof("attn_bwd_dkv_simt", s, (double)sizeof(T) * D * (double)B * H * (2.0 * Lq + 4.0 * Lk));
   attn_bwd_dkv_simt_kernel<T, D><<<g2, kAttnWarps * 32, 0, s>>>((int)H, (int)Lq, (int)Lk, (const T*)q, ldq, (const T*)k,
                                                                ldk, (const T*)v, ldv, (const T*)dout, lddo, lse, delta,
                                                                (T*)dk, lddk, (T*)dv, lddv, scale);

@@ -14,6 +14,23 @@ void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 bool device_ok();
 
+// Optional per-launch timing (mmsa_prof_enable): brackets one kernel launch with CUDA events on the
+// launching stream and books its duration and algorithmic work (FLOPs or bytes) under `name`.
+// Costs one predictable branch when disabled.  Not usable during CUDA-graph capture.
+extern int g_prof_on;
+void prof_begin(const char* name, cudaStream_t s, double work);
+void prof_end(cudaStream_t s);
+struct ProfScope {
+  cudaStream_t s_;
+  bool on_;
+  ProfScope(const char* name, cudaStream_t s, double work = 0.0) : s_(s), on_(g_prof_on != 0) {
+    if (on_) prof_begin(name, s, work);
+  }
+  ~ProfScope() {
+    if (on_) prof_end(s_);
+  }
+};
+
 #define MMSA_REQUIRE(cond, ...)                \
   do {                                         \
     if (!(cond)) {                             \

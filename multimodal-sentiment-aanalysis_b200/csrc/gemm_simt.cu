@@ -113,6 +113,7 @@ int gemm_simt(const GemmDesc& d, int splits, cudaStream_t s) {
   p.k_per_split = kps;
   int real_splits = (int)ceil_div(Kt, kps);
   dim3 grid((unsigned)ceil_div(d.N, SBN), (unsigned)ceil_div(d.M, SBM), (unsigned)real_splits);
+  ProfScope prof(sizeof(T) == 4 ? "gemm_simt_f32" : "gemm_simt_bf16", s, 2.0 * (double)d.M * (double)d.N * (double)Kt);
   gemm_simt_kernel<T><<<grid, 256, 0, s>>>(p);
   MMSA_LAUNCH_CHECK("gemm_simt_kernel");
   return MMSA_OK;

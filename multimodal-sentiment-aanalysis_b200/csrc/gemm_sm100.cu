@@ -400,7 +400,10 @@ static int launch_gemm(const GemmDesc& d, int splits_req, cudaStream_t s) {
     if (e != cudaSuccess) { set_error("mmsa: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return MMSA_ERR_CUDA; }
     attr_set = true;
   }
-  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, s>>>(tmA, tmA2, tmB, p);
+  {
+    ProfScope prof("gemm_tcgen05", s, 2.0 * (double)d.M * (double)d.N * (double)Kt);
+    kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, s>>>(tmA, tmA2, tmB, p);
+  }
   MMSA_LAUNCH_CHECK("gemm_tcgen05_kernel");
   return MMSA_OK;
 }

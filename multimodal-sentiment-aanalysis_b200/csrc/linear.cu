@@ -149,6 +149,7 @@ int mmsa_linear_wgrad(int dtype, int64_t M, int64_t N, int64_t K, const void* dy
       int64_t total = N * K;
       int64_t blocks = ceil_div(total, 256);
       if (blocks > 148 * 8) blocks = 148 * 8;
+      ProfScope prof("reduce_splits", s, 4.0 * (double)N * K * (real + 1));
       reduce_splits_kernel<<<(unsigned)blocks, 256, 0, s>>>(ws, real, N * K, N, K, K, dw, lddw);
       MMSA_LAUNCH_CHECK("reduce_splits_kernel");
     }
@@ -159,8 +160,12 @@ int mmsa_linear_wgrad(int dtype, int64_t M, int64_t N, int64_t K, const void* dy
     int64_t rpb = ceil_div(M, rs);
     rs = (int)ceil_div(M, rpb);
     dim3 block(32, 8), grid((unsigned)ceil_div(N, 32), (unsigned)rs);
-    MMSA_DISPATCH_DTYPE(dtype, T, (colsum_partial_kernel<T><<<grid, block, 0, s>>>(M, N, (const T*)dy, lddy, rpb, ws_colsum)));
+    {
+      ProfScope prof("colsum_partial", s, (double)M * N * (dtype == MMSA_F32 ? 4 : 2));
+      MMSA_DISPATCH_DTYPE(dtype, T, (colsum_partial_kernel<T><<<grid, block, 0, s>>>(M, N, (const T*)dy, lddy, rpb, ws_colsum)));
+    }
     MMSA_LAUNCH_CHECK("colsum_partial_kernel");
+    ProfScope prof("reduce_splits", s, 4.0 * (double)N * (rs + 1));
     reduce_splits_kernel<<<(unsigned)ceil_div(N, 256), 256, 0, s>>>(ws_colsum, rs, N, 1, N, N, db, N);
     MMSA_LAUNCH_CHECK("reduce_splits_kernel");
   }

@@ -424,6 +424,7 @@ int mmsa_gate_ln_fwd(int dtype, int64_t M, int64_t E, const void* gate_pre, cons
   MMSA_REQUIRE(E % 8 == 0 && E <= 1024 && E > 0, "mmsa_gate_ln_fwd: E=%lld must be a multiple of 8 and <= 1024", (long long)E);
   if (M == 0) return MMSA_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  ProfScope prof("gate_ln_fwd", s, (double)M * E * (dtype == MMSA_F32 ? 4 : 2) * (y ? 5.0 : 4.0));
   unsigned grid = (unsigned)ceil_div(M, kRowWarps);
   MMSA_DISPATCH_DTYPE(dtype, T, (gate_ln_fwd_kernel<T><<<grid, kRowWarps * 32, 0, s>>>(
       M, (int)E, (const T*)gate_pre, (const T*)q, (const T*)attn, gamma, beta, eps, (T*)g_out, (T*)y, mean, rstd)));
@@ -448,6 +449,7 @@ int mmsa_gate_ln_bwd(int dtype, int64_t M, int64_t E, const void* dy, int64_t dy
   MMSA_REQUIRE(dq_bcast == nullptr || bcast_rows > 0, "mmsa_gate_ln_bwd: dq_bcast needs bcast_rows > 0");
   if (M == 0) return MMSA_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  ProfScope prof("gate_ln_bwd", s, (double)M * E * (dtype == MMSA_F32 ? 4 : 2) * (dy_rows_per_sample > 0 ? 6.0 : 7.0));
   int64_t nblk = mmsa_gate_ln_bwd_blocks(M);
   MMSA_DISPATCH_DTYPE(dtype, T, (gate_ln_bwd_kernel<T><<<(unsigned)nblk, kRowWarps * 32, 0, s>>>(
       M, (int)E, (const T*)dy, dy_rows_per_sample, (const T*)g, (const T*)q, (const T*)attn, gamma, mean, rstd,
@@ -465,6 +467,7 @@ int mmsa_pool_fwd(int dtype, int64_t B, int64_t L, int64_t E, const void* x, int
   MMSA_REQUIRE(L > 0, "mmsa_pool_fwd: L must be > 0");
   if (B == 0) return MMSA_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  ProfScope prof("pool_fwd", s, (double)B * (L + 1) * E * (dtype == MMSA_F32 ? 4 : 2));
   MMSA_DISPATCH_DTYPE(dtype, T, {
     constexpr int VN = VecN<T>::N;
     int nvec = (int)E / VN;
@@ -489,6 +492,7 @@ int mmsa_pool_bwd(int dtype, int64_t B, int64_t L, int64_t E, const void* dy, in
   MMSA_REQUIRE(E % 8 == 0 && E > 0, "mmsa_pool_bwd: E must be a multiple of 8");
   if (B == 0 || L == 0) return MMSA_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  ProfScope prof("pool_bwd", s, (double)B * (L + 1) * E * (dtype == MMSA_F32 ? 4 : 2));
   MMSA_DISPATCH_DTYPE(dtype, T, {
     int64_t total = B * L * (E / VecN<T>::N);
     if (is_max) pool_bwd_kernel<T, true><<<grid_for(total, 256), 256, 0, s>>>(B, L, (int)E, (const T*)dy, argmax, (T*)dx);
@@ -507,6 +511,7 @@ int mmsa_modal_concat_fwd(int dtype, int64_t B, int64_t E, int S, const void* lo
   SlotPtrs sp{};
   for (int i = 0; i < S; ++i) sp.p[i] = slots_host[i];
   cudaStream_t s = (cudaStream_t)stream;
+  ProfScope prof("modal_concat_fwd", s, (double)B * E * S * 2.0 * (dtype == MMSA_F32 ? 4 : 2));
   MMSA_DISPATCH_DTYPE(dtype, T, (modal_concat_fwd_kernel<T><<<(unsigned)ceil_div(B, kRowWarps), kRowWarps * 32, 0, s>>>(
       B, (int)E, S, (const T*)logits, sp, w, (T*)fused)));
   MMSA_LAUNCH_CHECK("modal_concat_fwd_kernel");
@@ -522,6 +527,7 @@ int mmsa_modal_concat_bwd(int dtype, int64_t B, int64_t E, int S, const void* df
   SlotPtrs sp{};
   for (int i = 0; i < S; ++i) { sp.p[i] = slots_host[i]; sp.d[i] = dslots_host[i]; }
   cudaStream_t s = (cudaStream_t)stream;
+  ProfScope prof("modal_concat_bwd", s, (double)B * E * S * 3.0 * (dtype == MMSA_F32 ? 4 : 2));
   MMSA_DISPATCH_DTYPE(dtype, T, (modal_concat_bwd_kernel<T><<<(unsigned)ceil_div(B, kRowWarps), kRowWarps * 32, 0, s>>>(
       B, (int)E, S, (const T*)dfused, w, sp, (T*)dlogits)));
   MMSA_LAUNCH_CHECK("modal_concat_bwd_kernel");
@@ -532,6 +538,7 @@ int mmsa_act_fwd(int dtype, int64_t n, const void* x, int act, void* y, void* st
   MMSA_REQUIRE_DEVICE();
   if (n == 0) return MMSA_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  ProfScope prof("act_fwd", s, (double)n * 2.0 * (dtype == MMSA_F32 ? 4 : 2));
   MMSA_DISPATCH_DTYPE(dtype, T, (act_fwd_kernel<T><<<grid_for(n / 4 + 1, 256), 256, 0, s>>>(n, (const T*)x, act, (T*)y)));
   MMSA_LAUNCH_CHECK("act_fwd_kernel");
   return MMSA_OK;
@@ -541,6 +548,7 @@ int mmsa_act_bwd(int dtype, int64_t n, const void* x, const void* dy, int act, v
   MMSA_REQUIRE_DEVICE();
   if (n == 0) return MMSA_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  ProfScope prof("act_bwd", s, (double)n * 3.0 * (dtype == MMSA_F32 ? 4 : 2));
   MMSA_DISPATCH_DTYPE(dtype, T, (act_bwd_kernel<T><<<grid_for(n, 256), 256, 0, s>>>(n, (const T*)x, (const T*)dy, act, (T*)dx)));
   MMSA_LAUNCH_CHECK("act_bwd_kernel");
   return MMSA_OK;
@@ -550,6 +558,7 @@ int mmsa_l2norm_fwd(int dtype, int64_t B, int64_t E, const void* x, void* y, flo
   MMSA_REQUIRE_DEVICE();
   if (B == 0) return MMSA_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  ProfScope prof("l2norm_fwd", s, (double)B * E * 2.0 * (dtype == MMSA_F32 ? 4 : 2));
   MMSA_DISPATCH_DTYPE(dtype, T, (l2norm_fwd_kernel<T><<<(unsigned)ceil_div(B, kRowWarps), kRowWarps * 32, 0, s>>>(
       B, (int)E, (const T*)x, (T*)y, norm)));
   MMSA_LAUNCH_CHECK("l2norm_fwd_kernel");
@@ -561,6 +570,7 @@ int mmsa_l2norm_bwd(int dtype, int64_t B, int64_t E, const void* y, const float*
   MMSA_REQUIRE_DEVICE();
   if (B == 0) return MMSA_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  ProfScope prof("l2norm_bwd", s, (double)B * E * ((dtype == MMSA_F32 ? 4 : 2) * 2.0 + (dy2 ? 8.0 : 4.0)));
   MMSA_DISPATCH_DTYPE(dtype, T, (l2norm_bwd_kernel<T><<<(unsigned)ceil_div(B, kRowWarps), kRowWarps * 32, 0, s>>>(
       B, (int)E, (const T*)y, norm, dy1, dy2, (T*)dx)));
   MMSA_LAUNCH_CHECK("l2norm_bwd_kernel");

@@ -218,17 +218,22 @@ contrastive_fwd_kernel(int kind, int64_t B, int64_t Bg, int64_t row_offset, cons
       long long oa = __shfl_xor_sync(0xffffffffu, (long long)am, o);
       if (om > mx || (om == mx && oa < am)) { mx = om; am = oa; }
     }
-    float all = 0.f, pos = 0.f;
+    // The arg-max column contributes exp(0) = 1 exactly; summing the REST separately keeps
+    // all - 1 and pos - [argmax is a positive] exact, which the backward needs when the other
+    // terms underflow against 1 (the T = 0.01 regime the reference starts in).
+    float all_rest = 0.f, pos_rest = 0.f;
     for (int64_t j = lane; j < Bg; j += 32) {
+      if (j == am) continue;
       float e = expf(row[j] / T - mx);
-      all += e;
-      if (j != gi && lab_c[j] == yi) pos += e;
+      all_rest += e;
+      if (j != gi && lab_c[j] == yi) pos_rest += e;
     }
-    all = warp_sum(all); pos = warp_sum(pos);
+    all_rest = warp_sum(all_rest); pos_rest = warp_sum(pos_rest);
     if (lane == 0) {
-      row_stats[i * 4 + 0] = mx; row_stats[i * 4 + 1] = all; row_stats[i * 4 + 2] = pos;
+      const float am_pos = (am != gi && lab_c[am] == yi) ? 1.f : 0.f;
+      row_stats[i * 4 + 0] = mx; row_stats[i * 4 + 1] = all_rest; row_stats[i * 4 + 2] = pos_rest;
       row_stats[i * 4 + 3] = __int_as_float((int)am);
-      row_loss[i] = -logf((pos + 1e-12f) / (all + 1e-12f));
+      row_loss[i] = log1pf(all_rest + 1e-12f) - logf(pos_rest + am_pos + 1e-12f);
     }
   } else if (kind == MMSA_LOSS_SUPCON) {
     const int64_t yi = lab_r[i];
@@ -278,16 +283,24 @@ contrastive_bwd_kernel(int kind, int64_t B, int64_t Bg, int64_t row_offset, cons
   float dts = 0.f;   // sum_j gs_ij * s_ij
   if (kind == MMSA_LOSS_INFONCE) {
     const int64_t yi = lab_r[i];
-    const float mx = row_stats[i * 4 + 0], all = row_stats[i * 4 + 1], pos = row_stats[i * 4 + 2];
+    const float mx = row_stats[i * 4 + 0], all_rest = row_stats[i * 4 + 1], pos_rest = row_stats[i * 4 + 2];
     const int64_t am = (int64_t)__float_as_int(row_stats[i * 4 + 3]);
-    const float ia = 1.f / (all + 1e-12f), ip = 1.f / (pos + 1e-12f);
-    const float gmax = pos * ip - all * ia;     // gradient that flows through the subtracted row max
+    const float am_pos = (am != gi && lab_c[am] == yi) ? 1.f : 0.f;
+    const float ia = 1.f / (1.f + all_rest + 1e-12f), ip = 1.f / (pos_rest + am_pos + 1e-12f);
+    // d/ds_ij of -log((pos+eps)/(all+eps)) with s_ij = sim_ij/T - max_i: e_ij/all' - [pos_ij] e_ij/pos'.
+    // Autograd also flows through the subtracted row max (MultimodalModel.py:245): the arg-max column
+    // (first index on ties) receives pos/pos' - all/all' on top; with e_am = 1 the two combine to
+    // -all_rest/all' + pos_rest/pos', free of cancellation.
+    const float g_am = pos_rest * ip - all_rest * ia;
     for (int64_t j = lane; j < Bg; j += 32) {
       float s = row[j] / T;
-      float e = expf(s - mx);
-      float gs = e * ia;
-      if (j != gi && lab_c[j] == yi) gs -= e * ip;
-      if (j == am) gs += gmax;
+      float gs;
+      if (j == am) gs = g_am;
+      else {
+        float e = expf(s - mx);
+        gs = e * ia;
+        if (j != gi && lab_c[j] == yi) gs -= e * ip;
+      }
       gs *= up;
       dts += gs * s;
       grow[j] = from_f<TG>(gs / T);
@@ -369,6 +382,7 @@ int mmsa_bn_act_fwd(int dtype, int64_t B, int64_t N, int order, const void* x, c
   MMSA_REQUIRE(!(training && dropout_p > 0.f) || keep_mask != nullptr, "mmsa_bn_act_fwd: dropout needs keep_mask storage");
   MMSA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "mmsa_bn_act_fwd: dropout_p out of [0,1)");
   cudaStream_t s = (cudaStream_t)stream;
+  ProfScope prof("bn_act_fwd", s, (double)B * N * 2.0 * (dtype == MMSA_F32 ? 4 : 2));
   dim3 block(32, 8);
   MMSA_DISPATCH_DTYPE(dtype, T, (bn_act_fwd_kernel<T><<<(unsigned)ceil_div(N, 32), block, 0, s>>>(
       B, (int)N, order, (const T*)x, gamma, beta, running_mean, running_var, momentum, eps, training, dropout_p,
@@ -384,6 +398,7 @@ int mmsa_bn_act_bwd(int dtype, int64_t B, int64_t N, int order, const void* x, c
   MMSA_REQUIRE_DEVICE();
   MMSA_REQUIRE(B > 0 && N > 0, "mmsa_bn_act_bwd: empty input");
   cudaStream_t s = (cudaStream_t)stream;
+  ProfScope prof("bn_act_bwd", s, (double)B * N * 3.0 * (dtype == MMSA_F32 ? 4 : 2));
   dim3 block(32, 8);
   MMSA_DISPATCH_DTYPE(dtype, T, (bn_act_bwd_kernel<T><<<(unsigned)ceil_div(N, 32), block, 0, s>>>(
       B, (int)N, order, (const T*)x, (const T*)dy, gamma, beta, save_mean, save_rstd, training, dropout_p, keep_mask,
@@ -397,6 +412,7 @@ int mmsa_ce_fwd(int64_t B, int64_t C, const float* logits, const int64_t* labels
   MMSA_REQUIRE_DEVICE();
   MMSA_REQUIRE(B > 0 && C > 0 && C <= 64, "mmsa_ce_fwd: bad shape B=%lld C=%lld", (long long)B, (long long)C);
   cudaStream_t s = (cudaStream_t)stream;
+  ProfScope prof("ce_fwd", s, (double)B * (C * 4.0 + 20.0));
   ce_fwd_kernel<<<(unsigned)ceil_div(B, 128), 128, 0, s>>>(B, (int)C, logits, labels, pred, row_loss);
   MMSA_LAUNCH_CHECK("ce_fwd_kernel");
   sum_scale_kernel<<<1, 256, 0, s>>>(row_loss, B, 1.f / (float)B, loss);
@@ -409,6 +425,7 @@ int mmsa_ce_bwd(int64_t B, int64_t C, const float* logits, const int64_t* labels
   MMSA_REQUIRE_DEVICE();
   MMSA_REQUIRE(B > 0 && C > 0 && C <= 64, "mmsa_ce_bwd: bad shape");
   cudaStream_t s = (cudaStream_t)stream;
+  ProfScope prof("ce_bwd", s, (double)B * (C * 8.0 + 8.0));
   ce_bwd_kernel<<<(unsigned)ceil_div(B, 128), 128, 0, s>>>(B, (int)C, logits, labels, dloss, dlogits);
   MMSA_LAUNCH_CHECK("ce_bwd_kernel");
   return MMSA_OK;
@@ -423,6 +440,7 @@ int mmsa_contrastive_fwd(int kind, int64_t B, int64_t Bg, int64_t row_offset, co
   MMSA_REQUIRE(B > 0 && Bg > 0 && denom > 0, "mmsa_contrastive_fwd: empty input");
   MMSA_REQUIRE(kind == MMSA_LOSS_NTXENT || (labels_rows && labels_cols), "mmsa_contrastive_fwd: labels required");
   cudaStream_t s = (cudaStream_t)stream;
+  ProfScope prof("contrastive_fwd", s, (double)B * Bg * 4.0);
   contrastive_fwd_kernel<<<(unsigned)ceil_div(B, 8), 256, 0, s>>>(kind, B, Bg, row_offset, sim, labels_rows,
                                                                   labels_cols, temperature, temperature_const,
                                                                   row_stats, row_loss);
@@ -440,6 +458,7 @@ int mmsa_contrastive_bwd(int kind, int64_t B, int64_t Bg, int64_t row_offset, co
   MMSA_REQUIRE(kind >= 0 && kind <= 2, "mmsa_contrastive_bwd: bad kind %d", kind);
   MMSA_REQUIRE(B > 0 && Bg > 0 && denom > 0, "mmsa_contrastive_bwd: empty input");
   cudaStream_t s = (cudaStream_t)stream;
+  ProfScope prof("contrastive_bwd", s, (double)B * Bg * (4.0 + (g_dtype == MMSA_F32 ? 4 : 2)));
   float inv_denom = 1.f / (float)denom;
   if (g_dtype == MMSA_F32)
     contrastive_bwd_kernel<float><<<(unsigned)ceil_div(B, 8), 256, 0, s>>>(
@@ -461,6 +480,7 @@ int mmsa_sumsq(const float* x, int64_t n, float* partials, int64_t nblk, float* 
   MMSA_REQUIRE_DEVICE();
   MMSA_REQUIRE(nblk > 0 && nblk <= 4096, "mmsa_sumsq: nblk out of range");
   cudaStream_t s = (cudaStream_t)stream;
+  ProfScope prof("sumsq", s, (double)n * 4.0);
   sumsq_partial_kernel<<<(unsigned)nblk, 256, 0, s>>>(x, n, partials);
   MMSA_LAUNCH_CHECK("sumsq_partial_kernel");
   sum_scale_kernel<<<1, 256, 0, s>>>(partials, nblk, 1.f, out);
@@ -475,6 +495,7 @@ int mmsa_clip_adamw(float* p, const float* g, float* m, float* v, int64_t n, con
   MMSA_REQUIRE(step >= 1, "mmsa_clip_adamw: step starts at 1");
   if (n == 0) return MMSA_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  ProfScope prof("clip_adamw", s, (double)n * 28.0);
   float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
   int64_t blocks = ceil_div(n, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
@@ -513,6 +534,7 @@ extern "C" int mmsa_dropout(int dtype, int64_t n, const void* x, float p, uint8_
   MMSA_REQUIRE(p >= 0.f && p < 1.f && keep_mask != nullptr, "mmsa_dropout: bad arguments");
   if (n == 0) return MMSA_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  ProfScope prof("dropout", s, (double)n * (2.0 * (dtype == MMSA_F32 ? 4 : 2) + 1.0));
   int64_t blocks = mmsa::ceil_div(n, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   MMSA_DISPATCH_DTYPE(dtype, T, (mmsa::dropout_kernel<T><<<(unsigned)blocks, 256, 0, s>>>(

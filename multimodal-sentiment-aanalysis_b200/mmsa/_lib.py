@@ -26,6 +26,8 @@ _PROTOS = {
     "mmsa_last_error": (ctypes.c_char_p, []),
     "mmsa_check_device": (I, []),
     "mmsa_launch_count": (L, []),
+    "mmsa_prof_enable": (None, [I]),
+    "mmsa_prof_collect": (I, [P, I, P, P, P, I]),
     "mmsa_cast": (I, [P, I, P, I, L, P]),
     "mmsa_linear_fwd": (I, [I, L, L, L, L, P, L, P, L, P, L, P, P, L, I, P, L, I, P]),
     "mmsa_linear_dgrad": (I, [I, L, L, L, P, L, P, L, P, L, P, L, I, P]),
@@ -99,3 +101,24 @@ def call(name: str, *args):
 
 def launch_count() -> int:
     return int(load().mmsa_launch_count())
+
+
+def prof_enable(on: bool) -> None:
+    """Start (clearing earlier records) or stop per-launch device timing (include/mmsa.h)."""
+    load().mmsa_prof_enable(1 if on else 0)
+
+
+def prof_collect(max_entries: int = 128):
+    """-> {kernel name: {"count", "ms", "work"}} summed since prof_enable(True); synchronises."""
+    stride = 48
+    names = ctypes.create_string_buffer(stride * max_entries)
+    counts = (ctypes.c_int64 * max_entries)()
+    ms = (ctypes.c_double * max_entries)()
+    work = (ctypes.c_double * max_entries)()
+    n = load().mmsa_prof_collect(ctypes.cast(names, c_void_p), stride, ctypes.cast(counts, c_void_p),
+                                 ctypes.cast(ms, c_void_p), ctypes.cast(work, c_void_p), max_entries)
+    out = {}
+    for i in range(n):
+        nm = names.raw[i * stride:(i + 1) * stride].split(b"\0", 1)[0].decode()
+        out[nm] = {"count": int(counts[i]), "ms": float(ms[i]), "work": float(work[i])}
+    return out

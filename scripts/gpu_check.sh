@@ -1,6 +1,6 @@
 #!/bin/bash
 # One gpurun call: kernel tests (GEMM first, isolated, so a hung tcgen05 pipeline cannot take the rest down),
-# model tests, then an optional bench.  Logs land in gpurun_out/.
+# model tests, diagnostics, then the bench.  Logs land in gpurun_out/.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
 run() { # name, timeout, args...
@@ -13,8 +13,9 @@ run() { # name, timeout, args...
 run gemm 300 tests/test_gpu_kernels.py -m gpu -k "linear"
 run kernels 600 tests/test_gpu_kernels.py -m gpu -k "not linear"
 run model 900 tests/test_gpu_model.py -m gpu
-if [ -f bench.py ] && [ "$1" != "nobench" ]; then
-  timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.log 2>&1; echo "bench exit=$?" | tee -a gpurun_out/summary.txt
-  tail -n 2 gpurun_out/bench.log
+if [ "$1" != "nodiag" ]; then
+  timeout 600 python scripts/diag_parity.py > gpurun_out/diag.log 2>&1; echo "diag exit=$?" | tee -a gpurun_out/summary.txt
 fi
+timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit=$?" | tee -a gpurun_out/summary.txt
+tail -c 3000 gpurun_out/bench.log; tail -n 5 gpurun_out/bench.err
 cat gpurun_out/summary.txt

@@ -126,8 +126,12 @@ def test_attention(cuda_device, dtype, B, H, Lq, Lk, D):
     dq = torch.empty_like(q)
     dkv = torch.empty_like(kv)
     k_.attn_bwd(q, kk, vv, o, do, lse, B, H, Lq, Lk, D, dq, dkv[:, :E], dkv[:, E:])
-    assert rel_err(dq, qr.grad) <= TOL[dtype]
-    assert rel_err(dkv[:, :E], kr.grad) <= TOL[dtype]
+    if Lk == 1:     # softmax over one key is constant: dq = dk = 0 exactly; compare against the scale of dv
+        assert float(dq.float().abs().max()) <= TOL[dtype] * float(vr.grad.abs().max())
+        assert float(dkv[:, :E].float().abs().max()) <= TOL[dtype] * float(vr.grad.abs().max())
+    else:
+        assert rel_err(dq, qr.grad) <= TOL[dtype]
+        assert rel_err(dkv[:, :E], kr.grad) <= TOL[dtype]
     assert rel_err(dkv[:, E:], vr.grad) <= TOL[dtype]
 
 

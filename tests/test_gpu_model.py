@@ -8,7 +8,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from parity_util import O, build_model, oracle_step, rel_err, run_fusion_parity
+from parity_util import O, build_model, oracle_step, rel_err, run_fusion_parity, zero_grad_bias_keys
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -85,8 +85,11 @@ def test_native_against_reference_goldens(cuda_device, case):
     assert rel_err(loss, c["loss"]) <= 1e-5
     assert torch.equal(a.argmax(1).cpu(), c["arousal"].argmax(1))
     tol = 1e-5 if c["temperature"] >= 0.05 else 1e-4
+    zero_keys = zero_grad_bias_keys(c["grads"].keys())
     for k, prm in model.named_parameters():
-        if k in c["grads"]:
+        if k in zero_keys:      # exactly-zero gradient (bias in front of BatchNorm): magnitude check
+            assert float(prm.grad.abs().max()) <= 1e-5 * c["grads"][k[:-5] + ".weight"]["absmax"], k
+        elif k in c["grads"]:
             _check_digest(prm.grad, c["grads"][k], tol * 5, k)
     for k, b in model.named_buffers():
         assert rel_err(b.float(), c["buffers_after"][k].float()) <= 1e-5, k
@@ -109,7 +112,13 @@ def test_single_contract_native(cuda_device):
     loss = crit(out, labels.to(cuda_device)) + w * closs
     loss.backward()
     torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
-    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters())
+    # the single-task contract never runs valence_head (Trainer.py:60 has one logits tensor), so its
+    # parameters keep grad None, which clip_grad_norm_ / AdamW skip; everything else must be finite
+    for n, p in model.named_parameters():
+        if n.startswith("valence_head."):
+            assert p.grad is None, n
+        else:
+            assert p.grad is not None and torch.isfinite(p.grad).all(), n
     assert w.grad is not None
 
 
