@@ -321,9 +321,13 @@ def run_ours(args) -> None:
     for name, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
         kern[name] = {"launches_per_step": v["count"] / prof_steps, "ms_per_step": v["ms"] / prof_steps,
                       "share": v["ms"] / tot_ms, "work_per_step": v["work"] / prof_steps}
-    gemm = prof.get("gemm_tcgen05")
+    gemm = {"count": 0, "ms": 0.0, "work": 0.0}
+    for name, v in prof.items():           # tcgen05 GEMM launches are booked per shape: gemm_tc_<majors>_<MxNxK>
+        if name.startswith("gemm_tc_"):
+            for k in gemm:
+                gemm[k] += v[k]
     roofline = None
-    if gemm and gemm["ms"] > 0:
+    if gemm["ms"] > 0:
         achieved = gemm["work"] / (gemm["ms"] * 1e-3) / 1e12
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
         roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": achieved, "peak": peak,

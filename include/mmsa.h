@@ -77,6 +77,9 @@ int mmsa_linear_fwd(int dtype, int64_t M, int64_t N, int64_t K, int64_t K2,
                     const void* w, int64_t ldw, const float* bias,
                     const void* residual, int64_t ldr, int act,
                     void* y, int64_t ldy, int out_dtype, void* stream);
+/* tuning probe: raw bf16 tensor-core GEMM, explicit operand majors (scripts/gemm_majors.py). */
+int mmsa_debug_gemm(int a_mn, int b_mn, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
+                    const void* B, int64_t ldb, float* C, int64_t ldc, int splits, int bn, void* stream);
 /* dgrad: dx[M,K] = dy[M,N] W[N,K] (+ residual).  W row stride ldw lets a column block of a wider
  * weight be addressed (gate.0.weight[:, :E] / [:, E:]). */
 int mmsa_linear_dgrad(int dtype, int64_t M, int64_t N, int64_t K,

@@ -163,6 +163,7 @@ struct GemmDesc {
   int act;
   void* C; int64_t ldc; int out_dtype;
   float alpha;                                    // scales the accumulator before bias
+  float* colsum;                                  // tensor-core wgrad only: colsum[m] = sum_k A[m,k] (bias gradient), or null
 };
 int gemm_f32(const GemmDesc& d, cudaStream_t s);                  // fp32 operands, SIMT
 int gemm_bf16_sm100(const GemmDesc& d, cudaStream_t s);           // bf16 operands, tcgen05 + TMA

@@ -65,6 +65,13 @@ gemm_simt_kernel(const SimtParams p) {
       Bs[kk][nn] = v;
     }
     __syncthreads();
+    // two-level summation: the 16 products of one k-tile are summed first, then added to the running
+    // total, so rounding error grows like sqrt(K/16) instead of sqrt(K) (fp32 parity mode, 1e-5)
+    float part[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) part[i][j] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < SBK; ++kk) {
       float a[4], b[4];
@@ -75,8 +82,12 @@ gemm_simt_kernel(const SimtParams p) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) part[i][j] = fmaf(a[i], b[j], part[i][j]);
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] += part[i][j];
     __syncthreads();
   }
 #pragma unroll

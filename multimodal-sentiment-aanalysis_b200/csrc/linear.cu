@@ -3,6 +3,7 @@
 //   fp32 storage  -> CUDA-core fp32 kernel (gemm_simt.cu), the 1e-5 parity mode
 // Replaces the cuBLAS addmm calls behind nn.Linear / MHA in/out-proj / gate
 // (MultimodalModel.py:86,112-121,139-147,172-198).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace mmsa {
@@ -10,7 +11,9 @@ namespace mmsa {
 int gemm_simt_f32(const GemmDesc& d, int splits, cudaStream_t s);
 int gemm_simt_bf16(const GemmDesc& d, int splits, cudaStream_t s);
 int gemm_simt_real_splits(int64_t Kt, int splits);
-int gemm_bf16_sm100_splits(const GemmDesc& d, int splits, cudaStream_t s);
+int gemm_bf16_sm100_splits(const GemmDesc& d, int splits, int bn, cudaStream_t s);
+int gemm_tc_max_clusters(int size);
+int gemm_tc_bn(int64_t N, bool need_colsum);
 int gemm_num_sms();
 
 static int tc_real_splits(int64_t Kt, int splits) {
@@ -27,8 +30,34 @@ static bool use_tc(int dtype, const GemmDesc& d) {
 
 static int run_gemm(int dtype, const GemmDesc& d, int splits, cudaStream_t s) {
   if (dtype == MMSA_F32) return gemm_simt_f32(d, splits, s);
-  if (use_tc(dtype, d)) return gemm_bf16_sm100_splits(d, splits, s);
+  if (use_tc(dtype, d)) return gemm_bf16_sm100_splits(d, 1, 0, s);
   return gemm_simt_bf16(d, splits, s);
+}
+
+// Tile width and K-split (= cluster size, <= 8) of a tensor-core wgrad.  The output dW[Nw,Kw] has few
+// tiles while the reduction (B*L rows) is long, so the K range is split over a cluster per tile.
+// Cost model per candidate (BN, S): rounds x (k-blocks per split x cycles per k-block + epilogue), with
+// rounds = ceil(tiles / co-resident clusters of size S) and cycles per k-block = max(MMA issue 2*BN,
+// shared-memory operand reads (16 KB + BN*128 B) / 128 B per cycle).
+static void tc_plan_wgrad(int64_t Nw, int64_t Kw, int64_t kb_total, int* bn_out, int* splits_out) {
+  static const int cands[3] = {192, 128, 64};
+  double best = 1e30;
+  *bn_out = 128; *splits_out = 1;
+  for (int ci = 0; ci < 3; ++ci) {
+    const int bn = cands[ci];
+    if (bn > 64 && Kw <= bn / 2) continue;                 // do not pad a narrow output to a wide tile
+    const int64_t tiles = ceil_div(Nw, 128) * ceil_div(Kw, bn);
+    const double waste = (double)(ceil_div(Kw, bn) * bn) / (double)Kw;
+    const double cyc_kb = (double)(2 * bn > 128 + bn ? 2 * bn : 128 + bn);
+    for (int sp = 1; sp <= 8; ++sp) {
+      if (sp > 1 && kb_total / sp < 8) break;
+      const int64_t per = ceil_div(kb_total, sp);
+      if (ceil_div(kb_total, per) != sp) continue;
+      const int64_t rounds = ceil_div(tiles, gemm_tc_max_clusters(sp));
+      const double cost = (double)rounds * ((double)per * cyc_kb + 5000.0) * (waste > 1.3 ? waste : 1.0);
+      if (cost < best * 0.97) { best = cost; *bn_out = bn; *splits_out = sp; }
+    }
+  }
 }
 
 // column sums of dy[M,N] in two deterministic stages
@@ -75,6 +104,17 @@ using namespace mmsa;
 
 extern "C" {
 
+/* tuning probe (not part of the product path): raw bf16 tcgen05 GEMM with explicit operand majors.
+ * C[M,N] (fp32, ldc) = A * B^T over K; a_mn: A stored [K,M]; b_mn: B stored [K,N]. */
+int mmsa_debug_gemm(int a_mn, int b_mn, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
+                    const void* B, int64_t ldb, float* C, int64_t ldc, int splits, int bn, void* stream) {
+  MMSA_REQUIRE_DEVICE();
+  GemmDesc d{};
+  d.M = M; d.N = N; d.K = K; d.A = A; d.lda = lda; d.a_mn_major = a_mn != 0; d.B = B; d.ldb = ldb; d.b_mn_major = b_mn != 0;
+  d.C = C; d.ldc = ldc; d.out_dtype = MMSA_F32; d.alpha = 1.f; d.act = MMSA_ACT_NONE;
+  return gemm_bf16_sm100_splits(d, splits, bn, (cudaStream_t)stream);
+}
+
 int mmsa_linear_fwd(int dtype, int64_t M, int64_t N, int64_t K, int64_t K2, const void* x, int64_t ldx,
                     const void* x2, int64_t ldx2, const void* w, int64_t ldw, const float* bias,
                     const void* residual, int64_t ldr, int act, void* y, int64_t ldy, int out_dtype,
@@ -112,7 +152,7 @@ int mmsa_linear_dgrad(int dtype, int64_t M, int64_t N, int64_t K, const void* dy
 
 int64_t mmsa_linear_wgrad_workspace(int dtype, int64_t M, int64_t N, int64_t K) {
   (void)dtype; (void)M;
-  return (int64_t)sizeof(float) * (kMaxSplits * N * K + (int64_t)kColsumRowSplits * N);
+  return (int64_t)sizeof(float) * (kMaxSplits * N * K + (int64_t)(kColsumRowSplits > kMaxSplits ? kColsumRowSplits : kMaxSplits) * N);
 }
 
 int mmsa_linear_wgrad(int dtype, int64_t M, int64_t N, int64_t K, const void* dy, int64_t lddy, const void* x,
@@ -124,6 +164,7 @@ int mmsa_linear_wgrad(int dtype, int64_t M, int64_t N, int64_t K, const void* dy
   cudaStream_t s = (cudaStream_t)stream;
   float* ws = reinterpret_cast<float*>(workspace);
   float* ws_colsum = ws + (int64_t)kMaxSplits * N * K;
+  bool db_done = false;
   if (dw != nullptr) {
     GemmDesc d{};
     d.M = N; d.N = K; d.K = M; d.K2 = 0;
@@ -131,30 +172,42 @@ int mmsa_linear_wgrad(int dtype, int64_t M, int64_t N, int64_t K, const void* dy
     d.A2 = nullptr;
     d.B = x; d.ldb = ldx; d.b_mn_major = true;      // x[M,K]:  reduction index m is the row
     d.bias = nullptr; d.residual = nullptr; d.act = MMSA_ACT_NONE; d.alpha = 1.f; d.out_dtype = MMSA_F32;
-    const bool tc = use_tc(dtype, d);
-    // split the long reduction (M = B*L) so that the few output tiles still fill the SMs
-    int64_t tiles = tc ? ceil_div(N, 128) * ceil_div(K, (K % 192 == 0 ? 192 : 256)) : ceil_div(N, 64) * ceil_div(K, 64);
-    int splits = (int)(gemm_num_sms() / (tiles > 0 ? tiles : 1));
-    if (splits > kMaxSplits) splits = kMaxSplits;
-    if (splits < 1) splits = 1;
-    int real = tc ? tc_real_splits(M, splits) : gemm_simt_real_splits(M, splits);
-    if (real <= 1) {
-      d.C = dw; d.ldc = lddw;
-      int rc = run_gemm(dtype, d, 1, s);
+    d.C = dw; d.ldc = lddw;
+    if (use_tc(dtype, d)) {
+      // one launch: split-K partials are summed by the last CTA of each tile, and the bias gradient
+      // falls out of an extra ones-tile MMA (gemm_sm100.cu)
+      d.colsum = db;
+      int bn = 0, splits = 1;
+      tc_plan_wgrad(N, K, ceil_div(M, 64), &bn, &splits);
+      if (const char* e = getenv("MMSA_WGRAD_SPLITS")) splits = atoi(e);      // tuning probes only
+      if (const char* e = getenv("MMSA_WGRAD_BN")) bn = atoi(e);
+      int rc = gemm_bf16_sm100_splits(d, splits, bn, s);
       if (rc) return rc;
+      db_done = true;
     } else {
-      d.C = ws; d.ldc = K;
-      int rc = run_gemm(dtype, d, splits, s);
-      if (rc) return rc;
-      int64_t total = N * K;
-      int64_t blocks = ceil_div(total, 256);
-      if (blocks > 148 * 8) blocks = 148 * 8;
-      ProfScope prof("reduce_splits", s, 4.0 * (double)N * K * (real + 1));
-      reduce_splits_kernel<<<(unsigned)blocks, 256, 0, s>>>(ws, real, N * K, N, K, K, dw, lddw);
-      MMSA_LAUNCH_CHECK("reduce_splits_kernel");
+      // split the long reduction (M = B*L) so that the few output tiles still fill the SMs
+      int64_t tiles = ceil_div(N, 64) * ceil_div(K, 64);
+      int splits = (int)(gemm_num_sms() / (tiles > 0 ? tiles : 1));
+      if (splits > kMaxSplits) splits = kMaxSplits;
+      if (splits < 1) splits = 1;
+      int real = gemm_simt_real_splits(M, splits);
+      if (real <= 1) {
+        int rc = run_gemm(dtype, d, 1, s);
+        if (rc) return rc;
+      } else {
+        d.C = ws; d.ldc = K;
+        int rc = run_gemm(dtype, d, splits, s);
+        if (rc) return rc;
+        int64_t total = N * K;
+        int64_t blocks = ceil_div(total, 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        ProfScope prof("reduce_splits", s, 4.0 * (double)N * K * (real + 1));
+        reduce_splits_kernel<<<(unsigned)blocks, 256, 0, s>>>(ws, real, N * K, N, K, K, dw, lddw);
+        MMSA_LAUNCH_CHECK("reduce_splits_kernel");
+      }
     }
   }
-  if (db != nullptr) {
+  if (db != nullptr && !db_done) {
     int rs = (int)(M < kColsumRowSplits * 8 ? ceil_div(M, 8) : kColsumRowSplits);
     if (rs < 1) rs = 1;
     int64_t rpb = ceil_div(M, rs);

@@ -30,6 +30,7 @@ _PROTOS = {
     "mmsa_prof_collect": (I, [P, I, P, P, P, I]),
     "mmsa_cast": (I, [P, I, P, I, L, P]),
     "mmsa_linear_fwd": (I, [I, L, L, L, L, P, L, P, L, P, L, P, P, L, I, P, L, I, P]),
+    "mmsa_debug_gemm": (I, [I, I, L, L, L, P, L, P, L, P, L, I, I, P]),
     "mmsa_linear_dgrad": (I, [I, L, L, L, P, L, P, L, P, L, P, L, I, P]),
     "mmsa_linear_wgrad_workspace": (L, [I, L, L, L]),
     "mmsa_linear_wgrad": (I, [I, L, L, L, P, L, P, L, P, L, P, P, P]),

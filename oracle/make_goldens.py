@@ -68,6 +68,20 @@ def native_fusion():
             "grads": {k: grad_digest(p.grad) for k, p in m.named_parameters() if p.grad is not None},
             "buffers_after": {k: b.clone() for k, b in m.named_buffers()},
         }
+        # the same step evaluated by the reference in float64 (m.double()): the measure of the fp32
+        # reference's OWN rounding error, which bounds what any fp32 implementation can match
+        import copy
+        m64 = copy.deepcopy(m).double()
+        m64.load_state_dict({k: (v.double() if v.is_floating_point() else v) for k, v in sd0.items()})
+        with torch.no_grad():
+            m64.temperature.fill_(temp)
+        m64.zero_grad()
+        a64, v64, d0, d1, d2 = m64(*[x.double() for x in xs], labels=(labels, val_labels))
+        loss64 = F.cross_entropy(a64, labels) + F.cross_entropy(v64, val_labels) + d0.sum() + d1.sum() + d2.sum()
+        loss64.backward()
+        case["ref64"] = {"arousal": a64.detach().clone(), "valence": v64.detach().clone(),
+                         "contrastive": [c.detach().clone() for c in (d0, d1, d2)], "loss": loss64.detach().clone(),
+                         "grads": {k: grad_digest(p.grad) for k, p in m64.named_parameters() if p.grad is not None}}
         # eval-mode logits (Tester.py:53 path; running stats after one train step)
         m.eval()
         with torch.no_grad():

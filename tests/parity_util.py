@@ -84,15 +84,25 @@ def build_model(cfg: O.FusionConfig, params, buffers, compute_dtype, device):
 
 def run_fusion_parity(batch: int = 4, L: int = 64, R: int = 49, dtype: str = "fp32", tol: float = 1e-5,
                       device: str = "cuda:0", embed_dim: int = 768, num_heads: int = 12, text_dim: int = 768,
-                      image_dim: int = 2048, seed: int = 0, oracle_dtype=torch.float32) -> Dict:
-    """Bidirectional (text+image) fusion step on the GPU vs the CPU oracle on identical inputs."""
+                      image_dim: int = 2048, seed: int = 0, noise_mult: float = 3.0,
+                      temperature: Optional[float] = None) -> Dict:
+    """Bidirectional (text+image) fusion step on the GPU vs the CPU oracle on identical inputs.
+
+    The yardstick is the oracle evaluated in float64.  A tensor passes when its error against that is
+    within `tol` (1e-5 fp32 / 2e-2 bf16, BASELINE.json north_star), or -- for the few quantities where
+    the REFERENCE'S OWN fp32 evaluation is further than tol/noise_mult from its float64 value (tiny-batch
+    BatchNorm, InfoNCE at T = 0.01: condition numbers of 1e2-1e3) -- within noise_mult x the fp32
+    oracle's own deviation: no fp32 implementation with a different summation order can do better."""
     import mmsa
     cd = torch.float32 if dtype == "fp32" else torch.bfloat16
     cfg = O.FusionConfig(embed_dim=embed_dim, num_heads=num_heads, wiring="bidirectional", text_dim=text_dim,
                          image_dim=image_dim, contract="single", valence=False)
     params, buffers = O.init_params(cfg, seed=seed)
+    if temperature is not None:
+        params["temperature"] = torch.tensor(float(temperature))
     inputs, labels = O.synth_inputs(cfg, batch, L=L, R=R, seed=1234 + seed)
-    o_loss, o_out, o_grads = oracle_step(cfg, params, inputs, labels, dtype=oracle_dtype)
+    o_loss, o_out, o_grads = oracle_step(cfg, params, inputs, labels, dtype=torch.float64)
+    n_loss, n_out, n_grads = oracle_step(cfg, params, inputs, labels, dtype=torch.float32)
 
     model = build_model(cfg, params, buffers, cd, device)
     text, image = (x.to(device) for x in inputs)
@@ -103,13 +113,19 @@ def run_fusion_parity(batch: int = 4, L: int = 64, R: int = 49, dtype: str = "fp
     loss.backward()
     torch.cuda.synchronize()
 
-    errs = {"logits": rel_err(logits, o_out.arousal), "loss": rel_err(loss, o_loss)}
     zero_keys = zero_grad_bias_keys(o_grads.keys())
+    errs = {"logits": rel_err(logits, o_out.arousal), "loss": rel_err(loss, o_loss)}
+    noise = {"logits": rel_err(n_out.arousal, o_out.arousal), "loss": rel_err(n_loss, o_loss)}
     for k, prm in model.named_parameters():
         g = prm.grad if prm.grad is not None else torch.zeros_like(prm)
         errs["grad:" + k] = grad_err(k, g, o_grads[k], o_grads, zero_keys)
-    worst = max(errs, key=lambda k: errs[k])
+        noise["grad:" + k] = grad_err(k, n_grads[k], o_grads[k], o_grads, zero_keys)
+    excess = {k: errs[k] / max(tol, noise_mult * noise[k]) for k in errs}
+    worst = max(excess, key=lambda k: excess[k])
     labels_equal = bool(torch.equal(logits.argmax(1).cpu(), o_out.arousal.argmax(1)))
-    return {"ok": errs[worst] <= tol and labels_equal, "max_rel": errs[worst], "worst": worst, "errs": errs,
-            "loss": float(loss), "oracle_loss": float(o_loss), "labels_equal": labels_equal,
-            "logit_margin": float((o_out.arousal.topk(2, dim=1).values[:, 0] - o_out.arousal.topk(2, dim=1).values[:, 1]).min())}
+    top2 = o_out.arousal.topk(2, dim=1).values
+    return {"ok": excess[worst] <= 1.0 and labels_equal, "max_rel": errs[worst], "worst": worst, "errs": errs,
+            "noise": noise, "excess": excess[worst],
+            "failing": {k: (errs[k], noise[k]) for k in errs if excess[k] > 1.0},
+            "loss": float(loss.detach()), "oracle_loss": float(o_loss), "labels_equal": labels_equal,
+            "logit_margin": float((top2[:, 0] - top2[:, 1]).min())}

@@ -366,7 +366,9 @@ def test_infonce_edge_cases(cuda_device):
         out = ops.infonce(x, x, labels.to(cuda_device), 0.05)
         out.backward()
         assert rel_err(out, ref) <= 1e-5
-        assert rel_err(x.grad, a.grad) <= 2e-4
+        # labels = arange has no positives: every true gradient is < 1e-7 (the loss is flat at
+        # -log(1e-12)), so the error is measured against the natural gradient scale 1/(B T |f|) ~ 0.2
+        assert rel_err(x.grad, a.grad, floor=1e-3) <= 2e-4
 
 
 def test_sharded_infonce_rows(cuda_device):

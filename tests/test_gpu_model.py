@@ -14,28 +14,36 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
-def _check_digest(grad: torch.Tensor, dig, tol: float, name: str):
+def _digest_err(flat: torch.Tensor, dig) -> float:
+    """error of a gradient against a stored digest (64 sampled elements, tensor absmax as scale)."""
+    scale = max(dig["absmax"], 1e-30)
+    return float((flat[dig["idx"]].double() - dig["vals"].double()).abs().max()) / scale
+
+
+def _check_digest(grad: torch.Tensor, dig32, dig64, tol: float, name: str, noise_mult: float = 3.0):
+    """ours vs the reference's float64 gradient, within max(tol, 3 x the fp32 reference's own deviation)."""
     flat = grad.detach().reshape(-1).cpu()
-    scale = max(dig["absmax"], 1e-12)
-    err = float((flat[dig["idx"]] - dig["vals"]).abs().max()) / scale
-    assert err <= tol, f"{name}: sampled grad err {err:.3e}"
-    n_err = abs(float(flat.double().norm()) - dig["norm"]) / max(dig["norm"], 1e-12)
-    assert n_err <= max(tol, 1e-5) * 10, f"{name}: grad norm err {n_err:.3e}"
+    dig64 = dig64 if dig64 is not None else dig32
+    noise = float((dig32["vals"].double() - dig64["vals"].double()).abs().max()) / max(dig64["absmax"], 1e-30)
+    err = _digest_err(flat, dig64)
+    assert err <= max(tol, noise_mult * noise), f"{name}: sampled grad err {err:.3e} (fp32 reference noise {noise:.3e})"
+    n_err = abs(float(flat.double().norm()) - dig64["norm"]) / max(dig64["norm"], 1e-12)
+    n_noise = abs(dig32["norm"] - dig64["norm"]) / max(dig64["norm"], 1e-12)
+    assert n_err <= max(tol * 10, noise_mult * n_noise), f"{name}: grad norm err {n_err:.3e}"
 
 
 # ------------------------------------------------------------------ re-skinned (text + image) path
-@pytest.mark.parametrize("batch,L", [(4, 64), (3, 128), (2, 512)])
+@pytest.mark.parametrize("batch,L", [(8, 64), (6, 128), (4, 512)])
 def test_fusion_step_fp32(cuda_device, batch, L):
     rep = run_fusion_parity(batch=batch, L=L, R=49, dtype="fp32", tol=1e-5)
     assert rep["labels_equal"]
-    assert rep["ok"], (rep["worst"], rep["max_rel"], {k: v for k, v in rep["errs"].items() if v > 1e-5})
+    assert rep["ok"], (rep["worst"], rep["max_rel"], rep["failing"])
 
 
-@pytest.mark.parametrize("batch,L", [(8, 64), (4, 128)])
-def test_fusion_step_bf16(cuda_device, batch, L):
-    rep = run_fusion_parity(batch=batch, L=L, R=49, dtype="bf16", tol=2e-2)
-    assert rep["ok"], (rep["worst"], rep["max_rel"], rep["logit_margin"],
-                       {k: v for k, v in rep["errs"].items() if v > 2e-2})
+@pytest.mark.parametrize("batch,L,temp", [(32, 64, None), (16, 128, None), (16, 128, 0.07)])
+def test_fusion_step_bf16(cuda_device, batch, L, temp):
+    rep = run_fusion_parity(batch=batch, L=L, R=49, dtype="bf16", tol=2e-2, temperature=temp)
+    assert rep["ok"], (rep["worst"], rep["max_rel"], rep["logit_margin"], rep["failing"])
 
 
 def test_fusion_eval_and_contracts(cuda_device):
@@ -79,24 +87,30 @@ def test_native_against_reference_goldens(cuda_device, case):
     assert a.shape == c["arousal"].shape and c0.shape == (1,)
     loss = mmsa.cross_entropy(a, labels) + mmsa.cross_entropy(v, vlabels) + c0.sum() + c1.sum() + c2.sum()
     loss.backward()
-    assert rel_err(a, c["arousal"]) <= 1e-5 and rel_err(v, c["valence"]) <= 1e-5
-    for got, want in zip((c0, c1, c2), c["contrastive"]):
-        assert rel_err(got, want) <= 1e-5
-    assert rel_err(loss, c["loss"]) <= 1e-5
+    r64 = c["ref64"]        # the reference evaluated in float64; c[...] itself is the fp32 reference
+
+    def close(got, want32, want64, tol=1e-5):
+        return rel_err(got, want64) <= max(tol, 3.0 * rel_err(want32, want64))
+    assert close(a, c["arousal"], r64["arousal"]) and close(v, c["valence"], r64["valence"])
+    for got, w32, w64 in zip((c0, c1, c2), c["contrastive"], r64["contrastive"]):
+        assert close(got, w32, w64)
+    assert close(loss, c["loss"], r64["loss"])
     assert torch.equal(a.argmax(1).cpu(), c["arousal"].argmax(1))
-    tol = 1e-5 if c["temperature"] >= 0.05 else 1e-4
     zero_keys = zero_grad_bias_keys(c["grads"].keys())
     for k, prm in model.named_parameters():
         if k in zero_keys:      # exactly-zero gradient (bias in front of BatchNorm): magnitude check
             assert float(prm.grad.abs().max()) <= 1e-5 * c["grads"][k[:-5] + ".weight"]["absmax"], k
         elif k in c["grads"]:
-            _check_digest(prm.grad, c["grads"][k], tol * 5, k)
+            _check_digest(prm.grad, c["grads"][k], r64["grads"].get(k), 1e-5, k)
     for k, b in model.named_buffers():
         assert rel_err(b.float(), c["buffers_after"][k].float()) <= 1e-5, k
     model.eval()
     with torch.no_grad():
         ea, ev = model(*xs)
-    assert rel_err(ea, c["eval_arousal"]) <= 1e-5 and rel_err(ev, c["eval_valence"]) <= 1e-5
+    # eval mode reads the running statistics written by the train step above; with B = 2 those carry
+    # the amplified noise of the 2-sample variance
+    etol = 1e-5 if c["B"] >= 8 else 3.0 * max(rel_err(c["arousal"], r64["arousal"]), 1e-5)
+    assert rel_err(ea, c["eval_arousal"]) <= etol and rel_err(ev, c["eval_valence"]) <= etol
 
 
 def test_single_contract_native(cuda_device):
@@ -157,7 +171,7 @@ def test_memhacl_against_reference_goldens(cuda_device):
     for x, d in zip(xs, g["mean"]["dfeats"]):
         assert rel_err(x.grad, d) <= 1e-5
     for k, p in enc.multihead_attn.named_parameters():
-        _check_digest(p.grad, g["mean"]["grads"][k], 5e-5, k)
+        _check_digest(p.grad, g["mean"]["grads"][k], None, 5e-5, k)
     # max variant (MultimodalModel.py:388-406)
     enc2 = mmsa.MultiModalEncoder(variant="max")
     enc2.load_state_dict(g["max"]["state_dict"], strict=True)
@@ -180,7 +194,7 @@ def test_memhacl_against_reference_goldens(cuda_device):
     z.square().sum().backward()
     assert rel_err(z, g["projection"]["out"]) <= 1e-5 and rel_err(x.grad, g["projection"]["dx"]) <= 1e-5
     for k, p in ph.named_parameters():
-        _check_digest(p.grad, g["projection"]["grads"][k], 5e-5, k)
+        _check_digest(p.grad, g["projection"]["grads"][k], None, 5e-5, k)
     cl = mmsa.Classifier()
     cl.load_state_dict(g["classifier"]["state_dict"], strict=True)
     for m in cl.modules():
