@@ -66,6 +66,10 @@ int mmsa_prof_collect(char* names_host, int name_stride, int64_t* counts_host, d
 
 /* ---- dtype plumbing (host `.float()` boundary, Trainer.py:53-54) ---------------------------- */
 int mmsa_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+/* `count` independent casts in one launch (fp32 master weights -> bf16 operand copies, once per step):
+ * src_host/dst_host/numel_host are HOST arrays of device pointers / element counts. */
+int mmsa_cast_multi(int count, const void* const* src_host, void* const* dst_host, const int64_t* numel_host,
+                    int src_dtype, int dst_dtype, void* stream);
 
 /* ---- Linear: y = x W^T + b   (nn.Linear: MultimodalModel.py:86,112-121,172-198) -------------
  * x:[M,K] (row stride ldx), optional second operand x2:[M,K2] concatenated on the feature axis
@@ -132,6 +136,22 @@ int mmsa_gate_ln_bwd(int dtype, int64_t M, int64_t E, const void* dy, int64_t dy
                      void* dq_part, void* dattn_part, void* dgate_pre,
                      float* dgamma, float* dbeta, float* partials, void* stream);
 
+/* Fused form for a block whose output only feeds a token mean-pool (the text+image path pools t' and
+ * v' straight away): y is never written; pooled_y[b,:] = mean over the L rows of sample b of LN(u)
+ * and pooled_q[b,:] = mean of q are accumulated in fp32 (pooled_q_lp: optional copy in `dtype`, the
+ * operand of the modality-weight GEMM).  g_out, mean, rstd are saved for the backward. */
+int mmsa_gate_ln_pool_fwd(int dtype, int64_t B, int64_t L, int64_t E, const void* gate_pre, const void* q,
+                          const void* attn, const float* gamma, const float* beta, float eps, void* g_out,
+                          float* mean, float* rstd, float* pooled_y, float* pooled_q, void* pooled_q_lp,
+                          void* stream);
+/* dpooled_y/dpooled_q: [B,E] fp32 gradients of the two pooled outputs (dpooled_q may be NULL); dq_add
+ * (or NULL): [B*L,E] extra gradient w.r.t. q.  Outputs as mmsa_gate_ln_bwd. */
+int mmsa_gate_ln_pool_bwd(int dtype, int64_t B, int64_t L, int64_t E, const float* dpooled_y,
+                          const float* dpooled_q, const void* dq_add, const void* g, const void* q,
+                          const void* attn, const float* gamma, const float* mean, const float* rstd,
+                          void* dq_part, void* dattn_part, void* dgate_pre, float* dgamma, float* dbeta,
+                          float* partials, void* stream);
+
 /* ---- token pooling (mean: MultimodalModel.py:76 / ME-MHACL/model.py:73; max: MultimodalModel.py:401)
  * x:[B,L,E] -> y:[B,E]; argmax:[B,E] int32 only for max. */
 int mmsa_pool_fwd(int dtype, int64_t B, int64_t L, int64_t E, const void* x, int is_max,
@@ -140,13 +160,18 @@ int mmsa_pool_bwd(int dtype, int64_t B, int64_t L, int64_t E, const void* dy, in
                   const int32_t* argmax, void* dx, void* stream);
 
 /* ---- modality weights softmax + weighted concat (MultimodalModel.py:171-176 tail, :299-306) --
- * logits:[B,S] (dtype) -> w = softmax(logits) (fp32 [B,S]); fused[B,S*E] = cat_s(slot_s * w[:,s]). */
+ * Mixed-precision rule of the [B,*] tail: every GEMM OUTPUT is fp32, every GEMM OPERAND is `dtype`;
+ * the elementwise kernels between two GEMMs read fp32 and write `dtype` (identity in fp32 mode), so
+ * reductions over the batch (BatchNorm statistics, bias gradients) never see bf16-rounded values.
+ * logits:[B,S] fp32, slots: S x [B,E] fp32 -> w = softmax(logits) (fp32 [B,S]);
+ * fused[B,S*E] (dtype) = cat_s(slot_s * w[:,s]).  bwd: dfused fp32 -> dslots fp32, dlogits (dtype). */
 int mmsa_modal_concat_fwd(int dtype, int64_t B, int64_t E, int S, const void* logits,
                           const void* const* slots_host, float* w, void* fused, void* stream);
 int mmsa_modal_concat_bwd(int dtype, int64_t B, int64_t E, int S, const void* dfused, const float* w,
                           const void* const* slots_host, void* const* dslots_host, void* dlogits, void* stream);
 
-/* ---- activation (nn.GELU exact-erf, MultimodalModel.py:173; ReLU, ME-MHACL/model.py:108) ---- */
+/* ---- activation (nn.GELU exact-erf, MultimodalModel.py:173; ReLU, ME-MHACL/model.py:108) ----
+ * x (and dy) fp32, y / dx in `dtype`. */
 int mmsa_act_fwd(int dtype, int64_t n, const void* x, int act, void* y, void* stream);
 int mmsa_act_bwd(int dtype, int64_t n, const void* x, const void* dy, int act, void* dx, void* stream);
 
@@ -155,7 +180,7 @@ int mmsa_act_bwd(int dtype, int64_t n, const void* x, const void* dy, int act, v
  * training!=0: batch statistics (biased var), running stats updated in place with momentum and
  * unbiased var; else running stats.  keep_mask:[B,N] uint8 or NULL: if dropout_p>0 and
  * mask_given==0 the kernel draws it (Philox, seed/offset) and writes it; if mask_given it reads it.
- * save_mean/save_rstd:[N] fp32. */
+ * save_mean/save_rstd:[N] fp32.  x (and dy in bwd) are fp32 GEMM outputs; y / dx are written in `dtype`. */
 int mmsa_bn_act_fwd(int dtype, int64_t B, int64_t N, int order, const void* x,
                     const float* gamma, const float* beta, float* running_mean, float* running_var,
                     float momentum, float eps, int training,
@@ -164,9 +189,12 @@ int mmsa_bn_act_fwd(int dtype, int64_t B, int64_t N, int order, const void* x,
 int mmsa_bn_act_bwd(int dtype, int64_t B, int64_t N, int order, const void* x, const void* dy,
                     const float* gamma, const float* beta, const float* save_mean, const float* save_rstd, int training,
                     float dropout_p, const uint8_t* keep_mask,
-                    void* dx, float* dgamma, float* dbeta, void* stream);
+                    void* dx, float* dgamma, float* dbeta, float* dbias_prev, void* stream);
+/* dbias_prev (or NULL): [N] fp32 column sums of dx BEFORE rounding to `dtype` -- the bias gradient of the
+ * Linear in front of the BatchNorm (exactly zero in exact arithmetic when training). */
 
 /* ---- stand-alone dropout (nn.Dropout after ReLU, ME-MHACL/model.py:105-109); y = keep ? x/(1-p) : 0.
+ * x fp32, y in `dtype`.
  * keep_mask:[n] uint8 is drawn (Philox) and written unless mask_given; backward = same call on dy
  * with mask_given=1. */
 int mmsa_dropout(int dtype, int64_t n, const void* x, float p, uint8_t* keep_mask, int mask_given,
@@ -176,8 +204,9 @@ int mmsa_dropout(int dtype, int64_t n, const void* x, float p, uint8_t* keep_mas
  * logits:[B,C] fp32, labels:[B] int64; loss:[1] fp32, pred:[B] int64 (argmax, Trainer.py:87). */
 int mmsa_ce_fwd(int64_t B, int64_t C, const float* logits, const int64_t* labels,
                 float* loss, int64_t* pred, float* row_loss, void* stream);
-int mmsa_ce_bwd(int64_t B, int64_t C, const float* logits, const int64_t* labels,
-                const float* dloss, float* dlogits, void* stream);
+/* dlogits:[B,C] in `dtype` (the operand type of the head's dgrad / wgrad GEMMs). */
+int mmsa_ce_bwd(int dtype, int64_t B, int64_t C, const float* logits, const int64_t* labels,
+                const float* dloss, void* dlogits, void* stream);
 
 /* ---- L2 row normalisation (F.normalize, MultimodalModel.py:234-235) -------------------------- */
 int mmsa_l2norm_fwd(int dtype, int64_t B, int64_t E, const void* x, void* y, float* norm, void* stream);

@@ -90,6 +90,42 @@ __global__ void cast_kernel(const S* __restrict__ src, D* __restrict__ dst, int6
   for (int64_t k = nvec * 8 + i; k < n; k += stride) dst[k] = from_f<D>(to_f(src[k]));
 }
 
+// one launch casting many tensors (the fp32 master weights -> bf16 operand copies of a training step)
+constexpr int kCastMaxTensors = 64;
+constexpr int kCastChunk = 8192;          // elements per block
+struct CastTable {
+  const void* src[kCastMaxTensors];
+  void* dst[kCastMaxTensors];
+  long long n[kCastMaxTensors];
+  int blk_start[kCastMaxTensors + 1];
+  int count;
+};
+template <typename S, typename D>
+__global__ void __launch_bounds__(256) cast_multi_kernel(const CastTable tb) {
+  int t = 0;
+  while (t + 1 < tb.count && (int)blockIdx.x >= tb.blk_start[t + 1]) ++t;
+  const long long off = (long long)((int)blockIdx.x - tb.blk_start[t]) * kCastChunk;
+  const long long n = tb.n[t];
+  const S* src = reinterpret_cast<const S*>(tb.src[t]);
+  D* dst = reinterpret_cast<D*>(tb.dst[t]);
+  const long long end = off + kCastChunk < n ? off + kCastChunk : n;
+  if ((n & 7) == 0) {
+    for (long long i = off + threadIdx.x * 8; i < end; i += 256 * 8) {
+      float f[8];
+      if (sizeof(S) == 4) {
+        load_vec<float>(reinterpret_cast<const float*>(src) + i, f);
+        load_vec<float>(reinterpret_cast<const float*>(src) + i + 4, f + 4);
+      } else load_vec<bf16>(reinterpret_cast<const bf16*>(src) + i, f);
+      if (sizeof(D) == 4) {
+        store_vec<float>(reinterpret_cast<float*>(dst) + i, f);
+        store_vec<float>(reinterpret_cast<float*>(dst) + i + 4, f + 4);
+      } else store_vec<bf16>(reinterpret_cast<bf16*>(dst) + i, f);
+    }
+  } else {
+    for (long long i = off + threadIdx.x; i < end; i += 256) dst[i] = from_f<D>(to_f(src[i]));
+  }
+}
+
 }  // namespace mmsa
 
 using namespace mmsa;
@@ -165,6 +201,36 @@ int mmsa_cast(const void* src, int sdt, void* dst, int ddt, int64_t n, void* str
     return MMSA_ERR_ARG;
   }
   MMSA_LAUNCH_CHECK("cast_kernel");
+  return MMSA_OK;
+}
+
+int mmsa_cast_multi(int count, const void* const* src_host, void* const* dst_host, const int64_t* numel_host,
+                    int sdt, int ddt, void* stream) {
+  MMSA_REQUIRE_DEVICE();
+  MMSA_REQUIRE(count >= 0, "mmsa_cast_multi: bad count");
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int base = 0; base < count; base += kCastMaxTensors) {
+    CastTable tb{};
+    int c = count - base < kCastMaxTensors ? count - base : kCastMaxTensors;
+    int blocks = 0;
+    double bytes = 0;
+    for (int i = 0; i < c; ++i) {
+      MMSA_REQUIRE(((uintptr_t)src_host[base + i] % 16 == 0) && ((uintptr_t)dst_host[base + i] % 16 == 0),
+                   "mmsa_cast_multi: pointers must be 16B aligned");
+      tb.src[i] = src_host[base + i]; tb.dst[i] = dst_host[base + i]; tb.n[i] = numel_host[base + i];
+      tb.blk_start[i] = blocks;
+      blocks += (int)ceil_div(numel_host[base + i], kCastChunk);
+      bytes += (double)numel_host[base + i] * ((sdt == MMSA_F32 ? 4 : 2) + (ddt == MMSA_F32 ? 4 : 2));
+    }
+    tb.blk_start[c] = blocks;
+    tb.count = c;
+    if (blocks == 0) continue;
+    ProfScope prof("cast_multi", s, bytes);
+    if (sdt == MMSA_F32 && ddt == MMSA_BF16) cast_multi_kernel<float, bf16><<<blocks, 256, 0, s>>>(tb);
+    else if (sdt == MMSA_BF16 && ddt == MMSA_F32) cast_multi_kernel<bf16, float><<<blocks, 256, 0, s>>>(tb);
+    else { set_error("mmsa_cast_multi: bad dtypes %d -> %d", sdt, ddt); return MMSA_ERR_ARG; }
+    MMSA_LAUNCH_CHECK("cast_multi_kernel");
+  }
   return MMSA_OK;
 }
 

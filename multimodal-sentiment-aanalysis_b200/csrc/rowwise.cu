@@ -187,6 +187,238 @@ gate_ln_bwd_kernel(int64_t M, int E, const T* __restrict__ dy, int64_t dy_rows_p
   }
 }
 
+// ------------------------------------------------------------------ gate + blend + LayerNorm + token mean-pool
+// A block whose output only feeds a token mean-pool (the re-skinned path: t' and v' are pooled right
+// away) never needs y[M,E] in HBM: one CTA per sample walks the sample's L rows (one warp per row),
+// keeps LN(u) in fp32 registers and accumulates the pooled sums -- so the pooled features carry no
+// bf16 rounding -- and pools the query stream q on the way (the raw-feature slot, MultimodalModel.py:299).
+// F = fp32 values per lane (E <= 32*F); registers are budgeted for two 256-thread CTAs per SM.
+template <typename T> __device__ __forceinline__ void unpack_vec(const uint4& r, float* out);
+template <> __device__ __forceinline__ void unpack_vec<float>(const uint4& r, float* out) {
+  out[0] = __uint_as_float(r.x); out[1] = __uint_as_float(r.y); out[2] = __uint_as_float(r.z); out[3] = __uint_as_float(r.w);
+}
+template <> __device__ __forceinline__ void unpack_vec<bf16>(const uint4& r, float* out) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); out[2 * i] = f.x; out[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {       // streamed once: do not keep in L1
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+template <typename T, int F>
+__global__ void __launch_bounds__(kRowWarps * 32, 2)
+gate_ln_pool_fwd_kernel(int L, int E, const T* __restrict__ gate_pre, const T* __restrict__ q,
+                        const T* __restrict__ attn, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, float eps, T* __restrict__ g_out,
+                        float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                        float* __restrict__ pooled_y, float* __restrict__ pooled_q, T* __restrict__ pooled_q_lp) {
+  constexpr int VN = VecN<T>::N;
+  constexpr int NV = F / VN;
+  extern __shared__ float sm_f[];          // gamma[E], beta[E], red[kRowWarps][E]
+  float* gm_s = sm_f; float* bt_s = sm_f + E; float* red = sm_f + 2 * E;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t b = blockIdx.x;
+  const int nvec = E / VN;
+  for (int c = threadIdx.x; c < E; c += blockDim.x) { gm_s[c] = gamma[c]; bt_s[c] = beta[c]; }
+  __syncthreads();
+  float ysum[F], qsum[F];
+#pragma unroll
+  for (int i = 0; i < F; ++i) { ysum[i] = 0.f; qsum[i] = 0.f; }
+  for (int l = warp; l < L; l += kRowWarps) {
+    const int64_t row = b * L + l;
+    const int64_t base = row * (int64_t)E;
+    uint4 rg[NV], rq[NV], ra[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        rg[i] = ldg_stream(gate_pre + base + v * VN);
+        rq[i] = ldg_stream(q + base + v * VN);
+        ra[i] = ldg_stream(attn + base + v * VN);
+      }
+    }
+    float u[F];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        float gp[VN], qv[VN], av[VN], gv[VN];
+        unpack_vec<T>(rg[i], gp); unpack_vec<T>(rq[i], qv); unpack_vec<T>(ra[i], av);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) {
+          const float g = round_to<T>(sigmoidf_(gp[j]));
+          gv[j] = g;
+          const float uu = g * qv[j] + (1.f - g) * av[j];
+          u[i * VN + j] = uu;
+          sum += uu;
+          qsum[i * VN + j] += qv[j];
+        }
+        store_vec<T>(g_out + base + v * VN, gv);
+      } else {
+#pragma unroll
+        for (int j = 0; j < VN; ++j) u[i * VN + j] = 0.f;
+      }
+    }
+    const float mean = warp_sum(sum) / (float)E;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+#pragma unroll
+        for (int j = 0; j < VN; ++j) { const float d = u[i * VN + j] - mean; sq += d * d; }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)E + eps);
+    if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+#pragma unroll
+        for (int j = 0; j < VN; ++j) {
+          const int c = v * VN + j;
+          ysum[i * VN + j] += (u[i * VN + j] - mean) * rstd * gm_s[c] + bt_s[c];
+        }
+      }
+    }
+  }
+  // cross-warp sums in a fixed order (deterministic), then the two pooled rows of this sample
+  const float invL = 1.f / (float)L;
+  for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 1 && pooled_q == nullptr && pooled_q_lp == nullptr) break;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+#pragma unroll
+        for (int j = 0; j < VN; ++j) red[warp * E + v * VN + j] = pass == 0 ? ysum[i * VN + j] : qsum[i * VN + j];
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < E; c += blockDim.x) {
+      float a = 0.f;
+#pragma unroll
+      for (int w = 0; w < kRowWarps; ++w) a += red[w * E + c];
+      a *= invL;
+      if (pass == 0) pooled_y[b * E + c] = a;
+      else {
+        if (pooled_q) pooled_q[b * E + c] = a;
+        if (pooled_q_lp) pooled_q_lp[b * E + c] = from_f<T>(a);
+      }
+    }
+  }
+}
+
+// backward of gate_ln_pool_fwd.  dy of every row of sample b is dpooled_y[b,:] / L; the gradient w.r.t.
+// the pooled query stream (dpooled_q[b,:] / L) and an optional per-row extra gradient dq_add are folded
+// into dq_part, so no [M,E] broadcast is ever materialised.  One warp per row; g, q, attn are read
+// from HBM once and kept packed in registers between the statistics pass and the output pass.
+template <typename T, int F>
+__global__ void __launch_bounds__(kRowWarps * 32, (sizeof(T) == 2 ? 2 : 1))
+gate_ln_pool_bwd_kernel(int64_t M, int L, int E, const float* __restrict__ dpooled_y,
+                        const float* __restrict__ dpooled_q, const T* __restrict__ dq_add,
+                        const T* __restrict__ g, const T* __restrict__ q, const T* __restrict__ attn,
+                        const float* __restrict__ gamma, const float* __restrict__ mean,
+                        const float* __restrict__ rstd, T* __restrict__ dq_part, T* __restrict__ dattn_part,
+                        T* __restrict__ dgate_pre, float* __restrict__ partials /* [gridDim.x, 2, E] */) {
+  constexpr int VN = VecN<T>::N;
+  constexpr int NV = F / VN;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = E / VN;
+  float dgam[F], dbet[F];
+#pragma unroll
+  for (int i = 0; i < F; ++i) { dgam[i] = 0.f; dbet[i] = 0.f; }
+  const float invL = 1.f / (float)L;
+  for (int64_t row = (int64_t)blockIdx.x * kRowWarps + warp; row < M; row += (int64_t)gridDim.x * kRowWarps) {
+    const int64_t base = row * (int64_t)E;
+    const int64_t sb = (row / L) * (int64_t)E;
+    const float mu = mean[row], rs = rstd[row];
+    uint4 rg[NV], rq[NV], ra[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        rg[i] = ldg_stream(g + base + v * VN);
+        rq[i] = ldg_stream(q + base + v * VN);
+        ra[i] = ldg_stream(attn + base + v * VN);
+      }
+    }
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        float g8[VN], q8[VN], a8[VN];
+        unpack_vec<T>(rg[i], g8); unpack_vec<T>(rq[i], q8); unpack_vec<T>(ra[i], a8);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) {
+          const int c = v * VN + j;
+          const float uu = g8[j] * q8[j] + (1.f - g8[j]) * a8[j];
+          const float x = (uu - mu) * rs;
+          const float d = __ldg(dpooled_y + sb + c) * invL;
+          const float dg_ = d * __ldg(gamma + c);
+          c1 += dg_;
+          c2 += dg_ * x;
+          dgam[i * VN + j] += d * x;
+          dbet[i * VN + j] += d;
+        }
+      }
+    }
+    c1 = warp_sum(c1) / (float)E;
+    c2 = warp_sum(c2) / (float)E;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        float g8[VN], q8[VN], a8[VN], o1[VN], o2[VN], o3[VN], ad[VN];
+        unpack_vec<T>(rg[i], g8); unpack_vec<T>(rq[i], q8); unpack_vec<T>(ra[i], a8);
+        if (dq_add != nullptr) load_vec<T>(dq_add + base + v * VN, ad);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) {
+          const int c = v * VN + j;
+          const float gg = g8[j];
+          const float x = (gg * q8[j] + (1.f - gg) * a8[j] - mu) * rs;
+          const float dg_ = __ldg(dpooled_y + sb + c) * invL * __ldg(gamma + c);
+          const float du = rs * (dg_ - c1 - x * c2);
+          float extra = dpooled_q != nullptr ? __ldg(dpooled_q + sb + c) * invL : 0.f;
+          if (dq_add != nullptr) extra += ad[j];
+          o1[j] = du * gg + extra;
+          o2[j] = du * (1.f - gg);
+          o3[j] = du * (q8[j] - a8[j]) * gg * (1.f - gg);
+        }
+        store_vec<T>(dq_part + base + v * VN, o1);
+        store_vec<T>(dattn_part + base + v * VN, o2);
+        store_vec<T>(dgate_pre + base + v * VN, o3);
+      }
+    }
+  }
+  __shared__ float red[kRowWarps][2][32];
+#pragma unroll
+  for (int i = 0; i < F; ++i) {
+    __syncthreads();
+    red[warp][0][lane] = dgam[i];
+    red[warp][1][lane] = dbet[i];
+    __syncthreads();
+    if (warp == 0) {
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int w = 0; w < kRowWarps; ++w) { a += red[w][0][lane]; b += red[w][1][lane]; }
+      const int v = lane + 32 * (i / VN);
+      const int c = v * VN + (i % VN);
+      if (v < nvec) {
+        partials[((int64_t)blockIdx.x * 2 + 0) * E + c] = a;
+        partials[((int64_t)blockIdx.x * 2 + 1) * E + c] = b;
+      }
+    }
+  }
+}
+
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, int64_t nblk, int E,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -280,52 +512,48 @@ __global__ void pool_bwd_kernel(int64_t B, int64_t L, int E, const T* __restrict
 struct SlotPtrs { const void* p[4]; void* d[4]; };
 
 template <typename T>
-__global__ void modal_concat_fwd_kernel(int64_t B, int E, int S, const T* __restrict__ logits, SlotPtrs sp,
+__global__ void modal_concat_fwd_kernel(int64_t B, int E, int S, const float* __restrict__ logits, SlotPtrs sp,
                                         float* __restrict__ w, T* __restrict__ fused) {
-  constexpr int VN = VecN<T>::N;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t b = (int64_t)blockIdx.x * kRowWarps + warp;
   if (b >= B) return;
   float lg[4], mx = -INFINITY, den = 0.f;
-  for (int s = 0; s < S; ++s) { lg[s] = to_f(logits[b * S + s]); mx = fmaxf(mx, lg[s]); }
+  for (int s = 0; s < S; ++s) { lg[s] = logits[b * S + s]; mx = fmaxf(mx, lg[s]); }
   for (int s = 0; s < S; ++s) { lg[s] = expf(lg[s] - mx); den += lg[s]; }
   for (int s = 0; s < S; ++s) { lg[s] /= den; if (lane == 0) w[b * S + s] = lg[s]; }
-  const int nvec = E / VN;
   for (int s = 0; s < S; ++s) {
-    const T* src = reinterpret_cast<const T*>(sp.p[s]) + b * (int64_t)E;
+    const float* src = reinterpret_cast<const float*>(sp.p[s]) + b * (int64_t)E;
     T* dst = fused + b * (int64_t)S * E + (int64_t)s * E;
-    for (int v = lane; v < nvec; v += 32) {
-      float x[VN];
-      load_vec<T>(src + v * VN, x);
+    for (int c = lane * 4; c < E; c += 128) {
+      float x[4];
+      load_vec<float>(src + c, x);
 #pragma unroll
-      for (int j = 0; j < VN; ++j) x[j] *= lg[s];
-      store_vec<T>(dst + v * VN, x);
+      for (int j = 0; j < 4; ++j) dst[c + j] = from_f<T>(x[j] * lg[s]);
     }
   }
 }
 
+// dfused fp32 (a dgrad output), slots fp32 -> dslots fp32, dlogits T (operand of the next dgrad)
 template <typename T>
-__global__ void modal_concat_bwd_kernel(int64_t B, int E, int S, const T* __restrict__ dfused,
+__global__ void modal_concat_bwd_kernel(int64_t B, int E, int S, const float* __restrict__ dfused,
                                         const float* __restrict__ w, SlotPtrs sp, T* __restrict__ dlogits) {
-  constexpr int VN = VecN<T>::N;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t b = (int64_t)blockIdx.x * kRowWarps + warp;
   if (b >= B) return;
-  const int nvec = E / VN;
   float ws[4], dw[4];
   for (int s = 0; s < S; ++s) {
     ws[s] = w[b * S + s];
-    const T* src = reinterpret_cast<const T*>(sp.p[s]) + b * (int64_t)E;
-    const T* df = dfused + b * (int64_t)S * E + (int64_t)s * E;
-    T* dslot = reinterpret_cast<T*>(sp.d[s]);
+    const float* src = reinterpret_cast<const float*>(sp.p[s]) + b * (int64_t)E;
+    const float* df = dfused + b * (int64_t)S * E + (int64_t)s * E;
+    float* dslot = reinterpret_cast<float*>(sp.d[s]);
     float acc = 0.f;
-    for (int v = lane; v < nvec; v += 32) {
-      float x[VN], d[VN];
-      load_vec<T>(src + v * VN, x);
-      load_vec<T>(df + v * VN, d);
+    for (int c = lane * 4; c < E; c += 128) {
+      float x[4], d[4];
+      load_vec<float>(src + c, x);
+      load_vec<float>(df + c, d);
 #pragma unroll
-      for (int j = 0; j < VN; ++j) { acc += x[j] * d[j]; d[j] *= ws[s]; }
-      if (dslot != nullptr) store_vec<T>(dslot + b * (int64_t)E + v * VN, d);
+      for (int j = 0; j < 4; ++j) { acc += x[j] * d[j]; d[j] *= ws[s]; }
+      if (dslot != nullptr) store_vec<float>(dslot + b * (int64_t)E + c, d);
     }
     dw[s] = warp_sum(acc);
   }
@@ -337,18 +565,9 @@ __global__ void modal_concat_bwd_kernel(int64_t B, int E, int S, const T* __rest
 
 // ------------------------------------------------------------------ activations
 template <typename T>
-__global__ void act_fwd_kernel(int64_t n, const T* __restrict__ x, int act, T* __restrict__ y) {
-  constexpr int VN = VecN<T>::N;
-  int64_t nvec = n / VN;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-    float v[VN];
-    load_vec<T>(x + i * VN, v);
-#pragma unroll
-    for (int j = 0; j < VN; ++j) v[j] = apply_act(v[j], act);
-    store_vec<T>(y + i * VN, v);
-  }
-  for (int64_t k = nvec * VN + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
-    y[k] = from_f<T>(apply_act(to_f(x[k]), act));
+__global__ void act_fwd_kernel(int64_t n, const float* __restrict__ x, int act, T* __restrict__ y) {
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+    y[k] = from_f<T>(apply_act(x[k], act));
 }
 
 __device__ __forceinline__ float act_grad(float x, int act) {
@@ -361,9 +580,9 @@ __device__ __forceinline__ float act_grad(float x, int act) {
 }
 
 template <typename T>
-__global__ void act_bwd_kernel(int64_t n, const T* __restrict__ x, const T* __restrict__ dy, int act, T* __restrict__ dx) {
+__global__ void act_bwd_kernel(int64_t n, const float* __restrict__ x, const float* __restrict__ dy, int act, T* __restrict__ dx) {
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
-    dx[k] = from_f<T>(to_f(dy[k]) * act_grad(to_f(x[k]), act));
+    dx[k] = from_f<T>(dy[k] * act_grad(x[k], act));
 }
 
 // ------------------------------------------------------------------ L2 row normalisation
@@ -460,6 +679,65 @@ int mmsa_gate_ln_bwd(int dtype, int64_t M, int64_t E, const void* dy, int64_t dy
   return MMSA_OK;
 }
 
+
+int mmsa_gate_ln_pool_fwd(int dtype, int64_t B, int64_t L, int64_t E, const void* gate_pre, const void* q,
+                          const void* attn, const float* gamma, const float* beta, float eps, void* g_out,
+                          float* mean, float* rstd, float* pooled_y, float* pooled_q, void* pooled_q_lp,
+                          void* stream) {
+  MMSA_REQUIRE_DEVICE();
+  MMSA_REQUIRE(E % 8 == 0 && E <= 1024 && E > 0, "mmsa_gate_ln_pool_fwd: E=%lld must be a multiple of 8 and <= 1024", (long long)E);
+  MMSA_REQUIRE(L > 0 && L < (1 << 30) && pooled_y != nullptr, "mmsa_gate_ln_pool_fwd: bad arguments");
+  if (B == 0) return MMSA_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  ProfScope prof("gate_ln_pool_fwd", s, (double)B * L * E * (dtype == MMSA_F32 ? 4 : 2) * 4.0);
+  const size_t smem = (size_t)(2 + kRowWarps) * E * sizeof(float);
+#define MMSA_GLP_FWD(F_)                                                                                        \
+  MMSA_DISPATCH_DTYPE(dtype, T, {                                                                               \
+    auto kfn = gate_ln_pool_fwd_kernel<T, F_>;                                                                  \
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
+    kfn<<<(unsigned)B, kRowWarps * 32, smem, s>>>((int)L, (int)E, (const T*)gate_pre, (const T*)q, (const T*)attn, \
+                                                  gamma, beta, eps, (T*)g_out, mean, rstd, pooled_y, pooled_q,   \
+                                                  (T*)pooled_q_lp);                                             \
+  })
+  if (E <= 256) MMSA_GLP_FWD(8);
+  else if (E <= 512) MMSA_GLP_FWD(16);
+  else if (E <= 768) MMSA_GLP_FWD(24);
+  else MMSA_GLP_FWD(32);
+#undef MMSA_GLP_FWD
+  MMSA_LAUNCH_CHECK("gate_ln_pool_fwd_kernel");
+  return MMSA_OK;
+}
+
+int mmsa_gate_ln_pool_bwd(int dtype, int64_t B, int64_t L, int64_t E, const float* dpooled_y,
+                          const float* dpooled_q, const void* dq_add, const void* g, const void* q,
+                          const void* attn, const float* gamma, const float* mean, const float* rstd,
+                          void* dq_part, void* dattn_part, void* dgate_pre, float* dgamma, float* dbeta,
+                          float* partials, void* stream) {
+  MMSA_REQUIRE_DEVICE();
+  MMSA_REQUIRE(E % 8 == 0 && E <= 1024 && E > 0, "mmsa_gate_ln_pool_bwd: E=%lld must be a multiple of 8 and <= 1024", (long long)E);
+  MMSA_REQUIRE(L > 0 && L < (1 << 30) && dpooled_y != nullptr, "mmsa_gate_ln_pool_bwd: bad arguments");
+  if (B == 0) return MMSA_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t M = B * L;
+  int64_t nblk = mmsa_gate_ln_bwd_blocks(M);
+  {
+    ProfScope prof("gate_ln_pool_bwd", s, (double)M * E * (dtype == MMSA_F32 ? 4 : 2) * (dq_add ? 7.0 : 6.0));
+#define MMSA_GLP_BWD(F_)                                                                                        \
+  MMSA_DISPATCH_DTYPE(dtype, T, (gate_ln_pool_bwd_kernel<T, F_><<<(unsigned)nblk, kRowWarps * 32, 0, s>>>(       \
+      M, (int)L, (int)E, dpooled_y, dpooled_q, (const T*)dq_add, (const T*)g, (const T*)q, (const T*)attn, gamma, \
+      mean, rstd, (T*)dq_part, (T*)dattn_part, (T*)dgate_pre, partials)))
+    if (E <= 256) MMSA_GLP_BWD(8);
+    else if (E <= 512) MMSA_GLP_BWD(16);
+    else if (E <= 768) MMSA_GLP_BWD(24);
+    else MMSA_GLP_BWD(32);
+#undef MMSA_GLP_BWD
+  }
+  MMSA_LAUNCH_CHECK("gate_ln_pool_bwd_kernel");
+  reduce_partials_kernel<<<(unsigned)ceil_div(E, 128), 128, 0, s>>>(partials, nblk, (int)E, dgamma, dbeta);
+  MMSA_LAUNCH_CHECK("reduce_partials_kernel");
+  return MMSA_OK;
+}
+
 int mmsa_pool_fwd(int dtype, int64_t B, int64_t L, int64_t E, const void* x, int is_max, void* y,
                   int32_t* argmax, void* stream) {
   MMSA_REQUIRE_DEVICE();
@@ -506,14 +784,14 @@ int mmsa_modal_concat_fwd(int dtype, int64_t B, int64_t E, int S, const void* lo
                           const void* const* slots_host, float* w, void* fused, void* stream) {
   MMSA_REQUIRE_DEVICE();
   MMSA_REQUIRE(S >= 1 && S <= 4, "mmsa_modal_concat_fwd: S=%d out of [1,4]", S);
-  MMSA_REQUIRE(E % 8 == 0, "mmsa_modal_concat_fwd: E must be a multiple of 8");
+  MMSA_REQUIRE(E % 4 == 0, "mmsa_modal_concat_fwd: E must be a multiple of 4");
   if (B == 0) return MMSA_OK;
   SlotPtrs sp{};
   for (int i = 0; i < S; ++i) sp.p[i] = slots_host[i];
   cudaStream_t s = (cudaStream_t)stream;
   ProfScope prof("modal_concat_fwd", s, (double)B * E * S * 2.0 * (dtype == MMSA_F32 ? 4 : 2));
   MMSA_DISPATCH_DTYPE(dtype, T, (modal_concat_fwd_kernel<T><<<(unsigned)ceil_div(B, kRowWarps), kRowWarps * 32, 0, s>>>(
-      B, (int)E, S, (const T*)logits, sp, w, (T*)fused)));
+      B, (int)E, S, (const float*)logits, sp, w, (T*)fused)));
   MMSA_LAUNCH_CHECK("modal_concat_fwd_kernel");
   return MMSA_OK;
 }
@@ -522,14 +800,14 @@ int mmsa_modal_concat_bwd(int dtype, int64_t B, int64_t E, int S, const void* df
                           const void* const* slots_host, void* const* dslots_host, void* dlogits, void* stream) {
   MMSA_REQUIRE_DEVICE();
   MMSA_REQUIRE(S >= 1 && S <= 4, "mmsa_modal_concat_bwd: S=%d out of [1,4]", S);
-  MMSA_REQUIRE(E % 8 == 0, "mmsa_modal_concat_bwd: E must be a multiple of 8");
+  MMSA_REQUIRE(E % 4 == 0, "mmsa_modal_concat_bwd: E must be a multiple of 4");
   if (B == 0) return MMSA_OK;
   SlotPtrs sp{};
   for (int i = 0; i < S; ++i) { sp.p[i] = slots_host[i]; sp.d[i] = dslots_host[i]; }
   cudaStream_t s = (cudaStream_t)stream;
   ProfScope prof("modal_concat_bwd", s, (double)B * E * S * 3.0 * (dtype == MMSA_F32 ? 4 : 2));
   MMSA_DISPATCH_DTYPE(dtype, T, (modal_concat_bwd_kernel<T><<<(unsigned)ceil_div(B, kRowWarps), kRowWarps * 32, 0, s>>>(
-      B, (int)E, S, (const T*)dfused, w, sp, (T*)dlogits)));
+      B, (int)E, S, (const float*)dfused, w, sp, (T*)dlogits)));
   MMSA_LAUNCH_CHECK("modal_concat_bwd_kernel");
   return MMSA_OK;
 }
@@ -539,7 +817,7 @@ int mmsa_act_fwd(int dtype, int64_t n, const void* x, int act, void* y, void* st
   if (n == 0) return MMSA_OK;
   cudaStream_t s = (cudaStream_t)stream;
   ProfScope prof("act_fwd", s, (double)n * 2.0 * (dtype == MMSA_F32 ? 4 : 2));
-  MMSA_DISPATCH_DTYPE(dtype, T, (act_fwd_kernel<T><<<grid_for(n / 4 + 1, 256), 256, 0, s>>>(n, (const T*)x, act, (T*)y)));
+  MMSA_DISPATCH_DTYPE(dtype, T, (act_fwd_kernel<T><<<grid_for(n, 256), 256, 0, s>>>(n, (const float*)x, act, (T*)y)));
   MMSA_LAUNCH_CHECK("act_fwd_kernel");
   return MMSA_OK;
 }
@@ -549,7 +827,7 @@ int mmsa_act_bwd(int dtype, int64_t n, const void* x, const void* dy, int act, v
   if (n == 0) return MMSA_OK;
   cudaStream_t s = (cudaStream_t)stream;
   ProfScope prof("act_bwd", s, (double)n * 3.0 * (dtype == MMSA_F32 ? 4 : 2));
-  MMSA_DISPATCH_DTYPE(dtype, T, (act_bwd_kernel<T><<<grid_for(n, 256), 256, 0, s>>>(n, (const T*)x, (const T*)dy, act, (T*)dx)));
+  MMSA_DISPATCH_DTYPE(dtype, T, (act_bwd_kernel<T><<<grid_for(n, 256), 256, 0, s>>>(n, (const float*)x, (const float*)dy, act, (T*)dx)));
   MMSA_LAUNCH_CHECK("act_bwd_kernel");
   return MMSA_OK;
 }

@@ -27,7 +27,7 @@ __device__ __forceinline__ uint32_t philox_first(uint64_t seed, uint64_t ctr) {
 // block (32 columns, 8 row lanes); one block per 32 columns; three passes over the (tiny) [B,N] input.
 template <typename T>
 __global__ void __launch_bounds__(256)
-bn_act_fwd_kernel(int64_t B, int N, int order, const T* __restrict__ x, const float* __restrict__ gamma,
+bn_act_fwd_kernel(int64_t B, int N, int order, const float* __restrict__ x, const float* __restrict__ gamma,
                   const float* __restrict__ beta, float* __restrict__ running_mean,
                   float* __restrict__ running_var, float momentum, float eps, int training,
                   float dropout_p, uint8_t* __restrict__ keep_mask, int mask_given, uint64_t seed,
@@ -104,11 +104,11 @@ bn_act_fwd_kernel(int64_t B, int N, int order, const T* __restrict__ x, const fl
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-bn_act_bwd_kernel(int64_t B, int N, int order, const T* __restrict__ x, const T* __restrict__ dy,
+bn_act_bwd_kernel(int64_t B, int N, int order, const float* __restrict__ x, const float* __restrict__ dy,
                   const float* __restrict__ gamma, const float* __restrict__ beta,
                   const float* __restrict__ save_mean, const float* __restrict__ save_rstd, int training,
                   float dropout_p, const uint8_t* __restrict__ keep_mask, T* __restrict__ dx,
-                  float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                  float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias_prev) {
   __shared__ float red[2][8][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int col = blockIdx.x * 32 + tx;
@@ -136,19 +136,31 @@ bn_act_bwd_kernel(int64_t B, int N, int order, const T* __restrict__ x, const T*
   sdz = 0.f; sdzx = 0.f;
 #pragma unroll
   for (int k = 0; k < 8; ++k) { sdz += red[0][k][tx]; sdzx += red[1][k][tx]; }
-  if (!ok) return;
-  if (ty == 0) { dgamma[col] = sdzx; dbeta[col] = sdz; }
+  if (ok && ty == 0) { dgamma[col] = sdzx; dbeta[col] = sdz; }
   const float invB = 1.f / (float)B;
-  for (int64_t r = ty; r < B; r += 8) {
-    float raw = to_f(x[r * N + col]);
-    float v = pre_relu ? fmaxf(raw, 0.f) : raw;
-    float xh = (v - mean) * rstd;
-    float d = to_f(dy[r * N + col]);
-    if (drop) d = keep_mask[r * N + col] ? d * keep_scale : 0.f;
-    if (order == MMSA_BN_THEN_GELU) d *= gelu_erf_grad(xh * gm + bt);
-    float dv = training ? gm * rstd * (d - sdz * invB - xh * sdzx * invB) : gm * rstd * d;
-    if (pre_relu && raw <= 0.f) dv = 0.f;
-    dx[r * N + col] = from_f<T>(dv);
+  float sdx = 0.f;
+  if (ok)
+    for (int64_t r = ty; r < B; r += 8) {
+      float raw = to_f(x[r * N + col]);
+      float v = pre_relu ? fmaxf(raw, 0.f) : raw;
+      float xh = (v - mean) * rstd;
+      float d = to_f(dy[r * N + col]);
+      if (drop) d = keep_mask[r * N + col] ? d * keep_scale : 0.f;
+      if (order == MMSA_BN_THEN_GELU) d *= gelu_erf_grad(xh * gm + bt);
+      float dv = training ? gm * rstd * (d - sdz * invB - xh * sdzx * invB) : gm * rstd * d;
+      if (pre_relu && raw <= 0.f) dv = 0.f;
+      sdx += dv;
+      dx[r * N + col] = from_f<T>(dv);
+    }
+  // column sums of dx (no early exits above: every thread of the block reaches these barriers)
+  __syncthreads();
+  red[0][ty][tx] = sdx;
+  __syncthreads();
+  if (ok && ty == 0 && dbias_prev != nullptr) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[0][k][tx];
+    dbias_prev[col] = t;
   }
 }
 
@@ -176,8 +188,9 @@ __global__ void sum_scale_kernel(const float* __restrict__ v, int64_t n, float s
   if (threadIdx.x == 0) out[0] = s * scale;
 }
 
+template <typename T>
 __global__ void ce_bwd_kernel(int64_t B, int C, const float* __restrict__ logits, const int64_t* __restrict__ labels,
-                              const float* __restrict__ dloss, float* __restrict__ dlogits) {
+                              const float* __restrict__ dloss, T* __restrict__ dlogits) {
   int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= B) return;
   const float* z = logits + r * C;
@@ -187,7 +200,7 @@ __global__ void ce_bwd_kernel(int64_t B, int C, const float* __restrict__ logits
   for (int c = 0; c < C; ++c) s += expf(z[c] - mx);
   float g = dloss[0] / (float)B;
   int64_t y = labels[r];
-  for (int c = 0; c < C; ++c) dlogits[r * C + c] = g * (expf(z[c] - mx) / s - (c == y ? 1.f : 0.f));
+  for (int c = 0; c < C; ++c) dlogits[r * C + c] = from_f<T>(g * (expf(z[c] - mx) / s - (c == y ? 1.f : 0.f)));
 }
 
 // ------------------------------------------------------------------ contrastive row kernels
@@ -292,6 +305,9 @@ contrastive_bwd_kernel(int kind, int64_t B, int64_t Bg, int64_t row_offset, cons
     // (first index on ties) receives pos/pos' - all/all' on top; with e_am = 1 the two combine to
     // -all_rest/all' + pos_rest/pos', free of cancellation.
     const float g_am = pos_rest * ip - all_rest * ia;
+    // dL/dT = -(1/T) sum_j g_ij s_ij.  The g_ij of a row sum to zero exactly (see above), so s_ij may
+    // be replaced by the shifted s_ij - max_i: the arg-max term drops out and the remaining terms are
+    // all of the size of the e_ij -- no cancellation between logits of magnitude 1/T.
     for (int64_t j = lane; j < Bg; j += 32) {
       float s = row[j] / T;
       float gs;
@@ -300,9 +316,9 @@ contrastive_bwd_kernel(int kind, int64_t B, int64_t Bg, int64_t row_offset, cons
         float e = expf(s - mx);
         gs = e * ia;
         if (j != gi && lab_c[j] == yi) gs -= e * ip;
+        dts += gs * up * (s - mx);
       }
       gs *= up;
-      dts += gs * s;
       grow[j] = from_f<TG>(gs / T);
     }
   } else if (kind == MMSA_LOSS_SUPCON) {
@@ -385,7 +401,7 @@ int mmsa_bn_act_fwd(int dtype, int64_t B, int64_t N, int order, const void* x, c
   ProfScope prof("bn_act_fwd", s, (double)B * N * 2.0 * (dtype == MMSA_F32 ? 4 : 2));
   dim3 block(32, 8);
   MMSA_DISPATCH_DTYPE(dtype, T, (bn_act_fwd_kernel<T><<<(unsigned)ceil_div(N, 32), block, 0, s>>>(
-      B, (int)N, order, (const T*)x, gamma, beta, running_mean, running_var, momentum, eps, training, dropout_p,
+      B, (int)N, order, (const float*)x, gamma, beta, running_mean, running_var, momentum, eps, training, dropout_p,
       keep_mask, mask_given, seed, offset, (T*)y, save_mean, save_rstd)));
   MMSA_LAUNCH_CHECK("bn_act_fwd_kernel");
   return MMSA_OK;
@@ -394,15 +410,15 @@ int mmsa_bn_act_fwd(int dtype, int64_t B, int64_t N, int order, const void* x, c
 int mmsa_bn_act_bwd(int dtype, int64_t B, int64_t N, int order, const void* x, const void* dy,
                     const float* gamma, const float* beta, const float* save_mean, const float* save_rstd,
                     int training, float dropout_p, const uint8_t* keep_mask, void* dx, float* dgamma,
-                    float* dbeta, void* stream) {
+                    float* dbeta, float* dbias_prev, void* stream) {
   MMSA_REQUIRE_DEVICE();
   MMSA_REQUIRE(B > 0 && N > 0, "mmsa_bn_act_bwd: empty input");
   cudaStream_t s = (cudaStream_t)stream;
   ProfScope prof("bn_act_bwd", s, (double)B * N * 3.0 * (dtype == MMSA_F32 ? 4 : 2));
   dim3 block(32, 8);
   MMSA_DISPATCH_DTYPE(dtype, T, (bn_act_bwd_kernel<T><<<(unsigned)ceil_div(N, 32), block, 0, s>>>(
-      B, (int)N, order, (const T*)x, (const T*)dy, gamma, beta, save_mean, save_rstd, training, dropout_p, keep_mask,
-      (T*)dx, dgamma, dbeta)));
+      B, (int)N, order, (const float*)x, (const float*)dy, gamma, beta, save_mean, save_rstd, training, dropout_p, keep_mask,
+      (T*)dx, dgamma, dbeta, dbias_prev)));
   MMSA_LAUNCH_CHECK("bn_act_bwd_kernel");
   return MMSA_OK;
 }
@@ -420,13 +436,13 @@ int mmsa_ce_fwd(int64_t B, int64_t C, const float* logits, const int64_t* labels
   return MMSA_OK;
 }
 
-int mmsa_ce_bwd(int64_t B, int64_t C, const float* logits, const int64_t* labels, const float* dloss,
-                float* dlogits, void* stream) {
+int mmsa_ce_bwd(int dtype, int64_t B, int64_t C, const float* logits, const int64_t* labels, const float* dloss,
+                void* dlogits, void* stream) {
   MMSA_REQUIRE_DEVICE();
   MMSA_REQUIRE(B > 0 && C > 0 && C <= 64, "mmsa_ce_bwd: bad shape");
   cudaStream_t s = (cudaStream_t)stream;
   ProfScope prof("ce_bwd", s, (double)B * (C * 8.0 + 8.0));
-  ce_bwd_kernel<<<(unsigned)ceil_div(B, 128), 128, 0, s>>>(B, (int)C, logits, labels, dloss, dlogits);
+  MMSA_DISPATCH_DTYPE(dtype, T, (ce_bwd_kernel<T><<<(unsigned)ceil_div(B, 128), 128, 0, s>>>(B, (int)C, logits, labels, dloss, (T*)dlogits)));
   MMSA_LAUNCH_CHECK("ce_bwd_kernel");
   return MMSA_OK;
 }
@@ -512,7 +528,7 @@ int mmsa_clip_adamw(float* p, const float* g, float* m, float* v, int64_t n, con
 // Backward is the same kernel applied to dy with the saved mask.
 namespace mmsa {
 template <typename T>
-__global__ void dropout_kernel(int64_t n, const T* __restrict__ x, float p, uint8_t* __restrict__ keep_mask,
+__global__ void dropout_kernel(int64_t n, const float* __restrict__ x, float p, uint8_t* __restrict__ keep_mask,
                                int mask_given, uint64_t seed, uint64_t offset, T* __restrict__ y) {
   const float scale = 1.f / (1.f - p);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -538,7 +554,7 @@ extern "C" int mmsa_dropout(int dtype, int64_t n, const void* x, float p, uint8_
   int64_t blocks = mmsa::ceil_div(n, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   MMSA_DISPATCH_DTYPE(dtype, T, (mmsa::dropout_kernel<T><<<(unsigned)blocks, 256, 0, s>>>(
-      n, (const T*)x, p, keep_mask, mask_given, seed, offset, (T*)y)));
+      n, (const float*)x, p, keep_mask, mask_given, seed, offset, (T*)y)));
   MMSA_LAUNCH_CHECK("dropout_kernel");
   return MMSA_OK;
 }

@@ -29,6 +29,7 @@ _PROTOS = {
     "mmsa_prof_enable": (None, [I]),
     "mmsa_prof_collect": (I, [P, I, P, P, P, I]),
     "mmsa_cast": (I, [P, I, P, I, L, P]),
+    "mmsa_cast_multi": (I, [I, P, P, P, I, I, P]),
     "mmsa_linear_fwd": (I, [I, L, L, L, L, P, L, P, L, P, L, P, P, L, I, P, L, I, P]),
     "mmsa_debug_gemm": (I, [I, I, L, L, L, P, L, P, L, P, L, I, I, P]),
     "mmsa_linear_dgrad": (I, [I, L, L, L, P, L, P, L, P, L, P, L, I, P]),
@@ -40,6 +41,8 @@ _PROTOS = {
     "mmsa_gate_ln_fwd": (I, [I, L, L, P, P, P, P, P, F, P, P, P, P, P]),
     "mmsa_gate_ln_bwd_blocks": (L, [L]),
     "mmsa_gate_ln_bwd": (I, [I, L, L, P, L, P, P, P, P, P, P, P, L, P, P, P, P, P, P, P, P]),
+    "mmsa_gate_ln_pool_fwd": (I, [I, L, L, L, P, P, P, P, P, F, P, P, P, P, P, P, P]),
+    "mmsa_gate_ln_pool_bwd": (I, [I, L, L, L, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P]),
     "mmsa_pool_fwd": (I, [I, L, L, L, P, I, P, P, P]),
     "mmsa_pool_bwd": (I, [I, L, L, L, P, I, P, P, P]),
     "mmsa_modal_concat_fwd": (I, [I, L, L, I, P, P, P, P, P]),
@@ -47,10 +50,10 @@ _PROTOS = {
     "mmsa_act_fwd": (I, [I, L, P, I, P, P]),
     "mmsa_act_bwd": (I, [I, L, P, P, I, P, P]),
     "mmsa_bn_act_fwd": (I, [I, L, L, I, P, P, P, P, P, F, F, I, F, P, I, U, U, P, P, P, P]),
-    "mmsa_bn_act_bwd": (I, [I, L, L, I, P, P, P, P, P, P, I, F, P, P, P, P, P]),
+    "mmsa_bn_act_bwd": (I, [I, L, L, I, P, P, P, P, P, P, I, F, P, P, P, P, P, P]),
     "mmsa_dropout": (I, [I, L, P, F, P, I, U, U, P, P]),
     "mmsa_ce_fwd": (I, [L, L, P, P, P, P, P, P]),
-    "mmsa_ce_bwd": (I, [L, L, P, P, P, P, P]),
+    "mmsa_ce_bwd": (I, [I, L, L, P, P, P, P, P]),
     "mmsa_l2norm_fwd": (I, [I, L, L, P, P, P, P]),
     "mmsa_l2norm_bwd": (I, [I, L, L, P, P, P, P, P, P]),
     "mmsa_contrastive_fwd": (I, [I, L, L, L, P, P, P, P, F, L, P, P, P, P]),

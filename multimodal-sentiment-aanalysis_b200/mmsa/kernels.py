@@ -156,6 +156,43 @@ def gate_ln_bwd(dy: Tensor, rows_per_sample: int, g, q, attn, gamma, mean, rstd,
     return dq_part, dattn_part, dgate_pre, dgamma, dbeta
 
 
+def gate_ln_pool_fwd(gate_pre: Tensor, q: Tensor, attn: Tensor, gamma: Tensor, beta: Tensor, eps: float, B: int, L: int,
+                     want_q_lp: bool = True):
+    """Fused sigmoid-gate + blend + LayerNorm + token mean-pool (y is never written).
+    -> g [M,E], mean [M], rstd [M], pooled_y [B,E] fp32, pooled_q [B,E] fp32, pooled_q_lp [B,E] (q.dtype) or None."""
+    _check(gate_pre, q, attn, gamma, beta)
+    M, E = q.shape
+    assert M == B * L
+    g = torch.empty_like(q)
+    mean = torch.empty((M,), device=q.device, dtype=torch.float32)
+    rstd = torch.empty((M,), device=q.device, dtype=torch.float32)
+    py = torch.empty((B, E), device=q.device, dtype=torch.float32)
+    pq = torch.empty((B, E), device=q.device, dtype=torch.float32)
+    pq_lp = torch.empty((B, E), device=q.device, dtype=q.dtype) if (want_q_lp and q.dtype != torch.float32) else None
+    call("mmsa_gate_ln_pool_fwd", dt(q), B, L, E, gate_pre.data_ptr(), q.data_ptr(), attn.data_ptr(), gamma.data_ptr(),
+         beta.data_ptr(), float(eps), g.data_ptr(), mean.data_ptr(), rstd.data_ptr(), py.data_ptr(), pq.data_ptr(),
+         _p(pq_lp), _stream())
+    return g, mean, rstd, py, pq, pq_lp
+
+
+def gate_ln_pool_bwd(dpy: Tensor, dpq: Optional[Tensor], dq_add: Optional[Tensor], g, q, attn, gamma, mean, rstd,
+                     B: int, L: int):
+    _check(dpy, dpq, dq_add, g, q, attn)
+    M, E = q.shape
+    assert dpy.dtype == torch.float32 and (dpq is None or dpq.dtype == torch.float32)
+    dq_part = torch.empty_like(q)
+    dattn_part = torch.empty_like(q)
+    dgate_pre = torch.empty_like(q)
+    dgamma = torch.empty((E,), device=q.device, dtype=torch.float32)
+    dbeta = torch.empty((E,), device=q.device, dtype=torch.float32)
+    nblk = _lib.load().mmsa_gate_ln_bwd_blocks(M)
+    partials = torch.empty((nblk, 2, E), device=q.device, dtype=torch.float32)
+    call("mmsa_gate_ln_pool_bwd", dt(q), B, L, E, dpy.data_ptr(), _p(dpq), _p(dq_add), g.data_ptr(), q.data_ptr(),
+         attn.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dq_part.data_ptr(), dattn_part.data_ptr(),
+         dgate_pre.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), partials.data_ptr(), _stream())
+    return dq_part, dattn_part, dgate_pre, dgamma, dbeta
+
+
 def pool_fwd(x: Tensor, B: int, L: int, is_max: bool = False):
     _check(x)
     E = x.shape[-1]
@@ -180,79 +217,105 @@ def _ptr_array(ts: Sequence[Optional[Tensor]]):
     return arr
 
 
-def modal_concat_fwd(logits: Tensor, slots: Sequence[Tensor]):
+def cast_multi(srcs: Sequence[Tensor], dsts: Sequence[Tensor]) -> None:
+    """One launch: dsts[i] <- srcs[i] (fp32 -> bf16 weight copies of a step)."""
+    if not srcs:
+        return
+    _check(*srcs, *dsts)
+    n = len(srcs)
+    a1, a2 = _ptr_array(srcs), _ptr_array(dsts)
+    numel = (ctypes.c_int64 * n)(*[t.numel() for t in srcs])
+    call("mmsa_cast_multi", n, ctypes.cast(a1, ctypes.c_void_p), ctypes.cast(a2, ctypes.c_void_p),
+         ctypes.cast(numel, ctypes.c_void_p), dt(srcs[0]), dt(dsts[0]), _stream())
+
+
+# ---- [B,*] tail: elementwise kernels read fp32 (GEMM outputs) and write `out_dtype` (GEMM operands) ----
+def modal_concat_fwd(logits: Tensor, slots: Sequence[Tensor], out_dtype: torch.dtype):
+    """logits [B,S] fp32, slots S x [B,E] fp32 -> w [B,S] fp32, fused [B,S*E] (out_dtype)."""
     _check(logits, *slots)
+    assert logits.dtype == torch.float32 and all(s.dtype == torch.float32 for s in slots)
     B, E = slots[0].shape
     S = len(slots)
     w = torch.empty((B, S), device=logits.device, dtype=torch.float32)
-    fused = torch.empty((B, S * E), device=logits.device, dtype=slots[0].dtype)
+    fused = torch.empty((B, S * E), device=logits.device, dtype=out_dtype)
     arr = _ptr_array(slots)
-    call("mmsa_modal_concat_fwd", dt(slots[0]), B, E, S, logits.data_ptr(), ctypes.cast(arr, ctypes.c_void_p),
+    call("mmsa_modal_concat_fwd", dt(out_dtype), B, E, S, logits.data_ptr(), ctypes.cast(arr, ctypes.c_void_p),
          w.data_ptr(), fused.data_ptr(), _stream())
     return w, fused
 
 
-def modal_concat_bwd(dfused: Tensor, w: Tensor, slots: Sequence[Tensor], need: Sequence[bool]):
+def modal_concat_bwd(dfused: Tensor, w: Tensor, slots: Sequence[Tensor], need: Sequence[bool], out_dtype: torch.dtype):
+    """dfused [B,S*E] fp32 -> dslots fp32 (where needed), dlogits [B,S] (out_dtype)."""
     _check(dfused, w, *slots)
+    assert dfused.dtype == torch.float32
     B, E = slots[0].shape
     S = len(slots)
     dslots = [torch.empty_like(s) if n else None for s, n in zip(slots, need)]
-    dlogits = torch.empty((B, S), device=dfused.device, dtype=slots[0].dtype)
+    dlogits = torch.empty((B, S), device=dfused.device, dtype=out_dtype)
     a1, a2 = _ptr_array(slots), _ptr_array(dslots)
-    call("mmsa_modal_concat_bwd", dt(slots[0]), B, E, S, dfused.data_ptr(), w.data_ptr(),
+    call("mmsa_modal_concat_bwd", dt(out_dtype), B, E, S, dfused.data_ptr(), w.data_ptr(),
          ctypes.cast(a1, ctypes.c_void_p), ctypes.cast(a2, ctypes.c_void_p), dlogits.data_ptr(), _stream())
     return dslots, dlogits
 
 
-def act_fwd(x: Tensor, act: int) -> Tensor:
+def act_fwd(x: Tensor, act: int, out_dtype: torch.dtype) -> Tensor:
     _check(x)
-    y = torch.empty_like(x)
-    call("mmsa_act_fwd", dt(x), x.numel(), x.data_ptr(), act, y.data_ptr(), _stream())
+    assert x.dtype == torch.float32
+    y = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    call("mmsa_act_fwd", dt(out_dtype), x.numel(), x.data_ptr(), act, y.data_ptr(), _stream())
     return y
 
 
-def act_bwd(x: Tensor, dy: Tensor, act: int) -> Tensor:
+def act_bwd(x: Tensor, dy: Tensor, act: int, out_dtype: torch.dtype) -> Tensor:
     _check(x, dy)
-    dx = torch.empty_like(x)
-    call("mmsa_act_bwd", dt(x), x.numel(), x.data_ptr(), dy.data_ptr(), act, dx.data_ptr(), _stream())
+    assert x.dtype == torch.float32 and dy.dtype == torch.float32
+    dx = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    call("mmsa_act_bwd", dt(out_dtype), x.numel(), x.data_ptr(), dy.data_ptr(), act, dx.data_ptr(), _stream())
     return dx
 
 
 def bn_act_fwd(x: Tensor, gamma, beta, running_mean, running_var, momentum: float, eps: float, training: bool,
-               order: int, dropout_p: float, keep_mask: Optional[Tensor], seed: int, offset: int):
+               order: int, dropout_p: float, keep_mask: Optional[Tensor], seed: int, offset: int,
+               out_dtype: torch.dtype):
     _check(x, gamma, beta)
+    assert x.dtype == torch.float32
     B, N = x.shape
-    y = torch.empty_like(x)
+    y = torch.empty((B, N), device=x.device, dtype=out_dtype)
     save_mean = torch.empty((N,), device=x.device, dtype=torch.float32)
     save_rstd = torch.empty((N,), device=x.device, dtype=torch.float32)
     mask_given = keep_mask is not None
     if training and dropout_p > 0 and keep_mask is None:
         keep_mask = torch.empty((B, N), device=x.device, dtype=torch.uint8)
-    call("mmsa_bn_act_fwd", dt(x), B, N, order, x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _p(running_mean),
+    call("mmsa_bn_act_fwd", dt(out_dtype), B, N, order, x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _p(running_mean),
          _p(running_var), float(momentum), float(eps), int(training), float(dropout_p), _p(keep_mask),
          int(mask_given), seed, offset, y.data_ptr(), save_mean.data_ptr(), save_rstd.data_ptr(), _stream())
     return y, save_mean, save_rstd, keep_mask
 
 
-def bn_act_bwd(x, dy, gamma, beta, save_mean, save_rstd, training: bool, order: int, dropout_p: float, keep_mask):
+def bn_act_bwd(x, dy, gamma, beta, save_mean, save_rstd, training: bool, order: int, dropout_p: float, keep_mask,
+               out_dtype: torch.dtype):
     _check(x, dy)
+    assert x.dtype == torch.float32 and dy.dtype == torch.float32
     B, N = x.shape
-    dx = torch.empty_like(x)
+    dx = torch.empty((B, N), device=x.device, dtype=out_dtype)
     dgamma = torch.empty((N,), device=x.device, dtype=torch.float32)
     dbeta = torch.empty((N,), device=x.device, dtype=torch.float32)
-    call("mmsa_bn_act_bwd", dt(x), B, N, order, x.data_ptr(), dy.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+    dbias_prev = torch.empty((N,), device=x.device, dtype=torch.float32)
+    call("mmsa_bn_act_bwd", dt(out_dtype), B, N, order, x.data_ptr(), dy.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
          save_mean.data_ptr(), save_rstd.data_ptr(), int(training), float(dropout_p), _p(keep_mask), dx.data_ptr(),
-         dgamma.data_ptr(), dbeta.data_ptr(), _stream())
-    return dx, dgamma, dbeta
+         dgamma.data_ptr(), dbeta.data_ptr(), dbias_prev.data_ptr(), _stream())
+    return dx, dgamma, dbeta, dbias_prev
 
 
-def dropout(x: Tensor, p: float, keep_mask: Optional[Tensor], mask_given: bool, seed: int, offset: int):
+def dropout(x: Tensor, p: float, keep_mask: Optional[Tensor], mask_given: bool, seed: int, offset: int,
+            out_dtype: torch.dtype):
     _check(x, keep_mask)
-    y = torch.empty_like(x)
+    assert x.dtype == torch.float32
+    y = torch.empty(x.shape, device=x.device, dtype=out_dtype)
     if keep_mask is None:
         keep_mask = torch.empty(x.shape, device=x.device, dtype=torch.uint8)
-    call("mmsa_dropout", dt(x), x.numel(), x.data_ptr(), float(p), keep_mask.data_ptr(), int(mask_given), seed, offset,
-         y.data_ptr(), _stream())
+    call("mmsa_dropout", dt(out_dtype), x.numel(), x.data_ptr(), float(p), keep_mask.data_ptr(), int(mask_given), seed,
+         offset, y.data_ptr(), _stream())
     return y, keep_mask
 
 
@@ -267,11 +330,12 @@ def ce_fwd(logits: Tensor, labels: Tensor):
     return loss, pred
 
 
-def ce_bwd(logits: Tensor, labels: Tensor, dloss: Tensor) -> Tensor:
+def ce_bwd(logits: Tensor, labels: Tensor, dloss: Tensor, out_dtype: torch.dtype = torch.float32) -> Tensor:
     _check(logits, labels, dloss)
     B, C = logits.shape
-    dlogits = torch.empty_like(logits)
-    call("mmsa_ce_bwd", B, C, logits.data_ptr(), labels.data_ptr(), dloss.data_ptr(), dlogits.data_ptr(), _stream())
+    dlogits = torch.empty((B, C), device=logits.device, dtype=out_dtype)
+    call("mmsa_ce_bwd", dt(out_dtype), B, C, logits.data_ptr(), labels.data_ptr(), dloss.data_ptr(), dlogits.data_ptr(),
+         _stream())
     return dlogits
 
 

@@ -16,73 +16,18 @@ import torch.nn as nn
 
 from . import kernels as K
 from . import ops
-from ._lib import BN_THEN_GELU, RELU_THEN_BN
 
 Tensor = torch.Tensor
 
 
-class _DropoutState:
-    """Seeds for the in-kernel Philox dropout; parity tests may inject explicit keep masks."""
-
-    def __init__(self, seed: int = 0x5EED):
-        self.seed = seed
-        self.offset = 0
-        self.mask_provider: Optional[Callable[[str, Tuple[int, ...]], Optional[Tensor]]] = None
-
-    def next(self, name: str, shape) -> Tuple[Optional[Tensor], int, int]:
-        mask = self.mask_provider(name, tuple(shape)) if self.mask_provider else None
-        off = self.offset
-        n = 1
-        for s in shape:
-            n *= int(s)
-        self.offset += n
-        return mask, self.seed, off
+_DropoutState = ops._DropoutState
 
 
-def run_sequential(x: Tensor, seq: nn.Sequential, drop: _DropoutState, name: str, logits_fp32: bool) -> Tensor:
-    """Execute an nn.Sequential of the reference's head/fusion layouts on the CUDA kernels.
-    Recognised groups: Linear[-BatchNorm1d-GELU[-Dropout]] (MultimodalModel.py:179-225),
-    Linear[-ReLU-BatchNorm1d[-Dropout]] (ME-MHACL/model.py:82-97), Linear-ReLU[-Dropout] (:105-109),
-    Linear-GELU (:172-173), trailing Linear, trailing Softmax handled by the caller."""
-    mods = list(seq.children())
-    i, n = 0, len(mods)
-    while i < n:
-        m = mods[i]
-        if isinstance(m, nn.Linear):
-            nxt = mods[i + 1:i + 4]
-            last = (i == n - 1) or all(isinstance(z, nn.Softmax) for z in mods[i + 1:])
-            x = ops.linear(x, m.weight, m.bias, out_fp32=(last and logits_fp32))
-            i += 1
-            if len(nxt) >= 2 and isinstance(nxt[0], nn.BatchNorm1d) and isinstance(nxt[1], nn.GELU):
-                p, used = 0.0, 2
-                if len(nxt) >= 3 and isinstance(nxt[2], nn.Dropout):
-                    p, used = nxt[2].p, 3
-                mask, seed, off = drop.next(f"{name}.{i + used - 1}", x.shape) if (p > 0 and seq.training) else (None, 0, 0)
-                x = ops.bn_act(x, nxt[0], BN_THEN_GELU, p, mask, seed, off)
-                i += used
-            elif len(nxt) >= 2 and isinstance(nxt[0], nn.ReLU) and isinstance(nxt[1], nn.BatchNorm1d):
-                p, used = 0.0, 2
-                if len(nxt) >= 3 and isinstance(nxt[2], nn.Dropout):
-                    p, used = nxt[2].p, 3
-                mask, seed, off = drop.next(f"{name}.{i + used - 1}", x.shape) if (p > 0 and seq.training) else (None, 0, 0)
-                x = ops.bn_act(x, nxt[1], RELU_THEN_BN, p, mask, seed, off)
-                i += used
-        elif isinstance(m, nn.GELU):
-            x = ops.gelu(x)
-            i += 1
-        elif isinstance(m, nn.ReLU):
-            x = ops.relu(x)
-            i += 1
-        elif isinstance(m, nn.Dropout):
-            if m.p > 0 and seq.training:
-                mask, seed, off = drop.next(f"{name}.{i}", x.shape)
-                x = ops.dropout(x, m.p, True, mask, seed, off)
-            i += 1
-        elif isinstance(m, nn.Softmax):
-            i += 1          # the 3-way modality softmax is fused into modal_concat
-        else:
-            raise NotImplementedError(f"mmsa: no kernel mapping for {type(m).__name__} in {name}")
-    return x
+def run_sequential(x: Tensor, seq: nn.Sequential, drop: _DropoutState, name: str, cd: torch.dtype,
+                   x2: Optional[Tensor] = None) -> Tensor:
+    """Execute an nn.Sequential of the reference's head/fusion layouts on the CUDA kernels
+    (ops.sequential: one autograd node per Sequential; fp32 in, fp32 out, `cd` GEMM operands)."""
+    return ops.sequential(x, seq, drop, name, cd, x2=x2)
 
 
 class FeatureProjection(nn.Module):
@@ -95,6 +40,11 @@ class FeatureProjection(nn.Module):
 
     def forward(self, x: Tensor) -> Tensor:
         return ops.linear(x, self.proj.weight, self.proj.bias)
+
+
+def _prepare(module: nn.Module, cd: torch.dtype) -> None:
+    """Refresh the compute-dtype operand copies of every weight matrix of `module` in one launch."""
+    ops.prepare_weights([p for p in module.parameters() if p.ndim >= 2], cd)
 
 
 class CrossModalTransformer(nn.Module):
@@ -191,22 +141,29 @@ class MultimodalTransformerModel(nn.Module):
     def _cd(self, x: Tensor) -> Tensor:
         if not x.is_floating_point():
             x = x.float()
-        return K.cast(x.contiguous(), self.compute_dtype)
+        return ops.cast(x.contiguous(), self.compute_dtype)
 
     def compute_contrastive_loss(self, feat1: Tensor, feat2: Tensor, labels: Tensor) -> Tensor:
         """MultimodalModel.py:232-260."""
         return ops.infonce(feat1, feat2, labels, self.temperature)
 
+    def prepare_step(self) -> None:
+        """Call once per training step (after the optimiser update): one launch re-casts every fp32
+        master weight matrix to its bf16 operand copy.  Without it the copies are refreshed lazily,
+        one cast per weight, whenever a parameter's version changed."""
+        _prepare(self, self.compute_dtype)
+
     def _tail(self, raw_a: Tensor, raw_b: Optional[Tensor], slots: Sequence[Tensor]):
-        aw = self.attention_weights
-        h = ops.gelu(ops.linear(raw_a, aw[0].weight, aw[0].bias, x2=raw_b))
-        logits3 = ops.linear(h, aw[2].weight, aw[2].bias)
+        """modality weights (:171-176, :299-301) -> weighted concat (:302-306) -> fusion (:309) -> heads (:312-313).
+        Everything here is [B,*]: fp32 at the autograd boundaries, `compute_dtype` GEMM operands inside."""
+        cd = self.compute_dtype
+        logits3 = run_sequential(raw_a, self.attention_weights, self._drop, "attention_weights", cd, x2=raw_b)
         fused, w = ops.modal_concat(logits3, slots)
-        fused = run_sequential(fused, self.fusion, self._drop, "fusion", False)
-        arousal = run_sequential(fused, self.arousal_head, self._drop, "arousal_head", True)
+        fused = run_sequential(fused, self.fusion, self._drop, "fusion", cd)
+        arousal = run_sequential(fused, self.arousal_head, self._drop, "arousal_head", cd)
         valence = None
         if self.valence_head is not None and self.contract == "multitask":
-            valence = run_sequential(fused, self.valence_head, self._drop, "valence_head", True)
+            valence = run_sequential(fused, self.valence_head, self._drop, "valence_head", cd)
         return arousal, valence
 
     # -- forward ------------------------------------------------------------------------------------
@@ -227,8 +184,9 @@ class MultimodalTransformerModel(nn.Module):
                     contrastive.append(ops.infonce(f, f, con_labels, self.temperature))
             e1 = self.cross_attn_e2p(f0, f1, f1)                     # :287
             e2 = self.cross_attn_p2e(f0, f2, f2)                     # :293
-            raw_a, raw_b = torch.cat([f0, f1, f2], dim=1), None      # :300 (tiny [B,3E] copy)
-            slots = (f0, e1, e2)
+            f32 = torch.float32
+            raw_a, raw_b = torch.cat([ops.cast(f, f32) for f in (f0, f1, f2)], dim=1), None   # :300 (tiny [B,3E] copy)
+            slots = (ops.cast(f0, f32), ops.cast(e1, f32), ops.cast(e2, f32))
         else:
             text, image = self._cd(eeg), self._cd(eye)
             f0, fv, e1, e2 = ops.fusion_core(text, image, self.eeg_net.proj.weight, self.eeg_net.proj.bias,
@@ -280,7 +238,7 @@ class MultiModalEncoder(nn.Module):
 
     def forward(self, eeg: Tensor, eye: Tensor, pps: Tensor, labels=None) -> Tensor:
         cd = self.compute_dtype
-        feats = [K.cast(n(x).float().contiguous(), cd) for n, x in
+        feats = [ops.cast(n(x).float().contiguous(), cd) for n, x in
                  ((self.eeg_net, eeg), (self.eye_net, eye), (self.pps_net, pps))]
         if self.variant == "max":                                    # MultimodalModel.py:388-390
             feats = [ops.l2_normalize(f) for f in feats]
@@ -288,16 +246,18 @@ class MultiModalEncoder(nn.Module):
         a = self.multihead_attn
         y = ops.self_attention(x, a.in_proj_weight, a.in_proj_bias, a.out_proj.weight, a.out_proj.bias, self.num_heads)
         if self.variant == "mean":
-            return ops.mean_pool(y)                                  # ME-MHACL/model.py:73
+            return ops.cast(ops.mean_pool(y), torch.float32)         # ME-MHACL/model.py:73
         fused = ops.max_pool(y)                                      # MultimodalModel.py:401
-        return run_sequential(fused, self.fusion_mlp, self._drop, "fusion_mlp", False)
+        return run_sequential(fused, self.fusion_mlp, self._drop, "fusion_mlp", cd)
 
 
 class ProjectionHead(nn.Module):
     """ME-MHACL/model.py:77-97 (Linear-ReLU-BN-Dropout x2 + Linear)."""
 
-    def __init__(self, in_dim: int = 256, hidden_dim: int = 256, out_dim: int = 128):
+    def __init__(self, in_dim: int = 256, hidden_dim: int = 256, out_dim: int = 128,
+                 compute_dtype: torch.dtype = torch.float32):
         super().__init__()
+        self.compute_dtype = compute_dtype
         self.net = nn.Sequential(
             nn.Linear(in_dim, hidden_dim), nn.ReLU(inplace=True), nn.BatchNorm1d(hidden_dim), nn.Dropout(0.5),
             nn.Linear(hidden_dim, out_dim), nn.ReLU(inplace=True), nn.BatchNorm1d(out_dim), nn.Dropout(0.5),
@@ -305,21 +265,24 @@ class ProjectionHead(nn.Module):
         self._drop = _DropoutState()
 
     def forward(self, x: Tensor) -> Tensor:
-        return run_sequential(x, self.net, self._drop, "net", False)
+        return run_sequential(x, self.net, self._drop, "net", self.compute_dtype)
 
 
 class Classifier(nn.Module):
     """ME-MHACL/model.py:100-119 / MultimodalModel.py:432-451 (num_out = 2 or 3)."""
 
-    def __init__(self, in_dim: int = 256, hidden_dim: int = 128, num_out: int = 3):
+    def __init__(self, in_dim: int = 256, hidden_dim: int = 128, num_out: int = 3,
+                 compute_dtype: torch.dtype = torch.float32):
         super().__init__()
+        self.compute_dtype = compute_dtype
         self.shared = nn.Sequential(nn.Linear(in_dim, hidden_dim), nn.ReLU(inplace=True), nn.Dropout(0.5))
         self.fc_arousal = nn.Linear(hidden_dim, num_out)
         self.fc_valence = nn.Linear(hidden_dim, num_out)
         self._drop = _DropoutState()
 
     def forward(self, x: Tensor):
-        h = run_sequential(x, self.shared, self._drop, "shared", False)
-        out_a = ops.linear(h, self.fc_arousal.weight, self.fc_arousal.bias, out_fp32=True)
-        out_v = ops.linear(h, self.fc_valence.weight, self.fc_valence.bias, out_fp32=True)
+        cd = self.compute_dtype
+        h = run_sequential(x, self.shared, self._drop, "shared", cd)
+        out_a = ops.linear(h, self.fc_arousal.weight, self.fc_arousal.bias, out_fp32=True, cd=cd)
+        out_v = ops.linear(h, self.fc_valence.weight, self.fc_valence.bias, out_fp32=True, cd=cd)
         return out_a, out_v

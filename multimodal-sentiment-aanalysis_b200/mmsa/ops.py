@@ -1,13 +1,16 @@
 """torch.autograd.Functions over the C ABI.  Every forward/backward below is a sequence of
 mmsa_* calls; PyTorch supplies storage, streams and the autograd tape only.
 
-Storage mode: activations are fp32 (parity mode, 1e-5) or bf16 (performance mode, fp32 accumulate,
-fp32 master parameters); the mode is the dtype of the activation tensors handed in."""
+Storage mode ("compute dtype", cd): activations of the token streams are fp32 (parity mode, 1e-5) or
+bf16 (performance mode, fp32 accumulation, fp32 master parameters).  Everything that crosses an
+autograd boundary on the small [B,*] side (pooled features, fused vector, logits, losses) is fp32 in
+both modes; inside a Function the GEMM operands are cd and the GEMM outputs fp32 (include/mmsa.h)."""
 from __future__ import annotations
 
-from typing import List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
+import torch.nn as nn
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
@@ -17,36 +20,81 @@ from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, BN_ONLY, BN_THEN_G
 
 Tensor = torch.Tensor
 
+# ------------------------------------------------------------------------------------------ weight copies
+# fp32 master weight -> bf16 operand copy.  prepare_weights() refreshes every copy of a model in ONE
+# launch (call it once per step, after the optimiser update); _w() falls back to a single cast when a
+# parameter was modified since (tensor._version) or never prepared.
+_WCACHE: Dict[int, Tuple[int, Tensor]] = {}
+
+
+def prepare_weights(params: Sequence[Tensor], dtype: torch.dtype) -> None:
+    if dtype == torch.float32:
+        return
+    srcs, dsts = [], []
+    for p in params:
+        if p.ndim < 2 or not p.is_cuda:
+            continue
+        ent = _WCACHE.get(id(p))
+        if ent is None or ent[1].shape != p.shape or ent[1].device != p.device or ent[1].dtype != dtype:
+            ent = (-1, torch.empty(p.shape, device=p.device, dtype=dtype))
+        srcs.append(p.detach())
+        dsts.append(ent[1])
+        _WCACHE[id(p)] = (p._version, ent[1])
+    K.cast_multi(srcs, dsts)
+
 
 def _w(w: Tensor, dtype: torch.dtype) -> Tensor:
-    """fp32 master weight -> compute-dtype copy (mmsa_cast); identity in fp32 mode."""
-    w = w.detach()
-    if not w.is_contiguous():
-        w = w.contiguous()
-    return K.cast(w, dtype)
+    """operand copy of a weight in the compute dtype; identity in fp32 mode."""
+    if dtype == torch.float32:
+        wd = w.detach()
+        return wd if wd.is_contiguous() else wd.contiguous()
+    ent = _WCACHE.get(id(w))
+    if ent is not None and ent[0] == w._version and ent[1].shape == w.shape and ent[1].dtype == dtype \
+            and ent[1].device == w.device:
+        return ent[1]
+    wd = w.detach()
+    return K.cast(wd if wd.is_contiguous() else wd.contiguous(), dtype)
 
 
 def _c(t: Tensor) -> Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+class CastFn(Function):
+    """dtype change with a gradient (fp32 <-> compute dtype); mmsa_cast both ways."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.src = x.dtype
+        return K.cast(_c(x), dtype)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        return K.cast(_c(dy), ctx.src), None
+
+
+def cast(x: Tensor, dtype: torch.dtype) -> Tensor:
+    return x if x.dtype == dtype else CastFn.apply(x, dtype)
+
+
 # ------------------------------------------------------------------------------------------ Linear
 class LinearFn(Function):
-    """nn.Linear (MultimodalModel.py:86,172-198): y = x W^T + b over the last dim.
+    """nn.Linear (MultimodalModel.py:86,172-198): y = x W^T + b over the last dim, operands in `cd`.
     x may be split in two feature segments (x, x2) to avoid materialising a concat."""
 
     @staticmethod
-    def forward(ctx, x, x2, w, b, out_fp32: bool):
-        cd = x.dtype
+    def forward(ctx, x, x2, w, b, cd, out_fp32: bool):
         lead = x.shape[:-1]
-        x2d = _c(x).view(-1, x.shape[-1])
-        x22d = None if x2 is None else _c(x2).view(-1, x2.shape[-1])
+        x2d = K.cast(_c(x).view(-1, x.shape[-1]), cd)
+        x22d = None if x2 is None else K.cast(_c(x2).view(-1, x2.shape[-1]), cd)
         wc = _w(w, cd)
         od = torch.float32 if out_fp32 else cd
         y = K.linear_fwd(x2d, wc, None if b is None else b.detach(), x2=x22d, out_dtype=od)
         ctx.save_for_backward(x2d, x22d, wc)
         ctx.has_bias = b is not None
         ctx.in_shapes = (x.shape, None if x2 is None else x2.shape)
+        ctx.in_dtypes = (x.dtype, None if x2 is None else x2.dtype)
         ctx.cd = cd
         return y.view(*lead, w.shape[0])
 
@@ -59,9 +107,9 @@ class LinearFn(Function):
         Kx = x2d.shape[1]
         dx = dx2 = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = K.linear_dgrad(dy2d, wc[:, :Kx]).view(ctx.in_shapes[0])
+            dx = K.linear_dgrad(dy2d, wc[:, :Kx], out_dtype=ctx.in_dtypes[0]).view(ctx.in_shapes[0])
         if x22d is not None and ctx.needs_input_grad[1]:
-            dx2 = K.linear_dgrad(dy2d, wc[:, Kx:]).view(ctx.in_shapes[1])
+            dx2 = K.linear_dgrad(dy2d, wc[:, Kx:], out_dtype=ctx.in_dtypes[1]).view(ctx.in_shapes[1])
         if ctx.needs_input_grad[2] or (ctx.has_bias and ctx.needs_input_grad[3]):
             want_w = ctx.needs_input_grad[2]
             want_b = ctx.has_bias and ctx.needs_input_grad[3]
@@ -73,50 +121,27 @@ class LinearFn(Function):
                 K.linear_wgrad(dy2d, x22d, dw=dw[:, Kx:], want_bias=False, want_weight=True)
                 if not want_w:
                     dw = None
-        return dx, dx2, dw, db, None
+        return dx, dx2, dw, db, None, None
 
 
-def linear(x: Tensor, w: Tensor, b: Optional[Tensor], x2: Optional[Tensor] = None, out_fp32: bool = False) -> Tensor:
-    return LinearFn.apply(x, x2, w, b, out_fp32)
-
-
-class ActFn(Function):
-    """nn.GELU (exact erf) / nn.ReLU / sigmoid, elementwise."""
-
-    @staticmethod
-    def forward(ctx, x, act: int):
-        x = _c(x)
-        ctx.save_for_backward(x)
-        ctx.act = act
-        return K.act_fwd(x, act)
-
-    @staticmethod
-    @once_differentiable
-    def backward(ctx, dy):
-        (x,) = ctx.saved_tensors
-        return K.act_bwd(x, K.cast(_c(dy), x.dtype), ctx.act), None
-
-
-def gelu(x):
-    return ActFn.apply(x, ACT_GELU)
-
-
-def relu(x):
-    return ActFn.apply(x, ACT_RELU)
+def linear(x: Tensor, w: Tensor, b: Optional[Tensor], x2: Optional[Tensor] = None, out_fp32: bool = False,
+           cd: Optional[torch.dtype] = None) -> Tensor:
+    return LinearFn.apply(x, x2, w, b, cd or x.dtype, out_fp32)
 
 
 # ------------------------------------------------------------------------------------------ cross block
 class _BlockState:
     """Tensors one CrossModalTransformer block keeps between forward and backward."""
     __slots__ = ("q_in", "kv_in", "Qp", "KVp", "O", "lse", "A", "G", "mean", "rstd", "w_in", "w_out", "w_gate",
-                 "gamma", "B", "Lq", "Lk", "E", "H")
+                 "gamma", "B", "Lq", "Lk", "E", "H", "pooled")
 
 
 def _block_fwd(q_in: Tensor, kv_in: Tensor, B: int, Lq: int, Lk: int, H: int, in_w, in_b, out_w, out_b, gate_w,
-               gate_b, ln_w, ln_b, eps: float = 1e-5) -> Tuple[Tensor, _BlockState]:
+               gate_b, ln_w, ln_b, eps: float = 1e-5, pooled: bool = False):
     """CrossModalTransformer.forward (MultimodalModel.py:124-149) on flattened [B*L, E] activations.
     MHA in-projection (q rows of in_proj_weight; packed k,v rows), attention core, out-projection,
-    gate GEMM over the two operands [q | attn] (no concat), fused sigmoid/blend/LayerNorm."""
+    gate GEMM over the two operands [q | attn] (no concat), fused sigmoid/blend/LayerNorm.
+    pooled=False -> (y [B*Lq,E], state); pooled=True -> ((mean_l y, mean_l q) fp32 [B,E] each, state)."""
     cd = q_in.dtype
     E = q_in.shape[1]
     st = _BlockState()
@@ -128,23 +153,33 @@ def _block_fwd(q_in: Tensor, kv_in: Tensor, B: int, Lq: int, Lk: int, H: int, in
     st.A = K.linear_fwd(st.O, st.w_out, out_b.detach())
     gate_pre = K.linear_fwd(q_in, st.w_gate, gate_b.detach(), x2=st.A)
     st.gamma = ln_w.detach()
-    st.G, y, st.mean, st.rstd = K.gate_ln_fwd(gate_pre, q_in, st.A, st.gamma, ln_b.detach(), eps)
+    st.pooled = pooled
+    if pooled:
+        st.G, st.mean, st.rstd, py, pq, _ = K.gate_ln_pool_fwd(gate_pre, q_in, st.A, st.gamma, ln_b.detach(), eps, B, Lq,
+                                                               want_q_lp=False)
+        out = (py, pq)
+    else:
+        st.G, out, st.mean, st.rstd = K.gate_ln_fwd(gate_pre, q_in, st.A, st.gamma, ln_b.detach(), eps)
     st.q_in, st.kv_in = q_in, kv_in
     st.B, st.Lq, st.Lk, st.E, st.H = B, Lq, Lk, E, H
-    return y, st
+    return out, st
 
 
-def _block_bwd(st: _BlockState, dy: Tensor, dy_rows_per_sample: int, *, dq_bcast: Optional[Tensor] = None,
-               dq_add: Optional[Tensor] = None, dkv_residual: Optional[Tensor] = None,
-               need_dq: bool = True, need_dkv: bool = True, need_w: bool = True):
-    """Backward of _block_fwd.  dy is [B*Lq,E], or [B,E] when dy_rows_per_sample=Lq (mean-pooled output).
+def _block_bwd(st: _BlockState, dy: Tensor, *, dpooled_q: Optional[Tensor] = None, dq_add: Optional[Tensor] = None,
+               dkv_residual: Optional[Tensor] = None, need_dq: bool = True, need_dkv: bool = True, need_w: bool = True):
+    """Backward of _block_fwd.  dy is [B*Lq,E] (cd) for a plain block, or the fp32 [B,E] gradient of the
+    pooled output for a pooled block (dpooled_q: fp32 [B,E] gradient of the pooled query stream).
     Returns (dq, dkv, grads) with grads = (d_in_w, d_in_b, d_out_w, d_out_b, d_gate_w, d_gate_b, d_ln_w, d_ln_b).
-    All accumulation of gradients w.r.t. q and kv happens in GEMM residual epilogues / the LN kernel."""
+    Every accumulation of gradients w.r.t. q and kv happens in GEMM residual epilogues / the LN kernel;
+    bias gradients fall out of the wgrad GEMMs (ones-tile MMA)."""
     E, B, Lq, Lk, H = st.E, st.B, st.Lq, st.Lk, st.H
     dev = dy.device
-    r0, r1, dgate, d_ln_w, d_ln_b = K.gate_ln_bwd(dy, dy_rows_per_sample, st.G, st.q_in, st.A, st.gamma, st.mean,
-                                                  st.rstd, dq_bcast=dq_bcast,
-                                                  bcast_rows=Lq if dq_bcast is not None else 0, dq_add=dq_add)
+    if st.pooled:
+        r0, r1, dgate, d_ln_w, d_ln_b = K.gate_ln_pool_bwd(dy, dpooled_q, dq_add, st.G, st.q_in, st.A, st.gamma,
+                                                           st.mean, st.rstd, B, Lq)
+    else:
+        r0, r1, dgate, d_ln_w, d_ln_b = K.gate_ln_bwd(dy, 0, st.G, st.q_in, st.A, st.gamma, st.mean, st.rstd,
+                                                      dq_add=dq_add)
     d_gate_w = d_gate_b = d_out_w = d_out_b = d_in_w = d_in_b = None
     if need_w:
         d_gate_w = torch.empty((E, 2 * E), device=dev, dtype=torch.float32)
@@ -186,7 +221,7 @@ class CrossBlockFn(Function):
     def backward(ctx, dy):
         st = ctx.st
         need_w = any(ctx.needs_input_grad[2:10])
-        dq, dkv, g = _block_bwd(st, K.cast(_c(dy), st.q_in.dtype).view(st.B * st.Lq, st.E), 0,
+        dq, dkv, g = _block_bwd(st, K.cast(_c(dy), st.q_in.dtype).view(st.B * st.Lq, st.E),
                                 need_dq=ctx.needs_input_grad[0], need_dkv=ctx.needs_input_grad[1], need_w=need_w)
         ctx.st = None
         dq = None if dq is None else dq.view(st.B, st.Lq, st.E)
@@ -203,10 +238,10 @@ class FusionCoreFn(Function):
     """The sequence part of the re-skinned path in ONE autograd node (SURVEY.md section 8(d) composition):
         t = Linear(text), v = Linear(image)                         (Subnetwork.proj pattern, :86)
         t2 = Block_e2p(query=t, kv=v), v2 = Block_p2e(query=v, kv=t) (:287-297, bidirectional)
-        returns mean_tokens(t), mean_tokens(v), mean_tokens(t2), mean_tokens(v2)   each [B,E]
+        returns mean_tokens(t), mean_tokens(v), mean_tokens(t2), mean_tokens(v2)   each fp32 [B,E]
     Keeping it one node lets every gradient accumulation on the big [B,L,E] tensors happen inside
-    GEMM epilogues instead of autograd's add kernels, and the pooled-output backward never
-    materialises a [B,L,E] broadcast."""
+    GEMM epilogues instead of autograd's add kernels; t2 / v2 are never written (the LayerNorm kernel
+    pools them in fp32 registers) and the pooled-output backward never materialises a [B,L,E] broadcast."""
 
     @staticmethod
     def forward(ctx, text, image, wt, bt, wi, bi, num_heads, *bp):
@@ -218,12 +253,8 @@ class FusionCoreFn(Function):
         wtc, wic = _w(wt, cd), _w(wi, cd)
         t = K.linear_fwd(text2d, wtc, bt.detach())
         v = K.linear_fwd(image2d, wic, bi.detach())
-        t2, st1 = _block_fwd(t, v, B, L, R, num_heads, *p1)
-        v2, st2 = _block_fwd(v, t, B, R, L, num_heads, *p2)
-        f0, _ = K.pool_fwd(t, B, L)
-        fv, _ = K.pool_fwd(v, B, R)
-        e1, _ = K.pool_fwd(t2, B, L)
-        e2, _ = K.pool_fwd(v2, B, R)
+        (e1, f0), st1 = _block_fwd(t, v, B, L, R, num_heads, *p1, pooled=True)
+        (e2, fv), st2 = _block_fwd(v, t, B, R, L, num_heads, *p2, pooled=True)
         ctx.st = (st1, st2, text2d, image2d)
         ctx.dims = (B, L, R)
         return f0, fv, e1, e2
@@ -233,15 +264,13 @@ class FusionCoreFn(Function):
     def backward(ctx, df0, dfv, de1, de2):
         st1, st2, text2d, image2d = ctx.st
         ctx.st = None
-        B, L, R = ctx.dims
-        cd = text2d.dtype
-        df0, dfv, de1, de2 = (K.cast(_c(x), cd) for x in (df0, dfv, de1, de2))
+        df0, dfv, de1, de2 = (K.cast(_c(x), torch.float32) for x in (df0, dfv, de1, de2))
         need_w1 = any(ctx.needs_input_grad[7:15])
         need_w2 = any(ctx.needs_input_grad[15:23])
         # block e2p: grad wrt t (as query, + pooled f0 broadcast), grad wrt v (as key/value)
-        dt1, dv1, g1 = _block_bwd(st1, de1, L, dq_bcast=df0, need_w=need_w1)
+        dt1, dv1, g1 = _block_bwd(st1, de1, dpooled_q=df0, need_w=need_w1)
         # block p2e: grad wrt v (as query, + pooled fv broadcast + dv1), grad wrt t (as kv, + dt1)
-        dv_tot, dt_tot, g2 = _block_bwd(st2, de2, R, dq_bcast=dfv, dq_add=dv1, dkv_residual=dt1, need_w=need_w2)
+        dv_tot, dt_tot, g2 = _block_bwd(st2, de2, dpooled_q=dfv, dq_add=dv1, dkv_residual=dt1, need_w=need_w2)
         dwt = dbt = dwi = dbi = None
         if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
             dwt, dbt = K.linear_wgrad(dt_tot, text2d)
@@ -340,15 +369,14 @@ def stack_tokens(feats: Sequence[Tensor]) -> Tensor:
 
 # ------------------------------------------------------------------------------------------ modality weights
 class ModalConcatFn(Function):
-    """softmax over S modality logits + weighted concat (MultimodalModel.py:175,299-306)."""
+    """softmax over S modality logits + weighted concat (MultimodalModel.py:175,299-306); all fp32."""
 
     @staticmethod
     def forward(ctx, logits, *slots):
-        slots = [_c(s) for s in slots]
-        w, fused = K.modal_concat_fwd(K.cast(_c(logits), slots[0].dtype), slots)
+        slots = [K.cast(_c(s), torch.float32) for s in slots]
+        w, fused = K.modal_concat_fwd(K.cast(_c(logits), torch.float32), slots, torch.float32)
         ctx.save_for_backward(w, *slots)
         ctx.mark_non_differentiable(w)
-        ctx.ldtype = logits.dtype
         return fused, w
 
     @staticmethod
@@ -356,69 +384,218 @@ class ModalConcatFn(Function):
     def backward(ctx, dfused, _dw):
         w, *slots = ctx.saved_tensors
         need = list(ctx.needs_input_grad[1:])
-        dslots, dlogits = K.modal_concat_bwd(K.cast(_c(dfused), slots[0].dtype), w, slots, need)
-        return (K.cast(dlogits, ctx.ldtype),) + tuple(dslots)
+        dslots, dlogits = K.modal_concat_bwd(K.cast(_c(dfused), torch.float32), w, slots, need, torch.float32)
+        return (dlogits,) + tuple(dslots)
 
 
 def modal_concat(logits, slots: Sequence[Tensor]):
     return ModalConcatFn.apply(logits, *slots)
 
 
-# ------------------------------------------------------------------------------------------ BN + act + dropout
-class BnActFn(Function):
-    """BatchNorm1d + GELU/ReLU + Dropout on [B,N] (MultimodalModel.py:180-183; ME-MHACL/model.py:84-87)."""
+# ------------------------------------------------------------------------------------------ nn.Sequential chains
+class _DropoutState:
+    """Seeds for the in-kernel Philox dropout; parity tests may inject explicit keep masks."""
+
+    def __init__(self, seed: int = 0x5EED):
+        self.seed = seed
+        self.offset = 0
+        self.mask_provider = None
+
+    def next(self, name: str, shape) -> Tuple[Optional[Tensor], int, int]:
+        mask = self.mask_provider(name, tuple(shape)) if self.mask_provider else None
+        off = self.offset
+        n = 1
+        for s in shape:
+            n *= int(s)
+        self.offset += n
+        return mask, self.seed, off
+
+
+def _plan(seq: nn.Sequential):
+    """nn.Sequential -> list of kernel steps.  Recognised layouts: Linear[-BatchNorm1d-GELU[-Dropout]]
+    (MultimodalModel.py:179-225), Linear[-ReLU-BatchNorm1d[-Dropout]] (ME-MHACL/model.py:82-97),
+    Linear-ReLU[-Dropout] (:105-109), Linear-GELU (:172-173), Linear-ReLU-BatchNorm1d (MultimodalModel.py:402),
+    trailing Linear; a trailing Softmax is left to the caller (fused into modal_concat)."""
+    mods = list(seq.children())
+    steps, i, n = [], 0, len(mods)
+    while i < n:
+        m = mods[i]
+        nxt = mods[i + 1:i + 4]
+        if isinstance(m, nn.Linear):
+            steps.append(("linear", m))
+            i += 1
+        elif isinstance(m, nn.BatchNorm1d):
+            if len(nxt) >= 1 and isinstance(nxt[0], nn.GELU):
+                if len(nxt) >= 2 and isinstance(nxt[1], nn.Dropout):
+                    steps.append(("bn_act", m, BN_THEN_GELU, nxt[1], i + 2)); i += 3
+                else:
+                    steps.append(("bn_act", m, BN_THEN_GELU, None, -1)); i += 2
+            else:
+                steps.append(("bn_act", m, BN_ONLY, None, -1)); i += 1
+        elif isinstance(m, nn.ReLU) and len(nxt) >= 1 and isinstance(nxt[0], nn.BatchNorm1d):
+            if len(nxt) >= 2 and isinstance(nxt[1], nn.Dropout):
+                steps.append(("bn_act", nxt[0], RELU_THEN_BN, nxt[1], i + 2)); i += 3
+            else:
+                steps.append(("bn_act", nxt[0], RELU_THEN_BN, None, -1)); i += 2
+        elif isinstance(m, nn.GELU):
+            steps.append(("act", ACT_GELU)); i += 1
+        elif isinstance(m, nn.ReLU):
+            steps.append(("act", ACT_RELU)); i += 1
+        elif isinstance(m, nn.Dropout):
+            steps.append(("dropout", m, i)); i += 1
+        elif isinstance(m, nn.Softmax):
+            i += 1
+        else:
+            raise NotImplementedError(f"mmsa: no kernel mapping for {type(m).__name__}")
+    return steps
+
+
+class SeqFn(Function):
+    """One nn.Sequential of the reference's head / fusion layouts as ONE autograd node.
+    Input x (and optional second feature segment x2) and output are fp32; inside, GEMM operands are
+    `cd`, GEMM outputs fp32, and the elementwise kernel that feeds the next GEMM writes `cd` directly."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, running_mean, running_var, momentum, eps, training, order, dropout_p,
-                keep_mask, seed, offset):
-        x = _c(x)
-        y, mean, rstd, mask = K.bn_act_fwd(x, gamma.detach(), beta.detach(), running_mean, running_var, momentum, eps,
-                                           training, order, dropout_p, keep_mask, seed, offset)
-        ctx.save_for_backward(x, gamma.detach(), beta.detach(), mean, rstd)
-        ctx.mask = mask
-        ctx.cfg = (training, order, dropout_p)
-        return y
+    def forward(ctx, x, x2, seq, steps, drop: _DropoutState, name: str, cd, *params):
+        training = seq.training
+        pi = 0
+        tape = []
+        cur = K.cast(_c(x), torch.float32)
+        a = K.cast(cur, cd)
+        a2 = None if x2 is None else K.cast(K.cast(_c(x2), torch.float32), cd)
+        n = len(steps)
+        for si, st in enumerate(steps):
+            last = si == n - 1
+            nxt_is_linear = (not last) and steps[si + 1][0] == "linear"
+            out_dt = cd if nxt_is_linear else torch.float32
+            kind = st[0]
+            if kind == "linear":
+                lin = st[1]
+                w, b = params[pi], (params[pi + 1] if lin.bias is not None else None)
+                pidx = pi
+                pi += 2 if lin.bias is not None else 1
+                if a is None:
+                    a = K.cast(cur, cd)
+                wc = _w(w, cd)
+                z = K.linear_fwd(a, wc, None if b is None else b.detach(), x2=a2, out_dtype=torch.float32)
+                tape.append(("linear", a, a2, wc, pidx, lin.bias is not None))
+                cur, a, a2 = z, (K.cast(z, cd) if nxt_is_linear else None), None
+            elif kind == "bn_act":
+                bn, order, dmod, didx = st[1], st[2], st[3], st[4]
+                gamma, beta = params[pi], params[pi + 1]
+                pidx = pi
+                pi += 2
+                p = dmod.p if (dmod is not None and training) else 0.0
+                mask, seed, off = drop.next(f"{name}.{didx}", cur.shape) if p > 0 else (None, 0, 0)
+                if training and bn.track_running_stats and bn.num_batches_tracked is not None:
+                    bn.num_batches_tracked += 1
+                y, mean, rstd, mask = K.bn_act_fwd(cur, gamma.detach(), beta.detach(), bn.running_mean, bn.running_var,
+                                                   0.1 if bn.momentum is None else bn.momentum, bn.eps, training, order,
+                                                   p, mask, seed, off, out_dt)
+                tape.append(("bn_act", cur, gamma.detach(), beta.detach(), mean, rstd, training, order, p, mask, pidx))
+                cur, a = (None, y) if nxt_is_linear else (y, None)
+            elif kind == "act":
+                y = K.act_fwd(cur, st[1], out_dt)
+                tape.append(("act", cur, st[1]))
+                cur, a = (None, y) if nxt_is_linear else (y, None)
+            elif kind == "dropout":
+                dmod, didx = st[1], st[2]
+                if training and dmod.p > 0:
+                    mask, seed, off = drop.next(f"{name}.{didx}", cur.shape)
+                    y, mask = K.dropout(cur, dmod.p, mask, mask is not None, seed, off, out_dt)
+                    tape.append(("dropout", dmod.p, mask))
+                    cur, a = (None, y) if nxt_is_linear else (y, None)
+                elif nxt_is_linear:
+                    a, cur = K.cast(cur, cd), None
+        ctx.tape = tape
+        ctx.cd = cd
+        ctx.n_params = len(params)
+        ctx.has_x2 = x2 is not None
+        ctx.in_dtypes = (x.dtype, None if x2 is None else x2.dtype)
+        ctx.in_shapes = (x.shape, None if x2 is None else x2.shape)
+        return cur
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
-        x, gamma, beta, mean, rstd = ctx.saved_tensors
-        training, order, p = ctx.cfg
-        dx, dgamma, dbeta = K.bn_act_bwd(x, K.cast(_c(dy), x.dtype), gamma, beta, mean, rstd, training, order, p,
-                                         ctx.mask)
-        return (dx, dgamma, dbeta) + (None,) * 10
+        tape, cd = ctx.tape, ctx.cd
+        ctx.tape = None
+        grads: List[Optional[Tensor]] = [None] * ctx.n_params
+        need = ctx.needs_input_grad[7:]
+        d = K.cast(_c(dy), torch.float32)          # fp32 unless an elementwise backward wrote cd for a GEMM
+        dx = dx2 = None
+        db_fp32 = None                             # bias gradient handed down by a BatchNorm backward
+        for ti in range(len(tape) - 1, -1, -1):
+            op = tape[ti]
+            prev_is_linear = ti > 0 and tape[ti - 1][0] == "linear"
+            out_dt = cd if prev_is_linear else torch.float32
+            kind = op[0]
+            if kind == "linear":
+                _, a, a2, wc, pidx, has_b = op
+                d_cd = K.cast(d, cd)
+                Kx = a.shape[1]
+                want_w = need[pidx]
+                want_b = has_b and need[pidx + 1]
+                if want_b and db_fp32 is not None:     # column sums taken on fp32 values by bn_act_bwd
+                    grads[pidx + 1] = db_fp32
+                    want_b = False
+                db_fp32 = None
+                if want_w or want_b:
+                    if a2 is None:
+                        dw, db = K.linear_wgrad(d_cd, a, want_bias=want_b, want_weight=want_w)
+                    else:
+                        dw = torch.empty(wc.shape, device=d.device, dtype=torch.float32)
+                        _, db = K.linear_wgrad(d_cd, a, dw=dw[:, :Kx], want_bias=want_b, want_weight=True)
+                        K.linear_wgrad(d_cd, a2, dw=dw[:, Kx:], want_bias=False, want_weight=True)
+                    grads[pidx] = dw if want_w else None
+                    if has_b and want_b:
+                        grads[pidx + 1] = db
+                earlier_needs = ti > 0 and any(need[:pidx])
+                if ti == 0:
+                    if ctx.needs_input_grad[0]:
+                        dx = K.linear_dgrad(d_cd, wc[:, :Kx], out_dtype=torch.float32)
+                    if a2 is not None and ctx.needs_input_grad[1]:
+                        dx2 = K.linear_dgrad(d_cd, wc[:, Kx:], out_dtype=torch.float32)
+                elif earlier_needs or ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+                    d = K.linear_dgrad(d_cd, wc, out_dtype=torch.float32)
+                else:
+                    break
+            elif kind == "bn_act":
+                _, xz, gamma, beta, mean, rstd, training, order, p, mask, pidx = op
+                d, dgamma, dbeta, dbp = K.bn_act_bwd(xz, K.cast(d, torch.float32), gamma, beta, mean, rstd, training,
+                                                     order, p, mask, out_dt)
+                db_fp32 = dbp if prev_is_linear else None
+                grads[pidx] = dgamma if need[pidx] else None
+                grads[pidx + 1] = dbeta if need[pidx + 1] else None
+            elif kind == "act":
+                d = K.act_bwd(op[1], K.cast(d, torch.float32), op[2], out_dt)
+            elif kind == "dropout":
+                d, _ = K.dropout(K.cast(d, torch.float32), op[1], op[2], True, 0, 0, out_dt)
+        if tape and tape[0][0] != "linear" and ctx.needs_input_grad[0]:
+            dx = K.cast(d, torch.float32)
+        if dx is not None:
+            dx = K.cast(dx, ctx.in_dtypes[0]).view(ctx.in_shapes[0])
+        if dx2 is not None:
+            dx2 = K.cast(dx2, ctx.in_dtypes[1]).view(ctx.in_shapes[1])
+        return (dx, dx2, None, None, None, None, None) + tuple(grads)
 
 
-def bn_act(x, bn: torch.nn.BatchNorm1d, order: int, dropout_p: float = 0.0, keep_mask: Optional[Tensor] = None,
-           seed: int = 0, offset: int = 0):
-    training = bn.training
-    if training and bn.track_running_stats and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked += 1
-    return BnActFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                         0.1 if bn.momentum is None else bn.momentum, bn.eps, training, order,
-                         dropout_p if training else 0.0, keep_mask, seed, offset)
-
-
-class DropoutFn(Function):
-    """nn.Dropout with no BatchNorm in front (Classifier.shared, ME-MHACL/model.py:105-109)."""
-
-    @staticmethod
-    def forward(ctx, x, p, keep_mask, seed, offset):
-        y, mask = K.dropout(_c(x), p, keep_mask, keep_mask is not None, seed, offset)
-        ctx.mask, ctx.p = mask, p
-        return y
-
-    @staticmethod
-    @once_differentiable
-    def backward(ctx, dy):
-        dx, _ = K.dropout(_c(dy), ctx.p, ctx.mask, True, 0, 0)
-        return dx, None, None, None, None
-
-
-def dropout(x, p: float, training: bool, keep_mask: Optional[Tensor] = None, seed: int = 0, offset: int = 0):
-    if not training or p <= 0.0:
-        return x
-    return DropoutFn.apply(x, p, keep_mask, seed, offset)
+def sequential(x: Tensor, seq: nn.Sequential, drop: _DropoutState, name: str, cd: torch.dtype,
+               x2: Optional[Tensor] = None) -> Tensor:
+    """Run an nn.Sequential (parameter container) on the CUDA kernels; fp32 in, fp32 out."""
+    steps = getattr(seq, "_mmsa_plan", None)
+    if steps is None:
+        steps = _plan(seq)
+        object.__setattr__(seq, "_mmsa_plan", steps)
+    params: List[Tensor] = []
+    for st in steps:
+        if st[0] == "linear":
+            params.append(st[1].weight)
+            if st[1].bias is not None:
+                params.append(st[1].bias)
+        elif st[0] == "bn_act":
+            params.extend([st[1].weight, st[1].bias])
+    return SeqFn.apply(x, x2, seq, steps, drop, name, cd, *params)
 
 
 # ------------------------------------------------------------------------------------------ losses

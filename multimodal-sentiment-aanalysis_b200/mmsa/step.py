@@ -49,6 +49,7 @@ class TrainStep:
 
     # the arithmetic of one step; every op below is a kernel of libmmsa.so
     def _body(self, s: _Slot) -> None:
+        self.model.prepare_step()                                            # bf16 operand copies of the weights
         logits, closs = self.model(s.text, s.image, None, s.labels)          # Trainer.py:60
         loss = ops.cross_entropy(logits, s.labels) + closs.sum()             # Trainer.py:68-71
         loss.backward()                                                      # Trainer.py:79

@@ -10,12 +10,12 @@ run() { # name, timeout, args...
   tail -n 3 gpurun_out/$name.log
 }
 : > gpurun_out/summary.txt
-run gemm 300 tests/test_gpu_kernels.py -m gpu -k "linear"
-run kernels 600 tests/test_gpu_kernels.py -m gpu -k "not linear"
-run model 900 tests/test_gpu_model.py -m gpu
+run gemm 120 tests/test_gpu_kernels.py -m gpu -k "linear"
+run kernels 150 tests/test_gpu_kernels.py -m gpu -k "not linear"
+run model 240 tests/test_gpu_model.py -m gpu
 if [ "$1" != "nodiag" ]; then
   timeout 600 python scripts/diag_parity.py > gpurun_out/diag.log 2>&1; echo "diag exit=$?" | tee -a gpurun_out/summary.txt
 fi
-timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit=$?" | tee -a gpurun_out/summary.txt
+timeout 400 python bench.py --steps 20 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit=$?" | tee -a gpurun_out/summary.txt
 tail -c 3000 gpurun_out/bench.log; tail -n 5 gpurun_out/bench.err
 cat gpurun_out/summary.txt

@@ -59,11 +59,18 @@ def grad_err(name: str, g: torch.Tensor, ref: torch.Tensor, ref_grads: Dict[str,
 
 
 def oracle_step(cfg: O.FusionConfig, params: Dict[str, torch.Tensor], inputs, labels, dtype=torch.float32,
-                gathered=None):
-    """Oracle fwd+bwd of the Trainer.py:60-79 step: loss = CE(arousal) + sum(contrastive)."""
+                gathered=None, autocast_bf16: bool = False):
+    """Oracle fwd+bwd of the Trainer.py:60-79 step: loss = CE(arousal) + sum(contrastive).
+    autocast_bf16: evaluate under torch.autocast(cpu, bfloat16) with fp32 parameters -- the reference's
+    arithmetic as PyTorch itself runs it in bf16 (matmuls in bf16, reductions / norms / losses in fp32)."""
     p = {k: v.detach().clone().to(dtype).requires_grad_(True) for k, v in params.items()}
     xs = tuple(x.to(dtype) for x in inputs)
-    loss, out = O.trainer_loss(cfg, p, xs, labels, training=True, gathered=gathered)
+    if autocast_bf16:
+        with torch.autocast(device_type="cpu", dtype=torch.bfloat16):
+            loss, out = O.trainer_loss(cfg, p, xs, labels, training=True, gathered=gathered)
+        loss = loss.float()
+    else:
+        loss, out = O.trainer_loss(cfg, p, xs, labels, training=True, gathered=gathered)
     loss.backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in p.items()}
     return loss.detach(), out, grads
@@ -90,9 +97,10 @@ def run_fusion_parity(batch: int = 4, L: int = 64, R: int = 49, dtype: str = "fp
 
     The yardstick is the oracle evaluated in float64.  A tensor passes when its error against that is
     within `tol` (1e-5 fp32 / 2e-2 bf16, BASELINE.json north_star), or -- for the few quantities where
-    the REFERENCE'S OWN fp32 evaluation is further than tol/noise_mult from its float64 value (tiny-batch
-    BatchNorm, InfoNCE at T = 0.01: condition numbers of 1e2-1e3) -- within noise_mult x the fp32
-    oracle's own deviation: no fp32 implementation with a different summation order can do better."""
+    the REFERENCE'S OWN evaluation at the same precision (fp32; bf16 = torch CPU autocast) is further than
+    tol/noise_mult from its float64 value (tiny-batch BatchNorm, InfoNCE at small T: condition numbers
+    of 1e2-1e3) -- within noise_mult x that deviation: no implementation at that precision with a
+    different summation order can do better."""
     import mmsa
     cd = torch.float32 if dtype == "fp32" else torch.bfloat16
     cfg = O.FusionConfig(embed_dim=embed_dim, num_heads=num_heads, wiring="bidirectional", text_dim=text_dim,
@@ -102,7 +110,10 @@ def run_fusion_parity(batch: int = 4, L: int = 64, R: int = 49, dtype: str = "fp
         params["temperature"] = torch.tensor(float(temperature))
     inputs, labels = O.synth_inputs(cfg, batch, L=L, R=R, seed=1234 + seed)
     o_loss, o_out, o_grads = oracle_step(cfg, params, inputs, labels, dtype=torch.float64)
-    n_loss, n_out, n_grads = oracle_step(cfg, params, inputs, labels, dtype=torch.float32)
+    # the reference arithmetic at the SAME working precision (fp32, or bf16 autocast): its deviation from
+    # the float64 value is the noise floor any implementation at that precision shares
+    n_loss, n_out, n_grads = oracle_step(cfg, params, inputs, labels, dtype=torch.float32,
+                                         autocast_bf16=(dtype == "bf16"))
 
     model = build_model(cfg, params, buffers, cd, device)
     text, image = (x.to(device) for x in inputs)
