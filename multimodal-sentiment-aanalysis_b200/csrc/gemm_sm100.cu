@@ -60,6 +60,16 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -110,6 +120,7 @@ struct GemmParams {
   int act; float alpha;
   // wgrad bias gradient: colsum[m] = sum_k A[m,k] (A = dY^T), from the ones-tile MMA of the n0 == 0 tiles
   float* colsum;
+  int tma_epi;              // 1: C (and the residual) go through shared-memory slabs and TMA (tmC / tmR)
 };
 
 template <int BN, bool A_MN, bool B_MN>
@@ -117,13 +128,23 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
-  static constexpr bool COLSUM_OK = A_MN && (2 * BN + 32 <= 512);    // room for 2 x 16 extra TMEM columns
-  static constexpr int TMEM_NEED = 2 * BN + (COLSUM_OK ? 32 : 0);
+  // epilogue staging (per epilogue warp, double-buffered): output slab 32 rows x 32 cols (<= 4 KB, fp32)
+  // and residual slab 32 x 32 bf16 (2 KB), both moved by TMA so that global traffic is line-granular
+  static constexpr int OUT_SLAB = 4096, RES_SLAB = 2048;
+  static constexpr int EPI_BYTES = 4 * 2 * (OUT_SLAB + RES_SLAB);
+  static constexpr int STAGE_BUDGET = 227 * 1024 - EPI_BYTES - 2048 /*ones*/ - 2048 /*align*/ - 256 - 2 * BN * 4;
+  static constexpr int STAGES = STAGE_BUDGET / STAGE_BYTES > 8 ? 8 : STAGE_BUDGET / STAGE_BYTES;
+  // accumulator buffers in TMEM: two, so the epilogue of tile i overlaps the main loop of tile i+1 --
+  // except the 256-wide wgrad tile (A MN-major), which runs one tile per CTA under split-K anyway and
+  // needs the columns for the bias-gradient accumulator
+  static constexpr int NACC = (A_MN && BN == 256) ? 1 : 2;
+  static constexpr bool COLSUM_OK = A_MN && (NACC * (BN + 16) <= 512);
+  static constexpr int TMEM_NEED = NACC * BN + (COLSUM_OK ? NACC * 16 : 0);
   static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
   static constexpr int ONES_BYTES = 2048;         // 16 rows x 128 B of bf16 1.0 (any swizzle of ones is ones)
   static constexpr int BIAS_BYTES = 2 * BN * 4;   // double-buffered bias tile for the epilogue warps
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + ONES_BYTES + 1024 /*align*/ + 256 /*barriers*/ + BIAS_BYTES;
+  static constexpr int AUX_BYTES = ((256 + BIAS_BYTES + 1023) / 1024) * 1024;    // barriers + bias, padded to 1 KB
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + ONES_BYTES + AUX_BYTES + EPI_BYTES + 1024 /*align*/;
   // split-K finish: each CTA parks its fp32 partial tile in the (then idle) stage buffers
   static constexpr int PART_LD = BN + 4;          // padded row (floats): conflict-free 16-byte row writes
   static constexpr int PART_BYTES = BM * PART_LD * 4 + BM * 4;
@@ -165,7 +186,8 @@ __device__ __forceinline__ void cluster_sync_all() {
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-                    const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                    const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
   using Cfg = GemmCfg<BN, A_MN, B_MN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -181,8 +203,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t part_full_bar = bar_base + 8u * (2 * STAGES + 4);
   const uint32_t read_done_bar = bar_base + 8u * (2 * STAGES + 5);
+  auto res_bar = [&](int w, int b) { return bar_base + 8u * (2 * STAGES + 6 + w * 2 + b); };   // per epilogue warp
   uint8_t* aux = smem_al + STAGES * Cfg::STAGE_BYTES + Cfg::ONES_BYTES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(aux + 8 * (2 * STAGES + 6));
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(aux + 8 * (2 * STAGES + 14));
+  const uint32_t epi_base = bar_base + Cfg::AUX_BYTES;      // 1024-aligned: [warp][buf] out slabs, then res slabs
   float* bias_s = reinterpret_cast<float*>(aux + 256);   // [2][BN]
   const bool colsum_on = Cfg::COLSUM_OK && p.colsum != nullptr;
   if (colsum_on) {   // constant tile of ones (generic-proxy writes, made visible to the tensor core below)
@@ -204,9 +228,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }   // only NACC are used
     mbar_init(part_full_bar, (uint32_t)S);
     mbar_init(read_done_bar, (uint32_t)S);
+    for (int w = 0; w < 4; ++w) { mbar_init(res_bar(w, 0), 1); mbar_init(res_bar(w, 1), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -270,7 +295,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        const uint32_t cs_tmem = tmem_base + (uint32_t)(2 * BN + acc * 16);
+        const uint32_t cs_tmem = tmem_base + (uint32_t)(Cfg::NACC * BN + acc * 16);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
@@ -288,7 +313,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (kb == kb1 - 1) tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1u; }
       }
     }
   } else {
@@ -297,6 +322,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int te = threadIdx.x - 64;                   // 0..127
     int acc = 0; uint32_t acc_phase = 0;
     uint32_t cl_phase = 0;
+    uint32_t epi_it = 0;                               // chunks this warp has pushed through its slabs
     float* part = reinterpret_cast<float*>(smem_al);   // [BM][PART_LD] fp32 + [BM] colsum (split-K only)
     float* part_cs = part + BM * Cfg::PART_LD;
     for (int unit = unit0; unit < tiles_mn; unit += unit_stride) {
@@ -328,7 +354,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (colsum_on && n0 == 0) {
           uint32_t cv;
           asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(cv)
-                       : "r"(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(2 * BN + acc * 16)) : "memory");
+                       : "r"(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(Cfg::NACC * BN + acc * 16)) : "memory");
           tmem_ld_wait();
           part_cs[quad * 32 + lane] = __uint_as_float(cv);
         }
@@ -378,7 +404,110 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int r = 0; r < S; ++r) mbar_arrive_remote(mapa_u32(read_done_bar, (uint32_t)r));
         mbar_wait_cluster(read_done_bar, cl_phase);        // peers are done with OUR partial: smem reusable
         cl_phase ^= 1u;
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1u; }
+        continue;
+      }
+      if (p.tma_epi) {
+        // ---- TMA epilogue: TMEM -> registers -> swizzled shared-memory slab -> cp.async.bulk.tensor store.
+        // Each warp owns two 32x32 output slabs and two residual slabs; the residual of chunk c+2 is
+        // fetched by TMA while chunk c is computed, and a slab is rewritten only after the bulk group
+        // that read it has drained.  Edge tiles need no bounds checks: TMA clips stores and zero-fills loads.
+        const uint32_t out_slab0 = epi_base + (uint32_t)(quad * 2) * Cfg::OUT_SLAB;
+        const uint32_t res_slab0 = epi_base + 8u * Cfg::OUT_SLAB + (uint32_t)(quad * 2) * Cfg::RES_SLAB;
+        const bool has_res = p.residual != nullptr;
+        const int row0 = m0 + quad * 32;
+        const int nc = min(BN / 32, (p.N - n0 + 31) / 32);
+        if (has_res && lane == 0) {
+          for (int c = 0; c < 2 && c < nc; ++c) {
+            const uint32_t b = (epi_it + c) & 1u;
+            mbar_expect_tx(res_bar(quad, b), Cfg::RES_SLAB);
+            tma_load_2d(res_slab0 + b * Cfg::RES_SLAB, &tmR, n0 + c * 32, row0, res_bar(quad, b));
+          }
+        }
+#pragma unroll 1
+        for (int c = 0; c < nc; ++c) {
+          const uint32_t b = epi_it & 1u;
+          uint32_t r[32];
+          tmem_ld32(t_row + c * 32, r);
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bs + c * 32 + j);
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          }
+          if (has_res) {
+            mbar_wait(res_bar(quad, b), (epi_it >> 1) & 1u);
+            const uint32_t rrow = res_slab0 + b * Cfg::RES_SLAB + (uint32_t)lane * 64u;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              uint4 raw;
+              const uint32_t a = rrow + (uint32_t)((cc ^ ((lane >> 1) & 3)) << 4);
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "r"(a));
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(h[q]); v[cc * 8 + 2 * q] += f.x; v[cc * 8 + 2 * q + 1] += f.y; }
+            }
+          }
+          if (p.act == MMSA_ACT_SIGMOID) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = sigmoidf_(v[j]);
+          } else if (p.act == MMSA_ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+          } else if (p.act == MMSA_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (lane == 0) tma_store_wait_read<1>();       // the group that read slab b two chunks ago has drained
+          __syncwarp();
+          const uint32_t oslab = out_slab0 + b * Cfg::OUT_SLAB;
+          if (p.out_is_f32) {
+            const uint32_t orow = oslab + (uint32_t)lane * 128u;
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+              const uint32_t a = orow + (uint32_t)((cc ^ (lane & 7)) << 4);
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[cc * 4]), "f"(v[cc * 4 + 1]), "f"(v[cc * 4 + 2]), "f"(v[cc * 4 + 3]) : "memory");
+            }
+          } else {
+            const uint32_t orow = oslab + (uint32_t)lane * 64u;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              uint4 pk;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(v[cc * 8 + 2 * q], v[cc * 8 + 2 * q + 1]);
+              const uint32_t a = orow + (uint32_t)((cc ^ ((lane >> 1) & 3)) << 4);
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w) : "memory");
+            }
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmC, oslab, n0 + c * 32, row0);
+            tma_store_commit();
+            if (has_res && c + 2 < nc) {               // residual slab b is free again: fetch chunk c+2 into it
+              mbar_expect_tx(res_bar(quad, b), Cfg::RES_SLAB);
+              tma_load_2d(res_slab0 + b * Cfg::RES_SLAB, &tmR, n0 + (c + 2) * 32, row0, res_bar(quad, b));
+            }
+          }
+          ++epi_it;
+        }
+        if (colsum_on && n0 == 0) {
+          uint32_t cv;
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(cv)
+                       : "r"(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(Cfg::NACC * BN + acc * 16)) : "memory");
+          tmem_ld_wait();
+          if (row_ok) p.colsum[row] = __uint_as_float(cv);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1u; }
         continue;
       }
 #pragma unroll 1
@@ -452,15 +581,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (colsum_on && n0 == 0) {    // bias-gradient column of this tile: one value per accumulator row
         uint32_t cv;
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(cv)
-                     : "r"(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(2 * BN + acc * 16)) : "memory");
+                     : "r"(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(Cfg::NACC * BN + acc * 16)) : "memory");
         tmem_ld_wait();
         if (row_ok) p.colsum[row] = __uint_as_float(cv);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1u; }
     }
+    if (p.tma_epi && lane == 0) tma_store_wait_all();  // bulk stores read shared memory: drain before exit
   }
 
   tc_fence_before();
@@ -503,6 +633,28 @@ static bool make_map(CUtensorMap* map, const void* base, int64_t inner, int64_t 
   if (r != CUDA_SUCCESS) {
     set_error("mmsa: cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld ld=%lld box=%dx%d base=%p", (int)r,
               (long long)inner, (long long)outer, (long long)ld, box_inner, box_outer, base);
+    return false;
+  }
+  return true;
+}
+
+// 2-D tensor map for the epilogue slabs (32 x 32 box): bf16 -> 64-byte rows / SWIZZLE_64B, fp32 -> 128-byte
+// rows / SWIZZLE_128B (the slab layouts the epilogue warps write).
+static bool make_epi_map(CUtensorMap* map, const void* base, bool is_f32, int64_t inner, int64_t outer, int64_t ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("mmsa: cuTensorMapEncodeTiled entry point not found"); return false; }
+  const int esz = is_f32 ? 4 : 2;
+  cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * esz};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base),
+                  gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  is_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("mmsa: cuTensorMapEncodeTiled (epilogue) failed (%d) inner=%lld outer=%lld ld=%lld base=%p", (int)r,
+              (long long)inner, (long long)outer, (long long)ld, base);
     return false;
   }
   return true;
@@ -559,6 +711,18 @@ static int launch_gemm(const GemmDesc& d, int splits_req, cudaStream_t s) {
   p.bias = d.bias; p.residual = d.residual; p.ldr = d.ldr; p.res_is_f32 = 0;
   p.C = d.C; p.ldc = d.ldc; p.out_is_f32 = (d.out_dtype == MMSA_F32);
   p.act = d.act; p.alpha = d.alpha;
+  // TMA epilogue when the output (and residual) rows are 16-byte addressable; else per-thread stores
+  CUtensorMap tmC = tmA, tmR = tmA;
+  {
+    const int esz = p.out_is_f32 ? 4 : 2;
+    bool ok = p.splits == 1 && ((uintptr_t)d.C % 16 == 0) && ((d.ldc * esz) % 16 == 0);
+    if (d.residual) ok = ok && ((uintptr_t)d.residual % 16 == 0) && ((d.ldr * 2) % 16 == 0);
+    if (ok) {
+      if (!make_epi_map(&tmC, d.C, p.out_is_f32, d.N, d.M, d.ldc)) return MMSA_ERR_CUDA;
+      if (d.residual && !make_epi_map(&tmR, d.residual, false, d.N, d.M, d.ldr)) return MMSA_ERR_CUDA;
+    }
+    p.tma_epi = ok ? 1 : 0;
+  }
   p.colsum = nullptr;
   if (d.colsum != nullptr) {
     if (!Cfg::COLSUM_OK) { set_error("mmsa: internal: colsum requested on a tile shape without TMEM room (BN=%d)", BN); return MMSA_ERR_ARG; }
@@ -577,7 +741,7 @@ static int launch_gemm(const GemmDesc& d, int splits_req, cudaStream_t s) {
   if (p.splits == 1) {
     int grid = tiles_mn < num_sms() ? tiles_mn : num_sms();
     ProfScope prof(nm, s, 2.0 * (double)d.M * (double)d.N * (double)Kt);
-    kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, s>>>(tmA, tmA2, tmB, p);
+    kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, s>>>(tmA, tmA2, tmB, tmC, tmR, p);
   } else {
     // one cluster of `splits` CTAs per output tile (co-scheduled by the hardware, so the in-kernel
     // cross-CTA reduction cannot deadlock); clusters loop over tiles when there are more tiles than slots
@@ -591,7 +755,7 @@ static int launch_gemm(const GemmDesc& d, int splits_req, cudaStream_t s) {
     const int nclusters = tiles_mn < max_clusters ? tiles_mn : max_clusters;
     cfg.gridDim = dim3((unsigned)(nclusters * p.splits));
     ProfScope prof(nm, s, 2.0 * (double)d.M * (double)d.N * (double)Kt);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmB, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmB, tmC, tmR, p);
     if (e != cudaSuccess) { set_error("mmsa: cluster launch of gemm_tcgen05_kernel (cluster %d) failed: %s", p.splits, cudaGetErrorString(e)); return MMSA_ERR_CUDA; }
   }
   MMSA_LAUNCH_CHECK("gemm_tcgen05_kernel");
@@ -603,7 +767,7 @@ static int pick_bn(int64_t N, bool need_colsum) {
   if (N <= 64) return 64;
   if (N <= 128) return 128;
   if (N % 192 == 0) return 192;
-  if (need_colsum) return (N % 128 == 0 || N > 384) ? 128 : 192;
+  if (need_colsum) return (N % 256 == 0 || N > 512) ? 256 : ((N % 128 == 0 || N > 384) ? 128 : 192);
   if (N % 256 == 0 || N > 512) return 256;
   if (N <= 192) return 192;
   return 256;

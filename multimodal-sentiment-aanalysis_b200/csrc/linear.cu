@@ -40,7 +40,8 @@ static int run_gemm(int dtype, const GemmDesc& d, int splits, cudaStream_t s) {
 // rounds = ceil(tiles / co-resident clusters of size S) and cycles per k-block = max(MMA issue 2*BN,
 // shared-memory operand reads (16 KB + BN*128 B) / 128 B per cycle).
 static void tc_plan_wgrad(int64_t Nw, int64_t Kw, int64_t kb_total, int* bn_out, int* splits_out) {
-  static const int cands[3] = {192, 128, 64};
+  // 192 is left out: with an MN-major A the 128x192 MMA runs ~20% below the 128x256 one (scripts/gemm_majors.py)
+  static const int cands[3] = {256, 128, 64};
   double best = 1e30;
   *bn_out = 128; *splits_out = 1;
   for (int ci = 0; ci < 3; ++ci) {
@@ -48,7 +49,9 @@ static void tc_plan_wgrad(int64_t Nw, int64_t Kw, int64_t kb_total, int* bn_out,
     if (bn > 64 && Kw <= bn / 2) continue;                 // do not pad a narrow output to a wide tile
     const int64_t tiles = ceil_div(Nw, 128) * ceil_div(Kw, bn);
     const double waste = (double)(ceil_div(Kw, bn) * bn) / (double)Kw;
-    const double cyc_kb = (double)(2 * bn > 128 + bn ? 2 * bn : 128 + bn);
+    // measured operand ingest per SM ~56 B/clk: (16 KB + bn*128 B) / 56 cycles per k-block; MMA issue 2*bn
+    const double ingest = (16384.0 + bn * 128.0) / 56.0;
+    const double cyc_kb = ingest > 2.0 * bn ? ingest : 2.0 * bn;
     for (int sp = 1; sp <= 8; ++sp) {
       if (sp > 1 && kb_total / sp < 8) break;
       const int64_t per = ceil_div(kb_total, sp);
