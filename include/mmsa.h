@@ -71,6 +71,14 @@ int mmsa_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t 
 int mmsa_cast_multi(int count, const void* const* src_host, void* const* dst_host, const int64_t* numel_host,
                     int src_dtype, int dst_dtype, void* stream);
 
+/* fp32 -> split-bf16 operand for an fp32-accurate tensor-core product (InfoNCE cosine block and its two backward
+ * GEMMs in bf16 mode, MultimodalModel.py:237): hi = bf16(x), lo = bf16(x - hi); three copies are concatenated along
+ * the reduction axis, (hi,hi,lo) for the A side (b_side = 0) or (hi,lo,hi) for the B side (b_side = 1), so that a
+ * plain bf16 GEMM over 3K yields hi.hi + hi.lo + lo.hi.  src:[R,C] fp32 (row stride ld); dst_col:[R,3C] bf16
+ * (K-major operand) and/or dst_row:[3R,C] bf16 (MN-major operand); either may be NULL. */
+int mmsa_split3(const float* src, int64_t R, int64_t C, int64_t ld, void* dst_col, int b_side_col, void* dst_row,
+                int b_side_row, void* stream);
+
 /* ---- Linear: y = x W^T + b   (nn.Linear: MultimodalModel.py:86,112-121,172-198) -------------
  * x:[M,K] (row stride ldx), optional second operand x2:[M,K2] concatenated on the feature axis
  * (the gate's cat[q, attn], MultimodalModel.py:147), W:[N,K+K2] fp32 master (row stride ldw) or

@@ -126,6 +126,31 @@ __global__ void __launch_bounds__(256) cast_multi_kernel(const CastTable tb) {
   }
 }
 
+// fp32 -> two-term bf16 split (hi = bf16(x), lo = bf16(x - hi)), laid out so that ONE bf16 tensor-core GEMM over a
+// three-times longer reduction reproduces the fp32 product to ~2^-16:  sum_k a_k b_k ~= hi_a.hi_b + hi_a.lo_b + lo_a.hi_b.
+// The A-side operand repeats (hi, hi, lo), the B-side (hi, lo, hi); the three copies are concatenated along the
+// reduction axis: along columns for a K-major operand (dst_col [R, 3C]) and along rows for an MN-major one
+// (dst_row [3R, C]).  Used by the InfoNCE similarity GEMM and its two backward GEMMs in bf16 mode.
+__global__ void __launch_bounds__(256)
+split3_kernel(const float* __restrict__ src, int64_t R, int64_t C, int64_t ld, bf16* __restrict__ dst_col, int b_side_col,
+              bf16* __restrict__ dst_row, int b_side_row) {
+  const int64_t total = R * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / C, c = i % C;
+    const float x = src[r * ld + c];
+    const bf16 hi = __float2bfloat16_rn(x);
+    const bf16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+    if (dst_col) {
+      bf16* d = dst_col + r * 3 * C + c;
+      d[0] = hi; d[C] = b_side_col ? lo : hi; d[2 * C] = b_side_col ? hi : lo;
+    }
+    if (dst_row) {
+      bf16* d = dst_row + r * C + c;
+      d[0] = hi; d[R * C] = b_side_row ? lo : hi; d[2 * R * C] = b_side_row ? hi : lo;
+    }
+  }
+}
+
 }  // namespace mmsa
 
 using namespace mmsa;
@@ -201,6 +226,20 @@ int mmsa_cast(const void* src, int sdt, void* dst, int ddt, int64_t n, void* str
     return MMSA_ERR_ARG;
   }
   MMSA_LAUNCH_CHECK("cast_kernel");
+  return MMSA_OK;
+}
+
+int mmsa_split3(const float* src, int64_t R, int64_t C, int64_t ld, void* dst_col, int b_side_col, void* dst_row,
+                int b_side_row, void* stream) {
+  MMSA_REQUIRE_DEVICE();
+  MMSA_REQUIRE(R >= 0 && C > 0 && ld >= C && src != nullptr && (dst_col != nullptr || dst_row != nullptr), "mmsa_split3: bad arguments");
+  if (R == 0) return MMSA_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  int64_t blocks = ceil_div(R * C, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  ProfScope prof("split3", s, (double)R * C * (4.0 + 6.0 * ((dst_col ? 1 : 0) + (dst_row ? 1 : 0))));
+  split3_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, R, C, ld, (bf16*)dst_col, b_side_col, (bf16*)dst_row, b_side_row);
+  MMSA_LAUNCH_CHECK("split3_kernel");
   return MMSA_OK;
 }
 

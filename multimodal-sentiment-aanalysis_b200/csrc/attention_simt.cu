@@ -76,19 +76,38 @@ attn_fwd_simt_kernel(int H, int Lq, int Lk, const T* __restrict__ q, int64_t ldq
   }
 }
 
-// delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]
+// delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d].  D/VN lanes per (row, head), one 16-byte vector each, so a
+// warp reads whole contiguous row segments of O and dO; the partial dots meet in a sub-warp shuffle tree.
 template <typename T, int D>
-__global__ void attn_delta_kernel(int64_t rows /*B*Lq*/, int H, int Lq, const T* __restrict__ o, int64_t ldo,
-                                  const T* __restrict__ dout, int64_t lddo, float* __restrict__ delta) {
-  const int lane = threadIdx.x & 31;
-  int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per (row, head)
-  if (w >= rows * H) return;
-  int64_t r = w / H; int h = (int)(w % H);
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(int64_t rows /*B*Lq*/, int H, int Lq, const T* __restrict__ o, int64_t ldo,
+                  const T* __restrict__ dout, int64_t lddo, float* __restrict__ delta, int vec_ok) {
+  constexpr int VN = VecN<T>::N;
+  constexpr int G = D / VN;                      // lanes per (row, head): 4, 8 or 16
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t item = t / G;
+  const int sub = (int)(t % G);
+  const bool ok = item < rows * H;
+  const int64_t r = ok ? item / H : 0;
+  const int h = ok ? (int)(item % H) : 0;
   float s = 0.f;
-  for (int d = lane; d < D; d += 32) s += to_f(o[r * ldo + h * D + d]) * to_f(dout[r * lddo + h * D + d]);
-  s = warp_sum(s);
-  if (lane == 0) {
-    int64_t b = r / Lq, i = r % Lq;
+  if (ok) {
+    const T* po = o + r * ldo + h * D + sub * VN;
+    const T* pd = dout + r * lddo + h * D + sub * VN;
+    if (vec_ok) {
+      float a[VN], b[VN];
+      load_vec<T>(po, a); load_vec<T>(pd, b);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) s += a[j] * b[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < VN; ++j) s += to_f(po[j]) * to_f(pd[j]);
+    }
+  }
+#pragma unroll
+  for (int off = G / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (ok && sub == 0) {
+    const int64_t b = r / Lq, i = r % Lq;
     delta[(b * H + h) * Lq + i] = s;
   }
 }
@@ -245,10 +264,13 @@ int attn_fwd_simt(int64_t B, int64_t H, int64_t Lq, int64_t Lk, const void* q, i
 template <typename T, int D>
 int attn_delta(int64_t B, int64_t H, int64_t Lq, const void* o, int64_t ldo, const void* dout, int64_t lddo, float* delta,
                cudaStream_t s) {
-  int64_t warps = B * Lq * H;
+  constexpr int VN = VecN<T>::N;
+  const int64_t threads = B * Lq * H * (D / VN);
+  const int vec_ok = ((uintptr_t)o % 16 == 0) && ((uintptr_t)dout % 16 == 0) && (ldo * sizeof(T)) % 16 == 0 &&
+                     (lddo * sizeof(T)) % 16 == 0;
   ProfScope prof("attn_delta", s, (double)sizeof(T) * D * (double)B * H * 2.0 * Lq);
-  attn_delta_kernel<T, D><<<(unsigned)ceil_div(warps * 32, 256), 256, 0, s>>>(B * Lq, (int)H, (int)Lq, (const T*)o, ldo,
-                                                                           (const T*)dout, lddo, delta);
+  attn_delta_kernel<T, D><<<(unsigned)ceil_div(threads, 256), 256, 0, s>>>(B * Lq, (int)H, (int)Lq, (const T*)o, ldo,
+                                                                          (const T*)dout, lddo, delta, vec_ok);
   MMSA_LAUNCH_CHECK("attn_delta_kernel");
   return MMSA_OK;
 }

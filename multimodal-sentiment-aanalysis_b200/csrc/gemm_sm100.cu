@@ -60,6 +60,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
+// 2-CTA form: the copy lands in THIS CTA's shared memory but signals the mbarrier of the pair's leader CTA
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(leader_bar)
+      : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
@@ -74,6 +81,18 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {      // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -123,10 +142,15 @@ struct GemmParams {
   int tma_epi;              // 1: C (and the residual) go through shared-memory slabs and TMA (tmC / tmR)
 };
 
-template <int BN, bool A_MN, bool B_MN>
+// PAIR: 2-CTA mode (tcgen05 cta_group::2).  Two CTAs on the SMs of one TPC compute a 256 x BN tile together: each stages
+// its own 128 rows of A and HALF of the B tile (BN/2 rows), the leader's MMA reads both halves, and each CTA's TMEM
+// receives its 128 accumulator rows.  Operand bytes pulled from L2 per FLOP drop by a third against 128 x 256 tiles --
+// the L2->SM path (~6.3 KB/clk chip-wide), not the tensor pipe, is what bounds the 1-CTA kernel.
+template <int BN, bool A_MN, bool B_MN, bool PAIR = false>
 struct GemmCfg {
+  static constexpr int CTA_N = PAIR ? BN / 2 : BN;    // B rows (output columns) staged by one CTA
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = CTA_N * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // epilogue staging (per epilogue warp, double-buffered): output slab 32 rows x 32 cols (<= 4 KB, fp32)
   // and residual slab 32 x 32 bf16 (2 KB), both moved by TMA so that global traffic is line-granular
@@ -138,7 +162,7 @@ struct GemmCfg {
   // except the 256-wide wgrad tile (A MN-major), which runs one tile per CTA under split-K anyway and
   // needs the columns for the bias-gradient accumulator
   static constexpr int NACC = (A_MN && BN == 256) ? 1 : 2;
-  static constexpr bool COLSUM_OK = A_MN && (NACC * (BN + 16) <= 512);
+  static constexpr bool COLSUM_OK = !PAIR && A_MN && (NACC * (BN + 16) <= 512);
   static constexpr int TMEM_NEED = NACC * BN + (COLSUM_OK ? NACC * 16 : 0);
   static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
   static constexpr int ONES_BYTES = 2048;         // 16 rows x 128 B of bf16 1.0 (any swizzle of ones is ones)
@@ -183,13 +207,14 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                     const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                     const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
-  using Cfg = GemmCfg<BN, A_MN, B_MN>;
+  using Cfg = GemmCfg<BN, A_MN, B_MN, PAIR>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int TILE_M = PAIR ? 2 * BM : BM;          // rows of the output tile a work unit covers
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -216,9 +241,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int S = p.splits;                                   // cluster size along x
+  const int S = PAIR ? 1 : p.splits;                        // split-K cluster size along x (never combined with PAIR)
   const int split = (S > 1) ? (int)cluster_ctarank() : 0;   // this CTA's K-slice
-  const int unit0 = blockIdx.x / S, unit_stride = gridDim.x / S;   // output tiles are dealt to clusters
+  const int pair_rank = PAIR ? (int)cluster_ctarank() : 0;  // 0 = leader (issues the MMAs), 1 = peer
+  const int CS = PAIR ? 2 : S;                              // CTAs per work unit
+  const int unit0 = blockIdx.x / CS, unit_stride = gridDim.x / CS;   // output tiles are dealt to clusters
   const int tiles_mn = p.tiles_m * p.tiles_n;
   const int kb0 = split * p.kb_per_split;
   const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -228,19 +255,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }   // only NACC are used
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), PAIR ? 8 : 4); }   // only NACC are used
     mbar_init(part_full_bar, (uint32_t)S);
     mbar_init(read_done_bar, (uint32_t)S);
     for (int w = 0; w < 4; ++w) { mbar_init(res_bar(w, 0), 1); mbar_init(res_bar(w, 1), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (S > 1) cluster_sync_all();        // every CTA's barriers are initialised before any remote arrive
+  if (S > 1 || PAIR) cluster_sync_all();        // every CTA's barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -250,7 +282,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int stage = 0; uint32_t phase = 0;
       uint32_t cl_phase = 0;
       for (int unit = unit0; unit < tiles_mn; unit += unit_stride) {
-        const int m0 = (unit / p.tiles_n) * BM, n0 = (unit % p.tiles_n) * BN;
+        const int m0 = (unit / p.tiles_n) * TILE_M + pair_rank * BM;           // this CTA's 128 rows of A
+        const int n0 = (unit % p.tiles_n) * BN + pair_rank * Cfg::CTA_N;       // this CTA's share of the B tile
         if (S > 1 && unit != unit0) {     // the stage buffers held the previous tile's partial: wait until read
           mbar_wait_cluster(read_done_bar, cl_phase);
           cl_phase ^= 1u;
@@ -259,31 +292,44 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + Cfg::A_BYTES;
-          mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          // PAIR: both CTAs' copies complete on the LEADER's barrier, which expects the bytes of both
+          const uint32_t fbar = PAIR ? mapa_u32(full_bar(stage), 0u) : full_bar(stage);
+          if (!PAIR) mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          else if (pair_rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
           const bool second = kb >= p.kb_a1;
           const CUtensorMap* ma = second ? &tmA2 : &tmA;
           const int ka = (second ? kb - p.kb_a1 : kb) * BK;
-          if (A_MN) {
+          if (PAIR) {
+            tma_load_2d_pair(sa, ma, ka, m0, fbar);
+            if (B_MN) {
 #pragma unroll
-            for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * 8192, ma, m0 + c * 64, ka, full_bar(stage));
+              for (int c = 0; c < Cfg::CTA_N / 64; ++c) tma_load_2d_pair(sb + c * 8192, &tmB, n0 + c * 64, kb * BK, fbar);
+            } else {
+              tma_load_2d_pair(sb, &tmB, kb * BK, n0, fbar);
+            }
           } else {
-            tma_load_2d(sa, ma, ka, m0, full_bar(stage));
-          }
-          if (B_MN) {
+            if (A_MN) {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * 8192, &tmB, n0 + c * 64, kb * BK, full_bar(stage));
-          } else {
-            tma_load_2d(sb, &tmB, kb * BK, n0, full_bar(stage));
+              for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * 8192, ma, m0 + c * 64, ka, full_bar(stage));
+            } else {
+              tma_load_2d(sa, ma, ka, m0, full_bar(stage));
+            }
+            if (B_MN) {
+#pragma unroll
+              for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * 8192, &tmB, n0 + c * 64, kb * BK, full_bar(stage));
+            } else {
+              tma_load_2d(sb, &tmB, kb * BK, n0, full_bar(stage));
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
+    if (lane == 0 && pair_rank == 0) {
+      // ===================== MMA issuer (the leader CTA only in PAIR mode) =====================
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
-                                 ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                                 ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
       // ones operand: K-major, 16 "n" rows, SWIZZLE_128B atoms of 8 rows x 128 B
       constexpr uint32_t idesc_ones = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
                                       ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -292,7 +338,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int acc = 0; uint32_t acc_phase = 0;
       for (int unit = unit0; unit < tiles_mn; unit += unit_stride) {
         const bool cs = colsum_on && (unit % p.tiles_n) == 0;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        if (PAIR) mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);     // 4 local + 4 remote epilogue warps
+        else mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         const uint32_t cs_tmem = tmem_base + (uint32_t)(Cfg::NACC * BN + acc * 16);
@@ -306,11 +353,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // K-major: advance 32 bytes inside the 128B swizzle row; MN-major: advance 16 rows of 128B
             const uint64_t ad = A_MN ? make_sdesc(sa + k * (UMMA_K * 128), 8192, 1024) : make_sdesc(sa + k * (UMMA_K * 2), 0, 1024);
             const uint64_t bd = B_MN ? make_sdesc(sb + k * (UMMA_K * 128), 8192, 1024) : make_sdesc(sb + k * (UMMA_K * 2), 0, 1024);
-            tc_mma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (PAIR) tc_mma_bf16_pair(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else tc_mma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             if (cs) tc_mma_bf16(cs_tmem, ad, ones_desc, idesc_ones, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          tc_commit(empty_bar(stage));                 // frees the smem slot when these MMAs retire
-          if (kb == kb1 - 1) tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+          if (PAIR) {                                    // both CTAs' slots / accumulators are released together
+            tc_commit_pair(empty_bar(stage));
+            if (kb == kb1 - 1) tc_commit_pair(tfull_bar(acc));
+          } else {
+            tc_commit(empty_bar(stage));                 // frees the smem slot when these MMAs retire
+            if (kb == kb1 - 1) tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1u; }
@@ -326,7 +379,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     float* part = reinterpret_cast<float*>(smem_al);   // [BM][PART_LD] fp32 + [BM] colsum (split-K only)
     float* part_cs = part + BM * Cfg::PART_LD;
     for (int unit = unit0; unit < tiles_mn; unit += unit_stride) {
-      const int m0 = (unit / p.tiles_n) * BM, n0 = (unit % p.tiles_n) * BN;
+      const int m0 = (unit / p.tiles_n) * TILE_M + pair_rank * BM, n0 = (unit % p.tiles_n) * BN;
       // stage this tile's bias slice in shared memory while the main loop is still running
       float* bs = bias_s + acc * BN;
       if (p.bias) {
@@ -506,7 +559,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_remote(mapa_u32(tempty_bar(acc), 0u));   // the leader's MMA warp owns the accumulators
+          else mbar_arrive(tempty_bar(acc));
+        }
         if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1u; }
         continue;
       }
@@ -587,7 +643,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_remote(mapa_u32(tempty_bar(acc), 0u));
+        else mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1u; }
     }
     if (p.tma_epi && lane == 0) tma_store_wait_all();  // bulk stores read shared memory: drain before exit
@@ -595,9 +654,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();         // the peer's shared memory / TMEM and the leader's barriers stay valid until both are done
   if (warp == 1) {
     __syncwarp();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
   }
 }
 
@@ -682,9 +743,10 @@ bool gemm_bf16_sm100_supported(const GemmDesc& d) {
 
 int gemm_tc_max_clusters(int size);
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool PAIR = false>
 static int launch_gemm(const GemmDesc& d, int splits_req, cudaStream_t s) {
-  using Cfg = GemmCfg<BN, A_MN, B_MN>;
+  using Cfg = GemmCfg<BN, A_MN, B_MN, PAIR>;
+  constexpr int TILE_M = PAIR ? 2 * BM : BM;
   CUtensorMap tmA, tmA2, tmB;
   // K-major operand [rows, K]: inner = K, outer = rows, box = {64, rows_tile}
   // MN-major operand [K, mn]: inner = mn, outer = K, box = {64, 64}
@@ -694,14 +756,15 @@ static int launch_gemm(const GemmDesc& d, int splits_req, cudaStream_t s) {
   else tmA2 = tmA;
   const int64_t Kt = d.K + (d.A2 ? d.K2 : 0);
   if (B_MN) { if (!make_map(&tmB, d.B, d.N, Kt, d.ldb, 64, BK)) return MMSA_ERR_CUDA; }
-  else      { if (!make_map(&tmB, d.B, Kt, d.N, d.ldb, BK, BN)) return MMSA_ERR_CUDA; }
+  else      { if (!make_map(&tmB, d.B, Kt, d.N, d.ldb, BK, Cfg::CTA_N)) return MMSA_ERR_CUDA; }
 
   GemmParams p{};
   p.M = (int)d.M; p.N = (int)d.N;
   p.kb_a1 = (int)ceil_div(d.K, BK);
   p.kb_total = p.kb_a1 + (d.A2 ? (int)ceil_div(d.K2, BK) : 0);
-  p.tiles_m = (int)ceil_div(d.M, BM); p.tiles_n = (int)ceil_div(d.N, BN);
+  p.tiles_m = (int)ceil_div(d.M, TILE_M); p.tiles_n = (int)ceil_div(d.N, BN);
   int splits = splits_req < 1 ? 1 : splits_req;
+  if (PAIR) splits = 1;
   if (splits > kMaxClusterSplits) splits = kMaxClusterSplits;
   if (splits > p.kb_total) splits = p.kb_total;
   // split-K runs as a cluster and sums fp32 partials through distributed shared memory: plain fp32 output only
@@ -728,7 +791,7 @@ static int launch_gemm(const GemmDesc& d, int splits_req, cudaStream_t s) {
     if (!Cfg::COLSUM_OK) { set_error("mmsa: internal: colsum requested on a tile shape without TMEM room (BN=%d)", BN); return MMSA_ERR_ARG; }
     p.colsum = d.colsum;
   }
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, PAIR>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -738,7 +801,21 @@ static int launch_gemm(const GemmDesc& d, int splits_req, cudaStream_t s) {
   const int tiles_mn = p.tiles_m * p.tiles_n;
   char nm[48];
   snprintf(nm, sizeof(nm), "gemm_tc_%c%c_%lldx%lldx%lld", A_MN ? 'm' : 'k', B_MN ? 'm' : 'k', (long long)d.M, (long long)d.N, (long long)Kt);
-  if (p.splits == 1) {
+  if (PAIR) {
+    // CTA pairs (cluster of 2 = the two SMs of a TPC), persistent over the 256 x BN tiles
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = s;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const int max_pairs = gemm_tc_max_clusters(2);
+    const int npairs = tiles_mn < max_pairs ? tiles_mn : max_pairs;
+    cfg.gridDim = dim3((unsigned)(npairs * 2));
+    ProfScope prof(nm, s, 2.0 * (double)d.M * (double)d.N * (double)Kt);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmB, tmC, tmR, p);
+    if (e != cudaSuccess) { set_error("mmsa: 2-CTA launch of gemm_tcgen05_kernel failed: %s", cudaGetErrorString(e)); return MMSA_ERR_CUDA; }
+  } else if (p.splits == 1) {
     int grid = tiles_mn < num_sms() ? tiles_mn : num_sms();
     ProfScope prof(nm, s, 2.0 * (double)d.M * (double)d.N * (double)Kt);
     kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, s>>>(tmA, tmA2, tmB, tmC, tmR, p);
@@ -776,8 +853,19 @@ static int pick_bn(int64_t N, bool need_colsum) {
 int gemm_tc_bn(int64_t N, bool need_colsum) { return pick_bn(N, need_colsum); }
 int gemm_tc_max_clusters(int size);
 
+// 2-CTA tiles (256 x 256) for the big activation GEMMs (forward, dgrad): enough rows for every CTA pair of the
+// chip to get several tiles, and an output wide enough for the 256-column tile.  bn < 0 forces the 1-CTA kernel (probe).
+static bool use_pair(const GemmDesc& d, int splits, int bn) {
+  return bn == 0 && splits <= 1 && !d.a_mn_major && d.colsum == nullptr && d.M >= 4096 && d.N >= 512 &&
+         (d.N % 256 == 0 || d.N >= 1024);
+}
+
 template <bool A_MN, bool B_MN>
 static int dispatch_bn(const GemmDesc& d, int splits, int bn, cudaStream_t s) {
+  if constexpr (!A_MN) {
+    if (use_pair(d, splits, bn)) return launch_gemm<256, A_MN, B_MN, true>(d, splits, s);
+  }
+  if (bn < 0) bn = 0;
   switch (bn > 0 ? bn : pick_bn(d.N, d.colsum != nullptr)) {
     case 64: return launch_gemm<64, A_MN, B_MN>(d, splits, s);
     case 128: return launch_gemm<128, A_MN, B_MN>(d, splits, s);
@@ -796,7 +884,7 @@ int gemm_tc_max_clusters(int size) {
   if (size > kMaxClusterSplits) size = kMaxClusterSplits;
   if (size == 1) return num_sms();
   if (cache[size] == 0) {
-    auto kern = gemm_tcgen05_kernel<192, true, true>;
+    auto kern = gemm_tcgen05_kernel<192, true, true, false>;
     using Cfg = GemmCfg<192, true, true>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     cudaLaunchConfig_t cfg{};

@@ -189,10 +189,14 @@ gate_ln_bwd_kernel(int64_t M, int E, const T* __restrict__ dy, int64_t dy_rows_p
 
 // ------------------------------------------------------------------ gate + blend + LayerNorm + token mean-pool
 // A block whose output only feeds a token mean-pool (the re-skinned path: t' and v' are pooled right
-// away) never needs y[M,E] in HBM: one CTA per sample walks the sample's L rows (one warp per row),
-// keeps LN(u) in fp32 registers and accumulates the pooled sums -- so the pooled features carry no
-// bf16 rounding -- and pools the query stream q on the way (the raw-feature slot, MultimodalModel.py:299).
-// F = fp32 values per lane (E <= 32*F); registers are budgeted for two 256-thread CTAs per SM.
+// away) never needs y[M,E] in HBM: LN(u) stays in fp32 registers and only the pooled sums are written --
+// so the pooled features carry no bf16 rounding -- and the query stream q is pooled on the way (the
+// raw-feature slot, MultimodalModel.py:299).
+// Both directions are HBM-bound streams of 1.5 KB rows.  Each warp owns a ring of shared-memory row
+// slots filled by 1-D bulk async copies (cp.async.bulk, the TMA engine; completion on a per-slot
+// mbarrier): the rows two steps ahead are already in flight while a row is being reduced, so the
+// memory system always sees several KB outstanding per warp instead of one synchronous row.
+// F = fp32 values per lane (E <= 32*F).
 template <typename T> __device__ __forceinline__ void unpack_vec(const uint4& r, float* out);
 template <> __device__ __forceinline__ void unpack_vec<float>(const uint4& r, float* out) {
   out[0] = __uint_as_float(r.x); out[1] = __uint_as_float(r.y); out[2] = __uint_as_float(r.z); out[3] = __uint_as_float(r.w);
@@ -202,14 +206,45 @@ template <> __device__ __forceinline__ void unpack_vec<bf16>(const uint4& r, flo
 #pragma unroll
   for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); out[2 * i] = f.x; out[2 * i + 1] = f.y; }
 }
-__device__ __forceinline__ uint4 ldg_stream(const void* p) {       // streamed once: do not keep in L1
+
+// sigmoid for the gate: exact expf/division in fp32 storage (1e-5 parity mode); ex2.approx + rcp.approx when the
+// result is rounded to bf16 anyway (2^-22 relative error against a 2^-9 rounding step)
+template <typename T> __device__ __forceinline__ float gate_sigmoid(float x) { return sigmoidf_(x); }
+template <> __device__ __forceinline__ float gate_sigmoid<bf16>(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+
+// row slots per warp (prefetch depth): two for bf16 rows; fp32 rows (parity mode) are twice as large and get one
+template <typename T> struct PipeStages { static constexpr int N = sizeof(T) == 2 ? 2 : 1; };
+
+__device__ __forceinline__ uint32_t rp_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rp_bar_init(uint32_t bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+}
+__device__ __forceinline__ void rp_expect(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void rp_copy(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void rp_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ uint4 rp_lds(uint32_t addr) {
   uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
   return r;
 }
 
+// shared-memory layout of the two pooled kernels:
+//   [0, 2E floats)                 gamma, beta (fwd) / gamma (bwd)
+//   [vec_bytes, +64)               kRowWarps * kPipeStages mbarriers
+//   [.., + warps*stages*NS*row)    row slots; after the main loop the same bytes hold the cross-warp reduction
 template <typename T, int F>
-__global__ void __launch_bounds__(kRowWarps * 32, 2)
+__global__ void __launch_bounds__(kRowWarps * 32, (sizeof(T) == 2 ? 2 : 1))
 gate_ln_pool_fwd_kernel(int L, int E, const T* __restrict__ gate_pre, const T* __restrict__ q,
                         const T* __restrict__ attn, const float* __restrict__ gamma,
                         const float* __restrict__ beta, float eps, T* __restrict__ g_out,
@@ -217,29 +252,47 @@ gate_ln_pool_fwd_kernel(int L, int E, const T* __restrict__ gate_pre, const T* _
                         float* __restrict__ pooled_y, float* __restrict__ pooled_q, T* __restrict__ pooled_q_lp) {
   constexpr int VN = VecN<T>::N;
   constexpr int NV = F / VN;
-  extern __shared__ float sm_f[];          // gamma[E], beta[E], red[kRowWarps][E]
-  float* gm_s = sm_f; float* bt_s = sm_f + E; float* red = sm_f + 2 * E;
+  constexpr int NS = 3;                               // streams: gate_pre, q, attn
+  constexpr int kPipeStages = PipeStages<T>::N;
+  extern __shared__ __align__(128) uint8_t sm_raw[];
+  float* gm_s = reinterpret_cast<float*>(sm_raw);
+  float* bt_s = gm_s + E;
+  const uint32_t row_bytes = (uint32_t)E * sizeof(T);
+  const uint32_t bar0 = rp_smem_u32(sm_raw) + 2u * E * 4u;
+  uint8_t* slots = sm_raw + 2 * E * 4 + 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t b = blockIdx.x;
   const int nvec = E / VN;
+  const uint32_t wslot = rp_smem_u32(slots) + (uint32_t)warp * kPipeStages * NS * row_bytes;
+  const uint32_t wbar = bar0 + (uint32_t)warp * kPipeStages * 8u;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kPipeStages; ++s) rp_bar_init(wbar + 8u * s);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   for (int c = threadIdx.x; c < E; c += blockDim.x) { gm_s[c] = gamma[c]; bt_s[c] = beta[c]; }
   __syncthreads();
+  const int nrows = warp < L ? (L - warp + kRowWarps - 1) / kRowWarps : 0;
+  auto issue = [&](int k) {
+    const int s = k % kPipeStages;
+    const int64_t base = (b * L + warp + (int64_t)k * kRowWarps) * (int64_t)E;
+    const uint32_t dst = wslot + (uint32_t)s * NS * row_bytes, bar = wbar + 8u * s;
+    rp_expect(bar, NS * row_bytes);
+    rp_copy(dst, gate_pre + base, row_bytes, bar);
+    rp_copy(dst + row_bytes, q + base, row_bytes, bar);
+    rp_copy(dst + 2 * row_bytes, attn + base, row_bytes, bar);
+  };
+  if (lane == 0)
+    for (int k = 0; k < kPipeStages && k < nrows; ++k) issue(k);
   float ysum[F], qsum[F];
 #pragma unroll
   for (int i = 0; i < F; ++i) { ysum[i] = 0.f; qsum[i] = 0.f; }
-  for (int l = warp; l < L; l += kRowWarps) {
-    const int64_t row = b * L + l;
+  for (int k = 0; k < nrows; ++k) {
+    const int s = k % kPipeStages;
+    const int64_t row = b * L + warp + (int64_t)k * kRowWarps;
     const int64_t base = row * (int64_t)E;
-    uint4 rg[NV], rq[NV], ra[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int v = lane + 32 * i;
-      if (v < nvec) {
-        rg[i] = ldg_stream(gate_pre + base + v * VN);
-        rq[i] = ldg_stream(q + base + v * VN);
-        ra[i] = ldg_stream(attn + base + v * VN);
-      }
-    }
+    const uint32_t src = wslot + (uint32_t)s * NS * row_bytes;
+    rp_wait(wbar + 8u * s, (uint32_t)(k / kPipeStages) & 1u);
     float u[F];
     float sum = 0.f;
 #pragma unroll
@@ -247,10 +300,12 @@ gate_ln_pool_fwd_kernel(int L, int E, const T* __restrict__ gate_pre, const T* _
       const int v = lane + 32 * i;
       if (v < nvec) {
         float gp[VN], qv[VN], av[VN], gv[VN];
-        unpack_vec<T>(rg[i], gp); unpack_vec<T>(rq[i], qv); unpack_vec<T>(ra[i], av);
+        unpack_vec<T>(rp_lds(src + v * 16), gp);
+        unpack_vec<T>(rp_lds(src + row_bytes + v * 16), qv);
+        unpack_vec<T>(rp_lds(src + 2 * row_bytes + v * 16), av);
 #pragma unroll
         for (int j = 0; j < VN; ++j) {
-          const float g = round_to<T>(sigmoidf_(gp[j]));
+          const float g = round_to<T>(gate_sigmoid<T>(gp[j]));
           gv[j] = g;
           const float uu = g * qv[j] + (1.f - g) * av[j];
           u[i * VN + j] = uu;
@@ -263,6 +318,8 @@ gate_ln_pool_fwd_kernel(int L, int E, const T* __restrict__ gate_pre, const T* _
         for (int j = 0; j < VN; ++j) u[i * VN + j] = 0.f;
       }
     }
+    __syncwarp();                                        // every lane has read the slot: refill it
+    if (lane == 0 && k + kPipeStages < nrows) issue(k + kPipeStages);
     const float mean = warp_sum(sum) / (float)E;
     float sq = 0.f;
 #pragma unroll
@@ -287,7 +344,9 @@ gate_ln_pool_fwd_kernel(int L, int E, const T* __restrict__ gate_pre, const T* _
       }
     }
   }
-  // cross-warp sums in a fixed order (deterministic), then the two pooled rows of this sample
+  // cross-warp sums in a fixed order (deterministic), then the two pooled rows of this sample;
+  // the reduction buffer reuses the row slots (all copies have landed and been consumed by now)
+  float* red = reinterpret_cast<float*>(slots);
   const float invL = 1.f / (float)L;
   for (int pass = 0; pass < 2; ++pass) {
     if (pass == 1 && pooled_q == nullptr && pooled_q_lp == nullptr) break;
@@ -317,11 +376,14 @@ gate_ln_pool_fwd_kernel(int L, int E, const T* __restrict__ gate_pre, const T* _
 
 // backward of gate_ln_pool_fwd.  dy of every row of sample b is dpooled_y[b,:] / L; the gradient w.r.t.
 // the pooled query stream (dpooled_q[b,:] / L) and an optional per-row extra gradient dq_add are folded
-// into dq_part, so no [M,E] broadcast is ever materialised.  One warp per row; g, q, attn are read
-// from HBM once and kept packed in registers between the statistics pass and the output pass.
+// into dq_part, so no [M,E] broadcast is ever materialised.  Each warp owns a CONTIGUOUS range of rows,
+// so the per-sample vectors (dy * gamma) live in registers and change at most every L rows; g, q, attn
+// (and dq_add) arrive through the warp's bulk-copy ring.  dgamma[c] = sum_b dy[b,c] * sum_{rows of b} xhat[row,c]
+// is accumulated per lane and reduced over blocks by reduce_pool_partials_kernel, which also forms
+// dbeta[c] = sum_b dpooled_y[b,c] (every row of a sample carries dpooled_y / L).
 template <typename T, int F>
 __global__ void __launch_bounds__(kRowWarps * 32, (sizeof(T) == 2 ? 2 : 1))
-gate_ln_pool_bwd_kernel(int64_t M, int L, int E, const float* __restrict__ dpooled_y,
+gate_ln_pool_bwd_kernel(int64_t M, int L, int E, int64_t rows_per_warp, const float* __restrict__ dpooled_y,
                         const float* __restrict__ dpooled_q, const T* __restrict__ dq_add,
                         const T* __restrict__ g, const T* __restrict__ q, const T* __restrict__ attn,
                         const float* __restrict__ gamma, const float* __restrict__ mean,
@@ -329,66 +391,136 @@ gate_ln_pool_bwd_kernel(int64_t M, int L, int E, const float* __restrict__ dpool
                         T* __restrict__ dgate_pre, float* __restrict__ partials /* [gridDim.x, 2, E] */) {
   constexpr int VN = VecN<T>::N;
   constexpr int NV = F / VN;
+  extern __shared__ __align__(128) uint8_t sm_raw[];
+  float* gm_s = reinterpret_cast<float*>(sm_raw);
+  const uint32_t row_bytes = (uint32_t)E * sizeof(T);
+  const uint32_t bar0 = rp_smem_u32(sm_raw) + 2u * E * 4u;
+  uint8_t* slots = sm_raw + 2 * E * 4 + 128;
+  const int NS = dq_add != nullptr ? 4 : 3;           // streams: g, q, attn (, dq_add)
+  constexpr int kPipeStages = PipeStages<T>::N;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nvec = E / VN;
-  float dgam[F], dbet[F];
+  const uint32_t wslot = rp_smem_u32(slots) + (uint32_t)warp * kPipeStages * NS * row_bytes;
+  const uint32_t wbar = bar0 + (uint32_t)warp * kPipeStages * 8u;
+  if (lane == 0) {
 #pragma unroll
-  for (int i = 0; i < F; ++i) { dgam[i] = 0.f; dbet[i] = 0.f; }
+    for (int s = 0; s < kPipeStages; ++s) rp_bar_init(wbar + 8u * s);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int c = threadIdx.x; c < E; c += blockDim.x) gm_s[c] = gamma[c];
+  __syncthreads();
+  const int64_t gw = (int64_t)blockIdx.x * kRowWarps + warp;
+  const int64_t r0 = gw * rows_per_warp;
+  const int64_t r1 = r0 + rows_per_warp < M ? r0 + rows_per_warp : M;
+  const int nrows = r1 > r0 ? (int)(r1 - r0) : 0;
+  auto issue = [&](int k) {
+    const int s = k % kPipeStages;
+    const int64_t base = (r0 + k) * (int64_t)E;
+    const uint32_t dst = wslot + (uint32_t)s * NS * row_bytes, bar = wbar + 8u * s;
+    rp_expect(bar, NS * row_bytes);
+    rp_copy(dst, g + base, row_bytes, bar);
+    rp_copy(dst + row_bytes, q + base, row_bytes, bar);
+    rp_copy(dst + 2 * row_bytes, attn + base, row_bytes, bar);
+    if (NS == 4) rp_copy(dst + 3 * row_bytes, dq_add + base, row_bytes, bar);
+  };
+  if (lane == 0)
+    for (int k = 0; k < kPipeStages && k < nrows; ++k) issue(k);
   const float invL = 1.f / (float)L;
-  for (int64_t row = (int64_t)blockIdx.x * kRowWarps + warp; row < M; row += (int64_t)gridDim.x * kRowWarps) {
-    const int64_t base = row * (int64_t)E;
-    const int64_t sb = (row / L) * (int64_t)E;
-    const float mu = mean[row], rs = rstd[row];
-    uint4 rg[NV], rq[NV], ra[NV];
+  float dgv[F], xs[F], dgam[F];      // dy*gamma of the current sample; sum of xhat over its rows; dgamma partial
+#pragma unroll
+  for (int i = 0; i < F; ++i) { dgv[i] = 0.f; xs[i] = 0.f; dgam[i] = 0.f; }
+  float c1 = 0.f;
+  int64_t cur_b = -1;
+  auto flush = [&]() {               // fold the finished sample segment into dgamma
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int v = lane + 32 * i;
       if (v < nvec) {
-        rg[i] = ldg_stream(g + base + v * VN);
-        rq[i] = ldg_stream(q + base + v * VN);
-        ra[i] = ldg_stream(attn + base + v * VN);
+        const float4* src = reinterpret_cast<const float4*>(dpooled_y + cur_b * (int64_t)E + v * VN);
+#pragma unroll
+        for (int h = 0; h < VN / 4; ++h) {
+          const float4 d4 = __ldg(src + h);
+          const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { dgam[i * VN + h * 4 + j] += dv[j] * invL * xs[i * VN + h * 4 + j]; xs[i * VN + h * 4 + j] = 0.f; }
+        }
       }
     }
-    float c1 = 0.f, c2 = 0.f;
+  };
+  for (int k = 0; k < nrows; ++k) {
+    const int s = k % kPipeStages;
+    const int64_t row = r0 + k;
+    const int64_t base = row * (int64_t)E;
+    const int64_t b = row / L;
+    if (b != cur_b) {
+      if (cur_b >= 0) flush();
+      cur_b = b;
+      float s0 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nvec) {
+          const float4* src = reinterpret_cast<const float4*>(dpooled_y + b * (int64_t)E + v * VN);
+#pragma unroll
+          for (int h = 0; h < VN / 4; ++h) {
+            const float4 d4 = __ldg(src + h);
+            const float4 g4 = *reinterpret_cast<const float4*>(gm_s + v * VN + h * 4);
+            dgv[i * VN + h * 4 + 0] = d4.x * invL * g4.x; dgv[i * VN + h * 4 + 1] = d4.y * invL * g4.y;
+            dgv[i * VN + h * 4 + 2] = d4.z * invL * g4.z; dgv[i * VN + h * 4 + 3] = d4.w * invL * g4.w;
+            s0 += dgv[i * VN + h * 4 + 0] + dgv[i * VN + h * 4 + 1] + dgv[i * VN + h * 4 + 2] + dgv[i * VN + h * 4 + 3];
+          }
+        }
+      }
+      c1 = warp_sum(s0) / (float)E;
+    }
+    const float mu = mean[row], rs = rstd[row];
+    const uint32_t src = wslot + (uint32_t)s * NS * row_bytes;
+    rp_wait(wbar + 8u * s, (uint32_t)(k / kPipeStages) & 1u);
+    float c2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int v = lane + 32 * i;
       if (v < nvec) {
         float g8[VN], q8[VN], a8[VN];
-        unpack_vec<T>(rg[i], g8); unpack_vec<T>(rq[i], q8); unpack_vec<T>(ra[i], a8);
+        unpack_vec<T>(rp_lds(src + v * 16), g8);
+        unpack_vec<T>(rp_lds(src + row_bytes + v * 16), q8);
+        unpack_vec<T>(rp_lds(src + 2 * row_bytes + v * 16), a8);
 #pragma unroll
         for (int j = 0; j < VN; ++j) {
-          const int c = v * VN + j;
           const float uu = g8[j] * q8[j] + (1.f - g8[j]) * a8[j];
-          const float x = (uu - mu) * rs;
-          const float d = __ldg(dpooled_y + sb + c) * invL;
-          const float dg_ = d * __ldg(gamma + c);
-          c1 += dg_;
-          c2 += dg_ * x;
-          dgam[i * VN + j] += d * x;
-          dbet[i * VN + j] += d;
+          c2 += dgv[i * VN + j] * ((uu - mu) * rs);
         }
       }
     }
-    c1 = warp_sum(c1) / (float)E;
     c2 = warp_sum(c2) / (float)E;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int v = lane + 32 * i;
       if (v < nvec) {
-        float g8[VN], q8[VN], a8[VN], o1[VN], o2[VN], o3[VN], ad[VN];
-        unpack_vec<T>(rg[i], g8); unpack_vec<T>(rq[i], q8); unpack_vec<T>(ra[i], a8);
-        if (dq_add != nullptr) load_vec<T>(dq_add + base + v * VN, ad);
+        float g8[VN], q8[VN], a8[VN], o1[VN], o2[VN], o3[VN], ex[VN];
+        unpack_vec<T>(rp_lds(src + v * 16), g8);
+        unpack_vec<T>(rp_lds(src + row_bytes + v * 16), q8);
+        unpack_vec<T>(rp_lds(src + 2 * row_bytes + v * 16), a8);
+        if (NS == 4) unpack_vec<T>(rp_lds(src + 3 * row_bytes + v * 16), ex);
+        else {
+#pragma unroll
+          for (int j = 0; j < VN; ++j) ex[j] = 0.f;
+        }
+        if (dpooled_q != nullptr) {
+          const float4* dq4 = reinterpret_cast<const float4*>(dpooled_q + b * (int64_t)E + v * VN);
+#pragma unroll
+          for (int h = 0; h < VN / 4; ++h) {
+            const float4 t4 = __ldg(dq4 + h);
+            ex[h * 4 + 0] += t4.x * invL; ex[h * 4 + 1] += t4.y * invL; ex[h * 4 + 2] += t4.z * invL; ex[h * 4 + 3] += t4.w * invL;
+          }
+        }
 #pragma unroll
         for (int j = 0; j < VN; ++j) {
-          const int c = v * VN + j;
           const float gg = g8[j];
           const float x = (gg * q8[j] + (1.f - gg) * a8[j] - mu) * rs;
-          const float dg_ = __ldg(dpooled_y + sb + c) * invL * __ldg(gamma + c);
-          const float du = rs * (dg_ - c1 - x * c2);
-          float extra = dpooled_q != nullptr ? __ldg(dpooled_q + sb + c) * invL : 0.f;
-          if (dq_add != nullptr) extra += ad[j];
-          o1[j] = du * gg + extra;
+          const float du = rs * (dgv[i * VN + j] - c1 - x * c2);
+          xs[i * VN + j] += x;
+          o1[j] = du * gg + ex[j];
           o2[j] = du * (1.f - gg);
           o3[j] = du * (q8[j] - a8[j]) * gg * (1.f - gg);
         }
@@ -397,39 +529,56 @@ gate_ln_pool_bwd_kernel(int64_t M, int L, int E, const float* __restrict__ dpool
         store_vec<T>(dgate_pre + base + v * VN, o3);
       }
     }
+    __syncwarp();                                        // every lane has read the slot: refill it
+    if (lane == 0 && k + kPipeStages < nrows) issue(k + kPipeStages);
   }
-  __shared__ float red[kRowWarps][2][32];
+  if (cur_b >= 0) flush();
+  // block partial of dgamma: cross-warp sum in warp order through the (now idle) row slots
+  float* red = reinterpret_cast<float*>(slots);
+  __syncthreads();
 #pragma unroll
-  for (int i = 0; i < F; ++i) {
-    __syncthreads();
-    red[warp][0][lane] = dgam[i];
-    red[warp][1][lane] = dbet[i];
-    __syncthreads();
-    if (warp == 0) {
-      float a = 0.f, b = 0.f;
+  for (int i = 0; i < NV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
 #pragma unroll
-      for (int w = 0; w < kRowWarps; ++w) { a += red[w][0][lane]; b += red[w][1][lane]; }
-      const int v = lane + 32 * (i / VN);
-      const int c = v * VN + (i % VN);
-      if (v < nvec) {
-        partials[((int64_t)blockIdx.x * 2 + 0) * E + c] = a;
-        partials[((int64_t)blockIdx.x * 2 + 1) * E + c] = b;
-      }
+      for (int j = 0; j < VN; ++j) red[warp * E + v * VN + j] = dgam[i * VN + j];
     }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < E; c += blockDim.x) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < kRowWarps; ++w) a += red[w * E + c];
+    partials[((int64_t)blockIdx.x * 2 + 0) * E + c] = a;
   }
 }
 
-__global__ void reduce_partials_kernel(const float* __restrict__ partials, int64_t nblk, int E,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= E) return;
+// dgamma[c] = sum_k partials[k,0,c], dbeta[c] = sum_k partials[k,1,c]; 32 columns x 8 k-slices per block,
+// k-slices combined in slice order (deterministic).  dbeta_src (pooled form): dbeta[c] = sum_b dbeta_src[b,c].
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float* __restrict__ partials, int64_t nblk, int E, const float* __restrict__ dbeta_src,
+                       int64_t nb, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ float red[2][8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
   float a = 0.f, b = 0.f;
-  for (int64_t k = 0; k < nblk; ++k) {
-    a += partials[(k * 2 + 0) * E + c];
-    b += partials[(k * 2 + 1) * E + c];
+  if (c < E) {
+    for (int64_t k = ty; k < nblk; k += 8) {
+      a += partials[(k * 2 + 0) * E + c];
+      if (dbeta_src == nullptr) b += partials[(k * 2 + 1) * E + c];
+    }
+    if (dbeta_src != nullptr)
+      for (int64_t k = ty; k < nb; k += 8) b += dbeta_src[k * E + c];
   }
-  dgamma[c] = a;
-  dbeta[c] = b;
+  red[0][ty][tx] = a; red[1][ty][tx] = b;
+  __syncthreads();
+  if (ty == 0 && c < E) {
+    float sa = 0.f, sb = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sa += red[0][k][tx]; sb += red[1][k][tx]; }
+    dgamma[c] = sa;
+    dbeta[c] = sb;
+  }
 }
 
 // ------------------------------------------------------------------ token pooling
@@ -674,7 +823,7 @@ int mmsa_gate_ln_bwd(int dtype, int64_t M, int64_t E, const void* dy, int64_t dy
       M, (int)E, (const T*)dy, dy_rows_per_sample, (const T*)g, (const T*)q, (const T*)attn, gamma, mean, rstd,
       (const T*)dq_bcast, bcast_rows, (const T*)dq_add, (T*)dq_part, (T*)dattn_part, (T*)dgate_pre, partials)));
   MMSA_LAUNCH_CHECK("gate_ln_bwd_kernel");
-  reduce_partials_kernel<<<(unsigned)ceil_div(E, 128), 128, 0, s>>>(partials, nblk, (int)E, dgamma, dbeta);
+  reduce_partials_kernel<<<(unsigned)ceil_div(E, 32), 256, 0, s>>>(partials, nblk, (int)E, nullptr, 0, dgamma, dbeta);
   MMSA_LAUNCH_CHECK("reduce_partials_kernel");
   return MMSA_OK;
 }
@@ -690,10 +839,14 @@ int mmsa_gate_ln_pool_fwd(int dtype, int64_t B, int64_t L, int64_t E, const void
   if (B == 0) return MMSA_OK;
   cudaStream_t s = (cudaStream_t)stream;
   ProfScope prof("gate_ln_pool_fwd", s, (double)B * L * E * (dtype == MMSA_F32 ? 4 : 2) * 4.0);
-  const size_t smem = (size_t)(2 + kRowWarps) * E * sizeof(float);
+  MMSA_REQUIRE(((uintptr_t)gate_pre | (uintptr_t)q | (uintptr_t)attn | (uintptr_t)g_out) % 16 == 0,
+               "mmsa_gate_ln_pool_fwd: operands must be 16-byte aligned");
 #define MMSA_GLP_FWD(F_)                                                                                        \
   MMSA_DISPATCH_DTYPE(dtype, T, {                                                                               \
     auto kfn = gate_ln_pool_fwd_kernel<T, F_>;                                                                  \
+    size_t slots = (size_t)kRowWarps * PipeStages<T>::N * 3 * E * sizeof(T);                                    \
+    size_t red = (size_t)kRowWarps * E * sizeof(float);                                                         \
+    size_t smem = (size_t)2 * E * sizeof(float) + 128 + (slots > red ? slots : red);                            \
     cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
     kfn<<<(unsigned)B, kRowWarps * 32, smem, s>>>((int)L, (int)E, (const T*)gate_pre, (const T*)q, (const T*)attn, \
                                                   gamma, beta, eps, (T*)g_out, mean, rstd, pooled_y, pooled_q,   \
@@ -716,16 +869,28 @@ int mmsa_gate_ln_pool_bwd(int dtype, int64_t B, int64_t L, int64_t E, const floa
   MMSA_REQUIRE_DEVICE();
   MMSA_REQUIRE(E % 8 == 0 && E <= 1024 && E > 0, "mmsa_gate_ln_pool_bwd: E=%lld must be a multiple of 8 and <= 1024", (long long)E);
   MMSA_REQUIRE(L > 0 && L < (1 << 30) && dpooled_y != nullptr, "mmsa_gate_ln_pool_bwd: bad arguments");
+  MMSA_REQUIRE(((uintptr_t)g | (uintptr_t)q | (uintptr_t)attn | (uintptr_t)dq_add | (uintptr_t)dq_part | (uintptr_t)dattn_part |
+                (uintptr_t)dgate_pre | (uintptr_t)dpooled_y | (uintptr_t)dpooled_q) % 16 == 0,
+               "mmsa_gate_ln_pool_bwd: operands must be 16-byte aligned");
   if (B == 0) return MMSA_OK;
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t M = B * L;
   int64_t nblk = mmsa_gate_ln_bwd_blocks(M);
   {
     ProfScope prof("gate_ln_pool_bwd", s, (double)M * E * (dtype == MMSA_F32 ? 4 : 2) * (dq_add ? 7.0 : 6.0));
+    const int64_t rpw = ceil_div(M, nblk * kRowWarps);
+    const int ns = dq_add ? 4 : 3;
 #define MMSA_GLP_BWD(F_)                                                                                        \
-  MMSA_DISPATCH_DTYPE(dtype, T, (gate_ln_pool_bwd_kernel<T, F_><<<(unsigned)nblk, kRowWarps * 32, 0, s>>>(       \
-      M, (int)L, (int)E, dpooled_y, dpooled_q, (const T*)dq_add, (const T*)g, (const T*)q, (const T*)attn, gamma, \
-      mean, rstd, (T*)dq_part, (T*)dattn_part, (T*)dgate_pre, partials)))
+  MMSA_DISPATCH_DTYPE(dtype, T, {                                                                               \
+    auto kfn = gate_ln_pool_bwd_kernel<T, F_>;                                                                  \
+    size_t slots = (size_t)kRowWarps * PipeStages<T>::N * ns * E * sizeof(T);                                   \
+    size_t red = (size_t)kRowWarps * E * sizeof(float);                                                         \
+    size_t smem = (size_t)2 * E * sizeof(float) + 128 + (slots > red ? slots : red);                            \
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
+    kfn<<<(unsigned)nblk, kRowWarps * 32, smem, s>>>(                                                           \
+      M, (int)L, (int)E, rpw, dpooled_y, dpooled_q, (const T*)dq_add, (const T*)g, (const T*)q, (const T*)attn, gamma, \
+      mean, rstd, (T*)dq_part, (T*)dattn_part, (T*)dgate_pre, partials);                                        \
+  })
     if (E <= 256) MMSA_GLP_BWD(8);
     else if (E <= 512) MMSA_GLP_BWD(16);
     else if (E <= 768) MMSA_GLP_BWD(24);
@@ -733,7 +898,7 @@ int mmsa_gate_ln_pool_bwd(int dtype, int64_t B, int64_t L, int64_t E, const floa
 #undef MMSA_GLP_BWD
   }
   MMSA_LAUNCH_CHECK("gate_ln_pool_bwd_kernel");
-  reduce_partials_kernel<<<(unsigned)ceil_div(E, 128), 128, 0, s>>>(partials, nblk, (int)E, dgamma, dbeta);
+  reduce_partials_kernel<<<(unsigned)ceil_div(E, 32), 256, 0, s>>>(partials, nblk, (int)E, dpooled_y, B, dgamma, dbeta);
   MMSA_LAUNCH_CHECK("reduce_partials_kernel");
   return MMSA_OK;
 }

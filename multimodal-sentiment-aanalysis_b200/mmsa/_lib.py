@@ -30,6 +30,7 @@ _PROTOS = {
     "mmsa_prof_collect": (I, [P, I, P, P, P, I]),
     "mmsa_cast": (I, [P, I, P, I, L, P]),
     "mmsa_cast_multi": (I, [I, P, P, P, I, I, P]),
+    "mmsa_split3": (I, [P, L, L, L, P, I, P, I, P]),
     "mmsa_linear_fwd": (I, [I, L, L, L, L, P, L, P, L, P, L, P, P, L, I, P, L, I, P]),
     "mmsa_debug_gemm": (I, [I, I, L, L, L, P, L, P, L, P, L, I, I, P]),
     "mmsa_linear_dgrad": (I, [I, L, L, L, P, L, P, L, P, L, P, L, I, P]),

@@ -55,7 +55,7 @@ def gather_labels(labels: Tensor, group=None) -> Tensor:
     return out
 
 
-def sharded_infonce(f1: Tensor, f2: Tensor, labels: Tensor, temperature, group=None) -> Tensor:
+def sharded_infonce(f1: Tensor, f2: Tensor, labels: Tensor, temperature, group=None, fast: bool = False) -> Tensor:
     """InfoNCE (MultimodalModel.py:232-260) over the GLOBAL batch with rows sharded by rank:
     this rank owns rows [rank*B, (rank+1)*B) of the B_g x B_g similarity matrix and all its columns.
     Returns the local mean over this rank's rows; averaging parameter gradients over ranks then
@@ -64,7 +64,7 @@ def sharded_infonce(f1: Tensor, f2: Tensor, labels: Tensor, temperature, group=N
     rank = dist.get_rank(group)
     f2_all = all_gather_rows(f2, group)
     labels_all = gather_labels(labels, group)
-    return ops.infonce(f1, f2_all, labels, temperature, labels_cols=labels_all, row_offset=rank * f1.shape[0])
+    return ops.infonce(f1, f2_all, labels, temperature, labels_cols=labels_all, row_offset=rank * f1.shape[0], fast=fast)
 
 
 def shard_contrastive(model, group=None):

@@ -48,6 +48,19 @@ def cast(x: Tensor, dtype: torch.dtype) -> Tensor:
     return y
 
 
+def split3(x: Tensor, col_side: Optional[str] = None, row_side: Optional[str] = None):
+    """fp32 [R,C] -> split-bf16 operands (mmsa_split3): col-concatenated [R,3C] and/or row-concatenated [3R,C];
+    side "a" = (hi,hi,lo), side "b" = (hi,lo,hi).  Returns (col or None, row or None)."""
+    _check(x)
+    assert x.dtype == torch.float32 and x.ndim == 2 and x.stride(1) == 1
+    R, C = x.shape
+    col = torch.empty((R, 3 * C), device=x.device, dtype=torch.bfloat16) if col_side else None
+    row = torch.empty((3 * R, C), device=x.device, dtype=torch.bfloat16) if row_side else None
+    call("mmsa_split3", x.data_ptr(), R, C, x.stride(0), _p(col), 1 if col_side == "b" else 0, _p(row),
+         1 if row_side == "b" else 0, _stream())
+    return col, row
+
+
 def linear_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor], *, x2: Optional[Tensor] = None,
                residual: Optional[Tensor] = None, act: int = 0, out_dtype: Optional[torch.dtype] = None,
                out: Optional[Tensor] = None) -> Tensor:

@@ -195,13 +195,14 @@ class MultimodalTransformerModel(nn.Module):
             raw_a, raw_b = f0, fv
             slots = (f0, e1, e2)
             if con_labels is not None:
+                fast = self.compute_dtype == torch.bfloat16      # split-bf16 tensor-core GEMMs (fp32-accurate)
                 if self.dp_group is not None:
                     from . import dist as mdist
-                    contrastive.append(mdist.sharded_infonce(e1, e2, con_labels, self.temperature, self.dp_group))
+                    contrastive.append(mdist.sharded_infonce(e1, e2, con_labels, self.temperature, self.dp_group, fast=fast))
                 else:
-                    contrastive.append(ops.infonce(e1, e2, con_labels, self.temperature))
+                    contrastive.append(ops.infonce(e1, e2, con_labels, self.temperature, fast=fast))
                 if self.contract == "multitask":
-                    contrastive.append(ops.infonce(e2, e1, con_labels, self.temperature))
+                    contrastive.append(ops.infonce(e2, e1, con_labels, self.temperature, fast=fast))
         arousal, valence = self._tail(raw_a, raw_b, slots)
         contrastive = [self.contrastive_weight * c for c in contrastive]     # :315-317 -> shape (1,)
         if self.contract == "single":

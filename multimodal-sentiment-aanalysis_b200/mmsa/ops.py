@@ -625,32 +625,45 @@ class ContrastiveFn(Function):
     """normalize -> cosine block f1n f2n^T -> row reductions (InfoNCE / SupCon / NT-Xent).
     f1:[B,E] local rows, f2:[Bg,E] columns (the gathered global batch under data parallelism).
     The small [B,E] embeddings are processed in fp32 whatever the storage mode: with T=0.01 a bf16
-    cosine (4e-3) would move the scaled logits by 0.4."""
+    cosine (4e-3) would move the scaled logits by 0.4.  `fast` (bf16 performance mode) runs the three
+    GEMMs on the tensor cores with split-bf16 operands (hi.hi + hi.lo + lo.hi over a 3x longer reduction,
+    ~2^-16 relative, fp32 accumulation); otherwise they run on the exact-fp32 CUDA-core GEMM (1e-5 parity mode)."""
 
     @staticmethod
-    def forward(ctx, f1, f2, labels_r, labels_c, temperature, temperature_const, kind, row_offset, denom, same):
+    def forward(ctx, f1, f2, labels_r, labels_c, temperature, temperature_const, kind, row_offset, denom, same, fast):
         a = K.cast(_c(f1.detach()), torch.float32)
         n1, norm1 = K.l2norm_fwd(a)
         if same:
             n2, norm2 = n1, norm1
         else:
             n2, norm2 = K.l2norm_fwd(K.cast(_c(f2.detach()), torch.float32))
-        sim = K.linear_fwd(n1, n2, None, out_dtype=torch.float32)
+        n1_row = n2_row = None
+        if fast:
+            n1_col, n1_row = K.split3(n1, col_side="a", row_side="b")       # A of the forward, B of dn2 = G^T n1
+            n2_col, n2_row = K.split3(n2, col_side="b", row_side="b")       # B of the forward, B of dn1 = G n2
+            sim = K.linear_fwd(n1_col, n2_col, None, out_dtype=torch.float32)
+        else:
+            sim = K.linear_fwd(n1, n2, None, out_dtype=torch.float32)
         tptr = None if temperature is None else temperature.detach().float().view(1)
         loss, stats = K.contrastive_fwd(kind, sim, labels_r, labels_c, tptr, temperature_const, row_offset, denom)
-        ctx.save_for_backward(n1, norm1, n2, norm2, sim, stats, labels_r, labels_c, tptr)
-        ctx.cfg = (temperature_const, kind, row_offset, denom, same, f1.dtype, f2.dtype)
+        ctx.save_for_backward(n1, norm1, n2, norm2, sim, stats, labels_r, labels_c, tptr, n1_row, n2_row)
+        ctx.cfg = (temperature_const, kind, row_offset, denom, same, f1.dtype, f2.dtype, fast)
         return loss.view(())
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dloss):
-        n1, norm1, n2, norm2, sim, stats, labels_r, labels_c, tptr = ctx.saved_tensors
-        tconst, kind, row_offset, denom, same, d1, d2 = ctx.cfg
+        n1, norm1, n2, norm2, sim, stats, labels_r, labels_c, tptr, n1_row, n2_row = ctx.saved_tensors
+        tconst, kind, row_offset, denom, same, d1, d2, fast = ctx.cfg
         G, dtemp = K.contrastive_bwd(kind, sim, labels_r, labels_c, tptr, tconst, row_offset, denom, stats,
                                      _c(dloss.float()).view(1), torch.float32)
-        dn1 = K.linear_dgrad(G, n2)
-        dn2, _ = K.linear_wgrad(G, n1, want_bias=False)
+        if fast:
+            g_col, g_row = K.split3(G, col_side="a", row_side="a")
+            dn1 = K.linear_dgrad(g_col, n2_row, out_dtype=torch.float32)
+            dn2, _ = K.linear_wgrad(g_row, n1_row, want_bias=False)
+        else:
+            dn1 = K.linear_dgrad(G, n2)
+            dn2, _ = K.linear_wgrad(G, n1, want_bias=False)
         if same:
             df1 = K.cast(K.l2norm_bwd(n1, norm1, dn1, dn2), d1)
             df2 = None
@@ -658,31 +671,31 @@ class ContrastiveFn(Function):
             df1 = K.cast(K.l2norm_bwd(n1, norm1, dn1, None), d1)
             df2 = K.cast(K.l2norm_bwd(n2, norm2, dn2, None), d2) if ctx.needs_input_grad[1] else None
         dT = dtemp.view(()) if (tptr is not None and ctx.needs_input_grad[4]) else None
-        return df1, df2, None, None, dT, None, None, None, None, None
+        return df1, df2, None, None, dT, None, None, None, None, None, None
 
 
 def infonce(f1: Tensor, f2: Tensor, labels: Tensor, temperature, labels_cols: Optional[Tensor] = None,
-            row_offset: int = 0) -> Tensor:
+            row_offset: int = 0, fast: bool = False) -> Tensor:
     """MultimodalTransformerModel.compute_contrastive_loss (MultimodalModel.py:232-260).
     `labels_cols`/`row_offset` describe a row block of a batch-sharded similarity matrix."""
     same = f1 is f2
     lc = labels if labels_cols is None else labels_cols
     t_tensor = temperature if isinstance(temperature, Tensor) else None
     t_const = 0.0 if t_tensor is not None else float(temperature)
-    return ContrastiveFn.apply(f1, f2, labels, lc, t_tensor, t_const, LOSS_INFONCE, row_offset, f1.shape[0], same)
+    return ContrastiveFn.apply(f1, f2, labels, lc, t_tensor, t_const, LOSS_INFONCE, row_offset, f1.shape[0], same, fast)
 
 
 def supcon(z1: Tensor, z2: Tensor, labels: Tensor, temperature: float = 0.1) -> Tensor:
     """train.py:16-40 contrastive_loss: SupCon over the 2B stacked views."""
     z = _StackFn.apply(z1, z2)
     lab = torch.cat([labels.view(-1), labels.view(-1)])
-    return ContrastiveFn.apply(z, z, lab, lab, None, float(temperature), LOSS_SUPCON, 0, z.shape[0], True)
+    return ContrastiveFn.apply(z, z, lab, lab, None, float(temperature), LOSS_SUPCON, 0, z.shape[0], True, False)
 
 
 def ntxent(z1: Tensor, z2: Tensor, temperature: float = 0.5) -> Tensor:
     """ME-MHACL/train.py:47-66 contrastive_loss: NT-Xent over the 2N stacked views."""
     z = _StackFn.apply(z1, z2)
-    return ContrastiveFn.apply(z, z, None, None, None, float(temperature), LOSS_NTXENT, 0, z.shape[0], True)
+    return ContrastiveFn.apply(z, z, None, None, None, float(temperature), LOSS_NTXENT, 0, z.shape[0], True, False)
 
 
 class _StackFn(Function):

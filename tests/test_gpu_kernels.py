@@ -33,6 +33,8 @@ GEMM_SHAPES = [
     (37, 64, 1536),       # tiny ragged everything
     (300, 3, 128),        # class head, N = 3 (CUDA-core path)
     (128, 128, 72),       # K not a multiple of 64 (TMA zero fill)
+    (4352, 768, 768),     # 2-CTA (cta_group::2) 256 x 256 tiles, 17 pair-rows
+    (5000, 1536, 264),    # 2-CTA, ragged M (5000 = 19*256 + 136: the peer CTA of the last pair is half empty) and ragged K
 ]
 
 
@@ -57,7 +59,7 @@ def test_linear_fwd(cuda_device, dtype, M, N, K):
 def test_linear_fwd_split_operand(cuda_device, dtype):
     """gate GEMM: cat[q, attn] @ Wg^T without the concat (MultimodalModel.py:147)."""
     k = _k()
-    M, E = 520, 768
+    M, E = (520 if dtype == torch.float32 else 4500), 768       # bf16: 2-CTA tiles with the two-tensor A operand
     q = _rand((M, E), dtype, cuda_device, 1)
     a = _rand((M, E), dtype, cuda_device, 2)
     w = _rand((E, 2 * E), dtype, cuda_device, 3, 0.02)
@@ -68,7 +70,8 @@ def test_linear_fwd_split_operand(cuda_device, dtype):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("M,N,K", [(256, 768, 768), (392, 1536, 768), (77, 3, 128), (640, 768, 1536)])
+@pytest.mark.parametrize("M,N,K", [(256, 768, 768), (392, 1536, 768), (77, 3, 128), (640, 768, 1536), (4200, 768, 768),
+                                   (6272, 1536, 768)])
 def test_linear_dgrad(cuda_device, dtype, M, N, K):
     k = _k()
     dy = _rand((M, N), dtype, cuda_device, 1)
@@ -365,6 +368,44 @@ def test_infonce_op(cuda_device, B, E, same, T):
     if not same:
         assert rel_err(y.grad, b.grad) <= 2e-4
     assert rel_err(tg.grad, tt.grad) <= 2e-4
+
+
+@pytest.mark.parametrize("B,Bg,E,T", [(64, 64, 768, 0.01), (256, 256, 768, 0.07), (128, 512, 768, 0.01), (40, 40, 128, 0.2)])
+def test_infonce_split_bf16_tensor_core(cuda_device, B, Bg, E, T):
+    """bf16-mode InfoNCE: the three GEMMs run on tcgen05 with split-bf16 operands (hi.hi + hi.lo + lo.hi,
+    mmsa_split3).  Against the float64 oracle the loss must stay within 1e-4 and the gradients within 2e-3
+    (bf16-mode bar is 2e-2); rows may be a block of a wider gathered batch (Bg > B)."""
+    from mmsa import ops
+    O = _oracle()
+    g = torch.Generator().manual_seed(B + Bg)
+    f1 = torch.randn(B, E, generator=g)
+    f2 = torch.randn(Bg, E, generator=g)
+    f2[:B] = f1 * 0.7 + 0.3 * f2[:B]
+    lab_c = torch.randint(0, 3, (Bg,), generator=g)
+    lab_r = lab_c[:B].clone()
+    a, b = f1.clone().double().requires_grad_(True), f2.clone().double().requires_grad_(True)
+    tt = torch.tensor(T, dtype=torch.float64, requires_grad=True)
+    ref = O.infonce(a, b, lab_r, tt, labels2=lab_c, row_offset=0)
+    ref.backward()
+    x, y = f1.clone().to(cuda_device).requires_grad_(True), f2.clone().to(cuda_device).requires_grad_(True)
+    tg = torch.tensor(T, device=cuda_device, requires_grad=True)
+    out = ops.infonce(x, y, lab_r.to(cuda_device), tg, labels_cols=lab_c.to(cuda_device), row_offset=0, fast=True)
+    out.backward()
+    assert rel_err(out, ref) <= 1e-4
+    assert rel_err(x.grad, a.grad) <= 2e-3 and rel_err(y.grad, b.grad) <= 2e-3
+    assert rel_err(tg.grad, tt.grad) <= 2e-3
+
+
+def test_split3_layout(cuda_device):
+    """mmsa_split3: hi + lo reproduces x to 2^-16 and the three copies land where the GEMMs expect them."""
+    from mmsa import kernels as K
+    x = torch.randn(37, 24, device=cuda_device)
+    col, row = K.split3(x, col_side="a", row_side="b")
+    hi = x.bfloat16()
+    lo = (x - hi.float()).bfloat16()
+    assert torch.equal(col[:, :24], hi) and torch.equal(col[:, 24:48], hi) and torch.equal(col[:, 48:], lo)
+    assert torch.equal(row[:37], hi) and torch.equal(row[37:74], lo) and torch.equal(row[74:], hi)
+    assert float((hi.float() + lo.float() - x).abs().max()) <= float(x.abs().max()) * 2.0 ** -16
 
 
 def test_infonce_edge_cases(cuda_device):

@@ -105,12 +105,22 @@ def test_native_against_reference_goldens(cuda_device, case):
             assert float(prm.grad.abs().max()) <= 1e-5 * c["grads"][k[:-5] + ".weight"]["absmax"], k
         elif k in c["grads"]:
             _check_digest(prm.grad, c["grads"][k], r64["grads"].get(k), 1e-5, k)
-    # running statistics: the golden holds the fp32 reference only.  With B = 2 every BatchNorm divides by a
-    # two-sample standard deviation, which amplifies fp32 rounding layer by layer (valence_head stacks four),
-    # so the deepest running_mean of either implementation sits ~1e-5 from the exact value
-    btol = 1e-5 if c["B"] >= 8 else 5e-5
+    # running statistics: the golden holds the fp32 reference only, so the float64 yardstick comes from the
+    # oracle (bit-identical to the reference in fp32, test_cpu_oracle_and_abi).  With B = 2 every BatchNorm
+    # divides by a two-sample standard deviation, which amplifies fp32 rounding layer by layer (valence_head
+    # stacks four): the reference's own fp32 buffers sit up to ~1e-4 from the exact value there
+    p64 = {k: v.double() for k, v in gp["state_dict"].items() if v.is_floating_point()}
+    p64["temperature"] = torch.tensor(c["temperature"], dtype=torch.float64)
+    b64 = {k: v.double() if v.is_floating_point() else v.clone() for k, v in gp["state_dict"].items()
+           if "running_" in k or "num_batches" in k}
+    O.fusion_forward(O.FusionConfig(), p64, [x.double() for x in c["inputs"]], c["labels"],
+                     training=True, buffers=b64)
     for k, b in model.named_buffers():
-        assert rel_err(b.float(), c["buffers_after"][k].float()) <= btol, k
+        if b.is_floating_point():
+            want32 = c["buffers_after"][k].float()
+            assert rel_err(b.float(), b64[k]) <= max(1e-5, 3.0 * rel_err(want32, b64[k])), k
+        else:
+            assert torch.equal(b.cpu(), c["buffers_after"][k]), k
     model.eval()
     with torch.no_grad():
         ea, ev = model(*xs)
