@@ -113,6 +113,8 @@ int mmsa_linear_wgrad(int dtype, int64_t M, int64_t N, int64_t K,
  * is applied to q before the product, as torch does.  D in {32, 64}. */
 /* test hook: route bf16 attention through the CUDA-core engine (engine cross-check). */
 void mmsa_debug_force_simt_attention(int on);
+/* test hook: bf16 forward engine, 0 = tcgen05 + TMA (default), 1 = mma.sync (engine cross-check). */
+void mmsa_debug_attention_engine(int engine);
 int mmsa_attn_fwd(int dtype, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t D,
                   const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                   void* o, int64_t ldo, float* lse, void* stream);

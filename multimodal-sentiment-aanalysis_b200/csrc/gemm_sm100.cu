@@ -721,6 +721,33 @@ static bool make_epi_map(CUtensorMap* map, const void* base, bool is_f32, int64_
   return true;
 }
 
+bool tc_make_map_bf16(CUtensorMap* map, const void* base, int64_t inner, int64_t outer, int64_t ld, int box_inner,
+                      int box_outer) {
+  return make_map(map, base, inner, outer, ld, box_inner, box_outer);
+}
+
+// 3-D bf16 tensor map over a [B, L, cols] view (row stride ld, sample stride L*ld): a box is box_inner columns x
+// box_rows rows of ONE sample, so rows past the end of a sample are out of bounds -- zero-filled (and not fetched) on
+// loads, clipped on stores.  Used by the attention kernels (attention_sm100.cu).
+bool tc_make_map3_bf16(CUtensorMap* map, const void* base, int64_t cols, int64_t L, int64_t B, int64_t ld, int box_inner,
+                       int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("mmsa: cuTensorMapEncodeTiled entry point not found"); return false; }
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)L, (cuuint64_t)B};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)L * (cuuint64_t)ld * 2};
+  cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("mmsa: cuTensorMapEncodeTiled (3-D) failed (%d) cols=%lld L=%lld B=%lld ld=%lld box=%dx%d base=%p", (int)r,
+              (long long)cols, (long long)L, (long long)B, (long long)ld, box_inner, box_rows, base);
+    return false;
+  }
+  return true;
+}
+
 static int g_num_sms = 0;
 static int num_sms() {
   if (g_num_sms == 0) {

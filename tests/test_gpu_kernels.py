@@ -112,7 +112,8 @@ def _attn_ref(q, k, v, B, H, Lq, Lk, D):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("B,H,Lq,Lk,D", [(3, 12, 64, 49, 64), (2, 12, 49, 128, 64), (2, 4, 1, 1, 64),
-                                         (5, 8, 3, 3, 32), (1, 12, 130, 70, 64), (2, 12, 49, 512, 64)])
+                                         (5, 8, 3, 3, 32), (1, 12, 130, 70, 64), (2, 12, 49, 512, 64),
+                                         (2, 12, 512, 49, 64), (3, 12, 128, 49, 64), (2, 2, 300, 64, 64)])
 def test_attention(cuda_device, dtype, B, H, Lq, Lk, D):
     k_ = _k()
     E = H * D
@@ -139,20 +140,32 @@ def test_attention(cuda_device, dtype, B, H, Lq, Lk, D):
 
 
 def test_attention_engines_agree(cuda_device):
-    """bf16: tensor-core engine vs CUDA-core engine on the same inputs."""
+    """bf16: the tcgen05/TMA engine (forward + fused backward) vs the mma.sync engine vs the CUDA-core engine."""
     from mmsa import _lib
     k_ = _k()
-    B, H, Lq, Lk, D = 2, 12, 128, 49, 64
-    E = H * D
-    q = _rand((B * Lq, E), torch.bfloat16, cuda_device, 1)
-    kv = _rand((B * Lk, 2 * E), torch.bfloat16, cuda_device, 2)
-    o1, l1 = k_.attn_fwd(q, kv[:, :E], kv[:, E:], B, H, Lq, Lk, D)
-    _lib.load().mmsa_debug_force_simt_attention(1)
-    try:
-        o2, l2 = k_.attn_fwd(q, kv[:, :E], kv[:, E:], B, H, Lq, Lk, D)
-    finally:
-        _lib.load().mmsa_debug_force_simt_attention(0)
-    assert rel_err(o1, o2) <= 2e-2 and rel_err(l1, l2) <= 2e-3
+    lib = _lib.load()
+    for (B, H, Lq, Lk) in [(2, 12, 128, 49), (2, 12, 49, 128), (1, 4, 256, 33)]:
+        D = 64
+        E = H * D
+        q = _rand((B * Lq, E), torch.bfloat16, cuda_device, 1)
+        kv = _rand((B * Lk, 2 * E), torch.bfloat16, cuda_device, 2)
+        do = _rand((B * Lq, E), torch.bfloat16, cuda_device, 3)
+        outs = {}
+        for name, eng, simt in (("tcgen05", 0, 0), ("mma.sync", 1, 0), ("simt", 0, 1)):
+            lib.mmsa_debug_attention_engine(eng)
+            lib.mmsa_debug_force_simt_attention(simt)
+            try:
+                o, lse = k_.attn_fwd(q, kv[:, :E], kv[:, E:], B, H, Lq, Lk, D)
+                dq = torch.empty_like(q)
+                dkv = torch.empty_like(kv)
+                k_.attn_bwd(q, kv[:, :E], kv[:, E:], o, do, lse, B, H, Lq, Lk, D, dq, dkv[:, :E], dkv[:, E:])
+            finally:
+                lib.mmsa_debug_attention_engine(0)
+                lib.mmsa_debug_force_simt_attention(0)
+            outs[name] = (o, lse, dq, dkv)
+        for other in ("mma.sync", "simt"):
+            for a, b, tol in zip(outs["tcgen05"], outs[other], (2e-2, 2e-3, 2e-2, 2e-2)):
+                assert rel_err(a, b) <= tol, (other, Lq, Lk)
 
 
 # ---------------------------------------------------------------------------------------- gate + LN
