@@ -70,6 +70,11 @@ __device__ __forceinline__ uint4 lds128(uint32_t a) {
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
   return r;
 }
+__device__ __forceinline__ float fast_exp2(float x) {      // MUFU.EX2; exp2(-inf) = 0, denormal results flush to 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h2);
@@ -280,13 +285,13 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
         for (int c = 0; c < 64; ++c) if (c < valid) mx = fmaxf(mx, __uint_as_float(sr[c]));
         const float m_new = fmaxf(m, mx);
-        const float alpha = exp2f((m - m_new) * p.scale_log2);     // first tile: exp2(-inf) = 0
+        const float alpha = fast_exp2((m - m_new) * p.scale_log2);     // first tile: exp2(-inf) = 0
         float rowsum = 0.f;
         uint32_t pk[32];
 #pragma unroll
         for (int c = 0; c < 64; c += 2) {
-          const float p0 = c < valid ? exp2f((__uint_as_float(sr[c]) - m_new) * p.scale_log2) : 0.f;
-          const float p1 = c + 1 < valid ? exp2f((__uint_as_float(sr[c + 1]) - m_new) * p.scale_log2) : 0.f;
+          const float p0 = c < valid ? fast_exp2((__uint_as_float(sr[c]) - m_new) * p.scale_log2) : 0.f;
+          const float p1 = c + 1 < valid ? fast_exp2((__uint_as_float(sr[c + 1]) - m_new) * p.scale_log2) : 0.f;
           rowsum += p0 + p1;
           pk[c >> 1] = pack_bf16(p0, p1);
         }
@@ -409,7 +414,9 @@ struct AttnBwdParams {
   float scale, scale_log2;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+constexpr int kThreadsBwd = 64 + 256;     // TMA warp, MMA warp, 8 compute warps (two per TMEM lane quadrant)
+
+__global__ void __launch_bounds__(kThreadsBwd, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
                    const __grid_constant__ CUtensorMap tmdO, const __grid_constant__ CUtensorMap tmdQ,
@@ -432,8 +439,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < 2; ++s) { mbar_init(qr_full(s), 1); mbar_init(qr_empty(s), 1); mbar_init(kr_full(s), 1); mbar_init(kr_empty(s), 1); }
-    mbar_init(sdp_full, 1); mbar_init(sdp_free, 4); mbar_init(ps_full, 4); mbar_init(ps_free, 1);
-    mbar_init(dq_full, 1); mbar_init(dq_free, 4); mbar_init(dkv_full, 1); mbar_init(dkv_free, 4);
+    mbar_init(sdp_full, 1); mbar_init(sdp_free, 8); mbar_init(ps_full, 8); mbar_init(ps_free, 1);
+    mbar_init(dq_full, 1); mbar_init(dq_free, 8); mbar_init(dkv_full, 1); mbar_init(dkv_free, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -539,13 +546,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
   } else {
-    // ===================== compute / output warps (2..5): thread <-> query row (and <-> key row for dK / dV) ==========
+    // ===================== compute / output warps (2..9) =====================
+    // Two warps per TMEM lane quadrant: thread (row r, half hh) owns columns [32 hh, 32 hh + 32) of row r of every
+    // accumulator -- half the exponentials / packing per thread, and twice the warps to hide TMEM and MUFU latency.
     const int quad = warp & 3;
+    const int hh = (warp - 2) >> 2;
     const int r = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     const uint32_t ps = base + B_SMEM_PS;
     const uint32_t dq_slab = base + B_SMEM_DQ + (uint32_t)quad * 4096u, dkv_slab = base + B_SMEM_DKV + (uint32_t)quad * 4096u;
     const float log2e = 1.4426950408889634f;
+    const bool issuer = hh == 0 && lane == 0;           // issues the TMA stores of this quadrant's slabs
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory"); };   // the two warps of a quadrant
     uint32_t sdpfull_ph = 0, psfree_ph = 0, dqfull_ph = 0, dkvfull_ph = 0;
     Cur x{(long long)blockIdx.x, 0, 0, 0, 0, 0};
     float lse_l2 = 0.f, delta = 0.f;
@@ -578,12 +590,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(ps_free, psfree_ph ^ 1u); psfree_ph ^= 1u;       // the MMAs that read the previous P / dS have retired
       tc_fence_after();
       const int kvalid = min(TK, p.Lk - kt * TK);
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
+      {
         uint32_t sr[32], dr[32];
-        tmem_ld32(tmem_S + lane_base + half * 32u, sr);
-        tmem_ld32(tmem_dP + lane_base + half * 32u, dr);
+        tmem_ld32(tmem_S + lane_base + hh * 32u, sr);
+        tmem_ld32(tmem_dP + lane_base + hh * 32u, dr);
         tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sdp_free);
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
           uint32_t pw[4], dw[4];
@@ -593,21 +607,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int cc = c4 * 8 + 2 * t + e;
-              const bool ok = row_valid && (half * 32 + cc < kvalid);
-              const float pp = ok ? exp2f(__uint_as_float(sr[cc]) * p.scale_log2 - lse_l2) : 0.f;
+              const bool ok = row_valid && (hh * 32 + cc < kvalid);
+              const float pp = ok ? fast_exp2(__uint_as_float(sr[cc]) * p.scale_log2 - lse_l2) : 0.f;
               pv[e] = pp;
               dv[e] = pp * (__uint_as_float(dr[cc]) - delta) * p.scale;
             }
             pw[t] = pack_bf16(pv[0], pv[1]);
             dw[t] = pack_bf16(dv[0], dv[1]);
           }
-          sts128(sw128(ps, r, half * 4 + c4), pw[0], pw[1], pw[2], pw[3]);
-          sts128(sw128(ps + P_BYTES, r, half * 4 + c4), dw[0], dw[1], dw[2], dw[3]);
+          sts128(sw128(ps, r, hh * 4 + c4), pw[0], pw[1], pw[2], pw[3]);
+          sts128(sw128(ps + P_BYTES, r, hh * 4 + c4), dw[0], dw[1], dw[2], dw[3]);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sdp_free);
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(ps_full);
@@ -615,54 +626,52 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (dq_done) {
         mbar_wait(dq_full, dqfull_ph); dqfull_ph ^= 1u;
         tc_fence_after();
-        if (lane == 0) tma_store_wait_read0();
-        __syncwarp();
-#pragma unroll 1
-        for (int cb = 0; cb < 2; ++cb) {
+        if (issuer) tma_store_wait_read0();
+        pair_sync();
+        {
           uint32_t orr[32];
-          tmem_ld32(tmem_dQ + lane_base + cb * 32u, orr);
+          tmem_ld32(tmem_dQ + lane_base + hh * 32u, orr);
           tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(dq_free);
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4)
-            sts128(sw128(dq_slab, lane, cb * 4 + c4),
+            sts128(sw128(dq_slab, lane, hh * 4 + c4),
                    pack_bf16(__uint_as_float(orr[c4 * 8]), __uint_as_float(orr[c4 * 8 + 1])),
                    pack_bf16(__uint_as_float(orr[c4 * 8 + 2]), __uint_as_float(orr[c4 * 8 + 3])),
                    pack_bf16(__uint_as_float(orr[c4 * 8 + 4]), __uint_as_float(orr[c4 * 8 + 5])),
                    pack_bf16(__uint_as_float(orr[c4 * 8 + 6]), __uint_as_float(orr[c4 * 8 + 7])));
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(dq_free);
         fence_async_smem();
-        __syncwarp();
-        if (lane == 0) { tma_store_3d(&tmdQ, dq_slab, h * HD, qt * TQ + quad * 32, b); tma_store_commit(); }
+        pair_sync();
+        if (issuer) { tma_store_3d(&tmdQ, dq_slab, h * HD, qt * TQ + quad * 32, b); tma_store_commit(); }
       }
       if (dkv_done) {
         mbar_wait(dkv_full, dkvfull_ph); dkvfull_ph ^= 1u;
         tc_fence_after();
-        if (lane == 0) tma_store_wait_read0();
-        __syncwarp();
+        if (issuer) tma_store_wait_read0();
+        pair_sync();
         // TMEM lanes 0-63 x columns 0-63 hold dV, lanes 64-127 x columns 64-127 hold dK (already scaled through dS)
         const uint32_t col0 = quad < 2 ? 0u : 64u;
-#pragma unroll 1
-        for (int cb = 0; cb < 2; ++cb) {
+        {
           uint32_t orr[32];
-          tmem_ld32(tmem_dKV + lane_base + col0 + cb * 32u, orr);
+          tmem_ld32(tmem_dKV + lane_base + col0 + hh * 32u, orr);
           tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(dkv_free);
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4)
-            sts128(sw128(dkv_slab, lane, cb * 4 + c4),
+            sts128(sw128(dkv_slab, lane, hh * 4 + c4),
                    pack_bf16(__uint_as_float(orr[c4 * 8]), __uint_as_float(orr[c4 * 8 + 1])),
                    pack_bf16(__uint_as_float(orr[c4 * 8 + 2]), __uint_as_float(orr[c4 * 8 + 3])),
                    pack_bf16(__uint_as_float(orr[c4 * 8 + 4]), __uint_as_float(orr[c4 * 8 + 5])),
                    pack_bf16(__uint_as_float(orr[c4 * 8 + 6]), __uint_as_float(orr[c4 * 8 + 7])));
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(dkv_free);
         fence_async_smem();
-        __syncwarp();
-        if (lane == 0) {
+        pair_sync();
+        if (issuer) {
           tma_store_3d(quad < 2 ? &tmdV : &tmdK, dkv_slab, h * HD, kt * TK + (quad & 1) * 32, b);
           tma_store_commit();
         }
@@ -757,7 +766,7 @@ int attn_bwd_tc_bf16(int64_t B, int64_t H, int64_t Lq, int64_t Lk, const void* q
   const long long grid = p.units < sms ? p.units : sms;
   // algorithmic bytes: Q, O, dO, dQ over Lq rows and K, V, dK, dV over Lk rows, 128 B per (row, head)
   ProfScope prof("attn_bwd_tc", s, 2.0 * 64 * (double)B * H * (4.0 * Lq + 4.0 * Lk));
-  attn_bwd_tc_kernel<<<(unsigned)grid, kThreads, B_SMEM_TOTAL, s>>>(tmQ, tmK, tmV, tmO, tmdO, tmdQ, tmdK, tmdV, p);
+  attn_bwd_tc_kernel<<<(unsigned)grid, kThreadsBwd, B_SMEM_TOTAL, s>>>(tmQ, tmK, tmV, tmO, tmdO, tmdQ, tmdK, tmdV, p);
   MMSA_LAUNCH_CHECK("attn_bwd_tc_kernel");
   return MMSA_OK;
 }

@@ -82,9 +82,9 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {      // arrives on `bar` in BOTH CTAs of the pair
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar, uint16_t mask) {      // arrives on `bar` in BOTH CTAs of the pair
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"((uint16_t)3) : "memory");
+               ::"r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -162,7 +162,7 @@ struct GemmCfg {
   // except the 256-wide wgrad tile (A MN-major), which runs one tile per CTA under split-K anyway and
   // needs the columns for the bias-gradient accumulator
   static constexpr int NACC = (A_MN && BN == 256) ? 1 : 2;
-  static constexpr bool COLSUM_OK = !PAIR && A_MN && (NACC * (BN + 16) <= 512);
+  static constexpr bool COLSUM_OK = A_MN && (NACC * (BN + 16) <= 512);
   static constexpr int TMEM_NEED = NACC * BN + (COLSUM_OK ? NACC * 16 : 0);
   static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
   static constexpr int ONES_BYTES = 2048;         // 16 rows x 128 B of bf16 1.0 (any swizzle of ones is ones)
@@ -241,10 +241,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int S = PAIR ? 1 : p.splits;                        // split-K cluster size along x (never combined with PAIR)
-  const int split = (S > 1) ? (int)cluster_ctarank() : 0;   // this CTA's K-slice
-  const int pair_rank = PAIR ? (int)cluster_ctarank() : 0;  // 0 = leader (issues the MMAs), 1 = peer
-  const int CS = PAIR ? 2 : S;                              // CTAs per work unit
+  // cluster = S K-slices x (PAIR ? 2 : 1) CTAs: rank = 2 * split + pair_rank in PAIR mode, rank = split otherwise
+  const int S = p.splits;
+  const int crank = (S > 1 || PAIR) ? (int)cluster_ctarank() : 0;
+  const int pair_rank = PAIR ? (crank & 1) : 0;             // 0 = leader (issues the MMAs), 1 = peer
+  const int split = PAIR ? (crank >> 1) : crank;            // this CTA's K-slice
+  const uint32_t leader = (uint32_t)(crank & ~1);           // PAIR: cluster rank of this pair's leader CTA
+  const int CS = (PAIR ? 2 : 1) * S;                        // CTAs per work unit
+  auto peer_of = [&](int sp) { return (uint32_t)(PAIR ? 2 * sp + pair_rank : sp); };   // same rows, K-slice sp
   const int unit0 = blockIdx.x / CS, unit_stride = gridDim.x / CS;   // output tiles are dealt to clusters
   const int tiles_mn = p.tiles_m * p.tiles_n;
   const int kb0 = split * p.kb_per_split;
@@ -293,14 +297,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + Cfg::A_BYTES;
           // PAIR: both CTAs' copies complete on the LEADER's barrier, which expects the bytes of both
-          const uint32_t fbar = PAIR ? mapa_u32(full_bar(stage), 0u) : full_bar(stage);
+          const uint32_t fbar = PAIR ? mapa_u32(full_bar(stage), leader) : full_bar(stage);
           if (!PAIR) mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
           else if (pair_rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
           const bool second = kb >= p.kb_a1;
           const CUtensorMap* ma = second ? &tmA2 : &tmA;
           const int ka = (second ? kb - p.kb_a1 : kb) * BK;
           if (PAIR) {
-            tma_load_2d_pair(sa, ma, ka, m0, fbar);
+            if (A_MN) {
+#pragma unroll
+              for (int c = 0; c < BM / 64; ++c) tma_load_2d_pair(sa + c * 8192, ma, m0 + c * 64, ka, fbar);
+            } else {
+              tma_load_2d_pair(sa, ma, ka, m0, fbar);
+            }
             if (B_MN) {
 #pragma unroll
               for (int c = 0; c < Cfg::CTA_N / 64; ++c) tma_load_2d_pair(sb + c * 8192, &tmB, n0 + c * 64, kb * BK, fbar);
@@ -332,7 +341,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                  ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
       // ones operand: K-major, 16 "n" rows, SWIZZLE_128B atoms of 8 rows x 128 B
       constexpr uint32_t idesc_ones = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) |
-                                      ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                                      ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+      const uint16_t pair_mask = (uint16_t)(3u << leader);
       const uint64_t ones_desc = make_sdesc(ones_base, 0, 1024);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -355,11 +365,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint64_t bd = B_MN ? make_sdesc(sb + k * (UMMA_K * 128), 8192, 1024) : make_sdesc(sb + k * (UMMA_K * 2), 0, 1024);
             if (PAIR) tc_mma_bf16_pair(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             else tc_mma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            if (cs) tc_mma_bf16(cs_tmem, ad, ones_desc, idesc_ones, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (cs) {
+              if (PAIR) tc_mma_bf16_pair(cs_tmem, ad, ones_desc, idesc_ones, (kb > kb0 || k > 0) ? 1u : 0u);
+              else tc_mma_bf16(cs_tmem, ad, ones_desc, idesc_ones, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
           }
           if (PAIR) {                                    // both CTAs' slots / accumulators are released together
-            tc_commit_pair(empty_bar(stage));
-            if (kb == kb1 - 1) tc_commit_pair(tfull_bar(acc));
+            tc_commit_pair(empty_bar(stage), pair_mask);
+            if (kb == kb1 - 1) tc_commit_pair(tfull_bar(acc), pair_mask);
           } else {
             tc_commit(empty_bar(stage));                 // frees the smem slot when these MMAs retire
             if (kb == kb1 - 1) tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
@@ -413,11 +426,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_remote(mapa_u32(tempty_bar(acc), leader));
+          else mbar_arrive(tempty_bar(acc));
+        }
         asm volatile("fence.acq_rel.cluster;" ::: "memory");
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (te == 0)
-          for (int r = 0; r < S; ++r) mbar_arrive_remote(mapa_u32(part_full_bar, (uint32_t)r));
+          for (int r = 0; r < S; ++r) mbar_arrive_remote(mapa_u32(part_full_bar, peer_of(r)));
         mbar_wait_cluster(part_full_bar, cl_phase);        // every CTA of the cluster has parked its partial
         // this CTA sums rows [split*rps, (split+1)*rps) of the tile over the S partials, in split order
         const int rps = (BM + S - 1) / S;
@@ -431,10 +447,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int r = r_lo + idx / c4n, c4 = idx % c4n;
           if (r >= rows_valid) continue;
           const uint32_t off = part_u32 + (uint32_t)((r * Cfg::PART_LD + c4 * 4) * 4);
-          float4 a = ld_dsmem_f4(mapa_u32(off, 0));
+          float4 a = ld_dsmem_f4(mapa_u32(off, peer_of(0)));
           for (int sp = 1; sp < S; ++sp) {
-            const float4 b = ld_dsmem_f4(mapa_u32(off, (uint32_t)sp));
+            const float4 b = ld_dsmem_f4(mapa_u32(off, peer_of(sp)));
             a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+          }
+          if (p.bias) {        // bias of the Linear, added once, after the split partials are summed
+            const int cb = n0 + c4 * 4;
+            a.x += cb < p.N ? __ldg(p.bias + cb) : 0.f; a.y += cb + 1 < p.N ? __ldg(p.bias + cb + 1) : 0.f;
+            a.z += cb + 2 < p.N ? __ldg(p.bias + cb + 2) : 0.f; a.w += cb + 3 < p.N ? __ldg(p.bias + cb + 3) : 0.f;
           }
           float* dst = Cf + (long long)(m0 + r) * p.ldc + n0 + c4 * 4;
           if (vec_ok) *reinterpret_cast<float4*>(dst) = a;
@@ -448,13 +469,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (r < r_hi && r < rows_valid) {
             const uint32_t off = part_u32 + (uint32_t)((BM * Cfg::PART_LD + r) * 4);
             float a = 0.f;
-            for (int sp = 0; sp < S; ++sp) a += ld_dsmem_f1(mapa_u32(off, (uint32_t)sp));
+            for (int sp = 0; sp < S; ++sp) a += ld_dsmem_f1(mapa_u32(off, peer_of(sp)));
             p.colsum[m0 + r] = a;
           }
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (te == 0)
-          for (int r = 0; r < S; ++r) mbar_arrive_remote(mapa_u32(read_done_bar, (uint32_t)r));
+          for (int r = 0; r < S; ++r) mbar_arrive_remote(mapa_u32(read_done_bar, peer_of(r)));
         mbar_wait_cluster(read_done_bar, cl_phase);        // peers are done with OUR partial: smem reusable
         cl_phase ^= 1u;
         if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1u; }
@@ -560,7 +581,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (PAIR) mbar_arrive_remote(mapa_u32(tempty_bar(acc), 0u));   // the leader's MMA warp owns the accumulators
+          if (PAIR) mbar_arrive_remote(mapa_u32(tempty_bar(acc), leader));   // the leader's MMA warp owns the accumulators
           else mbar_arrive(tempty_bar(acc));
         }
         if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1u; }
@@ -644,7 +665,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (PAIR) mbar_arrive_remote(mapa_u32(tempty_bar(acc), 0u));
+        if (PAIR) mbar_arrive_remote(mapa_u32(tempty_bar(acc), leader));
         else mbar_arrive(tempty_bar(acc));
       }
       if (++acc == Cfg::NACC) { acc = 0; acc_phase ^= 1u; }
@@ -791,11 +812,10 @@ static int launch_gemm(const GemmDesc& d, int splits_req, cudaStream_t s) {
   p.kb_total = p.kb_a1 + (d.A2 ? (int)ceil_div(d.K2, BK) : 0);
   p.tiles_m = (int)ceil_div(d.M, TILE_M); p.tiles_n = (int)ceil_div(d.N, BN);
   int splits = splits_req < 1 ? 1 : splits_req;
-  if (PAIR) splits = 1;
-  if (splits > kMaxClusterSplits) splits = kMaxClusterSplits;
+  if (splits > (PAIR ? kMaxClusterSplits / 2 : kMaxClusterSplits)) splits = PAIR ? kMaxClusterSplits / 2 : kMaxClusterSplits;
   if (splits > p.kb_total) splits = p.kb_total;
-  // split-K runs as a cluster and sums fp32 partials through distributed shared memory: plain fp32 output only
-  if (d.out_dtype != MMSA_F32 || d.bias || d.residual || d.act != MMSA_ACT_NONE || d.alpha != 1.f) splits = 1;
+  // split-K runs as a cluster and sums fp32 partials through distributed shared memory: fp32 output (+ bias) only
+  if (d.out_dtype != MMSA_F32 || d.residual || d.act != MMSA_ACT_NONE || d.alpha != 1.f) splits = 1;
   p.kb_per_split = (int)ceil_div(p.kb_total, splits);
   p.splits = (int)ceil_div(p.kb_total, p.kb_per_split);
   p.bias = d.bias; p.residual = d.residual; p.ldr = d.ldr; p.res_is_f32 = 0;
@@ -833,12 +853,13 @@ static int launch_gemm(const GemmDesc& d, int splits_req, cudaStream_t s) {
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    const int csize = 2 * p.splits;           // CTA pairs x K-slices (split-K partials meet through DSMEM)
+    attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = s;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    const int max_pairs = gemm_tc_max_clusters(2);
-    const int npairs = tiles_mn < max_pairs ? tiles_mn : max_pairs;
-    cfg.gridDim = dim3((unsigned)(npairs * 2));
+    const int max_cl = gemm_tc_max_clusters(csize);
+    const int ncl = tiles_mn < max_cl ? tiles_mn : max_cl;
+    cfg.gridDim = dim3((unsigned)(ncl * csize));
     ProfScope prof(nm, s, 2.0 * (double)d.M * (double)d.N * (double)Kt);
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmB, tmC, tmR, p);
     if (e != cudaSuccess) { set_error("mmsa: 2-CTA launch of gemm_tcgen05_kernel failed: %s", cudaGetErrorString(e)); return MMSA_ERR_CUDA; }
@@ -883,15 +904,17 @@ int gemm_tc_max_clusters(int size);
 // 2-CTA tiles (256 x 256) for the big activation GEMMs (forward, dgrad): enough rows for every CTA pair of the
 // chip to get several tiles, and an output wide enough for the 256-column tile.  bn < 0 forces the 1-CTA kernel (probe).
 static bool use_pair(const GemmDesc& d, int splits, int bn) {
+  if (bn == 512) return true;                  // wgrad planner / probes: explicit request
   return bn == 0 && splits <= 1 && !d.a_mn_major && d.colsum == nullptr && d.M >= 4096 && d.N >= 512 &&
          (d.N % 256 == 0 || d.N >= 1024);
 }
 
 template <bool A_MN, bool B_MN>
 static int dispatch_bn(const GemmDesc& d, int splits, int bn, cudaStream_t s) {
-  if constexpr (!A_MN) {
+  if constexpr (!A_MN || B_MN) {               // forward (K,K), dgrad (K,MN), wgrad (MN,MN)
     if (use_pair(d, splits, bn)) return launch_gemm<256, A_MN, B_MN, true>(d, splits, s);
   }
+  if (bn == 512) bn = 256;
   if (bn < 0) bn = 0;
   switch (bn > 0 ? bn : pick_bn(d.N, d.colsum != nullptr)) {
     case 64: return launch_gemm<64, A_MN, B_MN>(d, splits, s);

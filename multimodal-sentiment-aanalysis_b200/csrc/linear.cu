@@ -28,9 +28,30 @@ static bool use_tc(int dtype, const GemmDesc& d) {
   return dtype == MMSA_BF16 && d.N >= 16 && gemm_bf16_sm100_supported(d);
 }
 
+// Small-M products of the [B,*] tail (fusion.0: 256 x 256 x 2304) have one or two output tiles and a long reduction:
+// narrow tiles and a split-K cluster spread them over tens of SMs instead of two (latency-, not throughput-bound).
+static void tc_plan_small(const GemmDesc& d, int* bn, int* splits) {
+  *bn = 0; *splits = 1;
+  const int64_t Kt = d.K + (d.A2 ? d.K2 : 0);
+  const int64_t kb = ceil_div(Kt, 64);
+  if (d.M > 512 || kb < 16 || d.out_dtype != MMSA_F32 || d.residual || d.act != MMSA_ACT_NONE || d.a_mn_major) return;
+  const int b = d.N >= 64 ? 64 : 0;
+  const int64_t tiles = ceil_div(d.M, 128) * ceil_div(d.N, 64);
+  if (tiles > 32 || b == 0) return;
+  int sp = (int)(kb / 4);
+  if (sp > 8) sp = 8;
+  while (sp > 1 && tiles * sp > 128) --sp;
+  if (sp < 2) return;
+  *bn = b; *splits = sp;
+}
+
 static int run_gemm(int dtype, const GemmDesc& d, int splits, cudaStream_t s) {
   if (dtype == MMSA_F32) return gemm_simt_f32(d, splits, s);
-  if (use_tc(dtype, d)) return gemm_bf16_sm100_splits(d, 1, 0, s);
+  if (use_tc(dtype, d)) {
+    int bn = 0, sp = 1;
+    tc_plan_small(d, &bn, &sp);
+    return gemm_bf16_sm100_splits(d, sp, bn, s);
+  }
   return gemm_simt_bf16(d, splits, s);
 }
 

@@ -661,55 +661,70 @@ __global__ void pool_bwd_kernel(int64_t B, int64_t L, int E, const T* __restrict
 struct SlotPtrs { const void* p[4]; void* d[4]; };
 
 template <typename T>
-__global__ void modal_concat_fwd_kernel(int64_t B, int E, int S, const float* __restrict__ logits, SlotPtrs sp,
-                                        float* __restrict__ w, T* __restrict__ fused) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t b = (int64_t)blockIdx.x * kRowWarps + warp;
-  if (b >= B) return;
+__global__ void __launch_bounds__(256)
+modal_concat_fwd_kernel(int64_t B, int E, int S, const float* __restrict__ logits, SlotPtrs sp,
+                        float* __restrict__ w, T* __restrict__ fused) {
+  // one block per sample: every thread forms the S <= 4 softmax weights itself, then the S*E/4 vectors of the
+  // weighted concat are spread over the 256 threads (the [B,*] tail is latency-bound: short per-thread loops)
+  const int64_t b = blockIdx.x;
   float lg[4], mx = -INFINITY, den = 0.f;
   for (int s = 0; s < S; ++s) { lg[s] = logits[b * S + s]; mx = fmaxf(mx, lg[s]); }
   for (int s = 0; s < S; ++s) { lg[s] = expf(lg[s] - mx); den += lg[s]; }
-  for (int s = 0; s < S; ++s) { lg[s] /= den; if (lane == 0) w[b * S + s] = lg[s]; }
-  for (int s = 0; s < S; ++s) {
-    const float* src = reinterpret_cast<const float*>(sp.p[s]) + b * (int64_t)E;
-    T* dst = fused + b * (int64_t)S * E + (int64_t)s * E;
-    for (int c = lane * 4; c < E; c += 128) {
-      float x[4];
-      load_vec<float>(src + c, x);
+  for (int s = 0; s < S; ++s) { lg[s] /= den; if (threadIdx.x == 0) w[b * S + s] = lg[s]; }
+  const int ev = E / 4;
+  for (int v = threadIdx.x; v < S * ev; v += blockDim.x) {
+    const int sl = v / ev, c = (v - sl * ev) * 4;
+    float x[4];
+    load_vec<float>(reinterpret_cast<const float*>(sp.p[sl]) + b * (int64_t)E + c, x);
+    float ws = lg[0];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) dst[c + j] = from_f<T>(x[j] * lg[s]);
-    }
+    for (int t = 1; t < 4; ++t) if (sl == t) ws = lg[t];
+    T* dst = fused + b * (int64_t)S * E + (int64_t)sl * E + c;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) dst[t] = from_f<T>(x[t] * ws);
   }
 }
 
-// dfused fp32 (a dgrad output), slots fp32 -> dslots fp32, dlogits T (operand of the next dgrad)
 template <typename T>
-__global__ void modal_concat_bwd_kernel(int64_t B, int E, int S, const float* __restrict__ dfused,
-                                        const float* __restrict__ w, SlotPtrs sp, T* __restrict__ dlogits) {
+__global__ void __launch_bounds__(256)
+modal_concat_bwd_kernel(int64_t B, int E, int S, const float* __restrict__ dfused,
+                        const float* __restrict__ w, SlotPtrs sp, T* __restrict__ dlogits) {
+  // one block per sample; dw[s] = <slot_s, dfused_s> reduced warp by warp, then over the 8 warps in warp order
+  __shared__ float red[4][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t b = (int64_t)blockIdx.x * kRowWarps + warp;
-  if (b >= B) return;
-  float ws[4], dw[4];
-  for (int s = 0; s < S; ++s) {
-    ws[s] = w[b * S + s];
-    const float* src = reinterpret_cast<const float*>(sp.p[s]) + b * (int64_t)E;
-    const float* df = dfused + b * (int64_t)S * E + (int64_t)s * E;
-    float* dslot = reinterpret_cast<float*>(sp.d[s]);
-    float acc = 0.f;
-    for (int c = lane * 4; c < E; c += 128) {
-      float x[4], d[4];
-      load_vec<float>(src + c, x);
-      load_vec<float>(df + c, d);
+  const int64_t b = blockIdx.x;
+  float ws[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int s = 0; s < S; ++s) ws[s] = w[b * S + s];
+  const int ev = E / 4;
+  for (int v = threadIdx.x; v < S * ev; v += blockDim.x) {
+    const int sl = v / ev, c = (v - sl * ev) * 4;
+    float x[4], d[4];
+    load_vec<float>(reinterpret_cast<const float*>(sp.p[sl]) + b * (int64_t)E + c, x);
+    load_vec<float>(dfused + b * (int64_t)S * E + (int64_t)sl * E + c, d);
+    float wsl = ws[0];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { acc += x[j] * d[j]; d[j] *= ws[s]; }
-      if (dslot != nullptr) store_vec<float>(dslot + b * (int64_t)E + c, d);
-    }
-    dw[s] = warp_sum(acc);
+    for (int t = 1; t < 4; ++t) if (sl == t) wsl = ws[t];
+    float dot = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { dot += x[t] * d[t]; d[t] *= wsl; }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) if (sl == t) acc[t] += dot;
+    float* dslot = reinterpret_cast<float*>(sp.d[sl]);
+    if (dslot != nullptr) store_vec<float>(dslot + b * (int64_t)E + c, d);
   }
-  float dot = 0.f;
-  for (int s = 0; s < S; ++s) dot += ws[s] * dw[s];
-  if (lane == 0)
+#pragma unroll
+  for (int t = 0; t < 4; ++t) { const float r = warp_sum(acc[t]); if (lane == 0) red[t][warp] = r; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float dw[4], dot = 0.f;
+    for (int s = 0; s < S; ++s) {
+      float a = 0.f;
+      for (int k = 0; k < 8; ++k) a += red[s][k];
+      dw[s] = a;
+      dot += ws[s] * a;
+    }
     for (int s = 0; s < S; ++s) dlogits[b * S + s] = from_f<T>(ws[s] * (dw[s] - dot));
+  }
 }
 
 // ------------------------------------------------------------------ activations
@@ -955,7 +970,7 @@ int mmsa_modal_concat_fwd(int dtype, int64_t B, int64_t E, int S, const void* lo
   for (int i = 0; i < S; ++i) sp.p[i] = slots_host[i];
   cudaStream_t s = (cudaStream_t)stream;
   ProfScope prof("modal_concat_fwd", s, (double)B * E * S * 2.0 * (dtype == MMSA_F32 ? 4 : 2));
-  MMSA_DISPATCH_DTYPE(dtype, T, (modal_concat_fwd_kernel<T><<<(unsigned)ceil_div(B, kRowWarps), kRowWarps * 32, 0, s>>>(
+  MMSA_DISPATCH_DTYPE(dtype, T, (modal_concat_fwd_kernel<T><<<(unsigned)B, 256, 0, s>>>(
       B, (int)E, S, (const float*)logits, sp, w, (T*)fused)));
   MMSA_LAUNCH_CHECK("modal_concat_fwd_kernel");
   return MMSA_OK;
@@ -971,7 +986,7 @@ int mmsa_modal_concat_bwd(int dtype, int64_t B, int64_t E, int S, const void* df
   for (int i = 0; i < S; ++i) { sp.p[i] = slots_host[i]; sp.d[i] = dslots_host[i]; }
   cudaStream_t s = (cudaStream_t)stream;
   ProfScope prof("modal_concat_bwd", s, (double)B * E * S * 3.0 * (dtype == MMSA_F32 ? 4 : 2));
-  MMSA_DISPATCH_DTYPE(dtype, T, (modal_concat_bwd_kernel<T><<<(unsigned)ceil_div(B, kRowWarps), kRowWarps * 32, 0, s>>>(
+  MMSA_DISPATCH_DTYPE(dtype, T, (modal_concat_bwd_kernel<T><<<(unsigned)B, 256, 0, s>>>(
       B, (int)E, S, (const float*)dfused, w, sp, (T*)dlogits)));
   MMSA_LAUNCH_CHECK("modal_concat_bwd_kernel");
   return MMSA_OK;

@@ -24,25 +24,28 @@ __device__ __forceinline__ uint32_t philox_first(uint64_t seed, uint64_t ctr) {
 }
 
 // ------------------------------------------------------------------ BatchNorm1d + act + dropout
-// block (32 columns, 8 row lanes); one block per 32 columns; three passes over the (tiny) [B,N] input.
+// block (kBnCols columns x kBnRows row lanes = 1024 threads); one block per kBnCols columns; three passes over the
+// (tiny, L1-resident) [B,N] input.  The [B,*] tail is latency-bound: the wide block keeps each thread's serial row walk to
+// B / 64 rows, and 16-column blocks spread N = 128..256 over 8..16 SMs.
+constexpr int kBnCols = 16, kBnRows = 64;
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kBnCols * kBnRows)
 bn_act_fwd_kernel(int64_t B, int N, int order, const float* __restrict__ x, const float* __restrict__ gamma,
                   const float* __restrict__ beta, float* __restrict__ running_mean,
                   float* __restrict__ running_var, float momentum, float eps, int training,
                   float dropout_p, uint8_t* __restrict__ keep_mask, int mask_given, uint64_t seed,
                   uint64_t offset, T* __restrict__ y, float* __restrict__ save_mean,
                   float* __restrict__ save_rstd) {
-  __shared__ float red[8][33];
+  __shared__ float red[kBnRows][kBnCols + 1];
   const int tx = threadIdx.x, ty = threadIdx.y;
-  const int col = blockIdx.x * 32 + tx;
+  const int col = blockIdx.x * kBnCols + tx;
   const bool ok = col < N;
   const bool pre_relu = (order == MMSA_RELU_THEN_BN);
   float mean = 0.f, var = 1.f;
   if (training) {
     float s = 0.f;
     if (ok)
-      for (int64_t r = ty; r < B; r += 8) {
+      for (int64_t r = ty; r < B; r += kBnRows) {
         float v = to_f(x[r * N + col]);
         if (pre_relu) v = fmaxf(v, 0.f);
         s += v;
@@ -51,12 +54,12 @@ bn_act_fwd_kernel(int64_t B, int N, int order, const float* __restrict__ x, cons
     __syncthreads();
     s = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s += red[k][tx];
+    for (int k = 0; k < kBnRows; ++k) s += red[k][tx];
     mean = s / (float)B;
     __syncthreads();
     float q = 0.f;
     if (ok)
-      for (int64_t r = ty; r < B; r += 8) {
+      for (int64_t r = ty; r < B; r += kBnRows) {
         float v = to_f(x[r * N + col]);
         if (pre_relu) v = fmaxf(v, 0.f);
         float d = v - mean;
@@ -66,7 +69,7 @@ bn_act_fwd_kernel(int64_t B, int N, int order, const float* __restrict__ x, cons
     __syncthreads();
     q = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) q += red[k][tx];
+    for (int k = 0; k < kBnRows; ++k) q += red[k][tx];
     var = q / (float)B;
     if (ok && ty == 0 && running_mean != nullptr) {
       float unbiased = B > 1 ? q / (float)(B - 1) : var;
@@ -83,7 +86,7 @@ bn_act_fwd_kernel(int64_t B, int N, int order, const float* __restrict__ x, cons
   const float gm = gamma[col], bt = beta[col];
   const bool drop = training && dropout_p > 0.f;
   const float keep_scale = drop ? 1.f / (1.f - dropout_p) : 1.f;
-  for (int64_t r = ty; r < B; r += 8) {
+  for (int64_t r = ty; r < B; r += kBnRows) {
     float v = to_f(x[r * N + col]);
     if (pre_relu) v = fmaxf(v, 0.f);
     float z = (v - mean) * rstd * gm + bt;
@@ -103,15 +106,15 @@ bn_act_fwd_kernel(int64_t B, int N, int order, const float* __restrict__ x, cons
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kBnCols * kBnRows)
 bn_act_bwd_kernel(int64_t B, int N, int order, const float* __restrict__ x, const float* __restrict__ dy,
                   const float* __restrict__ gamma, const float* __restrict__ beta,
                   const float* __restrict__ save_mean, const float* __restrict__ save_rstd, int training,
                   float dropout_p, const uint8_t* __restrict__ keep_mask, T* __restrict__ dx,
                   float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias_prev) {
-  __shared__ float red[2][8][33];
+  __shared__ float red[2][kBnRows][kBnCols + 1];
   const int tx = threadIdx.x, ty = threadIdx.y;
-  const int col = blockIdx.x * 32 + tx;
+  const int col = blockIdx.x * kBnCols + tx;
   const bool ok = col < N;
   const bool pre_relu = (order == MMSA_RELU_THEN_BN);
   const bool drop = training && dropout_p > 0.f;
@@ -120,7 +123,7 @@ bn_act_bwd_kernel(int64_t B, int N, int order, const float* __restrict__ x, cons
   const float gm = ok ? gamma[col] : 0.f, bt = ok ? beta[col] : 0.f;
   float sdz = 0.f, sdzx = 0.f;
   if (ok)
-    for (int64_t r = ty; r < B; r += 8) {
+    for (int64_t r = ty; r < B; r += kBnRows) {
       float v = to_f(x[r * N + col]);
       if (pre_relu) v = fmaxf(v, 0.f);
       float xh = (v - mean) * rstd;
@@ -135,12 +138,12 @@ bn_act_bwd_kernel(int64_t B, int N, int order, const float* __restrict__ x, cons
   __syncthreads();
   sdz = 0.f; sdzx = 0.f;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { sdz += red[0][k][tx]; sdzx += red[1][k][tx]; }
+  for (int k = 0; k < kBnRows; ++k) { sdz += red[0][k][tx]; sdzx += red[1][k][tx]; }
   if (ok && ty == 0) { dgamma[col] = sdzx; dbeta[col] = sdz; }
   const float invB = 1.f / (float)B;
   float sdx = 0.f;
   if (ok)
-    for (int64_t r = ty; r < B; r += 8) {
+    for (int64_t r = ty; r < B; r += kBnRows) {
       float raw = to_f(x[r * N + col]);
       float v = pre_relu ? fmaxf(raw, 0.f) : raw;
       float xh = (v - mean) * rstd;
@@ -159,7 +162,7 @@ bn_act_bwd_kernel(int64_t B, int N, int order, const float* __restrict__ x, cons
   if (ok && ty == 0 && dbias_prev != nullptr) {
     float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += red[0][k][tx];
+    for (int k = 0; k < kBnRows; ++k) t += red[0][k][tx];
     dbias_prev[col] = t;
   }
 }
@@ -399,8 +402,8 @@ int mmsa_bn_act_fwd(int dtype, int64_t B, int64_t N, int order, const void* x, c
   MMSA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "mmsa_bn_act_fwd: dropout_p out of [0,1)");
   cudaStream_t s = (cudaStream_t)stream;
   ProfScope prof("bn_act_fwd", s, (double)B * N * 2.0 * (dtype == MMSA_F32 ? 4 : 2));
-  dim3 block(32, 8);
-  MMSA_DISPATCH_DTYPE(dtype, T, (bn_act_fwd_kernel<T><<<(unsigned)ceil_div(N, 32), block, 0, s>>>(
+  dim3 block(kBnCols, kBnRows);
+  MMSA_DISPATCH_DTYPE(dtype, T, (bn_act_fwd_kernel<T><<<(unsigned)ceil_div(N, kBnCols), block, 0, s>>>(
       B, (int)N, order, (const float*)x, gamma, beta, running_mean, running_var, momentum, eps, training, dropout_p,
       keep_mask, mask_given, seed, offset, (T*)y, save_mean, save_rstd)));
   MMSA_LAUNCH_CHECK("bn_act_fwd_kernel");
@@ -415,8 +418,8 @@ int mmsa_bn_act_bwd(int dtype, int64_t B, int64_t N, int order, const void* x, c
   MMSA_REQUIRE(B > 0 && N > 0, "mmsa_bn_act_bwd: empty input");
   cudaStream_t s = (cudaStream_t)stream;
   ProfScope prof("bn_act_bwd", s, (double)B * N * 3.0 * (dtype == MMSA_F32 ? 4 : 2));
-  dim3 block(32, 8);
-  MMSA_DISPATCH_DTYPE(dtype, T, (bn_act_bwd_kernel<T><<<(unsigned)ceil_div(N, 32), block, 0, s>>>(
+  dim3 block(kBnCols, kBnRows);
+  MMSA_DISPATCH_DTYPE(dtype, T, (bn_act_bwd_kernel<T><<<(unsigned)ceil_div(N, kBnCols), block, 0, s>>>(
       B, (int)N, order, (const float*)x, (const float*)dy, gamma, beta, save_mean, save_rstd, training, dropout_p, keep_mask,
       (T*)dx, dgamma, dbeta, dbias_prev)));
   MMSA_LAUNCH_CHECK("bn_act_bwd_kernel");
