@@ -353,7 +353,7 @@ def run_ours(args) -> None:
 
     if rank == 0:
         cpu = None
-        if world == 1 or True:
+        if world == 1:      # the CPU baseline is an N = 1 figure (torchrun also pins OMP_NUM_THREADS=1 on the ranks)
             try:
                 cpu = cpu_reference_samples_per_s(L, args.cpu_sample_batch, 3, 1)
             except Exception as ex:   # the baseline leg must never take the GPU numbers down with it

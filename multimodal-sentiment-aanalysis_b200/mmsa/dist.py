@@ -83,6 +83,9 @@ class GradAllReducer:
         self.group = group
         self.bucket_bytes = int(bucket_mb * (1 << 20))
         self._arenas: Optional[List[Tensor]] = None
+        self._flat: Optional[Tensor] = None
+        self._flat_views: List[Tensor] = []
+        self._flat_key = None
         self._slices = None
 
     def _plan(self):
@@ -102,9 +105,33 @@ class GradAllReducer:
 
     @torch.no_grad()
     def step(self):
+        """Average the parameter gradients over the group.  NCCL: ONE coalesced group call over the gradient tensors
+        where they lie (ncclGroupStart/End: no packing copies), reduction op AVG (no division kernel).  Other
+        backends (gloo, CPU tests): packed arenas, SUM, divide."""
+        world = dist.get_world_size(self.group)
+        if dist.get_backend(self.group) == "nccl":
+            # ONE flat fp32 arena: a multi-tensor pack (torch._foreach_copy_, plumbing), ONE all-reduce with op AVG (no
+            # division kernel; a single large message is launch-latency-optimal over NVSwitch), and .grad re-pointed at
+            # the arena views (no unpack).
+            live = [p for p in self.params if p.grad is not None]
+            if not live:
+                return
+            key = tuple(id(p) for p in live)
+            if self._flat is None or self._flat_key != key:
+                total = sum(p.numel() for p in live)
+                self._flat = torch.empty(total, device=live[0].device, dtype=torch.float32)
+                self._flat_views, off = [], 0
+                for p in live:
+                    self._flat_views.append(self._flat[off:off + p.numel()].view_as(p))
+                    off += p.numel()
+                self._flat_key = key
+            torch._foreach_copy_(self._flat_views, [p.grad for p in live])
+            dist.all_reduce(self._flat, op=dist.ReduceOp.AVG, group=self.group)
+            for p, v in zip(live, self._flat_views):
+                p.grad = v
+            return
         if self._arenas is None:
             self._plan()
-        world = dist.get_world_size(self.group)
         for p, (a, off, n) in zip(self.params, self._slices):
             view = self._arenas[a][off:off + n]
             if p.grad is None:

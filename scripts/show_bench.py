@@ -12,7 +12,7 @@ for line in open(path):
           f"eager_ms={d.get('eager_ms_per_step', 0):.3f}  gpus={d['n_gpus']}  launches={d.get('gpu_launches')}")
     print("roofline", json.dumps(d.get("roofline")))
     print("membound", json.dumps(d.get("memory_bound_kernels")))
-    print("clocks", d.get("clocks"), "cpu", d.get("cpu_baseline", {}).get("value"))
+    print("clocks", d.get("clocks"), "cpu", (d.get("cpu_baseline") or {}).get("value"))
     if k:
         tot = sum(v["ms_per_step"] for v in k.values())
         print(f"sum of kernel times {tot*1e3:.0f} us")
