@@ -119,6 +119,95 @@ __global__ void reduce_splits_kernel(const float* __restrict__ partials, int spl
   }
 }
 
+// ------------------------------------------------------------------ skinny Linear (N <= 8 output features)
+// The 3-way modality-weight and class heads (nn.Linear(64,3) / nn.Linear(128,3), MultimodalModel.py:174,198) are far
+// below any GEMM tile: one warp per row forward, one thread per element for dgrad, and ONE kernel for dW and db
+// (column blocks of 32 x 8 row lanes, shared-memory tree in lane order) instead of GEMM + split reduce + column sums.
+constexpr int kSkinnyMaxN = 8;
+
+__global__ void __launch_bounds__(256)
+skinny_fwd_kernel(int64_t M, int N, int K, const bf16* __restrict__ x, int64_t ldx, const bf16* __restrict__ w, int64_t ldw,
+                  const float* __restrict__ bias, void* __restrict__ y, int64_t ldy, int out_is_f32, int act) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t m = (int64_t)blockIdx.x * 8 + warp;
+  if (m >= M) return;
+  float acc[kSkinnyMaxN];
+#pragma unroll
+  for (int c = 0; c < kSkinnyMaxN; ++c) acc[c] = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float xv = to_f(x[m * ldx + k]);
+#pragma unroll
+    for (int c = 0; c < kSkinnyMaxN; ++c) if (c < N) acc[c] += xv * to_f(w[(int64_t)c * ldw + k]);
+  }
+#pragma unroll
+  for (int c = 0; c < kSkinnyMaxN; ++c) if (c < N) acc[c] = warp_sum(acc[c]);
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < kSkinnyMaxN; ++c) if (c < N) {
+      float v = apply_act(acc[c] + (bias ? bias[c] : 0.f), act);
+      if (out_is_f32) reinterpret_cast<float*>(y)[m * ldy + c] = v;
+      else reinterpret_cast<bf16*>(y)[m * ldy + c] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+skinny_dgrad_kernel(int64_t M, int N, int K, const bf16* __restrict__ dy, int64_t lddy, const bf16* __restrict__ w, int64_t ldw,
+                    void* __restrict__ dx, int64_t lddx, int out_is_f32) {
+  const int64_t total = M * K;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / K; const int k = (int)(i % K);
+    float a = 0.f;
+#pragma unroll
+    for (int c = 0; c < kSkinnyMaxN; ++c) if (c < N) a += to_f(dy[m * lddy + c]) * to_f(w[(int64_t)c * ldw + k]);
+    if (out_is_f32) reinterpret_cast<float*>(dx)[m * lddx + k] = a;
+    else reinterpret_cast<bf16*>(dx)[m * lddx + k] = __float2bfloat16_rn(a);
+  }
+}
+
+// block = 32 columns (k) x 8 row lanes; block x covers columns [32 x, 32 x + 32); block 0 also forms db
+__global__ void __launch_bounds__(256)
+skinny_wgrad_kernel(int64_t M, int N, int K, const bf16* __restrict__ dy, int64_t lddy, const bf16* __restrict__ x, int64_t ldx,
+                    float* __restrict__ dw, int64_t lddw, float* __restrict__ db) {
+  __shared__ float red[8][kSkinnyMaxN][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + tx;
+  float acc[kSkinnyMaxN], bsum = 0.f;
+#pragma unroll
+  for (int c = 0; c < kSkinnyMaxN; ++c) acc[c] = 0.f;
+  for (int64_t m = ty; m < M; m += 8) {
+    const float xv = k < K ? to_f(x[m * ldx + k]) : 0.f;
+#pragma unroll
+    for (int c = 0; c < kSkinnyMaxN; ++c) if (c < N) acc[c] += to_f(dy[m * lddy + c]) * xv;
+    if (db != nullptr && blockIdx.x == 0 && tx < N) bsum += to_f(dy[m * lddy + tx]);
+  }
+#pragma unroll
+  for (int c = 0; c < kSkinnyMaxN; ++c) red[ty][c][tx] = acc[c];
+  __syncthreads();
+  if (ty == 0 && k < K && dw != nullptr) {
+#pragma unroll
+    for (int c = 0; c < kSkinnyMaxN; ++c) if (c < N) {
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) t += red[r][c][tx];
+      dw[(int64_t)c * lddw + k] = t;
+    }
+  }
+  if (db != nullptr && blockIdx.x == 0) {
+    __syncthreads();
+    red[ty][0][tx] = bsum;
+    __syncthreads();
+    if (ty == 0 && tx < N) {
+      float t = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) t += red[r][0][tx];
+      db[tx] = t;
+    }
+  }
+}
+
+static bool skinny_ok(int dtype, int64_t N) { return dtype == MMSA_BF16 && N <= kSkinnyMaxN; }
+
 constexpr int kMaxSplits = 16;
 constexpr int kColsumRowSplits = 64;
 
@@ -148,6 +237,14 @@ int mmsa_linear_fwd(int dtype, int64_t M, int64_t N, int64_t K, int64_t K2, cons
   MMSA_REQUIRE(M >= 0 && N > 0 && K > 0, "mmsa_linear_fwd: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
   MMSA_REQUIRE(!(dtype == MMSA_F32 && out_dtype == MMSA_BF16), "mmsa_linear_fwd: fp32 mode writes fp32");
   if (M == 0) return MMSA_OK;
+  if (skinny_ok(dtype, N) && x2 == nullptr && residual == nullptr) {
+    cudaStream_t s = (cudaStream_t)stream;
+    ProfScope prof("skinny_fwd", s, 2.0 * (double)M * N * K);
+    skinny_fwd_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, s>>>(M, (int)N, (int)K, (const bf16*)x, ldx, (const bf16*)w, ldw, bias, y, ldy,
+                                                                out_dtype == MMSA_F32, act);
+    MMSA_LAUNCH_CHECK("skinny_fwd_kernel");
+    return MMSA_OK;
+  }
   GemmDesc d{};
   d.M = M; d.N = N; d.K = K; d.K2 = x2 ? K2 : 0;
   d.A = x; d.lda = ldx; d.a_mn_major = false; d.A2 = x2; d.lda2 = ldx2;
@@ -165,6 +262,16 @@ int mmsa_linear_dgrad(int dtype, int64_t M, int64_t N, int64_t K, const void* dy
   MMSA_REQUIRE(M >= 0 && N > 0 && K > 0, "mmsa_linear_dgrad: bad shape");
   MMSA_REQUIRE(!(dtype == MMSA_F32 && out_dtype == MMSA_BF16), "mmsa_linear_dgrad: fp32 mode writes fp32");
   if (M == 0) return MMSA_OK;
+  if (skinny_ok(dtype, N) && residual == nullptr) {
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t blocks = ceil_div(M * K, 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    ProfScope prof("skinny_dgrad", s, 2.0 * (double)M * N * K);
+    skinny_dgrad_kernel<<<(unsigned)blocks, 256, 0, s>>>(M, (int)N, (int)K, (const bf16*)dy, lddy, (const bf16*)w, ldw, dx, lddx,
+                                                        out_dtype == MMSA_F32);
+    MMSA_LAUNCH_CHECK("skinny_dgrad_kernel");
+    return MMSA_OK;
+  }
   GemmDesc d{};
   d.M = M; d.N = K; d.K = N; d.K2 = 0;
   d.A = dy; d.lda = lddy; d.a_mn_major = false; d.A2 = nullptr;
@@ -186,6 +293,13 @@ int mmsa_linear_wgrad(int dtype, int64_t M, int64_t N, int64_t K, const void* dy
   MMSA_REQUIRE(M > 0 && N > 0 && K > 0, "mmsa_linear_wgrad: bad shape");
   MMSA_REQUIRE(workspace != nullptr, "mmsa_linear_wgrad: workspace required");
   cudaStream_t s = (cudaStream_t)stream;
+  if (skinny_ok(dtype, N)) {
+    if (dw == nullptr && db == nullptr) return MMSA_OK;
+    ProfScope prof("skinny_wgrad", s, 2.0 * (double)M * N * K);
+    skinny_wgrad_kernel<<<(unsigned)ceil_div(K, 32), 256, 0, s>>>(M, (int)N, (int)K, (const bf16*)dy, lddy, (const bf16*)x, ldx, dw, lddw, db);
+    MMSA_LAUNCH_CHECK("skinny_wgrad_kernel");
+    return MMSA_OK;
+  }
   float* ws = reinterpret_cast<float*>(workspace);
   float* ws_colsum = ws + (int64_t)kMaxSplits * N * K;
   bool db_done = false;

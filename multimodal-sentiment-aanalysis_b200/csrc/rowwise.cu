@@ -294,7 +294,7 @@ gate_ln_pool_fwd_kernel(int L, int E, const T* __restrict__ gate_pre, const T* _
     const uint32_t src = wslot + (uint32_t)s * NS * row_bytes;
     rp_wait(wbar + 8u * s, (uint32_t)(k / kPipeStages) & 1u);
     float u[F];
-    float sum = 0.f;
+    float sum4[4] = {0.f, 0.f, 0.f, 0.f};      // four independent partial sums: the row reductions are latency chains
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int v = lane + 32 * i;
@@ -309,7 +309,7 @@ gate_ln_pool_fwd_kernel(int L, int E, const T* __restrict__ gate_pre, const T* _
           gv[j] = g;
           const float uu = g * qv[j] + (1.f - g) * av[j];
           u[i * VN + j] = uu;
-          sum += uu;
+          sum4[j & 3] += uu;
           qsum[i * VN + j] += qv[j];
         }
         store_vec<T>(g_out + base + v * VN, gv);
@@ -320,26 +320,31 @@ gate_ln_pool_fwd_kernel(int L, int E, const T* __restrict__ gate_pre, const T* _
     }
     __syncwarp();                                        // every lane has read the slot: refill it
     if (lane == 0 && k + kPipeStages < nrows) issue(k + kPipeStages);
-    const float mean = warp_sum(sum) / (float)E;
-    float sq = 0.f;
+    const float mean = warp_sum((sum4[0] + sum4[1]) + (sum4[2] + sum4[3])) / (float)E;
+    float sq4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int v = lane + 32 * i;
       if (v < nvec) {
 #pragma unroll
-        for (int j = 0; j < VN; ++j) { const float d = u[i * VN + j] - mean; sq += d * d; }
+        for (int j = 0; j < VN; ++j) { const float d = u[i * VN + j] - mean; sq4[j & 3] += d * d; }
       }
     }
-    const float rstd = rsqrtf(warp_sum(sq) / (float)E + eps);
+    const float rstd = rsqrtf(warp_sum((sq4[0] + sq4[1]) + (sq4[2] + sq4[3])) / (float)E + eps);
     if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int v = lane + 32 * i;
       if (v < nvec) {
 #pragma unroll
-        for (int j = 0; j < VN; ++j) {
-          const int c = v * VN + j;
-          ysum[i * VN + j] += (u[i * VN + j] - mean) * rstd * gm_s[c] + bt_s[c];
+        for (int h4 = 0; h4 < VN / 4; ++h4) {
+          const float4 g4 = *reinterpret_cast<const float4*>(gm_s + v * VN + h4 * 4);
+          const float4 b4 = *reinterpret_cast<const float4*>(bt_s + v * VN + h4 * 4);
+          const int o = i * VN + h4 * 4;
+          ysum[o + 0] += (u[o + 0] - mean) * rstd * g4.x + b4.x;
+          ysum[o + 1] += (u[o + 1] - mean) * rstd * g4.y + b4.y;
+          ysum[o + 2] += (u[o + 2] - mean) * rstd * g4.z + b4.z;
+          ysum[o + 3] += (u[o + 3] - mean) * rstd * g4.w + b4.w;
         }
       }
     }
@@ -476,7 +481,7 @@ gate_ln_pool_bwd_kernel(int64_t M, int L, int E, int64_t rows_per_warp, const fl
     const float mu = mean[row], rs = rstd[row];
     const uint32_t src = wslot + (uint32_t)s * NS * row_bytes;
     rp_wait(wbar + 8u * s, (uint32_t)(k / kPipeStages) & 1u);
-    float c2 = 0.f;
+    float c24[4] = {0.f, 0.f, 0.f, 0.f};       // independent partial sums (latency chain otherwise)
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int v = lane + 32 * i;
@@ -488,11 +493,11 @@ gate_ln_pool_bwd_kernel(int64_t M, int L, int E, int64_t rows_per_warp, const fl
 #pragma unroll
         for (int j = 0; j < VN; ++j) {
           const float uu = g8[j] * q8[j] + (1.f - g8[j]) * a8[j];
-          c2 += dgv[i * VN + j] * ((uu - mu) * rs);
+          c24[j & 3] += dgv[i * VN + j] * ((uu - mu) * rs);
         }
       }
     }
-    c2 = warp_sum(c2) / (float)E;
+    const float c2 = warp_sum((c24[0] + c24[1]) + (c24[2] + c24[3])) / (float)E;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int v = lane + 32 * i;

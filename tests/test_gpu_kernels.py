@@ -81,6 +81,8 @@ def test_linear_dgrad(cuda_device, dtype, M, N, K):
     dx = k.linear_dgrad(dy, w, residual=r)
     ref = dy.double() @ w.double() + r.double()
     assert rel_err(dx, ref) <= TOL[dtype]
+    dx0 = k.linear_dgrad(dy, w, out_dtype=torch.float32)          # no residual: the skinny (N <= 8) kernel in bf16 mode
+    assert rel_err(dx0, dy.double() @ w.double()) <= (1e-5 if dtype == torch.float32 else 2e-3)
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
