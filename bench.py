@@ -203,8 +203,13 @@ def run_ours(args) -> None:
     if world > 1:
         for p in model.parameters():            # replicas start identical
             dist.broadcast(p.data, 0)
-        mdist.shard_contrastive(model)
-        reducer = mdist.GradAllReducer(model.parameters())
+        # MMSA_BENCH_ABLATE (comma list: "shard", "reduce") switches a collective off to attribute the multi-GPU
+        # overhead; such a run is a diagnostic, flagged in config.ablate, never a result
+        ablate = set(filter(None, os.environ.get("MMSA_BENCH_ABLATE", "").split(",")))
+        if "shard" not in ablate:
+            mdist.shard_contrastive(model)
+        if "reduce" not in ablate:
+            reducer = mdist.GradAllReducer(model.parameters())
 
     # synthetic features: N(0,1), seeded per rank; host copies pinned, in the feature dtype
     g = torch.Generator().manual_seed(1234 + rank)
@@ -248,16 +253,25 @@ def run_ours(args) -> None:
     # ---- device-resident throughput (`value`) ----
     for _ in range(max(args.warmup, 3)):
         step.run(0); step.run(1)
-    barrier()
+    # the clock sampler (NVML init: tens of ms) starts BEFORE the barrier: anything rank 0 does between the barrier and
+    # its first launch shows up as a stall inside the other ranks' first collective
     sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n0 = _lib.launch_count()
+    trace = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)] if os.environ.get("MMSA_BENCH_TRACE") else None
     ev0.record()
     for i in range(args.steps):
         step.run(i & 1)
+        if trace is not None:
+            trace[i].record()
     ev1.record()
     barrier()
     ms_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+    if trace is not None:        # diagnostic: per-step device time (where do multi-GPU stalls sit?)
+        marks = [ev0] + trace
+        print(f"rank {rank} per-step ms: " + " ".join(f"{marks[i].elapsed_time(marks[i + 1]):.2f}" for i in range(args.steps)),
+              file=sys.stderr, flush=True)
     clocks = sampler.stop() if sampler is not None else None
     launches = (step.launches_per_step * args.steps) if graph_ok else (_lib.launch_count() - n0)
     loss_val = float(step.slots[0].loss.item())
@@ -367,7 +381,8 @@ def run_ours(args) -> None:
             "config": {"workload": f"configs[1]: ME-MHACL cross-modal 12-head attention fusion fwd+bwd "
                                    f"(projections, 2 cross-attention blocks, pool, fusion MLP, 3-class CE, InfoNCE), "
                                    f"L={L}, R={R}, E={E}, per-GPU batch {B}, global batch {B * world}",
-                       "parallelism": f"dp{world}", "cuda_graph": graph_ok, "dropout": "train mode, in-kernel Philox",
+                       "parallelism": f"dp{world}", "cuda_graph": graph_ok,
+                       **({"ablate": os.environ["MMSA_BENCH_ABLATE"]} if os.environ.get("MMSA_BENCH_ABLATE") else {}), "dropout": "train mode, in-kernel Philox",
                        "l2_policy": "per-step working set (> 1 GB of activations, 100 MB of inputs) exceeds the 126 MB L2; "
                                     "two input slots alternate",
                        "gflop_per_sample_fwd_bwd": gf["fwd_bwd"],
