@@ -349,8 +349,18 @@ def run_ours(args) -> None:
     if gemm["ms"] > 0:
         achieved = gemm["work"] / (gemm["ms"] * 1e-3) / 1e12
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        traffic, traffic_src = None, None      # DRAM bytes per launch from the committed ncu capture of this workload
+        try:
+            import glob
+            files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_gemm_traffic.json")))
+            if files and B == 256 and L == 128 and args.dtype == "bf16":
+                with open(files[-1]) as f:
+                    tj = json.load(f)
+                traffic, traffic_src = tj["traffic_bytes_per_launch"], os.path.relpath(files[-1], ROOT)
+        except Exception:
+            pass
         roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": achieved, "peak": peak,
-                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": f"{peaks['_source']} (MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long step)",
                     "launches_per_step": gemm["count"] / prof_steps,
                     "avg_launch_ms": gemm["ms"] / gemm["count"],

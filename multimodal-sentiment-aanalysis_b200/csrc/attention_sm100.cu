@@ -250,6 +250,41 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint32_t sfull_ph = 0, ofull_ph = 0;
     const uint32_t p_tile = base + SMEM_P;
     const uint32_t o_slab = base + SMEM_O + (uint32_t)quad * 4096u;      // this warp's 32 x 128 B output slab
+    // The output of a unit (O / l through this warp's staging slab and a TMA store -- rows past Lq are clipped by the
+    // 3-D tensor map -- and the row log-sum-exp) is DEFERRED into the next unit, after its scores have been
+    // exponentiated: the P V product is then never waited for.
+    struct FwdPending { bool on; float m, l; int h, b, qt; } pend{false, 0.f, 1.f, 0, 0, 0};
+    auto finish_prev = [&]() {
+      if (!pend.on) return;
+      pend.on = false;
+      mbar_wait(o_full, ofull_ph); ofull_ph ^= 1u;
+      tc_fence_after();
+      const float inv = 1.f / pend.l;
+      if (lane == 0) tma_store_wait_read0();               // the previous store of this slab has been read out
+      __syncwarp();
+#pragma unroll 1
+      for (int cb = 0; cb < 2; ++cb) {
+        uint32_t orr[32];
+        tmem_ld32(tmem_O + lane_base + cb * 32u, orr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t w[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            w[t] = pack_bf16(__uint_as_float(orr[c * 8 + 2 * t]) * inv, __uint_as_float(orr[c * 8 + 2 * t + 1]) * inv);
+          sts128(sw128(o_slab, lane, cb * 4 + c), w[0], w[1], w[2], w[3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) { tma_store_3d(&tmO, o_slab, pend.h * HD, pend.qt * TQ + quad * 32, pend.b); tma_store_commit(); }
+      const int i = pend.qt * TQ + r;
+      if (i < p.Lq) p.lse[((long long)pend.b * p.H + pend.h) * (long long)p.Lq + i] = pend.m * p.scale + logf(pend.l);
+    };
     for (long long unit = blockIdx.x; unit < p.units; unit += gridDim.x) {
       const int qt = (int)(unit % p.nq);
       const long long bh = unit / p.nq;
@@ -259,6 +294,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       // protocol going; its P rows stay stale, which only feeds accumulator rows nobody reads
       const bool live = qt * TQ + quad * 32 < p.Lq;
       if (!live) {
+        finish_prev();
         for (int j = 0; j < p.nkv; ++j) {
           mbar_wait(s_full, sfull_ph); sfull_ph ^= 1u;
           if (lane == 0) mbar_arrive(s_free);
@@ -312,6 +348,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             }
             tmem_st_wait();
           }
+        } else {
+          finish_prev();       // the previous unit's O: its P V ran while this unit's scores were exponentiated
         }
         l = l * alpha + rowsum;
         m = m_new;
@@ -323,59 +361,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
       }
-      // ---- output rows: O / l through this warp's staging slab and a TMA store (rows past Lq are clipped by the
-      //      3-D tensor map), and the log-sum-exp of the scaled scores ----
-      mbar_wait(o_full, ofull_ph); ofull_ph ^= 1u;
-      tc_fence_after();
-      const float inv = 1.f / l;
-      if (p.direct_store) {
-        const int ii = qt * TQ + r;
-#pragma unroll 1
-        for (int cb = 0; cb < 2; ++cb) {
-          uint32_t orr[32];
-          tmem_ld32(tmem_O + lane_base + cb * 32u, orr);
-          tmem_ld_wait();
-          if (ii < p.Lq) {
-            bf16* op = p.o + (b * p.Lq + ii) * p.ldo + h * HD + cb * 32;
-#pragma unroll
-            for (int c = 0; c < 32; c += 8) {
-              float v[8];
-#pragma unroll
-              for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(orr[c + t]) * inv;
-              store_vec<bf16>(op + c, v);
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(o_free);
-      } else {
-      if (lane == 0) tma_store_wait_read0();               // the previous store of this slab has been read out
-      __syncwarp();
-#pragma unroll 1
-      for (int cb = 0; cb < 2; ++cb) {
-        uint32_t orr[32];
-        tmem_ld32(tmem_O + lane_base + cb * 32u, orr);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t w[4];
-#pragma unroll
-          for (int t = 0; t < 4; ++t)
-            w[t] = pack_bf16(__uint_as_float(orr[c * 8 + 2 * t]) * inv, __uint_as_float(orr[c * 8 + 2 * t + 1]) * inv);
-          sts128(sw128(o_slab, lane, cb * 4 + c), w[0], w[1], w[2], w[3]);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(o_free);
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) { tma_store_3d(&tmO, o_slab, h * HD, qt * TQ + quad * 32, (int)b); tma_store_commit(); }
-      }
-      const int i = qt * TQ + r;
-      if (i < p.Lq) p.lse[(b * p.H + h) * (long long)p.Lq + i] = m * p.scale + logf(l);
+      pend = FwdPending{true, m, l, h, (int)b, qt};
     }
+    finish_prev();
     if (lane == 0) tma_store_wait_all();
   }
 
@@ -562,6 +550,65 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     Cur x{(long long)blockIdx.x, 0, 0, 0, 0, 0};
     float lse_l2 = 0.f, delta = 0.f;
     bool row_valid = false;
+    // The read-out of a step's dQ / dK / dV is DEFERRED until the next step's P / dS have been staged: the second MMA
+    // chain of step t (dQ, [dV;dK]) then runs while these warps already exponentiate step t+1, instead of being waited for.
+    struct Pending { bool dq, dkv; int h, b, qt, kt; } pend{false, false, 0, 0, 0, 0};
+    auto readout = [&]() {
+      if (pend.dq) {
+        mbar_wait(dq_full, dqfull_ph); dqfull_ph ^= 1u;
+        tc_fence_after();
+        if (issuer) tma_store_wait_read0();
+        pair_sync();
+        {
+          uint32_t orr[32];
+          tmem_ld32(tmem_dQ + lane_base + hh * 32u, orr);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(dq_free);
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4)
+            sts128(sw128(dq_slab, lane, hh * 4 + c4),
+                   pack_bf16(__uint_as_float(orr[c4 * 8]), __uint_as_float(orr[c4 * 8 + 1])),
+                   pack_bf16(__uint_as_float(orr[c4 * 8 + 2]), __uint_as_float(orr[c4 * 8 + 3])),
+                   pack_bf16(__uint_as_float(orr[c4 * 8 + 4]), __uint_as_float(orr[c4 * 8 + 5])),
+                   pack_bf16(__uint_as_float(orr[c4 * 8 + 6]), __uint_as_float(orr[c4 * 8 + 7])));
+        }
+        fence_async_smem();
+        pair_sync();
+        if (issuer) { tma_store_3d(&tmdQ, dq_slab, pend.h * HD, pend.qt * TQ + quad * 32, pend.b); tma_store_commit(); }
+      }
+      if (pend.dkv) {
+        mbar_wait(dkv_full, dkvfull_ph); dkvfull_ph ^= 1u;
+        tc_fence_after();
+        if (issuer) tma_store_wait_read0();
+        pair_sync();
+        // TMEM lanes 0-63 x columns 0-63 hold dV, lanes 64-127 x columns 64-127 hold dK (already scaled through dS)
+        const uint32_t col0 = quad < 2 ? 0u : 64u;
+        {
+          uint32_t orr[32];
+          tmem_ld32(tmem_dKV + lane_base + col0 + hh * 32u, orr);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(dkv_free);
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4)
+            sts128(sw128(dkv_slab, lane, hh * 4 + c4),
+                   pack_bf16(__uint_as_float(orr[c4 * 8]), __uint_as_float(orr[c4 * 8 + 1])),
+                   pack_bf16(__uint_as_float(orr[c4 * 8 + 2]), __uint_as_float(orr[c4 * 8 + 3])),
+                   pack_bf16(__uint_as_float(orr[c4 * 8 + 4]), __uint_as_float(orr[c4 * 8 + 5])),
+                   pack_bf16(__uint_as_float(orr[c4 * 8 + 6]), __uint_as_float(orr[c4 * 8 + 7])));
+        }
+        fence_async_smem();
+        pair_sync();
+        if (issuer) {
+          tma_store_3d(quad < 2 ? &tmdV : &tmdK, dkv_slab, pend.h * HD, pend.kt * TK + (quad & 1) * 32, pend.b);
+          tma_store_commit();
+        }
+      }
+      pend.dq = pend.dkv = false;
+    };
     while (x.unit < p.units) {
       const int h = (int)(x.unit % p.H);
       const int b = (int)(x.unit / p.H);
@@ -587,9 +634,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         delta = acc;
       }
       mbar_wait(sdp_full, sdpfull_ph); sdpfull_ph ^= 1u;
-      mbar_wait(ps_free, psfree_ph ^ 1u); psfree_ph ^= 1u;       // the MMAs that read the previous P / dS have retired
       tc_fence_after();
       const int kvalid = min(TK, p.Lk - kt * TK);
+      uint32_t pw[16], dw[16];
       {
         uint32_t sr[32], dr[32];
         tmem_ld32(tmem_S + lane_base + hh * 32u, sr);
@@ -599,85 +646,34 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(sdp_free);
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          uint32_t pw[4], dw[4];
+        for (int t = 0; t < 16; ++t) {
+          float pv[2], dv[2];
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            float pv[2], dv[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int cc = c4 * 8 + 2 * t + e;
-              const bool ok = row_valid && (hh * 32 + cc < kvalid);
-              const float pp = ok ? fast_exp2(__uint_as_float(sr[cc]) * p.scale_log2 - lse_l2) : 0.f;
-              pv[e] = pp;
-              dv[e] = pp * (__uint_as_float(dr[cc]) - delta) * p.scale;
-            }
-            pw[t] = pack_bf16(pv[0], pv[1]);
-            dw[t] = pack_bf16(dv[0], dv[1]);
+          for (int e = 0; e < 2; ++e) {
+            const int cc = 2 * t + e;
+            const bool ok = row_valid && (hh * 32 + cc < kvalid);
+            const float pp = ok ? fast_exp2(__uint_as_float(sr[cc]) * p.scale_log2 - lse_l2) : 0.f;
+            pv[e] = pp;
+            dv[e] = pp * (__uint_as_float(dr[cc]) - delta) * p.scale;
           }
-          sts128(sw128(ps, r, hh * 4 + c4), pw[0], pw[1], pw[2], pw[3]);
-          sts128(sw128(ps + P_BYTES, r, hh * 4 + c4), dw[0], dw[1], dw[2], dw[3]);
+          pw[t] = pack_bf16(pv[0], pv[1]);
+          dw[t] = pack_bf16(dv[0], dv[1]);
         }
+      }
+      mbar_wait(ps_free, psfree_ph ^ 1u); psfree_ph ^= 1u;       // the MMAs that read the previous P / dS have retired
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        sts128(sw128(ps, r, hh * 4 + c4), pw[c4 * 4], pw[c4 * 4 + 1], pw[c4 * 4 + 2], pw[c4 * 4 + 3]);
+        sts128(sw128(ps + P_BYTES, r, hh * 4 + c4), dw[c4 * 4], dw[c4 * 4 + 1], dw[c4 * 4 + 2], dw[c4 * 4 + 3]);
       }
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(ps_full);
-
-      if (dq_done) {
-        mbar_wait(dq_full, dqfull_ph); dqfull_ph ^= 1u;
-        tc_fence_after();
-        if (issuer) tma_store_wait_read0();
-        pair_sync();
-        {
-          uint32_t orr[32];
-          tmem_ld32(tmem_dQ + lane_base + hh * 32u, orr);
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(dq_free);
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4)
-            sts128(sw128(dq_slab, lane, hh * 4 + c4),
-                   pack_bf16(__uint_as_float(orr[c4 * 8]), __uint_as_float(orr[c4 * 8 + 1])),
-                   pack_bf16(__uint_as_float(orr[c4 * 8 + 2]), __uint_as_float(orr[c4 * 8 + 3])),
-                   pack_bf16(__uint_as_float(orr[c4 * 8 + 4]), __uint_as_float(orr[c4 * 8 + 5])),
-                   pack_bf16(__uint_as_float(orr[c4 * 8 + 6]), __uint_as_float(orr[c4 * 8 + 7])));
-        }
-        fence_async_smem();
-        pair_sync();
-        if (issuer) { tma_store_3d(&tmdQ, dq_slab, h * HD, qt * TQ + quad * 32, b); tma_store_commit(); }
-      }
-      if (dkv_done) {
-        mbar_wait(dkv_full, dkvfull_ph); dkvfull_ph ^= 1u;
-        tc_fence_after();
-        if (issuer) tma_store_wait_read0();
-        pair_sync();
-        // TMEM lanes 0-63 x columns 0-63 hold dV, lanes 64-127 x columns 64-127 hold dK (already scaled through dS)
-        const uint32_t col0 = quad < 2 ? 0u : 64u;
-        {
-          uint32_t orr[32];
-          tmem_ld32(tmem_dKV + lane_base + col0 + hh * 32u, orr);
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(dkv_free);
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4)
-            sts128(sw128(dkv_slab, lane, hh * 4 + c4),
-                   pack_bf16(__uint_as_float(orr[c4 * 8]), __uint_as_float(orr[c4 * 8 + 1])),
-                   pack_bf16(__uint_as_float(orr[c4 * 8 + 2]), __uint_as_float(orr[c4 * 8 + 3])),
-                   pack_bf16(__uint_as_float(orr[c4 * 8 + 4]), __uint_as_float(orr[c4 * 8 + 5])),
-                   pack_bf16(__uint_as_float(orr[c4 * 8 + 6]), __uint_as_float(orr[c4 * 8 + 7])));
-        }
-        fence_async_smem();
-        pair_sync();
-        if (issuer) {
-          tma_store_3d(quad < 2 ? &tmdV : &tmdK, dkv_slab, h * HD, kt * TK + (quad & 1) * 32, b);
-          tma_store_commit();
-        }
-      }
+      readout();                                                 // the PREVIOUS step's results
+      pend = Pending{dq_done, dkv_done, h, b, qt, kt};
       advance(x);
     }
+    readout();
     if (lane == 0) tma_store_wait_all();
   }
 

@@ -97,7 +97,42 @@ def full(rep: str, f):
         f.write(f"| `{short(d[idx['Kernel Name']])[:60]}` | {d[idx['Grid Size']]} | " + " | ".join(cells) + " |\n")
 
 
+def gemm_traffic():
+    """per-launch DRAM traffic of the tcgen05 GEMM launches of one step -> profiles/<tag>_gemm_traffic.json
+    (bench.py reads it for roofline.traffic)."""
+    import json
+    path = os.path.join(OUT, "gemm_traffic.csv")
+    if not os.path.exists(path):
+        return
+    rows = [r for r in csv.DictReader(l for l in open(path) if l.startswith('"'))]
+    per = collections.OrderedDict()
+    for r in rows:
+        d = per.setdefault(r["ID"], {"kernel": short(r["Kernel Name"]), "grid": r["Grid Size"]})
+        v = float(r["Metric Value"])
+        unit = r["Metric Unit"].lower()
+        if r["Metric Name"].startswith("dram__bytes"):
+            mult = {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1.0)
+            d[r["Metric Name"]] = v * mult
+        else:
+            mult = {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(unit, 1.0)
+            d["us"] = v * mult
+    launches = list(per.values())
+    n = len(launches)
+    if n == 0:
+        return
+    rd = sum(l.get("dram__bytes_read.sum", 0.0) for l in launches)
+    wr = sum(l.get("dram__bytes_write.sum", 0.0) for l in launches)
+    out = {"source": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum of the {n} gemm_tcgen05_kernel launches of one "
+                     "step of `python bench.py --steps 2 --warmup 1 --no-graph` (configs[1], B=256, L=128, bf16)",
+           "launches": n, "dram_read_bytes_per_launch": rd / n, "dram_write_bytes_per_launch": wr / n,
+           "traffic_bytes_per_launch": (rd + wr) / n, "total_us": sum(l.get("us", 0.0) for l in launches)}
+    with open(os.path.join(PROF, f"{tag}_gemm_traffic.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    shutil.copy(path, os.path.join(PROF, f"{tag}_gemm_traffic.csv"))
+
+
 launches()
+gemm_traffic()
 with open(os.path.join(PROF, f"{tag}_ncu_full.md"), "w") as f:
     f.write(f"# {tag}: `ncu --set full --clock-control none --import-source on` captures (key counters)\n\n"
             "dram rd / dram wr are per launch (`dram__bytes_read.sum`, `dram__bytes_write.sum`); tensor % is "

@@ -15,7 +15,7 @@ for (Nw, Kw, rows) in [(768, 768, 32768), (768, 768, 12544), (1536, 768, 32768),
     C = torch.zeros(Nw, Kw, device=dev)
     ref = dYs[0].float().t()[:256] @ Xs[0].float()
     line = f"dW[{Nw}x{Kw}] rows={rows}:"
-    for bn, sp_list in ((256, (4, 6, 8)), (512, (1, 2, 3, 4))):
+    for bn, sp_list in ((256, (6,)), (128, (2, 3, 4)), (192, (4, 6)), (64, (2,))):
         for sp in sp_list:
             def run(i):
                 j = i % nset
@@ -30,5 +30,5 @@ for (Nw, Kw, rows) in [(768, 768, 32768), (768, 768, 12544), (1536, 768, 32768),
             for i in range(12): run(i)
             e1.record(); torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 12
-            line += f"  {'pair' if bn == 512 else '1cta'} S={sp} {ms*1e3:5.1f}us {2.0*Nw*Kw*rows/ms/1e9:5.0f}TF e={err:.0e}"
+            line += f"  bn={bn} S={sp} {ms*1e3:5.1f}us {2.0*Nw*Kw*rows/ms/1e9:5.0f}TF e={err:.0e}"
     print(line, flush=True)
