@@ -130,6 +130,8 @@ class MultimodalTransformerModel(nn.Module):
         self._drop = _DropoutState()
         # data-parallel contrastive sharding (set by mmsa.dist.shard_contrastive)
         self.dp_group = None
+        self.overlap_contrastive = True      # contrastive branch on a second stream (text+image wiring)
+        self._side_stream = None
 
     # -- helpers ------------------------------------------------------------------------------------
     def set_dropout(self, p: float) -> "MultimodalTransformerModel":
@@ -175,6 +177,7 @@ class MultimodalTransformerModel(nn.Module):
         if con_labels is not None:
             con_labels = con_labels.contiguous().long()
         contrastive: List[Tensor] = []
+        side, weighted = None, False
         if self.wiring == "native":
             f0 = self._cd(self.eeg_net(eeg))
             f1 = self._cd(self.eye_net(eye))
@@ -196,15 +199,35 @@ class MultimodalTransformerModel(nn.Module):
             slots = (f0, e1, e2)
             if con_labels is not None:
                 fast = self.compute_dtype == torch.bfloat16      # split-bf16 tensor-core GEMMs (fp32-accurate)
-                if self.dp_group is not None:
-                    from . import dist as mdist
-                    contrastive.append(mdist.sharded_infonce(e1, e2, con_labels, self.temperature, self.dp_group, fast=fast))
-                else:
-                    contrastive.append(ops.infonce(e1, e2, con_labels, self.temperature, fast=fast))
-                if self.contract == "multitask":
-                    contrastive.append(ops.infonce(e2, e1, con_labels, self.temperature, fast=fast))
+                # The contrastive branch (normalise, similarity GEMM, row reductions, and under data parallelism the
+                # embedding all-gather) and the classifier tail are independent chains of small, latency-bound kernels
+                # hanging off the same pooled features: the branch is enqueued on a second stream, so both chains (and
+                # their backward halves, which autograd replays on the stream of the forward) overlap -- also as two
+                # parallel branches of the captured CUDA graph.
+                main = torch.cuda.current_stream(e1.device)
+                if self.overlap_contrastive:
+                    if self._side_stream is None:
+                        self._side_stream = torch.cuda.Stream(device=e1.device)
+                    side = self._side_stream
+                    side.wait_stream(main)
+                with torch.cuda.stream(side if side is not None else main):
+                    if self.dp_group is not None:
+                        from . import dist as mdist
+                        contrastive.append(mdist.sharded_infonce(e1, e2, con_labels, self.temperature, self.dp_group, fast=fast))
+                    else:
+                        contrastive.append(ops.infonce(e1, e2, con_labels, self.temperature, fast=fast))
+                    if self.contract == "multitask":
+                        contrastive.append(ops.infonce(e2, e1, con_labels, self.temperature, fast=fast))
+                    contrastive = [self.contrastive_weight * c for c in contrastive]     # :315-317 -> shape (1,)
+                    weighted = True
         arousal, valence = self._tail(raw_a, raw_b, slots)
-        contrastive = [self.contrastive_weight * c for c in contrastive]     # :315-317 -> shape (1,)
+        if side is not None:                                         # join the contrastive branch
+            cur = torch.cuda.current_stream(arousal.device)
+            cur.wait_stream(side)
+            for c in contrastive:
+                c.record_stream(cur)
+        if not weighted:
+            contrastive = [self.contrastive_weight * c for c in contrastive]     # :315-317 -> shape (1,)
         if self.contract == "single":
             if labels is None:
                 return arousal                                       # Tester.py:53
