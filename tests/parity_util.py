@@ -134,7 +134,7 @@ def run_fusion_parity(batch: int = 4, L: int = 64, R: int = 49, dtype: str = "fp
     excess = {k: errs[k] / max(tol, noise_mult * noise[k]) for k in errs}
     worst = max(excess, key=lambda k: excess[k])
     labels_equal = bool(torch.equal(logits.argmax(1).cpu(), o_out.arousal.argmax(1)))
-    top2 = o_out.arousal.topk(2, dim=1).values
+    top2 = o_out.arousal.detach().topk(2, dim=1).values
     return {"ok": excess[worst] <= 1.0 and labels_equal, "max_rel": errs[worst], "worst": worst, "errs": errs,
             "noise": noise, "excess": excess[worst],
             "failing": {k: (errs[k], noise[k]) for k in errs if excess[k] > 1.0},
