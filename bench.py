@@ -220,6 +220,11 @@ def run_ours(args) -> None:
                      torch.randn(B, R, DI, generator=g).to(cd).pin_memory(),
                      torch.randint(0, C, (B,), generator=g).pin_memory()))
 
+    opt = None
+    if args.optimizer:          # fused global-norm clip + AdamW after every step (Trainer.py:80-81)
+        opt = mmsa.FusedClipAdamW(model.parameters(), lr=1e-4, weight_decay=0.01, max_norm=1.0)
+        for grp in opt.param_groups:
+            opt._arena(grp)     # re-home the parameters into the flat arena BEFORE the step graph captures their addresses
     step = TrainStep(model, B, L, R, DT, DI, feature_dtype=cd, n_slots=2, use_graph=not args.no_graph,
                      post_backward=(reducer.step if reducer is not None else None), device=dev)
     for k, s in enumerate(step.slots):
@@ -252,7 +257,10 @@ def run_ours(args) -> None:
 
     # ---- device-resident throughput (`value`) ----
     for _ in range(max(args.warmup, 3)):
-        step.run(0); step.run(1)
+        for k in (0, 1):
+            step.run(k)
+            if opt is not None:
+                opt.step()
     # the clock sampler (NVML init: tens of ms) starts BEFORE the barrier: anything rank 0 does between the barrier and
     # its first launch shows up as a stall inside the other ranks' first collective
     sampler = ClockSampler(local_rank).start() if rank == 0 else None
@@ -263,6 +271,8 @@ def run_ours(args) -> None:
     ev0.record()
     for i in range(args.steps):
         step.run(i & 1)
+        if opt is not None:
+            opt.step()
         if trace is not None:
             trace[i].record()
     ev1.record()
@@ -273,7 +283,7 @@ def run_ours(args) -> None:
         print(f"rank {rank} per-step ms: " + " ".join(f"{marks[i].elapsed_time(marks[i + 1]):.2f}" for i in range(args.steps)),
               file=sys.stderr, flush=True)
     clocks = sampler.stop() if sampler is not None else None
-    launches = (step.launches_per_step * args.steps) if graph_ok else (_lib.launch_count() - n0)
+    launches = (step.launches_per_step * args.steps + (_lib.launch_count() - n0)) if graph_ok else (_lib.launch_count() - n0)
     loss_val = float(step.slots[0].loss.item())
 
     # ---- end-to-end through the public step API with host inputs (`e2e`) ----
@@ -298,6 +308,8 @@ def run_ours(args) -> None:
                 in_ready[k].record(copy_stream)
             main.wait_event(in_ready[k])
             loss = step.run(k)
+            if opt is not None:
+                opt.step()
             loss_host.copy_(loss, non_blocking=True)           # D2H read of the step's loss
             slot_free[k].record(main)
         main.synchronize()
@@ -392,6 +404,7 @@ def run_ours(args) -> None:
                                    f"(projections, 2 cross-attention blocks, pool, fusion MLP, 3-class CE, InfoNCE), "
                                    f"L={L}, R={R}, E={E}, per-GPU batch {B}, global batch {B * world}",
                        "parallelism": f"dp{world}", "cuda_graph": graph_ok,
+                       **({"optimizer": "mmsa.FusedClipAdamW after every step (eager: pack + sumsq + clip_adamw), lr 1e-4, wd 0.01, clip 1.0"} if opt is not None else {}),
                        **({"ablate": os.environ["MMSA_BENCH_ABLATE"]} if os.environ.get("MMSA_BENCH_ABLATE") else {}), "dropout": "train mode, in-kernel Philox",
                        "l2_policy": "per-step working set (> 1 GB of activations, 100 MB of inputs) exceeds the 126 MB L2; "
                                     "two input slots alternate",
@@ -426,6 +439,8 @@ def main() -> None:
     ap.add_argument("--L", type=int, default=128, help="text tokens per sample (configs[1]: 128)")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
+    ap.add_argument("--optimizer", action="store_true",
+                    help="also run the fused clip+AdamW update after every step (not part of the BASELINE metric)")
     ap.add_argument("--cpu-sample-batch", type=int, default=32, help="samples per CPU reference step")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -7,6 +7,9 @@ from . import _lib
 from .model import (Classifier, CrossModalTransformer, FeatureProjection, MultiModalEncoder,
                     MultimodalTransformerModel, ProjectionHead)
 from .ops import cross_entropy, infonce, ntxent, supcon
+from .optim import FusedClipAdamW
+from .io import FeatureBatches, load_reference_state_dict, strip_module_prefix
 
 __all__ = ["MultimodalTransformerModel", "CrossModalTransformer", "FeatureProjection", "MultiModalEncoder",
-           "ProjectionHead", "Classifier", "cross_entropy", "infonce", "supcon", "ntxent", "_lib"]
+           "ProjectionHead", "Classifier", "cross_entropy", "infonce", "supcon", "ntxent", "FusedClipAdamW",
+           "FeatureBatches", "load_reference_state_dict", "strip_module_prefix", "_lib"]

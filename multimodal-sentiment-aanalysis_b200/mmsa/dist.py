@@ -118,12 +118,10 @@ class GradAllReducer:
                 return
             key = tuple(id(p) for p in live)
             if self._flat is None or self._flat_key != key:
-                total = sum(p.numel() for p in live)
-                self._flat = torch.empty(total, device=live[0].device, dtype=torch.float32)
-                self._flat_views, off = [], 0
-                for p in live:
-                    self._flat_views.append(self._flat[off:off + p.numel()].view_as(p))
-                    off += p.numel()
+                from .optim import arena_layout          # same (256-byte aligned) layout as FusedClipAdamW's arenas
+                offs, total = arena_layout(live)
+                self._flat = torch.zeros(total, device=live[0].device, dtype=torch.float32)
+                self._flat_views = [self._flat[off:off + p.numel()].view_as(p) for p, off in zip(live, offs)]
                 self._flat_key = key
             torch._foreach_copy_(self._flat_views, [p.grad for p in live])
             dist.all_reduce(self._flat, op=dist.ReduceOp.AVG, group=self.group)

@@ -24,7 +24,16 @@ Tensor = torch.Tensor
 # fp32 master weight -> bf16 operand copy.  prepare_weights() refreshes every copy of a model in ONE
 # launch (call it once per step, after the optimiser update); _w() falls back to a single cast when a
 # parameter was modified since (tensor._version) or never prepared.
-_WCACHE: Dict[int, Tuple[int, Tensor]] = {}
+_WCACHE: Dict[int, Tuple[int, int, Tensor]] = {}      # id(param) -> (param._version, weights epoch, operand copy)
+_WEPOCH = 0
+
+
+def bump_weights_epoch() -> None:
+    """Mark every cached operand copy stale.  Called by optimisers that update parameters with their own kernels
+    (no autograd version bump); the copies are re-cast INTO THE SAME buffers, so addresses captured in a CUDA graph
+    stay valid."""
+    global _WEPOCH
+    _WEPOCH += 1
 
 
 def prepare_weights(params: Sequence[Tensor], dtype: torch.dtype) -> None:
@@ -35,11 +44,11 @@ def prepare_weights(params: Sequence[Tensor], dtype: torch.dtype) -> None:
         if p.ndim < 2 or not p.is_cuda:
             continue
         ent = _WCACHE.get(id(p))
-        if ent is None or ent[1].shape != p.shape or ent[1].device != p.device or ent[1].dtype != dtype:
-            ent = (-1, torch.empty(p.shape, device=p.device, dtype=dtype))
+        if ent is None or ent[2].shape != p.shape or ent[2].device != p.device or ent[2].dtype != dtype:
+            ent = (-1, -1, torch.empty(p.shape, device=p.device, dtype=dtype))
         srcs.append(p.detach())
-        dsts.append(ent[1])
-        _WCACHE[id(p)] = (p._version, ent[1])
+        dsts.append(ent[2])
+        _WCACHE[id(p)] = (p._version, _WEPOCH, ent[2])
     K.cast_multi(srcs, dsts)
 
 
@@ -49,11 +58,16 @@ def _w(w: Tensor, dtype: torch.dtype) -> Tensor:
         wd = w.detach()
         return wd if wd.is_contiguous() else wd.contiguous()
     ent = _WCACHE.get(id(w))
-    if ent is not None and ent[0] == w._version and ent[1].shape == w.shape and ent[1].dtype == dtype \
-            and ent[1].device == w.device:
-        return ent[1]
+    fits = ent is not None and ent[2].shape == w.shape and ent[2].dtype == dtype and ent[2].device == w.device
+    if fits and ent[0] == w._version and ent[1] == _WEPOCH:
+        return ent[2]
     wd = w.detach()
-    return K.cast(wd if wd.is_contiguous() else wd.contiguous(), dtype)
+    wd = wd if wd.is_contiguous() else wd.contiguous()
+    if fits:                                      # stale: refresh in place (stable address)
+        K.cast_multi([wd], [ent[2]])
+        _WCACHE[id(w)] = (w._version, _WEPOCH, ent[2])
+        return ent[2]
+    return K.cast(wd, dtype)
 
 
 def _c(t: Tensor) -> Tensor:

@@ -176,3 +176,34 @@ def test_state_dict_keys_match_reference_layout():
     # module. prefix stripping of Tester.load_model (Tester.py:32-33) round-trips
     sd = {"module." + k: v for k, v in model.state_dict().items()}
     model.load_state_dict({k[7:]: v for k, v in sd.items()}, strict=True)
+
+
+def test_io_adapters_batch_formats_and_checkpoints(tmp_path):
+    """mmsa.io: the reference's two batch formats (data/Dataset.py:65-67 dict batches, dataLoader/DataLoader.py:152-156
+    5-tuples) and checkpoint loading with the `module.` prefix of nn.DataParallel stripped (Tester.py:32-33)."""
+    import mmsa
+    n = 10
+    text, image = torch.randn(n, 4, 768), torch.randn(n, 49, 2048)
+    labels = torch.arange(n) % 3
+    batches = list(mmsa.FeatureBatches(text, image, labels, batch_size=4, fmt="dict"))
+    assert len(batches) == 3 and set(batches[0][0].keys()) == {"eeg", "eye", "pps"}
+    assert batches[0][0]["eeg"].shape == (4, 4, 768) and batches[2][1].shape == (2,)
+    assert torch.equal(torch.cat([b[1] for b in batches]), labels)
+    tup = next(iter(mmsa.FeatureBatches(text, image, labels, batch_size=4, fmt="tuple", valence_labels=labels.flip(0))))
+    assert len(tup) == 5 and tup[3].dtype == torch.int64 and torch.equal(tup[4], labels.flip(0)[:4])
+    shuffled = mmsa.FeatureBatches(text, image, labels, batch_size=4, fmt="tuple", shuffle=True, seed=1, drop_last=True)
+    assert len(shuffled) == 2 and len(list(shuffled)) == 2
+    # checkpoint written from a DataParallel-wrapped model: keys carry "module."
+    src = mmsa.MultimodalTransformerModel()
+    sd = {"module." + k: v.clone() + 1 for k, v in src.state_dict().items()}
+    path = str(tmp_path / "best_model.pth")
+    torch.save(sd, path)                                              # Trainer.py:111
+    dst = mmsa.MultimodalTransformerModel()
+    res = mmsa.load_reference_state_dict(dst, path)
+    assert not res.missing_keys and not res.unexpected_keys
+    for k, v in dst.state_dict().items():
+        assert torch.equal(v, sd["module." + k])
+    # a reference checkpoint also holds the out-of-scope encoder weights: dropped on request
+    sd2 = dict(sd)
+    sd2["module.eeg_net.conv1.weight"] = torch.zeros(3)
+    mmsa.load_reference_state_dict(dst, sd2, ignore_prefixes=("eeg_net.", "eye_net.", "pps_net."))

@@ -511,3 +511,45 @@ def test_not_sm100_message():
     """the device gate exists and reports (on the B200 box it passes)."""
     from mmsa import _lib
     assert _lib.load().mmsa_check_device() == 0
+
+
+def test_fused_clip_adamw_optimizer(cuda_device):
+    """mmsa.FusedClipAdamW (flat arenas, one clip+AdamW kernel per group) vs clip_grad_norm_ + torch.optim.AdamW on the
+    same multi-tensor parameter set: two groups (Trainer.py:24-26 adds the trainer's own weight as a second group), a
+    parameter without gradient, an lr change through param_groups (ReduceLROnPlateau, Trainer.py:28)."""
+    import mmsa
+    g = torch.Generator().manual_seed(5)
+    shapes = [(256, 768), (768,), (3, 128), (128, 128), (1,), ()]
+    base = [torch.randn(s, generator=g) * 0.1 for s in shapes]
+    ours = [torch.nn.Parameter(b.clone().to(cuda_device)) for b in base]
+    ref = [torch.nn.Parameter(b.clone().to(cuda_device)) for b in base]
+    extra_o, extra_r = torch.nn.Parameter(torch.ones(1, device=cuda_device)), torch.nn.Parameter(torch.ones(1, device=cuda_device))
+    opt_o = mmsa.FusedClipAdamW(ours, lr=1e-3, weight_decay=0.01, max_norm=1.0)
+    opt_r = torch.optim.AdamW(ref, lr=1e-3, weight_decay=0.01)
+    opt_o.add_param_group({"params": [extra_o], "lr": 1e-3})
+    opt_r.add_param_group({"params": [extra_r], "lr": 1e-3})
+    ids = [id(p) for p in ours]
+    for step in range(1, 6):
+        for i, (po, pr) in enumerate(zip(ours + [extra_o], ref + [extra_r])):
+            if i == 2 and step % 2 == 0:           # a parameter without gradient this step
+                po.grad, pr.grad = None, torch.zeros_like(pr)
+                continue
+            gr = torch.randn(po.shape, generator=g).to(cuda_device) * (0.5 * step)
+            po.grad, pr.grad = gr.clone(), gr.clone()
+        if step == 4:
+            for grp in opt_o.param_groups + opt_r.param_groups:
+                grp["lr"] *= 0.1
+        torch.nn.utils.clip_grad_norm_(ref + [extra_r], 1.0)
+        opt_r.step()
+        opt_o.step()
+        for po, pr in zip(ours + [extra_o], ref + [extra_r]):
+            assert rel_err(po, pr) <= 2e-6, step
+    assert [id(p) for p in ours] == ids            # Parameter identity survives the re-homing into the arena
+    # gradients that already live in one flat buffer in parameter order (GradAllReducer) are used in place
+    from mmsa.optim import arena_layout
+    offs, total = arena_layout(ours)
+    flat = torch.zeros(total, device=cuda_device)
+    for p, off in zip(ours, offs):
+        p.grad = flat[off:off + p.numel()].view_as(p)
+    a = opt_o._arena(opt_o.param_groups[0])
+    assert opt_o._flat_grad(a).data_ptr() == flat.data_ptr()
