@@ -70,6 +70,19 @@ def _w(w: Tensor, dtype: torch.dtype) -> Tensor:
     return K.cast(wd, dtype)
 
 
+_SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    """one helper stream per device for work that hangs off the main chain (tail weight gradients)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = _SIDE_STREAMS.get(idx)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _SIDE_STREAMS[idx] = st
+    return st
+
+
 def _c(t: Tensor) -> Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
@@ -537,6 +550,10 @@ class SeqFn(Function):
         grads: List[Optional[Tensor]] = [None] * ctx.n_params
         need = ctx.needs_input_grad[7:]
         d = K.cast(_c(dy), torch.float32)          # fp32 unless an elementwise backward wrote cd for a GEMM
+        main = torch.cuda.current_stream(dy.device)
+        side = _side_stream(dy.device)
+        keep: List[Optional[Tensor]] = []
+        used_side = False
         dx = dx2 = None
         db_fp32 = None                             # bias gradient handed down by a BatchNorm backward
         for ti in range(len(tape) - 1, -1, -1):
@@ -555,12 +572,18 @@ class SeqFn(Function):
                     want_b = False
                 db_fp32 = None
                 if want_w or want_b:
-                    if a2 is None:
-                        dw, db = K.linear_wgrad(d_cd, a, want_bias=want_b, want_weight=want_w)
-                    else:
-                        dw = torch.empty(wc.shape, device=d.device, dtype=torch.float32)
-                        _, db = K.linear_wgrad(d_cd, a, dw=dw[:, :Kx], want_bias=want_b, want_weight=True)
-                        K.linear_wgrad(d_cd, a2, dw=dw[:, Kx:], want_bias=False, want_weight=True)
+                    # weight gradients are leaves of the backward chain: they go to a second stream and overlap the
+                    # dgrad / BatchNorm chain (all of it small latency-bound kernels); joined before returning
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        if a2 is None:
+                            dw, db = K.linear_wgrad(d_cd, a, want_bias=want_b, want_weight=want_w)
+                        else:
+                            dw = torch.empty(wc.shape, device=d.device, dtype=torch.float32)
+                            _, db = K.linear_wgrad(d_cd, a, dw=dw[:, :Kx], want_bias=want_b, want_weight=True)
+                            K.linear_wgrad(d_cd, a2, dw=dw[:, Kx:], want_bias=False, want_weight=True)
+                    keep.extend((d_cd, a, a2, dw, db))     # alive until the join: no reuse of their memory by `main` meanwhile
+                    used_side = True
                     grads[pidx] = dw if want_w else None
                     if has_b and want_b:
                         grads[pidx + 1] = db
@@ -585,6 +608,9 @@ class SeqFn(Function):
                 d = K.act_bwd(op[1], K.cast(d, torch.float32), op[2], out_dt)
             elif kind == "dropout":
                 d, _ = K.dropout(K.cast(d, torch.float32), op[1], op[2], True, 0, 0, out_dt)
+        if used_side:
+            main.wait_stream(side)
+            keep.clear()
         if tape and tape[0][0] != "linear" and ctx.needs_input_grad[0]:
             dx = K.cast(d, torch.float32)
         if dx is not None:
