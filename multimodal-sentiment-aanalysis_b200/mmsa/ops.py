@@ -70,6 +70,7 @@ def _w(w: Tensor, dtype: torch.dtype) -> Tensor:
     return K.cast(wd, dtype)
 
 
+OVERLAP_WGRAD = True      # block weight gradients on a second stream (FusionCoreFn.backward)
 _SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
 
 
@@ -193,7 +194,8 @@ def _block_fwd(q_in: Tensor, kv_in: Tensor, B: int, Lq: int, Lk: int, H: int, in
 
 
 def _block_bwd(st: _BlockState, dy: Tensor, *, dpooled_q: Optional[Tensor] = None, dq_add: Optional[Tensor] = None,
-               dkv_residual: Optional[Tensor] = None, need_dq: bool = True, need_dkv: bool = True, need_w: bool = True):
+               dkv_residual: Optional[Tensor] = None, need_dq: bool = True, need_dkv: bool = True, need_w: bool = True,
+               wgrad_stream=None, keep: Optional[list] = None):
     """Backward of _block_fwd.  dy is [B*Lq,E] (cd) for a plain block, or the fp32 [B,E] gradient of the
     pooled output for a pooled block (dpooled_q: fp32 [B,E] gradient of the pooled query stream).
     Returns (dq, dkv, grads) with grads = (d_in_w, d_in_b, d_out_w, d_out_b, d_gate_w, d_gate_b, d_ln_w, d_ln_b).
@@ -208,14 +210,33 @@ def _block_bwd(st: _BlockState, dy: Tensor, *, dpooled_q: Optional[Tensor] = Non
         r0, r1, dgate, d_ln_w, d_ln_b = K.gate_ln_bwd(dy, 0, st.G, st.q_in, st.A, st.gamma, st.mean, st.rstd,
                                                       dq_add=dq_add)
     d_gate_w = d_gate_b = d_out_w = d_out_b = d_in_w = d_in_b = None
+    # The weight-gradient GEMMs are leaves of the backward chain and their split-K clusters cover 108 of the 148 SMs:
+    # they are enqueued on a second stream (joined by the caller, `wgrad_stream` is not None then), so the dgrad /
+    # attention / LayerNorm kernels of the main chain fill the SMs they leave idle.
+    main = torch.cuda.current_stream(dev)
+
+    def on_side(fn):
+        if wgrad_stream is None:
+            fn()
+            return
+        wgrad_stream.wait_stream(main)
+        with torch.cuda.stream(wgrad_stream):
+            fn()
+
     if need_w:
         d_gate_w = torch.empty((E, 2 * E), device=dev, dtype=torch.float32)
-        _, d_gate_b = K.linear_wgrad(dgate, st.q_in, dw=d_gate_w[:, :E])
-        K.linear_wgrad(dgate, st.A, dw=d_gate_w[:, E:], want_bias=False)
+        d_gate_b = torch.empty((E,), device=dev, dtype=torch.float32)
+
+        def gate_wgrads():
+            K.linear_wgrad(dgate, st.q_in, dw=d_gate_w[:, :E], db=d_gate_b)
+            K.linear_wgrad(dgate, st.A, dw=d_gate_w[:, E:], want_bias=False)
+        on_side(gate_wgrads)
     dA = K.linear_dgrad(dgate, st.w_gate[:, E:], residual=r1)
     dq_acc = K.linear_dgrad(dgate, st.w_gate[:, :E], residual=r0) if need_dq else None
     if need_w:
-        d_out_w, d_out_b = K.linear_wgrad(dA, st.O)
+        d_out_w = torch.empty((E, E), device=dev, dtype=torch.float32)
+        d_out_b = torch.empty((E,), device=dev, dtype=torch.float32)
+        on_side(lambda: K.linear_wgrad(dA, st.O, dw=d_out_w, db=d_out_b))
     dO = K.linear_dgrad(dA, st.w_out)
     dQp = torch.empty_like(st.Qp)
     dKVp = torch.empty_like(st.KVp)
@@ -224,10 +245,15 @@ def _block_bwd(st: _BlockState, dy: Tensor, *, dpooled_q: Optional[Tensor] = Non
     if need_w:
         d_in_w = torch.empty((3 * E, E), device=dev, dtype=torch.float32)
         d_in_b = torch.empty((3 * E,), device=dev, dtype=torch.float32)
-        K.linear_wgrad(dQp, st.q_in, dw=d_in_w[:E], db=d_in_b[:E])
-        K.linear_wgrad(dKVp, st.kv_in, dw=d_in_w[E:], db=d_in_b[E:])
+
+        def in_wgrads():
+            K.linear_wgrad(dQp, st.q_in, dw=d_in_w[:E], db=d_in_b[:E])
+            K.linear_wgrad(dKVp, st.kv_in, dw=d_in_w[E:], db=d_in_b[E:])
+        on_side(in_wgrads)
     dq = K.linear_dgrad(dQp, st.w_in[:E], residual=dq_acc) if need_dq else None
     dkv = K.linear_dgrad(dKVp, st.w_in[E:], residual=dkv_residual) if need_dkv else None
+    if keep is not None:
+        keep.extend((dgate, dA, dQp, dKVp, r0, r1))     # read by the side stream: alive until the join
     return dq, dkv, (d_in_w, d_in_b, d_out_w, d_out_b, d_gate_w, d_gate_b, d_ln_w, d_ln_b)
 
 
@@ -295,14 +321,21 @@ class FusionCoreFn(Function):
         need_w1 = any(ctx.needs_input_grad[7:15])
         need_w2 = any(ctx.needs_input_grad[15:23])
         # block e2p: grad wrt t (as query, + pooled f0 broadcast), grad wrt v (as key/value)
-        dt1, dv1, g1 = _block_bwd(st1, de1, dpooled_q=df0, need_w=need_w1)
+        main = torch.cuda.current_stream(df0.device)
+        side = _side_stream(df0.device) if OVERLAP_WGRAD else None
+        keep: list = []
+        dt1, dv1, g1 = _block_bwd(st1, de1, dpooled_q=df0, need_w=need_w1, wgrad_stream=side, keep=keep)
         # block p2e: grad wrt v (as query, + pooled fv broadcast + dv1), grad wrt t (as kv, + dt1)
-        dv_tot, dt_tot, g2 = _block_bwd(st2, de2, dpooled_q=dfv, dq_add=dv1, dkv_residual=dt1, need_w=need_w2)
+        dv_tot, dt_tot, g2 = _block_bwd(st2, de2, dpooled_q=dfv, dq_add=dv1, dkv_residual=dt1, need_w=need_w2,
+                                        wgrad_stream=side, keep=keep)
         dwt = dbt = dwi = dbi = None
         if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
             dwt, dbt = K.linear_wgrad(dt_tot, text2d)
         if ctx.needs_input_grad[4] or ctx.needs_input_grad[5]:
             dwi, dbi = K.linear_wgrad(dv_tot, image2d)
+        if side is not None:
+            main.wait_stream(side)
+        keep.clear()
         return (None, None, dwt, dbt, dwi, dbi, None) + g1 + g2
 
 
