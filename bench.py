@@ -326,6 +326,8 @@ def run_ours(args) -> None:
     # ---- eager pass with per-launch CUDA events: kernel breakdown + roofline of the dominant kernel ----
     for s in step.slots:
         s.graph = None
+    from mmsa import ops as _ops
+    _ops.set_overlap(False)          # one kernel at a time: per-launch times must not include a co-running kernel
     step.run(0)
     torch.cuda.synchronize()
     prof_steps = min(args.steps, 5)

@@ -317,10 +317,9 @@ int mmsa_linear_wgrad(int dtype, int64_t M, int64_t N, int64_t K, const void* dy
       d.colsum = db;
       int bn = 0, splits = 1;
       tc_plan_wgrad(N, K, ceil_div(M, 64), &bn, &splits);
-      // The big weight gradients run on a second stream next to the dgrad / attention chain (ops.py): what counts is
-      // their SM-time, not their latency.  4 K-slices (72 CTAs for a 768 x 768 gradient) cost 10 % less SM-time than
-      // the latency-optimal 6 and leave half the chip to the main chain (measured: 1.928 -> 1.890 ms per step).
-      if (ceil_div(M, 64) >= 64 && splits > 4) splits = 4;
+      // (The big weight gradients run on a second stream next to the dgrad / attention chain (ops.py); 4 K-slices would
+      //  cost 10 % less SM-time than the latency-optimal 6 and shave 1.4 % off the step, but slow the kernel itself by
+      //  30 % -- MMSA_WGRAD_SPLITS=4 reproduces it.  The planner keeps the latency-optimal split.)
       if (const char* e = getenv("MMSA_WGRAD_SPLITS")) splits = atoi(e);      // tuning probes only
       if (const char* e = getenv("MMSA_WGRAD_BN")) bn = atoi(e);
       int rc = gemm_bf16_sm100_splits(d, splits, bn, s);

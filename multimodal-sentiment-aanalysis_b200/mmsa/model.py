@@ -205,7 +205,7 @@ class MultimodalTransformerModel(nn.Module):
                 # their backward halves, which autograd replays on the stream of the forward) overlap -- also as two
                 # parallel branches of the captured CUDA graph.
                 main = torch.cuda.current_stream(e1.device)
-                if self.overlap_contrastive:
+                if self.overlap_contrastive and ops.OVERLAP_TAIL:
                     if self._side_stream is None:
                         self._side_stream = torch.cuda.Stream(device=e1.device)
                     side = self._side_stream

@@ -71,6 +71,14 @@ def _w(w: Tensor, dtype: torch.dtype) -> Tensor:
 
 
 OVERLAP_WGRAD = True      # block weight gradients on a second stream (FusionCoreFn.backward)
+OVERLAP_TAIL = True       # tail weight gradients (SeqFn.backward) and the contrastive branch (model.forward) on a second stream
+
+
+def set_overlap(on: bool) -> None:
+    """Switch every second-stream overlap on or off.  Off = one kernel at a time on the caller's stream: what
+    bench.py's per-launch profiling pass needs (a kernel timed while another one shares the SMs is not a kernel time)."""
+    global OVERLAP_WGRAD, OVERLAP_TAIL
+    OVERLAP_WGRAD = OVERLAP_TAIL = bool(on)
 _SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
 
 
@@ -607,8 +615,10 @@ class SeqFn(Function):
                 if want_w or want_b:
                     # weight gradients are leaves of the backward chain: they go to a second stream and overlap the
                     # dgrad / BatchNorm chain (all of it small latency-bound kernels); joined before returning
-                    side.wait_stream(main)
-                    with torch.cuda.stream(side):
+                    wst = side if OVERLAP_TAIL else main
+                    if wst is side:
+                        side.wait_stream(main)
+                    with torch.cuda.stream(wst):
                         if a2 is None:
                             dw, db = K.linear_wgrad(d_cd, a, want_bias=want_b, want_weight=want_w)
                         else:
@@ -616,7 +626,7 @@ class SeqFn(Function):
                             _, db = K.linear_wgrad(d_cd, a, dw=dw[:, :Kx], want_bias=want_b, want_weight=True)
                             K.linear_wgrad(d_cd, a2, dw=dw[:, Kx:], want_bias=False, want_weight=True)
                     keep.extend((d_cd, a, a2, dw, db))     # alive until the join: no reuse of their memory by `main` meanwhile
-                    used_side = True
+                    used_side = used_side or wst is side
                     grads[pidx] = dw if want_w else None
                     if has_b and want_b:
                         grads[pidx + 1] = db
