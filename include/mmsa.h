@@ -162,6 +162,19 @@ int mmsa_gate_ln_pool_bwd(int dtype, int64_t B, int64_t L, int64_t E, const floa
                           void* dq_part, void* dattn_part, void* dgate_pre, float* dgamma, float* dbeta,
                           float* partials, void* stream);
 
+/* ---- residual add + LayerNorm, positional table (the encoder tail in front of the path: Subnetwork,
+ *      MultimodalModel.py:83-105 = proj -> +PositionalEncoding (:19-20) -> 2 x post-norm nn.TransformerEncoderLayer -> LayerNorm;
+ *      SURVEY.md section 8(f) rank 2) -----------------------------------------------------------
+ * y = LayerNorm(x + r; gamma, beta, eps), r may be NULL (plain LayerNorm); mean/rstd:[M] fp32 saved.
+ * bwd: du = dL/d(x + r) (gradient of both summands); dgamma/dbeta:[E]; partials: [mmsa_gate_ln_bwd_blocks(M), 2, E] fp32. */
+int mmsa_add_ln_fwd(int dtype, int64_t M, int64_t E, const void* x, const void* r, const float* gamma, const float* beta,
+                    float eps, void* y, float* mean, float* rstd, void* stream);
+int mmsa_add_ln_bwd(int dtype, int64_t M, int64_t E, const void* dy, const void* x, const void* r, const float* gamma,
+                    const float* mean, const float* rstd, void* du, float* dgamma, float* dbeta, float* partials,
+                    void* stream);
+/* y[m,:] = x[m,:] + pe[m % L, :]  (pe:[>=L, E] fp32, the sinusoidal buffer); backward = identity. */
+int mmsa_add_rows(int dtype, int64_t M, int64_t E, int64_t L, const void* x, const float* pe, void* y, void* stream);
+
 /* ---- token pooling (mean: MultimodalModel.py:76 / ME-MHACL/model.py:73; max: MultimodalModel.py:401)
  * x:[B,L,E] -> y:[B,E]; argmax:[B,E] int32 only for max. */
 int mmsa_pool_fwd(int dtype, int64_t B, int64_t L, int64_t E, const void* x, int is_max,

@@ -187,6 +187,150 @@ gate_ln_bwd_kernel(int64_t M, int E, const T* __restrict__ dy, int64_t dy_rows_p
   }
 }
 
+// ------------------------------------------------------------------ residual add + LayerNorm (post-norm encoder layer)
+// y = LayerNorm(x + r) (r may be null: plain LayerNorm), nn.TransformerEncoderLayer's norm1(x + sa(x)) / norm2(x + ff(x))
+// and Subnetwork.norm (MultimodalModel.py:83-105).  One warp per row, the row in registers, fp32 math.
+template <typename T>
+__global__ void __launch_bounds__(kRowWarps * 32)
+add_ln_fwd_kernel(int64_t M, int E, const T* __restrict__ x, const T* __restrict__ r, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, float eps, T* __restrict__ y, float* __restrict__ mean_out,
+                  float* __restrict__ rstd_out) {
+  constexpr int VN = VecN<T>::N;
+  constexpr int NV = kMaxRowFloats / VN;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t row = (int64_t)blockIdx.x * kRowWarps + warp;
+  if (row >= M) return;
+  const int nvec = E / VN;
+  const int64_t base = row * (int64_t)E;
+  float u[kMaxRowFloats];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+      float xv[VN], rv[VN];
+      load_vec<T>(x + base + v * VN, xv);
+      if (r != nullptr) load_vec<T>(r + base + v * VN, rv);
+#pragma unroll
+      for (int j = 0; j < VN; ++j) {
+        const float uu = r != nullptr ? round_to<T>(xv[j] + rv[j]) : xv[j];     // torch materialises x + r in the storage type
+        u[i * VN + j] = uu;
+        sum += uu;
+      }
+    }
+  }
+  const float mean = warp_sum(sum) / (float)E;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+#pragma unroll
+      for (int j = 0; j < VN; ++j) { const float d = u[i * VN + j] - mean; sq += d * d; }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)E + eps);
+  if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = lane + 32 * i;
+    if (v < nvec) {
+      float out[VN];
+#pragma unroll
+      for (int j = 0; j < VN; ++j) {
+        const int c = v * VN + j;
+        out[j] = (u[i * VN + j] - mean) * rstd * gamma[c] + beta[c];
+      }
+      store_vec<T>(y + base + v * VN, out);
+    }
+  }
+}
+
+// du = dL/d(x + r) (the same tensor is the gradient of both summands); dgamma / dbeta partials per block
+template <typename T>
+__global__ void __launch_bounds__(kRowWarps * 32)
+add_ln_bwd_kernel(int64_t M, int E, const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ r,
+                  const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+                  T* __restrict__ du_out, float* __restrict__ partials /* [gridDim.x, 2, E] */) {
+  constexpr int VN = VecN<T>::N;
+  constexpr int NV = kMaxRowFloats / VN;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = E / VN;
+  float dgam[kMaxRowFloats], dbet[kMaxRowFloats];
+#pragma unroll
+  for (int i = 0; i < kMaxRowFloats; ++i) { dgam[i] = 0.f; dbet[i] = 0.f; }
+  for (int64_t row = (int64_t)blockIdx.x * kRowWarps + warp; row < M; row += (int64_t)gridDim.x * kRowWarps) {
+    const int64_t base = row * (int64_t)E;
+    const float mu = mean[row], rs = rstd[row];
+    float xh[kMaxRowFloats], dyg[kMaxRowFloats];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        float xv[VN], rv[VN], dyv[VN];
+        load_vec<T>(x + base + v * VN, xv);
+        if (r != nullptr) load_vec<T>(r + base + v * VN, rv);
+        load_vec<T>(dy + base + v * VN, dyv);
+#pragma unroll
+        for (int j = 0; j < VN; ++j) {
+          const float uu = r != nullptr ? round_to<T>(xv[j] + rv[j]) : xv[j];
+          const float xn = (uu - mu) * rs;
+          const float dg_ = dyv[j] * gamma[v * VN + j];
+          xh[i * VN + j] = xn;
+          dyg[i * VN + j] = dg_;
+          c1 += dg_;
+          c2 += dg_ * xn;
+          dgam[i * VN + j] += dyv[j] * xn;
+          dbet[i * VN + j] += dyv[j];
+        }
+      }
+    }
+    c1 = warp_sum(c1) / (float)E;
+    c2 = warp_sum(c2) / (float)E;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        float o[VN];
+#pragma unroll
+        for (int j = 0; j < VN; ++j) o[j] = rs * (dyg[i * VN + j] - c1 - xh[i * VN + j] * c2);
+        store_vec<T>(du_out + base + v * VN, o);
+      }
+    }
+  }
+  __shared__ float red[kRowWarps][2][32];
+#pragma unroll
+  for (int i = 0; i < kMaxRowFloats; ++i) {
+    __syncthreads();
+    red[warp][0][lane] = dgam[i];
+    red[warp][1][lane] = dbet[i];
+    __syncthreads();
+    if (warp == 0) {
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int w = 0; w < kRowWarps; ++w) { a += red[w][0][lane]; b += red[w][1][lane]; }
+      const int v = lane + 32 * (i / VN);
+      const int c = v * VN + (i % VN);
+      if (v < nvec) {
+        partials[((int64_t)blockIdx.x * 2 + 0) * E + c] = a;
+        partials[((int64_t)blockIdx.x * 2 + 1) * E + c] = b;
+      }
+    }
+  }
+}
+
+// y[m, :] = x[m, :] + pe[m % L, :]: the sinusoidal table of PositionalEncoding.forward (MultimodalModel.py:19-20),
+// broadcast over the batch.  The backward is the identity.
+template <typename T>
+__global__ void add_rows_kernel(int64_t M, int E, int64_t L, const T* __restrict__ x, const float* __restrict__ pe, T* __restrict__ y) {
+  const int64_t total = M * (int64_t)E;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / E; const int c = (int)(i % E);
+    y[i] = from_f<T>(to_f(x[i]) + pe[(m % L) * E + c]);
+  }
+}
+
 // ------------------------------------------------------------------ gate + blend + LayerNorm + token mean-pool
 // A block whose output only feeds a token mean-pool (the re-skinned path: t' and v' are pooled right
 // away) never needs y[M,E] in HBM: LN(u) stays in fp32 registers and only the pooled sums are written --
@@ -848,6 +992,50 @@ int mmsa_gate_ln_bwd(int dtype, int64_t M, int64_t E, const void* dy, int64_t dy
   return MMSA_OK;
 }
 
+
+int mmsa_add_ln_fwd(int dtype, int64_t M, int64_t E, const void* x, const void* r, const float* gamma, const float* beta,
+                    float eps, void* y, float* mean, float* rstd, void* stream) {
+  MMSA_REQUIRE_DEVICE();
+  MMSA_REQUIRE(E % 8 == 0 && E <= 1024 && E > 0, "mmsa_add_ln_fwd: E=%lld must be a multiple of 8 and <= 1024", (long long)E);
+  if (M == 0) return MMSA_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  ProfScope prof("add_ln_fwd", s, (double)M * E * (dtype == MMSA_F32 ? 4 : 2) * (r ? 3.0 : 2.0));
+  unsigned grid = (unsigned)ceil_div(M, kRowWarps);
+  MMSA_DISPATCH_DTYPE(dtype, T, (add_ln_fwd_kernel<T><<<grid, kRowWarps * 32, 0, s>>>(
+      M, (int)E, (const T*)x, (const T*)r, gamma, beta, eps, (T*)y, mean, rstd)));
+  MMSA_LAUNCH_CHECK("add_ln_fwd_kernel");
+  return MMSA_OK;
+}
+
+int mmsa_add_ln_bwd(int dtype, int64_t M, int64_t E, const void* dy, const void* x, const void* r, const float* gamma,
+                    const float* mean, const float* rstd, void* du, float* dgamma, float* dbeta, float* partials,
+                    void* stream) {
+  MMSA_REQUIRE_DEVICE();
+  MMSA_REQUIRE(E % 8 == 0 && E <= 1024 && E > 0, "mmsa_add_ln_bwd: E=%lld must be a multiple of 8 and <= 1024", (long long)E);
+  if (M == 0) return MMSA_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  int64_t nblk = mmsa_gate_ln_bwd_blocks(M);
+  {
+    ProfScope prof("add_ln_bwd", s, (double)M * E * (dtype == MMSA_F32 ? 4 : 2) * (r ? 4.0 : 3.0));
+    MMSA_DISPATCH_DTYPE(dtype, T, (add_ln_bwd_kernel<T><<<(unsigned)nblk, kRowWarps * 32, 0, s>>>(
+        M, (int)E, (const T*)dy, (const T*)x, (const T*)r, gamma, mean, rstd, (T*)du, partials)));
+  }
+  MMSA_LAUNCH_CHECK("add_ln_bwd_kernel");
+  reduce_partials_kernel<<<(unsigned)ceil_div(E, 32), 256, 0, s>>>(partials, nblk, (int)E, nullptr, 0, dgamma, dbeta);
+  MMSA_LAUNCH_CHECK("reduce_partials_kernel");
+  return MMSA_OK;
+}
+
+int mmsa_add_rows(int dtype, int64_t M, int64_t E, int64_t L, const void* x, const float* pe, void* y, void* stream) {
+  MMSA_REQUIRE_DEVICE();
+  MMSA_REQUIRE(M >= 0 && E > 0 && L > 0 && pe != nullptr, "mmsa_add_rows: bad arguments");
+  if (M == 0) return MMSA_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  ProfScope prof("add_rows", s, (double)M * E * (dtype == MMSA_F32 ? 4 : 2) * 2.0);
+  MMSA_DISPATCH_DTYPE(dtype, T, (add_rows_kernel<T><<<grid_for(M * E, 256), 256, 0, s>>>(M, (int)E, L, (const T*)x, pe, (T*)y)));
+  MMSA_LAUNCH_CHECK("add_rows_kernel");
+  return MMSA_OK;
+}
 
 int mmsa_gate_ln_pool_fwd(int dtype, int64_t B, int64_t L, int64_t E, const void* gate_pre, const void* q,
                           const void* attn, const float* gamma, const float* beta, float eps, void* g_out,

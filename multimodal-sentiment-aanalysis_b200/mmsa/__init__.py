@@ -5,11 +5,11 @@ over a C-ABI CUDA library (include/mmsa.h).  Importing the package does not need
 any op does, and raises if the extension is missing (no fallback)."""
 from . import _lib
 from .model import (Classifier, CrossModalTransformer, FeatureProjection, MultiModalEncoder,
-                    MultimodalTransformerModel, ProjectionHead)
+                    MultimodalTransformerModel, PositionalEncoding, ProjectionHead, Subnetwork)
 from .ops import cross_entropy, infonce, ntxent, supcon
 from .optim import FusedClipAdamW
 from .io import FeatureBatches, load_reference_state_dict, strip_module_prefix
 
 __all__ = ["MultimodalTransformerModel", "CrossModalTransformer", "FeatureProjection", "MultiModalEncoder",
-           "ProjectionHead", "Classifier", "cross_entropy", "infonce", "supcon", "ntxent", "FusedClipAdamW",
+           "ProjectionHead", "Classifier", "Subnetwork", "PositionalEncoding", "cross_entropy", "infonce", "supcon", "ntxent", "FusedClipAdamW",
            "FeatureBatches", "load_reference_state_dict", "strip_module_prefix", "_lib"]

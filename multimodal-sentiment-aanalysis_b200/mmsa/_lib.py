@@ -45,6 +45,9 @@ _PROTOS = {
     "mmsa_gate_ln_bwd": (I, [I, L, L, P, L, P, P, P, P, P, P, P, L, P, P, P, P, P, P, P, P]),
     "mmsa_gate_ln_pool_fwd": (I, [I, L, L, L, P, P, P, P, P, F, P, P, P, P, P, P, P]),
     "mmsa_gate_ln_pool_bwd": (I, [I, L, L, L, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P]),
+    "mmsa_add_ln_fwd": (I, [I, L, L, P, P, P, P, F, P, P, P, P]),
+    "mmsa_add_ln_bwd": (I, [I, L, L, P, P, P, P, P, P, P, P, P, P, P]),
+    "mmsa_add_rows": (I, [I, L, L, L, P, P, P, P]),
     "mmsa_pool_fwd": (I, [I, L, L, L, P, I, P, P, P]),
     "mmsa_pool_bwd": (I, [I, L, L, L, P, I, P, P, P]),
     "mmsa_modal_concat_fwd": (I, [I, L, L, I, P, P, P, P, P]),

@@ -395,3 +395,38 @@ def contrastive_bwd(kind: int, sim: Tensor, labels_rows, labels_cols, temperatur
          _p(temperature), float(temperature_const), denom, stats.data_ptr(), dloss.data_ptr(), G.data_ptr(),
          dt(g_dtype), dtemp_rows.data_ptr(), dtemp.data_ptr(), _stream())
     return G, dtemp
+
+
+# ---- encoder tail: residual add + LayerNorm, positional table ----
+def add_ln_fwd(x: Tensor, r: Optional[Tensor], gamma: Tensor, beta: Tensor, eps: float):
+    _check(x, r, gamma, beta)
+    M, E = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty((M,), device=x.device, dtype=torch.float32)
+    rstd = torch.empty((M,), device=x.device, dtype=torch.float32)
+    call("mmsa_add_ln_fwd", dt(x), M, E, x.data_ptr(), _p(r), gamma.data_ptr(), beta.data_ptr(), float(eps), y.data_ptr(),
+         mean.data_ptr(), rstd.data_ptr(), _stream())
+    return y, mean, rstd
+
+
+def add_ln_bwd(dy: Tensor, x: Tensor, r: Optional[Tensor], gamma: Tensor, mean: Tensor, rstd: Tensor):
+    _check(dy, x, r)
+    M, E = x.shape
+    du = torch.empty_like(x)
+    dgamma = torch.empty((E,), device=x.device, dtype=torch.float32)
+    dbeta = torch.empty((E,), device=x.device, dtype=torch.float32)
+    nblk = _lib.load().mmsa_gate_ln_bwd_blocks(M)
+    partials = torch.empty((nblk, 2, E), device=x.device, dtype=torch.float32)
+    call("mmsa_add_ln_bwd", dt(x), M, E, dy.data_ptr(), x.data_ptr(), _p(r), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+         du.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), partials.data_ptr(), _stream())
+    return du, dgamma, dbeta
+
+
+def add_rows(x: Tensor, pe: Tensor, L: int) -> Tensor:
+    """y[m,:] = x[m,:] + pe[m % L,:]; pe fp32 [>=L, E] contiguous."""
+    _check(x, pe)
+    M, E = x.shape
+    assert pe.dtype == torch.float32 and pe.is_contiguous() and pe.shape[-1] == E and pe.shape[-2] >= L
+    y = torch.empty_like(x)
+    call("mmsa_add_rows", dt(x), M, E, L, x.data_ptr(), pe.data_ptr(), y.data_ptr(), _stream())
+    return y

@@ -47,6 +47,59 @@ def _prepare(module: nn.Module, cd: torch.dtype) -> None:
     ops.prepare_weights([p for p in module.parameters() if p.ndim >= 2], cd)
 
 
+class PositionalEncoding(nn.Module):
+    """MultimodalModel.py:8-20: the sinusoidal table as a buffer `pe` [1, max_len, d_model] (parameter container; the add
+    runs in mmsa_add_rows)."""
+
+    def __init__(self, d_model: int, max_len: int = 5000):
+        super().__init__()
+        import math
+        pe = torch.zeros(max_len, d_model)
+        position = torch.arange(0, max_len, dtype=torch.float).unsqueeze(1)
+        div_term = torch.exp(torch.arange(0, d_model, 2).float() * (-math.log(10000.0) / d_model))
+        pe[:, 0::2] = torch.sin(position * div_term)
+        pe[:, 1::2] = torch.cos(position * div_term)
+        self.register_buffer("pe", pe.unsqueeze(0))
+
+
+class Subnetwork(nn.Module):
+    """Drop-in for MultimodalModel.Subnetwork (MultimodalModel.py:83-105), the encoder tail in front of the fusion path
+    (SURVEY.md section 8(f) rank 2): proj -> + positional table -> num_layers x post-norm TransformerEncoderLayer(d, nhead,
+    ff = 3d, ReLU, dropout 0.3) -> LayerNorm.  Same attribute names and state_dict keys.  The reference feeds [B, input_dim]
+    (one token); [B, L, input_dim] runs the same layers over L tokens (text tokens get a self-attention stage before the
+    cross-attention).  torch modules are parameter containers only; every op runs the sm_100a kernels."""
+
+    def __init__(self, input_dim: int, feat_dim: int = 256, num_layers: int = 2, nhead: int = 4,
+                 compute_dtype: torch.dtype = torch.float32):
+        super().__init__()
+        self.compute_dtype = compute_dtype
+        self.proj = nn.Linear(input_dim, feat_dim)
+        self.pos_encoder = PositionalEncoding(feat_dim, max_len=100)
+        layer = nn.TransformerEncoderLayer(d_model=feat_dim, nhead=nhead, dim_feedforward=feat_dim * 3, dropout=0.3,
+                                           batch_first=True)
+        self.transformer = nn.TransformerEncoder(layer, num_layers, enable_nested_tensor=False)
+        self.norm = nn.LayerNorm(feat_dim)
+        self._drop = _DropoutState()
+
+    def forward(self, x: Tensor) -> Tensor:
+        cd = self.compute_dtype
+        squeeze = x.ndim == 2
+        if squeeze:
+            x = x.unsqueeze(1)
+        B, L, D = x.shape
+        if L > self.pos_encoder.pe.shape[1]:
+            raise ValueError(f"mmsa.Subnetwork: sequence length {L} exceeds the positional table ({self.pos_encoder.pe.shape[1]})")
+        if not x.is_floating_point():
+            x = x.float()
+        h = ops.linear(ops.cast(x.contiguous(), cd).view(B * L, D), self.proj.weight, self.proj.bias)
+        h = ops.AddRowsFn.apply(h, self.pos_encoder.pe[0].contiguous(), L).view(B, L, -1)
+        for i, layer in enumerate(self.transformer.layers):
+            h = ops.encoder_layer(h, layer, self._drop, f"transformer.layers.{i}", cd)
+        h = ops.add_layer_norm(h, None, self.norm)
+        h = ops.cast(h, torch.float32)
+        return h.squeeze(1) if squeeze else h
+
+
 class CrossModalTransformer(nn.Module):
     """MultimodalModel.py:108-149.  forward(query, key, value) with 2-D [B,E] or 3-D [B,L,E] inputs;
     the gate concat runs on the feature axis, so Lq > 1 works (identical to the reference for Lq == 1)."""

@@ -796,3 +796,110 @@ class _StackFn(Function):
     @staticmethod
     def backward(ctx, dz):
         return dz[:ctx.n], dz[ctx.n:]
+
+
+# ------------------------------------------------------------------------------------------ encoder tail (section 8(f) rank 2)
+class AddLNFn(Function):
+    """y = LayerNorm(x + r) (post-norm residual of nn.TransformerEncoderLayer; r=None: plain LayerNorm)."""
+
+    @staticmethod
+    def forward(ctx, x, r, gamma, beta, eps: float):
+        x2 = _c(x).view(-1, x.shape[-1])
+        r2 = None if r is None else _c(r).view(-1, x.shape[-1])
+        y, mean, rstd = K.add_ln_fwd(x2, r2, gamma.detach(), beta.detach(), eps)
+        ctx.save_for_backward(x2, r2, gamma.detach(), mean, rstd)
+        ctx.shape = x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x2, r2, gamma, mean, rstd = ctx.saved_tensors
+        du, dgamma, dbeta = K.add_ln_bwd(K.cast(_c(dy), x2.dtype).view(-1, x2.shape[1]), x2, r2, gamma, mean, rstd)
+        du = du.view(ctx.shape)
+        return du, (du if r2 is not None else None), dgamma, dbeta, None
+
+
+def add_layer_norm(x: Tensor, r: Optional[Tensor], ln: nn.LayerNorm) -> Tensor:
+    return AddLNFn.apply(x, r, ln.weight, ln.bias, ln.eps)
+
+
+class AddRowsFn(Function):
+    """x + pe[:, :L] broadcast over the batch (PositionalEncoding.forward, MultimodalModel.py:19-20)."""
+
+    @staticmethod
+    def forward(ctx, x, pe, L: int):
+        return K.add_rows(_c(x).view(-1, x.shape[-1]), pe, L).view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, None, None
+
+
+class ActDropFn(Function):
+    """activation followed by dropout on a token stream: fp32 pre-activation in, compute dtype out
+    (the `dropout(activation(linear1(x)))` of nn.TransformerEncoderLayer's feed-forward block)."""
+
+    @staticmethod
+    def forward(ctx, z, act: int, p: float, training: bool, drop: _DropoutState, name: str, cd):
+        z = _c(z)
+        p_eff = p if training else 0.0
+        if p_eff > 0:
+            h = K.act_fwd(z, act, torch.float32)
+            mask, seed, off = drop.next(name, z.shape)
+            y, mask = K.dropout(h, p_eff, mask, mask is not None, seed, off, cd)
+        else:
+            y, mask = K.act_fwd(z, act, cd), None
+        ctx.save_for_backward(z, mask)
+        ctx.cfg = (act, p_eff, cd)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        z, mask = ctx.saved_tensors
+        act, p_eff, cd = ctx.cfg
+        d = K.cast(_c(dy), torch.float32)
+        if p_eff > 0:
+            d, _ = K.dropout(d, p_eff, mask, True, 0, 0, torch.float32)
+        return K.act_bwd(z, d, act, torch.float32), None, None, None, None, None, None
+
+
+class DropFn(Function):
+    """stand-alone dropout on a token stream (dropout1 / dropout2 of nn.TransformerEncoderLayer)."""
+
+    @staticmethod
+    def forward(ctx, x, p: float, drop: _DropoutState, name: str):
+        mask, seed, off = drop.next(name, x.shape)
+        y, mask = K.dropout(K.cast(_c(x), torch.float32), p, mask, mask is not None, seed, off, x.dtype)
+        ctx.save_for_backward(mask)
+        ctx.p = p
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        (mask,) = ctx.saved_tensors
+        d, _ = K.dropout(K.cast(_c(dy), torch.float32), ctx.p, mask, True, 0, 0, dy.dtype)
+        return d, None, None, None
+
+
+def token_dropout(x: Tensor, p: float, training: bool, drop: _DropoutState, name: str) -> Tensor:
+    return DropFn.apply(x, p, drop, name) if (training and p > 0) else x
+
+
+def encoder_layer(x: Tensor, layer: nn.TransformerEncoderLayer, drop: _DropoutState, name: str, cd) -> Tensor:
+    """One post-norm nn.TransformerEncoderLayer (norm_first=False, ReLU) on x:[B,S,E] in the compute dtype:
+        x = norm1(x + dropout1(self_attn(x)));  x = norm2(x + dropout2(linear2(dropout(relu(linear1(x))))))
+    Dropout on the attention PROBABILITIES (MultiheadAttention(dropout=0.3) in training mode) is not implemented."""
+    a = layer.self_attn
+    training = layer.training
+    B, S, E = x.shape
+    sa = self_attention(x, a.in_proj_weight, a.in_proj_bias, a.out_proj.weight, a.out_proj.bias, a.num_heads)
+    sa = token_dropout(sa, layer.dropout1.p, training, drop, name + ".dropout1")
+    x = add_layer_norm(x, sa, layer.norm1)
+    z = linear(x.reshape(B * S, E), layer.linear1.weight, layer.linear1.bias, out_fp32=True, cd=cd)
+    h = ActDropFn.apply(z, ACT_RELU, layer.dropout.p, training, drop, name + ".dropout", cd)
+    ff = linear(h, layer.linear2.weight, layer.linear2.bias, cd=cd).view(B, S, E)
+    ff = token_dropout(ff, layer.dropout2.p, training, drop, name + ".dropout2")
+    return add_layer_norm(x, ff, layer.norm2)

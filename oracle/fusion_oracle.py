@@ -423,3 +423,45 @@ def synth_inputs(cfg: FusionConfig, batch: int, L: int = 64, R: int = 49, seed: 
         xs = tuple(torch.randn(batch, cfg.embed_dim, generator=g, dtype=dtype) for _ in range(3))
     labels = torch.randint(0, cfg.num_classes, (batch,), generator=g)
     return xs, labels
+
+
+# --------------------------------------------------------------------------
+# Subnetwork encoder tail (MultimodalModel.py:83-105)
+# --------------------------------------------------------------------------
+def positional_table(d_model: int, max_len: int = 100, dtype=torch.float32) -> Tensor:
+    """PositionalEncoding.__init__ (MultimodalModel.py:9-17): [max_len, d_model]."""
+    pe = torch.zeros(max_len, d_model)
+    position = torch.arange(0, max_len, dtype=torch.float).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d_model, 2).float() * (-math.log(10000.0) / d_model))
+    pe[:, 0::2] = torch.sin(position * div_term)
+    pe[:, 1::2] = torch.cos(position * div_term)
+    return pe.to(dtype)
+
+
+def encoder_layer(x: Tensor, p: Params, prefix: str, num_heads: int) -> Tensor:
+    """One nn.TransformerEncoderLayer as Subnetwork builds it (MultimodalModel.py:89-95: post-norm, ReLU, batch_first),
+    dropout off: x = norm1(x + self_attn(x)); x = norm2(x + linear2(relu(linear1(x)))).  (third-party torch
+    nn/modules/transformer.py TransformerEncoderLayer._sa_block / _ff_block, norm_first=False branch.)"""
+    B, L, E = x.shape
+    sa = mha_self_seq_first(x.transpose(0, 1), p[prefix + "self_attn.in_proj_weight"], p[prefix + "self_attn.in_proj_bias"],
+                            p[prefix + "self_attn.out_proj.weight"], p[prefix + "self_attn.out_proj.bias"],
+                            num_heads).transpose(0, 1)
+    x = F.layer_norm(x + sa, (E,), p[prefix + "norm1.weight"], p[prefix + "norm1.bias"], 1e-5)
+    ff = F.linear(torch.relu(F.linear(x, p[prefix + "linear1.weight"], p[prefix + "linear1.bias"])),
+                  p[prefix + "linear2.weight"], p[prefix + "linear2.bias"])
+    return F.layer_norm(x + ff, (E,), p[prefix + "norm2.weight"], p[prefix + "norm2.bias"], 1e-5)
+
+
+def subnetwork(x: Tensor, p: Params, num_heads: int = 4, num_layers: int = 2) -> Tensor:
+    """Subnetwork.forward (MultimodalModel.py:99-105) with dropout off; x:[B,D] (one token, as the reference feeds it) or
+    [B,L,D] (generalised to L tokens)."""
+    squeeze = x.ndim == 2
+    if squeeze:
+        x = x.unsqueeze(1)                                           # :102
+    h = F.linear(x, p["proj.weight"], p["proj.bias"])               # :102
+    pe = p["pos_encoder.pe"] if "pos_encoder.pe" in p else positional_table(h.shape[-1], 100, h.dtype).unsqueeze(0)
+    h = h + pe[:, :h.shape[1]].to(h.dtype)                           # :103 (PositionalEncoding.forward :19-20)
+    for i in range(num_layers):
+        h = encoder_layer(h, p, f"transformer.layers.{i}.", num_heads)     # :104
+    h = F.layer_norm(h, (h.shape[-1],), p["norm.weight"], p["norm.bias"], 1e-5)   # :105
+    return h.squeeze(1) if squeeze else h

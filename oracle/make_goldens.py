@@ -190,7 +190,33 @@ def memhacl():
     print("memhacl", float(l1), float(l2))
 
 
+def subnetwork():
+    """Subnetwork encoder tail (MultimodalModel.py:83-105) from the imported reference, eval mode (dropout off; the
+    attention-probability dropout of its MultiheadAttention cannot be matched by any other RNG), gradients kept."""
+    sys.path.insert(0, REF)
+    import MultimodalModel as R
+    torch.manual_seed(11)
+    m = R.Subnetwork(38)
+    m.eval()
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(20, 38, generator=g)
+    xin = x.clone().requires_grad_(True)
+    y = m(xin)
+    # a random linear functional of the output: sum(y^2) is constant behind a LayerNorm (its gradient is rounding noise)
+    wgt = torch.randn(y.shape, generator=g)
+    (y * wgt).sum().backward()
+    out = {"state_dict": {k: v.clone() for k, v in m.state_dict().items()}, "x": x, "wgt": wgt, "out": y.detach().clone(),
+           "dx": xin.grad.clone(), "grads": {k: grad_digest(p.grad) for k, p in m.named_parameters()}}
+    torch.save(out, os.path.join(OUT, "subnetwork.pt"))
+    print("subnetwork", float(y.detach().abs().mean()))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    native_fusion()
-    memhacl()
+    which = sys.argv[1:] or ["native", "memhacl", "subnetwork"]
+    if "native" in which:
+        native_fusion()
+    if "memhacl" in which:
+        memhacl()
+    if "subnetwork" in which:
+        subnetwork()

@@ -207,3 +207,44 @@ def test_io_adapters_batch_formats_and_checkpoints(tmp_path):
     sd2 = dict(sd)
     sd2["module.eeg_net.conv1.weight"] = torch.zeros(3)
     mmsa.load_reference_state_dict(dst, sd2, ignore_prefixes=("eeg_net.", "eye_net.", "pps_net."))
+
+
+def test_oracle_subnetwork_reproduces_golden_and_torch():
+    """Encoder tail: the oracle restatement of Subnetwork (MultimodalModel.py:83-105) against the
+    golden generated from the imported reference, and -- for L > 1, where the reference is never run -- against torch's own
+    nn.TransformerEncoder built from the same parameters."""
+    g = torch.load(os.path.join(GOLD, "subnetwork.pt"))
+    p = {k: v.clone().requires_grad_(v.is_floating_point() and k != "pos_encoder.pe") for k, v in g["state_dict"].items()}
+    x = g["x"].clone().requires_grad_(True)
+    y = O.subnetwork(x, p)
+    (y * g["wgt"]).sum().backward()
+    assert rel_err(y, g["out"]) <= 1e-6 and rel_err(x.grad, g["dx"]) <= 1e-5
+    for k, dig in g["grads"].items():
+        flat = p[k].grad.reshape(-1)
+        assert float((flat[dig["idx"]] - dig["vals"]).abs().max()) <= 2e-5 * max(dig["absmax"], 1e-12), k
+    # L = 7 tokens against torch.nn.TransformerEncoder (eval mode: dropout off)
+    import torch.nn as nn
+    torch.manual_seed(3)
+    layer = nn.TransformerEncoderLayer(d_model=64, nhead=4, dim_feedforward=192, dropout=0.3, batch_first=True)
+    enc = nn.TransformerEncoder(layer, 2, enable_nested_tensor=False).eval()
+    proj, norm = nn.Linear(10, 64), nn.LayerNorm(64)
+    sd = {"proj.weight": proj.weight, "proj.bias": proj.bias, "norm.weight": norm.weight, "norm.bias": norm.bias}
+    sd.update({"transformer." + k: v for k, v in enc.state_dict().items()})
+    sd = {k: v.detach().clone() for k, v in sd.items()}
+    xs = torch.randn(3, 7, 10)
+    want = norm(enc(proj(xs) + O.positional_table(64, 100)[:7]))
+    got = O.subnetwork(xs, sd)
+    assert rel_err(got, want.detach()) <= 1e-5
+
+
+@pytest.mark.skipif(not has_ref, reason="reference tree not mounted (GPU box)")
+def test_oracle_subnetwork_bit_identical_to_reference():
+    sys.path.insert(0, REF)
+    import MultimodalModel as R
+    torch.manual_seed(5)
+    m = R.Subnetwork(230).eval()
+    x = torch.randn(9, 230)
+    with torch.no_grad():
+        want = m(x)
+    got = O.subnetwork(x, {k: v for k, v in m.state_dict().items()})
+    assert rel_err(got, want) <= 1e-6

@@ -312,3 +312,55 @@ def test_full_size_properties(cuda_device, batch, L):
         full = m32(t16.float(), i16.float(), None)
         head = m32(t16[:32].float().contiguous(), i16[:32].float().contiguous(), None)
     assert rel_err(head, full[:32]) <= 1e-5
+
+
+# ------------------------------------------------------------------ encoder tail
+def test_subnetwork_against_reference_golden(cuda_device):
+    """mmsa.Subnetwork (proj -> +PE -> 2 x post-norm TransformerEncoderLayer -> LayerNorm, MultimodalModel.py:83-105) against
+    the golden from the imported reference (eval mode), fp32 1e-5, every gradient."""
+    import mmsa
+    g = torch.load(os.path.join(GOLD, "subnetwork.pt"))
+    m = mmsa.Subnetwork(38)
+    assert list(m.state_dict().keys()) == list(g["state_dict"].keys())
+    m.load_state_dict(g["state_dict"], strict=True)
+    m = m.to(cuda_device).eval()
+    x = g["x"].to(cuda_device).requires_grad_(True)
+    y = m(x)
+    assert y.shape == g["out"].shape
+    (y * g["wgt"].to(cuda_device)).sum().backward()
+    assert rel_err(y, g["out"]) <= 1e-5
+    assert rel_err(x.grad, g["dx"]) <= 2e-5
+    for k, prm in m.named_parameters():
+        _check_digest(prm.grad, g["grads"][k], None, 5e-5, k)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+def test_subnetwork_token_sequences(cuda_device, dtype, tol):
+    """generalised to L > 1 (text tokens get a self-attention stage): [B, L, 768] -> [B, L, 256] against the float64 oracle."""
+    import mmsa
+    torch.manual_seed(21)
+    m = mmsa.Subnetwork(768, feat_dim=256, num_layers=2, nhead=4, compute_dtype=dtype)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.to(cuda_device).eval()
+    B, L = 6, 24
+    x = torch.randn(B, L, 768)
+    p64 = {k: v.double().requires_grad_(k != "pos_encoder.pe") for k, v in sd.items()}
+    x64 = x.double().requires_grad_(True)
+    wgt = torch.randn(B, L, 256)           # random linear functional: sum(y^2) is constant behind the final LayerNorm
+    want = O.subnetwork(x64, p64)
+    (want * wgt.double()).sum().backward()
+    xg = x.to(cuda_device).requires_grad_(True)
+    y = m(xg)
+    (y * wgt.to(cuda_device)).sum().backward()
+    assert y.shape == (B, L, 256) and y.dtype == torch.float32
+    assert rel_err(y, want.detach()) <= tol
+    # gradients: fp32 5e-5 element-wise; bf16 passes two layers of rounded activations and ReLU masks that flip near zero:
+    # tensor norm within 5e-2, element-wise (relative to the tensor's largest element) within 2e-1, as in the full-size test
+    def ok(got, want):
+        if dtype == torch.float32:
+            return rel_err(got, want) <= 5e-5
+        n_got, n_want = float(got.double().norm()), float(want.double().norm())
+        return abs(n_got - n_want) <= 5e-2 * n_want and rel_err(got, want) <= 2e-1
+    assert ok(xg.grad, x64.grad)
+    for k, prm in m.named_parameters():
+        assert ok(prm.grad, p64[k].grad), k
