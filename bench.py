@@ -170,6 +170,33 @@ def run_reference_arm(args) -> None:
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Pin this rank's host threads to the CPUs NVML reports as local to its GPU, BEFORE the pinned host buffers are
+    allocated (first touch places them on that NUMA node): at N >= 4 every rank streams ~100 MB of features per step
+    over PCIe, and a buffer on the far socket halves that rate.  Returns the CPU list, or None when unavailable."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        handle = None
+        try:
+            uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+            handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode() if not uuid.startswith("GPU-") else uuid.encode())
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = [w * 64 + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def run_ours(args) -> None:
     import torch
@@ -186,6 +213,7 @@ def run_ours(args) -> None:
         raise RuntimeError("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -415,7 +443,8 @@ def run_ours(args) -> None:
                        "step_frac_of_tensor_peak": value * gf["fwd_bwd"] / 1e3 / world / peaks.get("bf16_tflops_sustained", 1400.0)},
             "e2e": {"value": B * world / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e,
-                    "host_feature_dtype": args.dtype, "note": "pinned host features; H2D of step i+1 overlaps step i (2 slots)"},
+                    "host_feature_dtype": args.dtype, "note": "pinned host features; H2D of step i+1 overlaps step i (2 slots)",
+                    "numa_bound_cpus": (len(numa_cpus) if numa_cpus else None)},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
