@@ -31,7 +31,6 @@ bool attn_bwd_tc_supported(int64_t Lq, int64_t Lk);
 bool attn_mma_supported(int64_t D, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, const void* q, const void* k,
                         const void* v, const void* o);
 
-extern int g_attn_tc_debug;
 static int g_force_simt_attn = 0;
 static int g_attn_engine = 0;      // 0: tcgen05 forward (default), 1: mma.sync forward
 
@@ -44,7 +43,7 @@ extern "C" {
 // test hook: route bf16 attention through the CUDA-core engine (engine cross-check)
 void mmsa_debug_force_simt_attention(int on) { g_force_simt_attn = on; }
 // test hook: 0 = tcgen05/TMA forward (default), 1 = mma.sync forward (engine cross-check)
-void mmsa_debug_attention_engine(int engine) { g_attn_engine = engine & 0xff; g_attn_tc_debug = (engine >> 8) & 0xff; }
+void mmsa_debug_attention_engine(int engine) { g_attn_engine = engine; }
 
 int mmsa_attn_fwd(int dtype, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t D, const void* q, int64_t ldq,
                   const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo, float* lse, void* stream) {

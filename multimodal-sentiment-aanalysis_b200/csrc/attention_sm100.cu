@@ -130,8 +130,6 @@ struct AttnParams {
   bf16* o; long long ldo;
   float* lse;
   float scale, scale_log2;     // 1/sqrt(d_h), and the same times log2(e)
-  int flat_loads;              // probe: tensor maps over the flat [B*L, E] matrix (rows past a sample = next sample's)
-  int direct_store;            // probe: per-thread global stores instead of the staged TMA store
 };
 
 __global__ void __launch_bounds__(kThreads, 2)
@@ -180,20 +178,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const long long b = bh / p.H;
         mbar_wait(q_empty(qs), qph ^ 1u);
         mbar_expect_tx(q_full(qs), Q_BYTES);
-        if (p.flat_loads) tma_load_3d(base + SMEM_Q + qs * Q_BYTES, &tmQ, h * HD, (int)(b * p.Lq + qt * TQ), 0, q_full(qs));
-        else tma_load_3d(base + SMEM_Q + qs * Q_BYTES, &tmQ, h * HD, qt * TQ, (int)b, q_full(qs));
+        tma_load_3d(base + SMEM_Q + qs * Q_BYTES, &tmQ, h * HD, qt * TQ, (int)b, q_full(qs));
         if (++qs == QST) { qs = 0; qph ^= 1u; }
         for (int j = 0; j < p.nkv; ++j) {
           mbar_wait(kv_empty(ks), kph ^ 1u);
           mbar_expect_tx(kv_full(ks), 2 * K_BYTES);
           const uint32_t dst = base + SMEM_KV + ks * 2 * K_BYTES;
-          if (p.flat_loads) {
-            tma_load_3d(dst, &tmK, h * HD, (int)(b * p.Lk + j * TK), 0, kv_full(ks));
-            tma_load_3d(dst + K_BYTES, &tmV, h * HD, (int)(b * p.Lk + j * TK), 0, kv_full(ks));
-          } else {
-            tma_load_3d(dst, &tmK, h * HD, j * TK, (int)b, kv_full(ks));
-            tma_load_3d(dst + K_BYTES, &tmV, h * HD, j * TK, (int)b, kv_full(ks));
-          }
+          tma_load_3d(dst, &tmK, h * HD, j * TK, (int)b, kv_full(ks));
+          tma_load_3d(dst + K_BYTES, &tmV, h * HD, j * TK, (int)b, kv_full(ks));
           if (++ks == KST) { ks = 0; kph ^= 1u; }
         }
       }
@@ -687,8 +679,6 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
 }  // namespace
 
-int g_attn_tc_debug = 0;      // probe switches (mmsa_debug_attention_engine bits 8, 9): flat load maps, direct stores
-
 bool attn_tc_supported(int64_t D, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, const void* q, const void* k,
                        const void* v, const void* o) {
   auto al = [](const void* p) { return ((uintptr_t)p % 16) == 0; };
@@ -700,10 +690,9 @@ int attn_fwd_tc_bf16(int64_t B, int64_t H, int64_t Lq, int64_t Lk, const void* q
   CUtensorMap tmQ, tmK, tmV, tmO;
   // [B, L, H*64] views; a load box is one head (64 columns = one 128-byte swizzle row) of a row tile of ONE sample,
   // the store box one warp's 32 output rows
-  const bool flat = (g_attn_tc_debug & 1) != 0;
-  if (!tc_make_map3_bf16(&tmQ, q, H * HD, flat ? B * Lq : Lq, flat ? 1 : B, ldq, HD, TQ)) return MMSA_ERR_CUDA;
-  if (!tc_make_map3_bf16(&tmK, k, H * HD, flat ? B * Lk : Lk, flat ? 1 : B, ldk, HD, TK)) return MMSA_ERR_CUDA;
-  if (!tc_make_map3_bf16(&tmV, v, H * HD, flat ? B * Lk : Lk, flat ? 1 : B, ldv, HD, TK)) return MMSA_ERR_CUDA;
+  if (!tc_make_map3_bf16(&tmQ, q, H * HD, Lq, B, ldq, HD, TQ)) return MMSA_ERR_CUDA;
+  if (!tc_make_map3_bf16(&tmK, k, H * HD, Lk, B, ldk, HD, TK)) return MMSA_ERR_CUDA;
+  if (!tc_make_map3_bf16(&tmV, v, H * HD, Lk, B, ldv, HD, TK)) return MMSA_ERR_CUDA;
   if (!tc_make_map3_bf16(&tmO, o, H * HD, Lq, B, ldo, HD, 32)) return MMSA_ERR_CUDA;
   AttnParams p{};
   p.H = (int)H; p.Lq = (int)Lq; p.Lk = (int)Lk;
@@ -711,7 +700,6 @@ int attn_fwd_tc_bf16(int64_t B, int64_t H, int64_t Lq, int64_t Lk, const void* q
   p.units = B * H * p.nq;
   p.o = (bf16*)o; p.ldo = ldo; p.lse = lse;
   p.scale = 0.125f; p.scale_log2 = 0.125f * 1.4426950408889634f;
-  p.flat_loads = flat ? 1 : 0; p.direct_store = (g_attn_tc_debug & 2) ? 1 : 0;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
