@@ -542,6 +542,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     Cur x{(long long)blockIdx.x, 0, 0, 0, 0, 0};
     float lse_l2 = 0.f, delta = 0.f;
     bool row_valid = false;
+    bool ps_dirty = true;      // this thread's P / dS chunks may hold non-zero (or uninitialised) data
     // The read-out of a step's dQ / dK / dV is DEFERRED until the next step's P / dS have been staged: the second MMA
     // chain of step t (dQ, [dV;dK]) then runs while these warps already exponentiate step t+1, instead of being waited for.
     struct Pending { bool dq, dkv; int h, b, qt, kt; } pend{false, false, 0, 0, 0, 0};
@@ -627,6 +628,30 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       mbar_wait(sdp_full, sdpfull_ph); sdpfull_ph ^= 1u;
       tc_fence_after();
+      if (qt * TQ + quad * 32 >= p.Lq) {
+        // every query row of this warp lies past the end of the sample (Lq = 49: the two upper lane quadrants): no
+        // scores to read, and P = dS = 0 -- written once, the rows stay zero until the warp is live again
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sdp_free);
+        mbar_wait(ps_free, psfree_ph ^ 1u); psfree_ph ^= 1u;
+        if (ps_dirty) {
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            sts128(sw128(ps, r, hh * 4 + c4), 0u, 0u, 0u, 0u);
+            sts128(sw128(ps + P_BYTES, r, hh * 4 + c4), 0u, 0u, 0u, 0u);
+          }
+          ps_dirty = false;
+          fence_async_smem();
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ps_full);
+        readout();
+        pend = Pending{dq_done, dkv_done, h, b, qt, kt};
+        advance(x);
+        continue;
+      }
+      ps_dirty = true;
       const int kvalid = min(TK, p.Lk - kt * TK);
       uint32_t pw[16], dw[16];
       {
