@@ -67,6 +67,39 @@ def sharded_infonce(f1: Tensor, f2: Tensor, labels: Tensor, temperature, group=N
     return ops.infonce(f1, f2_all, labels, temperature, labels_cols=labels_all, row_offset=rank * f1.shape[0], fast=fast)
 
 
+def _sharded_two_view(z1: Tensor, z2: Tensor, labels: Optional[Tensor], temperature: float, kind: int, group=None) -> Tensor:
+    """SupCon (train.py:16-40) / NT-Xent (ME-MHACL/train.py:47-66) over the GLOBAL stacked batch [all first views; all
+    second views] with rows sharded by rank: both views are all-gathered (reduce-scatter in the backward), this rank
+    scores its B first-view rows (global offset rank*B) and its B second-view rows (offset Bg + rank*B) against all 2*Bg
+    columns, and returns the mean over its 2B rows -- averaging gradients over ranks then gives the global-batch mean."""
+    from . import ops
+    rank = dist.get_rank(group)
+    B = z1.shape[0]
+    z1_all = all_gather_rows(z1, group)
+    z2_all = all_gather_rows(z2, group)
+    Bg = z1_all.shape[0]
+    z_all = ops._StackFn.apply(z1_all, z2_all)
+    if labels is not None:
+        lab_all = gather_labels(labels.view(-1), group)
+        lab_cols = torch.cat([lab_all, lab_all])
+        lab_rows = labels.view(-1)
+    else:
+        lab_cols = lab_rows = None
+    a = ops.ContrastiveFn.apply(z1, z_all, lab_rows, lab_cols, None, float(temperature), kind, rank * B, 2 * B, False, False)
+    b = ops.ContrastiveFn.apply(z2, z_all, lab_rows, lab_cols, None, float(temperature), kind, Bg + rank * B, 2 * B, False, False)
+    return a + b
+
+
+def sharded_supcon(z1: Tensor, z2: Tensor, labels: Tensor, temperature: float = 0.1, group=None) -> Tensor:
+    from ._lib import LOSS_SUPCON
+    return _sharded_two_view(z1, z2, labels, temperature, LOSS_SUPCON, group)
+
+
+def sharded_ntxent(z1: Tensor, z2: Tensor, temperature: float = 0.5, group=None) -> Tensor:
+    from ._lib import LOSS_NTXENT
+    return _sharded_two_view(z1, z2, None, temperature, LOSS_NTXENT, group)
+
+
 def shard_contrastive(model, group=None):
     """Switch a MultimodalTransformerModel to the batch-sharded contrastive loss."""
     model.dp_group = group if group is not None else dist.group.WORLD

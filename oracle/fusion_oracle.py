@@ -224,6 +224,39 @@ def ntxent(z1: Tensor, z2: Tensor, temperature: float = 0.5) -> Tensor:
     return F.cross_entropy(sim, targets)
 
 
+def supcon_rows(z_rows: Tensor, z_all: Tensor, labels_rows: Tensor, labels_all: Tensor, row_offset: int,
+                temperature: float = 0.1) -> Tensor:
+    """Row block of train.py:16-40 under batch sharding: `z_all` [2Bg, D] is the stacked global batch (all first
+    views, then all second views), `z_rows` the local rows whose global indices start at `row_offset`.  Returns the SUM
+    of the row losses (the caller divides by the number of rows it averages over)."""
+    zr = F.normalize(z_rows, dim=1)
+    za = F.normalize(z_all, dim=1)
+    sim = torch.matmul(zr, za.T) / temperature
+    mask = torch.eq(labels_rows.view(-1, 1), labels_all.view(1, -1)).to(sim.dtype)
+    self_mask = torch.zeros_like(mask, dtype=torch.bool)
+    idx = torch.arange(z_rows.shape[0])
+    self_mask[idx, idx + row_offset] = True
+    mask = mask.masked_fill(self_mask, 0)
+    sim_exp = torch.exp(sim).masked_fill(self_mask, 0)
+    log_prob = sim - torch.log(sim_exp.sum(dim=1, keepdim=True) + 1e-8)
+    return (-(mask * log_prob).sum(dim=1) / (mask.sum(dim=1) + 1e-8)).sum()
+
+
+def ntxent_rows(z_rows: Tensor, z_all: Tensor, row_offset: int, temperature: float = 0.5) -> Tensor:
+    """Row block of ME-MHACL/train.py:47-66 under batch sharding (same conventions as supcon_rows): cross-entropy of each
+    local row against its partner view at global index (i + Bg) mod 2Bg, diagonal masked.  Returns the SUM over rows."""
+    zr = F.normalize(z_rows, dim=1)
+    za = F.normalize(z_all, dim=1)
+    sim = torch.matmul(zr, za.T)
+    n2 = z_all.shape[0]
+    idx = torch.arange(z_rows.shape[0])
+    gi = idx + row_offset
+    mask = torch.zeros_like(sim, dtype=torch.bool)
+    mask[idx, gi] = True
+    sim = sim.masked_fill(mask, -9e15) / temperature
+    return F.cross_entropy(sim, (gi + n2 // 2) % n2, reduction="sum")
+
+
 # --------------------------------------------------------------------------
 # MultimodalTransformerModel.forward hot path (MultimodalModel.py:262-322)
 # --------------------------------------------------------------------------

@@ -248,3 +248,22 @@ def test_oracle_subnetwork_bit_identical_to_reference():
         want = m(x)
     got = O.subnetwork(x, {k: v for k, v in m.state_dict().items()})
     assert rel_err(got, want) <= 1e-6
+
+
+def test_oracle_sharded_supcon_ntxent_equal_global():
+    """row-block forms (two ranks, rows sharded, both views gathered) reproduce train.py:16-40 / ME-MHACL/train.py:47-66."""
+    g = torch.Generator().manual_seed(4)
+    Bg, D, world = 12, 16, 2
+    B = Bg // world
+    z1, z2 = torch.randn(Bg, D, generator=g, dtype=torch.float64), torch.randn(Bg, D, generator=g, dtype=torch.float64)
+    labels = torch.randint(0, 3, (Bg,), generator=g)
+    z_all = torch.cat([z1, z2])
+    lab_all = torch.cat([labels, labels])
+    tot_s = tot_n = 0.0
+    for r in range(world):
+        sl = slice(r * B, (r + 1) * B)
+        tot_s = tot_s + O.supcon_rows(z1[sl], z_all, labels[sl], lab_all, r * B, 0.1) \
+                      + O.supcon_rows(z2[sl], z_all, labels[sl], lab_all, Bg + r * B, 0.1)
+        tot_n = tot_n + O.ntxent_rows(z1[sl], z_all, r * B, 0.5) + O.ntxent_rows(z2[sl], z_all, Bg + r * B, 0.5)
+    assert abs(float(tot_s) / (2 * Bg) - float(O.supcon(z1, z2, labels, 0.1))) < 1e-12
+    assert abs(float(tot_n) / (2 * Bg) - float(O.ntxent(z1, z2, 0.5))) < 1e-12

@@ -2,6 +2,7 @@
 of the same op on identical seeded inputs.  Tolerances (parity_util.rel_err, relative to tensor
 scale): fp32 storage 1e-5, bf16 storage 2e-2 (BASELINE.json north_star)."""
 import math
+import os
 
 import pytest
 import torch
@@ -553,3 +554,61 @@ def test_fused_clip_adamw_optimizer(cuda_device):
         p.grad = flat[off:off + p.numel()].view_as(p)
     a = opt_o._arena(opt_o.param_groups[0])
     assert opt_o._flat_grad(a).data_ptr() == flat.data_ptr()
+
+
+def test_sharded_supcon_ntxent_rows(cuda_device):
+    """SupCon / NT-Xent row blocks of a batch-sharded run (mmsa.dist._sharded_two_view's kernel calls), two emulated ranks in
+    one process: the per-rank means average to the oracle's global loss, gradients of local rows and gathered columns add up."""
+    from mmsa import ops
+    from mmsa._lib import LOSS_NTXENT, LOSS_SUPCON
+    O = _oracle()
+    g = torch.Generator().manual_seed(9)
+    Bg, D, world = 32, 128, 2
+    B = Bg // world
+    z1, z2 = torch.randn(Bg, D, generator=g), torch.randn(Bg, D, generator=g)
+    labels = torch.randint(0, 3, (Bg,), generator=g)
+    for kind, name in ((LOSS_SUPCON, "supcon"), (LOSS_NTXENT, "ntxent")):
+        a, b = z1.clone().double().requires_grad_(True), z2.clone().double().requires_grad_(True)
+        ref = O.supcon(a, b, labels, 0.1) if name == "supcon" else O.ntxent(a, b, 0.5)
+        ref.backward()
+        x, y = z1.clone().to(cuda_device).requires_grad_(True), z2.clone().to(cuda_device).requires_grad_(True)
+        z_all = torch.cat([x, y])                           # what the two all-gathers + stack produce on every rank
+        lab = labels.to(cuda_device)
+        lab_cols = torch.cat([lab, lab]) if name == "supcon" else None
+        T = 0.1 if name == "supcon" else 0.5
+        total = 0
+        for r in range(world):
+            sl = slice(r * B, (r + 1) * B)
+            lr = lab[sl] if name == "supcon" else None
+            la = ops.ContrastiveFn.apply(x[sl], z_all, lr, lab_cols, None, T, kind, r * B, 2 * B, False, False)
+            lb = ops.ContrastiveFn.apply(y[sl], z_all, lr, lab_cols, None, T, kind, Bg + r * B, 2 * B, False, False)
+            total = total + (la + lb) / world
+        total.backward()
+        assert rel_err(total, ref) <= 1e-5, name
+        assert rel_err(x.grad, a.grad) <= 5e-5 and rel_err(y.grad, b.grad) <= 5e-5, name
+
+
+def test_sharded_two_view_losses_single_rank_group(cuda_device, tmp_path):
+    """mmsa.dist.sharded_supcon / sharded_ntxent through a real (1-rank NCCL) process group == the single-GPU losses."""
+    import torch.distributed as dist
+    from mmsa import dist as mdist, ops
+    created = False
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", init_method=f"file://{tmp_path}/rendezvous", rank=0, world_size=1,
+                                device_id=cuda_device)            # file rendezvous: no port to collide on
+        created = True
+    try:
+        g = torch.Generator().manual_seed(10)
+        z1, z2 = torch.randn(24, 128, generator=g).to(cuda_device), torch.randn(24, 128, generator=g).to(cuda_device)
+        labels = torch.randint(0, 2, (24,), generator=g).to(cuda_device)
+        for fn_s, fn_1, args in ((mdist.sharded_supcon, ops.supcon, (labels, 0.1)), (mdist.sharded_ntxent, ops.ntxent, (0.5,))):
+            a1, a2 = z1.clone().requires_grad_(True), z2.clone().requires_grad_(True)
+            b1, b2 = z1.clone().requires_grad_(True), z2.clone().requires_grad_(True)
+            ls = fn_s(a1, a2, *args)
+            l1 = fn_1(b1, b2, *args)
+            ls.backward(); l1.backward()
+            assert rel_err(ls, l1) <= 1e-6
+            assert rel_err(a1.grad, b1.grad) <= 1e-5 and rel_err(a2.grad, b2.grad) <= 1e-5
+    finally:
+        if created:
+            dist.destroy_process_group()
