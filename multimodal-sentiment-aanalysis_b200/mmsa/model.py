@@ -54,11 +54,10 @@ class PositionalEncoding(nn.Module):
     def __init__(self, d_model: int, max_len: int = 5000):
         super().__init__()
         import math
-        pe = torch.zeros(max_len, d_model)
-        position = torch.arange(0, max_len, dtype=torch.float).unsqueeze(1)
-        div_term = torch.exp(torch.arange(0, d_model, 2).float() * (-math.log(10000.0) / d_model))
-        pe[:, 0::2] = torch.sin(position * div_term)
-        pe[:, 1::2] = torch.cos(position * div_term)
+        # angle[pos, i] = pos / 10000^(2i/d); even columns take the sine, odd columns the cosine (:11-15)
+        half = torch.arange(0, d_model, 2, dtype=torch.float32)
+        angle = torch.arange(max_len, dtype=torch.float32)[:, None] * torch.exp(half * (-math.log(10000.0) / d_model))[None, :]
+        pe = torch.stack([torch.sin(angle), torch.cos(angle)], dim=2).reshape(max_len, -1)[:, :d_model].contiguous()
         self.register_buffer("pe", pe.unsqueeze(0))
 
 

@@ -463,11 +463,9 @@ def synth_inputs(cfg: FusionConfig, batch: int, L: int = 64, R: int = 49, seed: 
 # --------------------------------------------------------------------------
 def positional_table(d_model: int, max_len: int = 100, dtype=torch.float32) -> Tensor:
     """PositionalEncoding.__init__ (MultimodalModel.py:9-17): [max_len, d_model]."""
-    pe = torch.zeros(max_len, d_model)
-    position = torch.arange(0, max_len, dtype=torch.float).unsqueeze(1)
-    div_term = torch.exp(torch.arange(0, d_model, 2).float() * (-math.log(10000.0) / d_model))
-    pe[:, 0::2] = torch.sin(position * div_term)
-    pe[:, 1::2] = torch.cos(position * div_term)
+    half = torch.arange(0, d_model, 2, dtype=torch.float32)
+    angle = torch.arange(max_len, dtype=torch.float32)[:, None] * torch.exp(half * (-math.log(10000.0) / d_model))[None, :]
+    pe = torch.stack([torch.sin(angle), torch.cos(angle)], dim=2).reshape(max_len, -1)[:, :d_model].contiguous()
     return pe.to(dtype)
 
 
