@@ -3,11 +3,11 @@
 //
 //   C[M,N] = act( alpha * A[M,Kt] * B[N,Kt]^T + bias[N] + residual[M,N] ),  fp32 accumulation
 //
-// One persistent CTA per SM, 192 threads, warp-specialised:
+// One persistent CTA per SM, 320 threads, warp-specialised:
 //   warp 0 (lane 0)  TMA producer      -- fills the smem ring, arrives on full[stage] with expect_tx
 //   warp 1 (lane 0)  MMA issuer        -- tcgen05.mma 128 x BN x 16, tcgen05.commit -> empty[stage];
 //                                         after the last k-block commit -> tmem_full[acc]
-//   warps 2..5       epilogue          -- tcgen05.ld 32 lanes x 32 columns, bias/residual/activation,
+//   warps 2..9       epilogue          -- tcgen05.ld 32 lanes x 32 columns, bias/residual/activation,
 //                                         vector stores; arrive tmem_empty[acc]
 // Two accumulator buffers in TMEM (2 x BN columns) let the epilogue of tile i overlap the main loop
 // of tile i+1.  Either operand may be K-major (row = M/N index, K contiguous: activations x,
@@ -27,7 +27,9 @@ namespace mmsa {
 static constexpr int BM = 128;
 static constexpr int BK = 64;           // 64 bf16 = 128 bytes = one swizzle row
 static constexpr int UMMA_K = 16;
-static constexpr int kGemmThreads = 192;
+static constexpr int kEpiWarps = 8;             // two per TMEM lane quadrant, alternating 32-column chunks
+static constexpr int kEpiThreads = kEpiWarps * 32;
+static constexpr int kGemmThreads = 64 + kEpiThreads;
 static constexpr int kMaxClusterSplits = 8;   // portable cluster size limit
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -152,10 +154,10 @@ struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = CTA_N * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  // epilogue staging (per epilogue warp, double-buffered): output slab 32 rows x 32 cols (<= 4 KB, fp32)
-  // and residual slab 32 x 32 bf16 (2 KB), both moved by TMA so that global traffic is line-granular
+  // epilogue staging per epilogue warp: a 4 KB output region (one 32 x 32 fp32 slab, or two bf16 slabs used
+  // alternately) and one residual slab 32 x 32 bf16 (2 KB), all moved by TMA so that global traffic is line-granular
   static constexpr int OUT_SLAB = 4096, RES_SLAB = 2048;
-  static constexpr int EPI_BYTES = 4 * 2 * (OUT_SLAB + RES_SLAB);
+  static constexpr int EPI_BYTES = kEpiWarps * (OUT_SLAB + RES_SLAB);
   static constexpr int STAGE_BUDGET = 227 * 1024 - EPI_BYTES - 2048 /*ones*/ - 2048 /*align*/ - 256 - 2 * BN * 4;
   static constexpr int STAGES = STAGE_BUDGET / STAGE_BYTES > 8 ? 8 : STAGE_BUDGET / STAGE_BYTES;
   // accumulator buffers in TMEM: two, so the epilogue of tile i overlaps the main loop of tile i+1 --
@@ -228,7 +230,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t part_full_bar = bar_base + 8u * (2 * STAGES + 4);
   const uint32_t read_done_bar = bar_base + 8u * (2 * STAGES + 5);
-  auto res_bar = [&](int w, int b) { return bar_base + 8u * (2 * STAGES + 6 + w * 2 + b); };   // per epilogue warp
+  auto res_bar = [&](int w) { return bar_base + 8u * (2 * STAGES + 6 + w); };   // per epilogue warp
   uint8_t* aux = smem_al + STAGES * Cfg::STAGE_BYTES + Cfg::ONES_BYTES;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(aux + 8 * (2 * STAGES + 14));
   const uint32_t epi_base = bar_base + Cfg::AUX_BYTES;      // 1024-aligned: [warp][buf] out slabs, then res slabs
@@ -259,10 +261,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA2) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), PAIR ? 8 : 4); }   // only NACC are used
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), (PAIR ? 2 : 1) * kEpiWarps); }   // only NACC are used
     mbar_init(part_full_bar, (uint32_t)S);
     mbar_init(read_done_bar, (uint32_t)S);
-    for (int w = 0; w < 4; ++w) { mbar_init(res_bar(w, 0), 1); mbar_init(res_bar(w, 1), 1); }
+    for (int w = 0; w < kEpiWarps; ++w) mbar_init(res_bar(w), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -348,7 +350,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int acc = 0; uint32_t acc_phase = 0;
       for (int unit = unit0; unit < tiles_mn; unit += unit_stride) {
         const bool cs = colsum_on && (unit % p.tiles_n) == 0;
-        if (PAIR) mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);     // 4 local + 4 remote epilogue warps
+        if (PAIR) mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);     // local + remote epilogue warps
         else mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -383,12 +385,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else {
-    // ===================== epilogue warps (2..5) =====================
+    // ===================== epilogue warps (2..9) =====================
+    // two warps per TMEM lane quadrant: warp w and w + 4 read the same 32 accumulator rows and take the even /
+    // odd 32-column chunks, so a 128 x 256 accumulator drains in 4 chunk times instead of 8
     const int quad = warp & 3;                         // TMEM lane quadrant this warp may read
-    const int te = threadIdx.x - 64;                   // 0..127
+    const int ew = warp - 2;                           // 0..7: staging region / residual barrier of this warp
+    const int hh = ew >> 2;                            // chunk parity this warp takes
+    const int te = threadIdx.x - 64;                   // 0..255
     int acc = 0; uint32_t acc_phase = 0;
     uint32_t cl_phase = 0;
-    uint32_t epi_it = 0;                               // chunks this warp has pushed through its slabs
+    uint32_t epi_it = 0, res_it = 0;                   // chunks / residual slabs this warp has pushed through its staging
     float* part = reinterpret_cast<float*>(smem_al);   // [BM][PART_LD] fp32 + [BM] colsum (split-K only)
     float* part_cs = part + BM * Cfg::PART_LD;
     for (int unit = unit0; unit < tiles_mn; unit += unit_stride) {
@@ -396,8 +402,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // stage this tile's bias slice in shared memory while the main loop is still running
       float* bs = bias_s + acc * BN;
       if (p.bias) {
-        for (int c = te; c < BN; c += 128) bs[c] = (n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");      // epilogue warps only
+        for (int c = te; c < BN; c += kEpiThreads) bs[c] = (n0 + c < p.N) ? __ldg(p.bias + n0 + c) : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");      // epilogue warps only
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -408,7 +414,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // ---- split-K: park the fp32 partial in shared memory; the cluster sums it below ----
         float* prow = part + (quad * 32 + lane) * Cfg::PART_LD;
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = hh; c < BN / 32; c += 2) {
           uint32_t r[32];
           tmem_ld32(t_row + c * 32, r);
           tmem_ld_wait();
@@ -417,7 +423,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             *reinterpret_cast<float4*>(prow + c * 32 + j) =
                 make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
         }
-        if (colsum_on && n0 == 0) {
+        if (colsum_on && n0 == 0 && hh == 0) {
           uint32_t cv;
           asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(cv)
                        : "r"(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(Cfg::NACC * BN + acc * 16)) : "memory");
@@ -431,7 +437,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           else mbar_arrive(tempty_bar(acc));
         }
         asm volatile("fence.acq_rel.cluster;" ::: "memory");
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         if (te == 0)
           for (int r = 0; r < S; ++r) mbar_arrive_remote(mapa_u32(part_full_bar, peer_of(r)));
         mbar_wait_cluster(part_full_bar, cl_phase);        // every CTA of the cluster has parked its partial
@@ -443,7 +449,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float* Cf = reinterpret_cast<float*>(p.C);
         const bool vec_ok = (cols & 3) == 0 && (p.ldc & 3) == 0 && ((uintptr_t)Cf & 15) == 0;
         const int c4n = (cols + 3) >> 2;
-        for (int idx = te; idx < (r_hi - r_lo) * c4n; idx += 128) {
+        for (int idx = te; idx < (r_hi - r_lo) * c4n; idx += kEpiThreads) {
           const int r = r_lo + idx / c4n, c4 = idx % c4n;
           if (r >= rows_valid) continue;
           const uint32_t off = part_u32 + (uint32_t)((r * Cfg::PART_LD + c4 * 4) * 4);
@@ -473,7 +479,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             p.colsum[m0 + r] = a;
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         if (te == 0)
           for (int r = 0; r < S; ++r) mbar_arrive_remote(mapa_u32(read_done_bar, peer_of(r)));
         mbar_wait_cluster(read_done_bar, cl_phase);        // peers are done with OUR partial: smem reusable
@@ -483,24 +489,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       if (p.tma_epi) {
         // ---- TMA epilogue: TMEM -> registers -> swizzled shared-memory slab -> cp.async.bulk.tensor store.
-        // Each warp owns two 32x32 output slabs and two residual slabs; the residual of chunk c+2 is
-        // fetched by TMA while chunk c is computed, and a slab is rewritten only after the bulk group
-        // that read it has drained.  Edge tiles need no bounds checks: TMA clips stores and zero-fills loads.
-        const uint32_t out_slab0 = epi_base + (uint32_t)(quad * 2) * Cfg::OUT_SLAB;
-        const uint32_t res_slab0 = epi_base + 8u * Cfg::OUT_SLAB + (uint32_t)(quad * 2) * Cfg::RES_SLAB;
+        // Each warp owns a 4 KB output region (two bf16 slabs used alternately, or one fp32 slab) and one residual
+        // slab; the residual of the warp's next chunk is fetched by TMA as soon as the current one has been read,
+        // and an output slab is rewritten only after the bulk group that read it has drained.  Edge tiles need no
+        // bounds checks: TMA clips stores and zero-fills loads.
+        const uint32_t out_slab0 = epi_base + (uint32_t)ew * Cfg::OUT_SLAB;
+        const uint32_t res_slab = epi_base + (uint32_t)kEpiWarps * Cfg::OUT_SLAB + (uint32_t)ew * Cfg::RES_SLAB;
         const bool has_res = p.residual != nullptr;
         const int row0 = m0 + quad * 32;
         const int nc = min(BN / 32, (p.N - n0 + 31) / 32);
-        if (has_res && lane == 0) {
-          for (int c = 0; c < 2 && c < nc; ++c) {
-            const uint32_t b = (epi_it + c) & 1u;
-            mbar_expect_tx(res_bar(quad, b), Cfg::RES_SLAB);
-            tma_load_2d(res_slab0 + b * Cfg::RES_SLAB, &tmR, n0 + c * 32, row0, res_bar(quad, b));
-          }
+        if (has_res && lane == 0 && hh < nc) {
+          mbar_expect_tx(res_bar(ew), Cfg::RES_SLAB);
+          tma_load_2d(res_slab, &tmR, n0 + hh * 32, row0, res_bar(ew));
         }
 #pragma unroll 1
-        for (int c = 0; c < nc; ++c) {
-          const uint32_t b = epi_it & 1u;
+        for (int c = hh; c < nc; c += 2) {
           uint32_t r[32];
           tmem_ld32(t_row + c * 32, r);
           tmem_ld_wait();
@@ -515,16 +518,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
           if (has_res) {
-            mbar_wait(res_bar(quad, b), (epi_it >> 1) & 1u);
-            const uint32_t rrow = res_slab0 + b * Cfg::RES_SLAB + (uint32_t)lane * 64u;
+            mbar_wait(res_bar(ew), res_it & 1u);
+            ++res_it;
+            const uint32_t rrow = res_slab + (uint32_t)lane * 64u;
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
               uint4 raw;
               const uint32_t a = rrow + (uint32_t)((cc ^ ((lane >> 1) & 3)) << 4);
-              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "r"(a));
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w) : "r"(a) : "memory");
               const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
               for (int q = 0; q < 4; ++q) { const float2 f = __bfloat1622float2(h[q]); v[cc * 8 + 2 * q] += f.x; v[cc * 8 + 2 * q + 1] += f.y; }
+            }
+            __syncwarp();                                // every lane has read the slab: refill it for chunk c + 2
+            if (lane == 0 && c + 2 < nc) {
+              mbar_expect_tx(res_bar(ew), Cfg::RES_SLAB);
+              tma_load_2d(res_slab, &tmR, n0 + (c + 2) * 32, row0, res_bar(ew));
             }
           }
           if (p.act == MMSA_ACT_SIGMOID) {
@@ -537,10 +546,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           }
-          if (lane == 0) tma_store_wait_read<1>();       // the group that read slab b two chunks ago has drained
-          __syncwarp();
-          const uint32_t oslab = out_slab0 + b * Cfg::OUT_SLAB;
+          uint32_t oslab;
           if (p.out_is_f32) {
+            if (lane == 0) tma_store_wait_read<0>();     // the single fp32 slab: the previous store has read it
+            __syncwarp();
+            oslab = out_slab0;
             const uint32_t orow = oslab + (uint32_t)lane * 128u;
 #pragma unroll
             for (int cc = 0; cc < 8; ++cc) {
@@ -548,6 +558,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[cc * 4]), "f"(v[cc * 4 + 1]), "f"(v[cc * 4 + 2]), "f"(v[cc * 4 + 3]) : "memory");
             }
           } else {
+            if (lane == 0) tma_store_wait_read<1>();     // the group that read this half two chunks ago has drained
+            __syncwarp();
+            oslab = out_slab0 + (epi_it & 1u) * (Cfg::OUT_SLAB / 2);
             const uint32_t orow = oslab + (uint32_t)lane * 64u;
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
@@ -564,14 +577,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (lane == 0) {
             tma_store_2d(&tmC, oslab, n0 + c * 32, row0);
             tma_store_commit();
-            if (has_res && c + 2 < nc) {               // residual slab b is free again: fetch chunk c+2 into it
-              mbar_expect_tx(res_bar(quad, b), Cfg::RES_SLAB);
-              tma_load_2d(res_slab0 + b * Cfg::RES_SLAB, &tmR, n0 + (c + 2) * 32, row0, res_bar(quad, b));
-            }
           }
           ++epi_it;
         }
-        if (colsum_on && n0 == 0) {
+        if (colsum_on && n0 == 0 && hh == 0) {
           uint32_t cv;
           asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(cv)
                        : "r"(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(Cfg::NACC * BN + acc * 16)) : "memory");
@@ -588,7 +597,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         continue;
       }
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = hh; c < BN / 32; c += 2) {
         uint32_t r[32];
         tmem_ld32(t_row + c * 32, r);
         tmem_ld_wait();
@@ -655,7 +664,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
       }
-      if (colsum_on && n0 == 0) {    // bias-gradient column of this tile: one value per accumulator row
+      if (colsum_on && n0 == 0 && hh == 0) {    // bias-gradient column of this tile: one value per accumulator row
         uint32_t cv;
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(cv)
                      : "r"(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(Cfg::NACC * BN + acc * 16)) : "memory");
@@ -925,7 +934,7 @@ static int dispatch_bn(const GemmDesc& d, int splits, int bn, cudaStream_t s) {
 }
 
 // max co-resident clusters of `size` CTAs of this kernel family (all instantiations use ~205 KB of
-// shared memory and 192 threads, so one query per size serves all); measured on B200:
+// shared memory and 320 threads, so one query per size serves all); measured on B200:
 // {1:148, 2:74, 3:45, 4:33, 5:26, 6:22, 7:15, 8:15}
 int gemm_tc_max_clusters(int size) {
   static int cache[kMaxClusterSplits + 1] = {0};
