@@ -79,6 +79,9 @@ int mmsa_cast_multi(int count, const void* const* src_host, void* const* dst_hos
 int mmsa_split3(const float* src, int64_t R, int64_t C, int64_t ld, void* dst_col, int b_side_col, void* dst_row,
                 int b_side_row, void* stream);
 
+/* test hook: bf16 products below 0.13 GFLOP (the [B,*] tail) run on the latency-optimised mma.sync cluster kernel;
+ * 1 keeps them on the tcgen05 engine (engine cross-check), 0 restores the default. */
+void mmsa_debug_gemm_engine(int engine);
 /* ---- Linear: y = x W^T + b   (nn.Linear: MultimodalModel.py:86,112-121,172-198) -------------
  * x:[M,K] (row stride ldx), optional second operand x2:[M,K2] concatenated on the feature axis
  * (the gate's cat[q, attn], MultimodalModel.py:147), W:[N,K+K2] fp32 master (row stride ldw) or

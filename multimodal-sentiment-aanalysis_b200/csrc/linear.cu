@@ -1,5 +1,6 @@
 // linear.cu -- C ABI of the three Linear products (fwd, dgrad, wgrad) over the two GEMM engines:
-//   bf16 storage  -> tcgen05/TMA kernel (gemm_sm100.cu); N < 16 or unaligned -> CUDA-core kernel
+//   bf16 storage  -> tcgen05/TMA kernel (gemm_sm100.cu); products below 0.13 GFLOP -> mma.sync cluster kernel
+//                    (gemm_small.cu); unaligned -> CUDA-core kernel
 //   fp32 storage  -> CUDA-core fp32 kernel (gemm_simt.cu), the 1e-5 parity mode
 // Replaces the cuBLAS addmm calls behind nn.Linear / MHA in/out-proj / gate
 // (MultimodalModel.py:86,112-121,139-147,172-198).
@@ -15,6 +16,11 @@ int gemm_bf16_sm100_splits(const GemmDesc& d, int splits, int bn, cudaStream_t s
 int gemm_tc_max_clusters(int size);
 int gemm_tc_bn(int64_t N, bool need_colsum);
 int gemm_num_sms();
+bool gemm_bf16_small_ok(const GemmDesc& d);                      // gemm_small.cu: the [B,*] tail, latency-bound
+int gemm_bf16_small(const GemmDesc& d, cudaStream_t s);
+
+static int g_gemm_engine = 0;     // test hook: 1 = keep small products on the tcgen05 / CUDA-core engines
+static bool small_ok(int dtype, const GemmDesc& d) { return dtype == MMSA_BF16 && g_gemm_engine != 1 && gemm_bf16_small_ok(d); }
 
 static int tc_real_splits(int64_t Kt, int splits) {
   int64_t kb = ceil_div(Kt, 64);
@@ -47,6 +53,7 @@ static void tc_plan_small(const GemmDesc& d, int* bn, int* splits) {
 
 static int run_gemm(int dtype, const GemmDesc& d, int splits, cudaStream_t s) {
   if (dtype == MMSA_F32) return gemm_simt_f32(d, splits, s);
+  if (splits == 1 && small_ok(dtype, d)) return gemm_bf16_small(d, s);
   if (use_tc(dtype, d)) {
     int bn = 0, sp = 1;
     tc_plan_small(d, &bn, &sp);
@@ -217,6 +224,9 @@ using namespace mmsa;
 
 extern "C" {
 
+/* test hook: 0 = products below 0.13 GFLOP use the mma.sync cluster kernel (default), 1 = they stay on tcgen05 */
+void mmsa_debug_gemm_engine(int engine) { g_gemm_engine = engine; }
+
 /* tuning probe (not part of the product path): raw bf16 tcgen05 GEMM with explicit operand majors.
  * C[M,N] (fp32, ldc) = A * B^T over K; a_mn: A stored [K,M]; b_mn: B stored [K,N]. */
 int mmsa_debug_gemm(int a_mn, int b_mn, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda,
@@ -311,7 +321,12 @@ int mmsa_linear_wgrad(int dtype, int64_t M, int64_t N, int64_t K, const void* dy
     d.B = x; d.ldb = ldx; d.b_mn_major = true;      // x[M,K]:  reduction index m is the row
     d.bias = nullptr; d.residual = nullptr; d.act = MMSA_ACT_NONE; d.alpha = 1.f; d.out_dtype = MMSA_F32;
     d.C = dw; d.ldc = lddw;
-    if (use_tc(dtype, d)) {
+    if (small_ok(dtype, d)) {
+      d.colsum = db;                                  // bias gradient from the ones-fragment MMA of the same launch
+      int rc = gemm_bf16_small(d, s);
+      if (rc) return rc;
+      db_done = true;
+    } else if (use_tc(dtype, d)) {
       // one launch: split-K partials are summed by the last CTA of each tile, and the bias gradient
       // falls out of an extra ones-tile MMA (gemm_sm100.cu)
       d.colsum = db;

@@ -38,6 +38,7 @@ _PROTOS = {
     "mmsa_linear_wgrad": (I, [I, L, L, L, P, L, P, L, P, L, P, P, P]),
     "mmsa_debug_force_simt_attention": (None, [I]),
     "mmsa_debug_attention_engine": (None, [I]),
+    "mmsa_debug_gemm_engine": (None, [I]),
     "mmsa_attn_fwd": (I, [I, L, L, L, L, L, P, L, P, L, P, L, P, L, P, P]),
     "mmsa_attn_bwd": (I, [I, L, L, L, L, L, P, L, P, L, P, L, P, L, P, L, P, P, P, L, P, L, P, L, P]),
     "mmsa_gate_ln_fwd": (I, [I, L, L, P, P, P, P, P, F, P, P, P, P, P]),

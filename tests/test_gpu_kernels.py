@@ -39,9 +39,22 @@ GEMM_SHAPES = [
 ]
 
 
+@pytest.fixture(params=[0, 1], ids=["auto", "tcgen05"])
+def gemm_engine(request):
+    """bf16 products below 0.13 GFLOP take the mma.sync cluster kernel (gemm_small.cu) by default; engine 1 keeps
+    them on the tcgen05 kernel so that both engines see the ragged shapes."""
+    from mmsa import _lib
+    lib = _lib.load()
+    lib.mmsa_debug_gemm_engine(request.param)
+    yield request.param
+    lib.mmsa_debug_gemm_engine(0)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
-def test_linear_fwd(cuda_device, dtype, M, N, K):
+def test_linear_fwd(cuda_device, gemm_engine, dtype, M, N, K):
+    if dtype == torch.float32 and gemm_engine:
+        pytest.skip("engine switch only affects bf16 storage")
     k = _k()
     x = _rand((M, K), dtype, cuda_device, 1)
     w = _rand((N, K), dtype, cuda_device, 2, 1 / math.sqrt(K))
@@ -73,7 +86,9 @@ def test_linear_fwd_split_operand(cuda_device, dtype):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("M,N,K", [(256, 768, 768), (392, 1536, 768), (77, 3, 128), (640, 768, 1536), (4200, 768, 768),
                                    (6272, 1536, 768)])
-def test_linear_dgrad(cuda_device, dtype, M, N, K):
+def test_linear_dgrad(cuda_device, gemm_engine, dtype, M, N, K):
+    if dtype == torch.float32 and gemm_engine:
+        pytest.skip("engine switch only affects bf16 storage")
     k = _k()
     dy = _rand((M, N), dtype, cuda_device, 1)
     wfull = _rand((N, K + 64), dtype, cuda_device, 2, 1 / math.sqrt(N))
@@ -87,8 +102,11 @@ def test_linear_dgrad(cuda_device, dtype, M, N, K):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("M,N,K", [(1024, 768, 768), (392, 768, 2048), (5000, 1536, 768), (300, 3, 128), (64, 256, 2304)])
-def test_linear_wgrad(cuda_device, dtype, M, N, K):
+@pytest.mark.parametrize("M,N,K", [(1024, 768, 768), (392, 768, 2048), (5000, 1536, 768), (300, 3, 128), (64, 256, 2304),
+                                   (256, 256, 2304), (100, 24, 40)])
+def test_linear_wgrad(cuda_device, gemm_engine, dtype, M, N, K):
+    if dtype == torch.float32 and gemm_engine:
+        pytest.skip("engine switch only affects bf16 storage")
     k = _k()
     dy = _rand((M, N), dtype, cuda_device, 1)
     x = _rand((M, K), dtype, cuda_device, 2)
@@ -100,6 +118,28 @@ def test_linear_wgrad(cuda_device, dtype, M, N, K):
     assert rel_err(dw, ref_w) <= tol
     assert rel_err(db, ref_b) <= tol
     assert float(dwfull[:, :8].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("M,N,K,K2", [(100, 256, 2304, 0), (256, 64, 768, 768), (100, 37, 72, 0), (33, 130, 8, 0),
+                                      (256, 128, 256, 0), (50, 768, 768, 768), (1, 16, 4096, 0)])
+@pytest.mark.parametrize("act", [0, 1, 2, 3])
+def test_linear_small_engine(cuda_device, M, N, K, K2, act):
+    """gemm_small.cu (mma.sync + cluster split-K): ragged edges, two-tensor A operand, activations, bf16 and fp32
+    outputs, and bit-equality of repeated launches (slice-ordered DSMEM sum)."""
+    k = _k()
+    x = _rand((M, K), torch.bfloat16, cuda_device, 1)
+    x2 = _rand((M, K2), torch.bfloat16, cuda_device, 2) if K2 else None
+    w = _rand((N, K + K2), torch.bfloat16, cuda_device, 3, 1 / math.sqrt(K + K2))
+    b = _rand((N,), torch.float32, cuda_device, 4)
+    r = _rand((M, N), torch.bfloat16, cuda_device, 5)
+    xa = torch.cat([x, x2], 1) if K2 else x
+    pre = xa.double() @ w.double().T + b.double() + r.double()
+    ref = [pre, torch.sigmoid(pre), F.gelu(pre), torch.relu(pre)][act]
+    y = k.linear_fwd(x, w, b, residual=r, x2=x2, act=act)
+    assert rel_err(y, ref) <= 2e-2
+    y32 = k.linear_fwd(x, w, b, residual=r, x2=x2, act=act, out_dtype=torch.float32)
+    assert rel_err(y32, ref) <= 2e-3
+    assert torch.equal(y32, k.linear_fwd(x, w, b, residual=r, x2=x2, act=act, out_dtype=torch.float32))
 
 
 # ---------------------------------------------------------------------------------------- attention
