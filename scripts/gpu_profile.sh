@@ -10,11 +10,11 @@ $CMD > gpurun_out/plain.log 2> gpurun_out/plain.err || { echo "plain run failed"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 300 --csv \
     --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list exit=$?"
-# DRAM bytes of the 49 GEMM launches of one step (after the 4 warm-up steps)
+# DRAM bytes of the 38 tcgen05 GEMM launches of one step (after the 4 warm-up steps)
 timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
-    -k regex:gemm_tcgen05 -s 196 -c 49 --csv --log-file gpurun_out/gemm_traffic.csv $CMD > gpurun_out/ncu_traffic.log 2>&1
+    -k regex:gemm_tcgen05 -s 152 -c 38 --csv --log-file gpurun_out/gemm_traffic.csv $CMD > gpurun_out/ncu_traffic.log 2>&1
 echo "gemm traffic exit=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 196 -c 14 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 152 -c 14 \
     -f -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu_gemm.log 2>&1
 echo "gemm capture exit=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:gate_ln_pool|attn_" -s 16 -c 8 \
