@@ -259,7 +259,7 @@ class MultimodalTransformerModel(nn.Module):
                 main = torch.cuda.current_stream(e1.device)
                 if self.overlap_contrastive and ops.OVERLAP_TAIL:
                     if self._side_stream is None:
-                        self._side_stream = torch.cuda.Stream(device=e1.device)
+                        self._side_stream = torch.cuda.Stream(device=e1.device, priority=ops.critical_priority())   # feeds the loss
                     side = self._side_stream
                     side.wait_stream(main)
                 with torch.cuda.stream(side if side is not None else main):

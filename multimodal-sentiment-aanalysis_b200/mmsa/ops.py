@@ -7,6 +7,7 @@ autograd boundary on the small [B,*] side (pooled features, fused vector, logits
 both modes; inside a Function the GEMM operands are cd and the GEMM outputs fp32 (include/mmsa.h)."""
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -80,6 +81,13 @@ def set_overlap(on: bool) -> None:
     global OVERLAP_WGRAD, OVERLAP_TAIL
     OVERLAP_WGRAD = OVERLAP_TAIL = bool(on)
 _SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def critical_priority() -> int:
+    """CUDA stream priority of the chains that feed the loss and its backward (-1 = high; the weight-gradient helper
+    stream keeps the default priority 0, so pending critical-path kernels get SMs first).  MMSA_STREAM_PRIO=0 turns
+    the distinction off (A/B measurements)."""
+    return -1 if os.environ.get("MMSA_STREAM_PRIO", "1") != "0" else 0
 
 
 def _side_stream(device) -> "torch.cuda.Stream":

@@ -69,6 +69,14 @@ class TrainStep:
         torch.cuda.current_stream(self.device).wait_stream(st)
         torch.cuda.synchronize(self.device)
 
+    def _capture_stream(self):
+        """The main chain is captured on a high-priority stream: its kernel nodes keep that priority in the graph, so
+        when a main-chain kernel and a weight-gradient GEMM of the helper stream (default priority, ops._side_stream) are
+        both pending, the SMs go to the critical path first and the weight gradients fill what is left."""
+        if getattr(self, "_cap_stream", None) is None:
+            self._cap_stream = torch.cuda.Stream(device=self.device, priority=ops.critical_priority())
+        return self._cap_stream
+
     def capture(self) -> None:
         from . import _lib
         if not self.use_graph:
@@ -80,7 +88,7 @@ class TrainStep:
             self.model.zero_grad(set_to_none=True)
             g = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
-            with torch.cuda.graph(g, pool=self._pool):
+            with torch.cuda.graph(g, pool=self._pool, stream=self._capture_stream()):
                 self._body(s)
             self.launches_per_step = _lib.launch_count() - n0
             if self._pool is None:
