@@ -273,11 +273,9 @@ int launch_small(const GemmDesc& d, cudaStream_t s) {
   p.slices = (p.kb_total + p.kb_per_slice - 1) / p.kb_per_slice;
   dim3 grid((unsigned)((p.N + Cfg::TN - 1) / Cfg::TN), (unsigned)((p.M + Cfg::TM - 1) / Cfg::TM), (unsigned)p.slices);
   auto kern = gemm_small_kernel<WT, A_MN, B_MN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (Cfg::SMEM_BYTES > 48 * 1024) {      // per device, so not cached in a static (WT = 16 stays below the opt-in limit)
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("mmsa: cudaFuncSetAttribute(gemm_small_kernel, smem=%d) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return MMSA_ERR_CUDA; }
-    attr_set = true;
   }
   char nm[64];
   snprintf(nm, sizeof nm, "gemm_small_%c%c_%dx%dx%d", A_MN ? 'm' : 'k', B_MN ? 'm' : 'k', p.M, p.N, Kt);
