@@ -79,3 +79,65 @@ def test_sharded_contrastive_and_grad_allreduce_gloo():
     for p in procs:
         p.join(timeout=30)
     assert all(ok for _, ok in results), results
+
+
+def _overlap_worker(rank, world, port, q):
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mmsa import dist as mdist
+        torch.manual_seed(0)                                   # identical replicas
+        net = torch.nn.Sequential(torch.nn.Linear(40, 64), torch.nn.Tanh(), torch.nn.Linear(64, 64), torch.nn.Tanh(),
+                                  torch.nn.Linear(64, 8), torch.nn.Linear(8, 3, bias=False))
+        unused = torch.nn.Parameter(torch.zeros(5))            # never gets a gradient
+        import copy
+        ref = copy.deepcopy(net)                               # same weights, no hooks: the yardstick
+        params = list(net.parameters()) + [unused]
+        red = mdist.GradAllReducer(params, overlap=True, late_frac=0.3)
+        ok = True
+        for it in range(4):
+            g = torch.Generator().manual_seed(100 + it)
+            xs = torch.randn(world, 6, 40, generator=g)            # every rank knows every shard
+            for p_ in params:
+                p_.grad = None
+            net(xs[rank]).square().sum().backward()
+            red.step()
+            ref.zero_grad(set_to_none=True)
+            for r in range(world):                              # sum over shards of the per-shard gradients
+                ref(xs[r]).square().sum().backward()
+            ok &= all(bool(torch.allclose(a.grad, b.grad / world, rtol=1e-5, atol=1e-6))
+                      for a, b in zip(net.parameters(), ref.parameters()))
+            ok &= unused.grad is None
+        # first step records the landing order, the other three reduce the early bucket from inside the backward
+        ok &= red.overlapped_steps == 3
+        # the late bucket is the first layer's weight (its gradient lands last), the early one everything else
+        ok &= red._early is not None and 0 not in red._early and len(red._early) == len(params) - 2
+        # gradients are views of ONE flat arena in parameter order (FusedClipAdamW's in-place path)
+        base = red._flat.data_ptr()
+        offs = [p_.grad.data_ptr() - base for p_ in net.parameters()]
+        ok &= offs == sorted(offs) and all(0 <= o < red._flat.numel() * 4 for o in offs)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_overlapped_two_bucket_grad_allreduce_gloo():
+    """GradAllReducer(overlap=True): landing-order recording, early bucket reduced from the post-accumulate hooks,
+    late bucket in step(), results equal to the mean of the per-shard gradients."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31000 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_overlap_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=100) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+    assert all(ok for _, ok in results), results
