@@ -267,3 +267,42 @@ def test_oracle_sharded_supcon_ntxent_equal_global():
         tot_n = tot_n + O.ntxent_rows(z1[sl], z_all, r * B, 0.5) + O.ntxent_rows(z2[sl], z_all, Bg + r * B, 0.5)
     assert abs(float(tot_s) / (2 * Bg) - float(O.supcon(z1, z2, labels, 0.1))) < 1e-12
     assert abs(float(tot_n) / (2 * Bg) - float(O.ntxent(z1, z2, 0.5))) < 1e-12
+
+
+def test_sass_shows_the_blackwell_paths():
+    """The built library really contains the hardware paths DESIGN.md claims (SASS mnemonics, B200_PROFILING.md):
+    tcgen05 MMA + TMEM loads + TMA in the GEMM and attention kernels, bulk copies in the row kernels, mma.sync +
+    cp.async + cluster barriers in the small-product kernel.  Guards against a silent fall-back after a refactor."""
+    import re
+    import shutil
+    import subprocess
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "multimodal-sentiment-aanalysis_b200",
+                      "mmsa", "libmmsa.so")
+    if shutil.which("cuobjdump") is None or not os.path.exists(so):
+        pytest.skip("cuobjdump or the built library is not available")
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, check=True).stdout
+    per = {}
+    cur = None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            per[cur] = set()
+            continue
+        if cur is not None:
+            for mn in re.findall(r"\b(UTC\w*MMA|LDTM|UTMALDG|UTMASTG|UBLKCP|HMMA|LDGSTS|UCGABAR_ARV)\b", line):
+                per[cur].add("UTCMMA" if mn.startswith("UTC") else mn)
+    def have(sub):
+        ks = [v for k, v in per.items() if sub in k]
+        assert ks, f"no kernel named *{sub}* in the library"
+        return ks
+    for v in have("gemm_tcgen05_kernel"):
+        assert {"UTCMMA", "LDTM", "UTMALDG", "UTMASTG"} <= v, v
+    for name in ("attn_fwd_tc_kernel", "attn_bwd_tc_kernel"):
+        for v in have(name):
+            assert {"UTCMMA", "LDTM", "UTMALDG", "UTMASTG"} <= v, (name, v)
+    for name in ("gate_ln_pool_fwd_kernel", "gate_ln_pool_bwd_kernel"):
+        for v in have(name):
+            assert "UBLKCP" in v, (name, v)
+    for v in have("gemm_small_kernel"):
+        assert {"HMMA", "LDGSTS", "UCGABAR_ARV"} <= v, v
