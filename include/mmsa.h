@@ -206,12 +206,15 @@ int mmsa_act_bwd(int dtype, int64_t n, const void* x, const void* dy, int act, v
  * training!=0: batch statistics (biased var), running stats updated in place with momentum and
  * unbiased var; else running stats.  keep_mask:[B,N] uint8 or NULL: if dropout_p>0 and
  * mask_given==0 the kernel draws it (Philox, seed/offset) and writes it; if mask_given it reads it.
+ * rng_state (device, {seed, position}) or NULL: when given, the kernel reads the seed from it and adds its
+ * position to `offset` -- the stream position then lives in device memory and moves with mmsa_rng_advance, so a
+ * captured CUDA graph draws a new mask on every replay (by-value seed/offset are frozen at capture).
  * save_mean/save_rstd:[N] fp32.  x (and dy in bwd) are fp32 GEMM outputs; y / dx are written in `dtype`. */
 int mmsa_bn_act_fwd(int dtype, int64_t B, int64_t N, int order, const void* x,
                     const float* gamma, const float* beta, float* running_mean, float* running_var,
                     float momentum, float eps, int training,
                     float dropout_p, uint8_t* keep_mask, int mask_given, uint64_t seed, uint64_t offset,
-                    void* y, float* save_mean, float* save_rstd, void* stream);
+                    const uint64_t* rng_state, void* y, float* save_mean, float* save_rstd, void* stream);
 int mmsa_bn_act_bwd(int dtype, int64_t B, int64_t N, int order, const void* x, const void* dy,
                     const float* gamma, const float* beta, const float* save_mean, const float* save_rstd, int training,
                     float dropout_p, const uint8_t* keep_mask,
@@ -224,7 +227,10 @@ int mmsa_bn_act_bwd(int dtype, int64_t B, int64_t N, int order, const void* x, c
  * keep_mask:[n] uint8 is drawn (Philox) and written unless mask_given; backward = same call on dy
  * with mask_given=1. */
 int mmsa_dropout(int dtype, int64_t n, const void* x, float p, uint8_t* keep_mask, int mask_given,
-                 uint64_t seed, uint64_t offset, void* y, void* stream);
+                 uint64_t seed, uint64_t offset, const uint64_t* rng_state, void* y, void* stream);
+/* rng_state[1] += n (one-thread kernel on `stream`): moves the device-resident Philox position past the n
+ * draws a step consumed; call once per step after the last dropout kernel of that step. */
+int mmsa_rng_advance(uint64_t* rng_state, uint64_t n, void* stream);
 
 /* ---- softmax cross-entropy, mean reduction (nn.CrossEntropyLoss, Trainer.py:17,68) ----------
  * logits:[B,C] fp32, labels:[B] int64; loss:[1] fp32, pred:[B] int64 (argmax, Trainer.py:87). */

@@ -55,16 +55,16 @@ void prof_end(cudaStream_t s) {
 }
 
 bool device_ok() {
-  static int cached_dev = -1;
-  static bool cached_ok = false;
+  static unsigned char state[kMaxDevices] = {};      // per device: 0 unknown, 1 sm_100, 2 something else
   int dev = -1;
   if (cudaGetDevice(&dev) != cudaSuccess) return false;
-  if (dev == cached_dev) return cached_ok;
-  int major = 0;
-  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return false;
-  cached_dev = dev;
-  cached_ok = (major == 10);
-  return cached_ok;
+  if (dev < 0 || dev >= kMaxDevices) return false;
+  if (state[dev] == 0) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return false;
+    state[dev] = (major == 10) ? 1 : 2;
+  }
+  return state[dev] == 1;
 }
 
 template <typename S, typename D>

@@ -725,11 +725,11 @@ int attn_fwd_tc_bf16(int64_t B, int64_t H, int64_t Lq, int64_t Lk, const void* q
   p.units = B * H * p.nq;
   p.o = (bf16*)o; p.ldo = ldo; p.lse = lse;
   p.scale = 0.125f; p.scale_log2 = 0.125f * 1.4426950408889634f;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.pending()) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
     if (e != cudaSuccess) { set_error("mmsa: cudaFuncSetAttribute(attn_fwd_tc, smem=%d) failed: %s", SMEM_TOTAL, cudaGetErrorString(e)); return MMSA_ERR_CUDA; }
-    attr_set = true;
+    attr_set.mark();
   }
   int sms = 148;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
@@ -764,11 +764,11 @@ int attn_bwd_tc_bf16(int64_t B, int64_t H, int64_t Lq, int64_t Lk, const void* q
   p.units = B * H;
   p.lse = lse;
   p.scale = 0.125f; p.scale_log2 = 0.125f * 1.4426950408889634f;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.pending()) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B_SMEM_TOTAL);
     if (e != cudaSuccess) { set_error("mmsa: cudaFuncSetAttribute(attn_bwd_tc, smem=%d) failed: %s", B_SMEM_TOTAL, cudaGetErrorString(e)); return MMSA_ERR_CUDA; }
-    attr_set = true;
+    attr_set.mark();
   }
   int sms = 148;
   { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }

@@ -151,6 +151,21 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Per-DEVICE one-time state (function attributes such as the >48 KB shared-memory opt-in, SM counts, occupancy
+// queries) is kept in arrays indexed by the current device: a process that drives several GPUs (nn.DataParallel,
+// a test touching cuda:1) must see each of them initialised, not only the first one used.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  return dev;
+}
+struct PerDeviceOnce {
+  unsigned char done[kMaxDevices] = {};
+  bool pending() const { return !done[current_device()]; }
+  void mark() { done[current_device()] = 1; }
+};
+
 // internal GEMM entry points (gemm_f32.cu / gemm_sm100.cu)
 struct GemmDesc {
   // C[M,N] = act( A[M,K(+K2)] * B^T + bias + residual ), reduction over K

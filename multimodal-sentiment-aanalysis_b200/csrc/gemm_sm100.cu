@@ -783,15 +783,14 @@ bool tc_make_map3_bf16(CUtensorMap* map, const void* base, int64_t cols, int64_t
   return true;
 }
 
-static int g_num_sms = 0;
+static int g_num_sms[kMaxDevices] = {0};
 static int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+  const int dev = current_device();
+  if (g_num_sms[dev] == 0) {
+    cudaDeviceGetAttribute(&g_num_sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms[dev] <= 0) g_num_sms[dev] = 148;
   }
-  return g_num_sms;
+  return g_num_sms[dev];
 }
 
 bool gemm_bf16_sm100_supported(const GemmDesc& d) {
@@ -853,11 +852,11 @@ static int launch_gemm(const GemmDesc& d, int splits_req, cudaStream_t s) {
     p.colsum = d.colsum;
   }
   auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, PAIR>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.pending()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("mmsa: cudaFuncSetAttribute(smem=%d) failed: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return MMSA_ERR_CUDA; }
-    attr_set = true;
+    attr_set.mark();
   }
   const int tiles_mn = p.tiles_m * p.tiles_n;
   char nm[48];
@@ -942,7 +941,8 @@ static int dispatch_bn(const GemmDesc& d, int splits, int bn, cudaStream_t s) {
 // shared memory and 320 threads, so one query per size serves all); measured on B200:
 // {1:148, 2:74, 3:45, 4:33, 5:26, 6:22, 7:15, 8:15}
 int gemm_tc_max_clusters(int size) {
-  static int cache[kMaxClusterSplits + 1] = {0};
+  static int cache_all[kMaxDevices][kMaxClusterSplits + 1] = {{0}};
+  int* cache = cache_all[current_device()];
   static const int fallback[kMaxClusterSplits + 1] = {0, 148, 74, 45, 33, 26, 22, 15, 15};
   if (size < 1) size = 1;
   if (size > kMaxClusterSplits) size = kMaxClusterSplits;

@@ -34,9 +34,10 @@ bn_act_fwd_kernel(int64_t B, int N, int order, const float* __restrict__ x, cons
                   const float* __restrict__ beta, float* __restrict__ running_mean,
                   float* __restrict__ running_var, float momentum, float eps, int training,
                   float dropout_p, uint8_t* __restrict__ keep_mask, int mask_given, uint64_t seed,
-                  uint64_t offset, T* __restrict__ y, float* __restrict__ save_mean,
-                  float* __restrict__ save_rstd) {
+                  uint64_t offset, const uint64_t* __restrict__ rng_state, T* __restrict__ y,
+                  float* __restrict__ save_mean, float* __restrict__ save_rstd) {
   __shared__ float red[kBnRows][kBnCols + 1];
+  if (rng_state != nullptr) { seed = rng_state[0]; offset += rng_state[1]; }   // device-resident stream position
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int col = blockIdx.x * kBnCols + tx;
   const bool ok = col < N;
@@ -394,7 +395,8 @@ extern "C" {
 int mmsa_bn_act_fwd(int dtype, int64_t B, int64_t N, int order, const void* x, const float* gamma,
                     const float* beta, float* running_mean, float* running_var, float momentum, float eps,
                     int training, float dropout_p, uint8_t* keep_mask, int mask_given, uint64_t seed,
-                    uint64_t offset, void* y, float* save_mean, float* save_rstd, void* stream) {
+                    uint64_t offset, const uint64_t* rng_state, void* y, float* save_mean, float* save_rstd,
+                    void* stream) {
   MMSA_REQUIRE_DEVICE();
   MMSA_REQUIRE(B > 0 && N > 0, "mmsa_bn_act_fwd: empty input");
   MMSA_REQUIRE(training || (running_mean && running_var), "mmsa_bn_act_fwd: eval mode needs running stats");
@@ -405,7 +407,7 @@ int mmsa_bn_act_fwd(int dtype, int64_t B, int64_t N, int order, const void* x, c
   dim3 block(kBnCols, kBnRows);
   MMSA_DISPATCH_DTYPE(dtype, T, (bn_act_fwd_kernel<T><<<(unsigned)ceil_div(N, kBnCols), block, 0, s>>>(
       B, (int)N, order, (const float*)x, gamma, beta, running_mean, running_var, momentum, eps, training, dropout_p,
-      keep_mask, mask_given, seed, offset, (T*)y, save_mean, save_rstd)));
+      keep_mask, mask_given, seed, offset, rng_state, (T*)y, save_mean, save_rstd)));
   MMSA_LAUNCH_CHECK("bn_act_fwd_kernel");
   return MMSA_OK;
 }
@@ -532,7 +534,9 @@ int mmsa_clip_adamw(float* p, const float* g, float* m, float* v, int64_t n, con
 namespace mmsa {
 template <typename T>
 __global__ void dropout_kernel(int64_t n, const float* __restrict__ x, float p, uint8_t* __restrict__ keep_mask,
-                               int mask_given, uint64_t seed, uint64_t offset, T* __restrict__ y) {
+                               int mask_given, uint64_t seed, uint64_t offset,
+                               const uint64_t* __restrict__ rng_state, T* __restrict__ y) {
+  if (rng_state != nullptr) { seed = rng_state[0]; offset += rng_state[1]; }
   const float scale = 1.f / (1.f - p);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     uint8_t keep;
@@ -548,7 +552,7 @@ __global__ void dropout_kernel(int64_t n, const float* __restrict__ x, float p, 
 }  // namespace mmsa
 
 extern "C" int mmsa_dropout(int dtype, int64_t n, const void* x, float p, uint8_t* keep_mask, int mask_given,
-                            uint64_t seed, uint64_t offset, void* y, void* stream) {
+                            uint64_t seed, uint64_t offset, const uint64_t* rng_state, void* y, void* stream) {
   MMSA_REQUIRE_DEVICE();
   MMSA_REQUIRE(p >= 0.f && p < 1.f && keep_mask != nullptr, "mmsa_dropout: bad arguments");
   if (n == 0) return MMSA_OK;
@@ -557,7 +561,23 @@ extern "C" int mmsa_dropout(int dtype, int64_t n, const void* x, float p, uint8_
   int64_t blocks = mmsa::ceil_div(n, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   MMSA_DISPATCH_DTYPE(dtype, T, (mmsa::dropout_kernel<T><<<(unsigned)blocks, 256, 0, s>>>(
-      n, (const float*)x, p, keep_mask, mask_given, seed, offset, (T*)y)));
+      n, (const float*)x, p, keep_mask, mask_given, seed, offset, rng_state, (T*)y)));
   MMSA_LAUNCH_CHECK("dropout_kernel");
+  return MMSA_OK;
+}
+
+// ------------------------------------------------------------------ device-resident Philox stream position
+// state = {seed, position}: the dropout kernels above add `position` to their by-value offset when given the state
+// pointer, and this one-thread kernel moves the position on by what a step consumed.  Both are ordinary kernel nodes,
+// so a captured CUDA graph draws a fresh mask on every replay (the by-value seed/offset alone would be frozen at capture).
+namespace mmsa {
+__global__ void rng_advance_kernel(uint64_t* __restrict__ state, uint64_t n) { state[1] += n; }
+}  // namespace mmsa
+
+extern "C" int mmsa_rng_advance(uint64_t* rng_state, uint64_t n, void* stream) {
+  MMSA_REQUIRE_DEVICE();
+  MMSA_REQUIRE(rng_state != nullptr, "mmsa_rng_advance: null state");
+  mmsa::rng_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(rng_state, n);
+  MMSA_LAUNCH_CHECK("rng_advance_kernel");
   return MMSA_OK;
 }

@@ -348,3 +348,40 @@ class GradAllReducer:
                 p.grad = (g / world).clone()
             else:
                 p.grad.copy_(g).div_(world)
+
+
+# --------------------------------------------------------------------------------------------- parity yardstick
+def emulate_data_parallel_step(model, text_all: Tensor, image_all: Tensor, labels_all: Tensor, world: int):
+    """The N-rank data-parallel step evaluated on ONE device with the same kernels -- the yardstick `bench.py` (dp_parity)
+    and the multi-rank tests hold the sharded run against.  Rank r's loss is CE over ITS shard (BatchNorm statistics per
+    shard: DDP-without-SyncBN semantics) plus the InfoNCE of its row block [r*B, (r+1)*B) against ALL columns of the global
+    batch (MultimodalModel.py:232-260 with the global diagonal); averaging parameter gradients over ranks is the gradient
+    of mean_r(loss_r).  `model` must be a bidirectional single-contract MultimodalTransformerModel with dp_group None
+    (typically a fresh copy of the replicated weights: the per-shard tails update its BatchNorm running statistics).
+    Returns (mean loss, [per-rank contrastive values], {parameter name: gradient})."""
+    from . import ops
+    assert model.wiring == "bidirectional" and model.contract == "single" and model.dp_group is None
+    Bg = text_all.shape[0]
+    assert Bg % world == 0
+    B = Bg // world
+    model.zero_grad(set_to_none=True)
+    model.prepare_step()
+    fast = model.compute_dtype == torch.bfloat16
+    f0, fv, e1, e2 = ops.fusion_core(model._cd(text_all), model._cd(image_all), model.eeg_net.proj.weight,
+                                     model.eeg_net.proj.bias, model.eye_net.proj.weight, model.eye_net.proj.bias,
+                                     model.num_heads, model.cross_attn_e2p.kernel_params(),
+                                     model.cross_attn_p2e.kernel_params())
+    total, contrastive = None, []
+    for r in range(world):
+        sl = slice(r * B, (r + 1) * B)
+        lab = labels_all[sl].contiguous()
+        arousal, _ = model._tail(f0[sl], fv[sl], (f0[sl], e1[sl], e2[sl]))
+        c = ops.infonce(e1[sl], e2, lab, model.temperature, labels_cols=labels_all.contiguous(), row_offset=r * B, fast=fast)
+        loss_r = ops.cross_entropy(arousal, lab) + (model.contrastive_weight * c).sum()
+        contrastive.append(c.detach())
+        total = loss_r if total is None else total + loss_r
+    total = total / world
+    total.backward()
+    model._drop.commit(text_all.device)
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    return total.detach(), contrastive, grads

@@ -36,20 +36,30 @@ class FeatureBatches:
 
     format="dict":  ({'eeg': text, 'eye': image, 'pps': third}, labels)          (Trainer.py:51-56)
     format="tuple": (text, image, third, arousal_labels, valence_labels)         (MultiTaskTrainer.py:186-195)
-    Host tensors are pinned once, so the trainers' `.to(device)` calls are asynchronous-capable copies."""
+    Every batch is gathered (torch.index_select(..., out=...)) into one of `n_staging` preallocated PINNED staging
+    buffers, rotated per batch, so the trainers' `.to(device)` copies (Trainer.py:53-56) read page-locked memory -- an
+    index with a tensor alone would return a fresh pageable copy.  A yielded batch stays valid until `n_staging - 1`
+    further batches have been drawn (the trainers consume each batch before asking for the next)."""
 
     def __init__(self, text: Tensor, image: Tensor, labels: Tensor, batch_size: int = 64, third: Optional[Tensor] = None,
                  valence_labels: Optional[Tensor] = None, fmt: str = "dict", shuffle: bool = False, seed: int = 0,
-                 drop_last: bool = False):
+                 drop_last: bool = False, n_staging: int = 3):
         assert fmt in ("dict", "tuple") and text.shape[0] == image.shape[0] == labels.shape[0]
-        pin = torch.cuda.is_available()
-        self.text = text.pin_memory() if pin else text
-        self.image = image.pin_memory() if pin else image
-        self.third = third if third is not None else torch.zeros(text.shape[0], 1)
-        self.labels = labels.long()
-        self.valence = (valence_labels if valence_labels is not None else labels).long()
+        self.pinned = torch.cuda.is_available()
+        self.text, self.image = text.contiguous(), image.contiguous()
+        self.third = (third if third is not None else torch.zeros(text.shape[0], 1)).contiguous()
+        self.labels = labels.long().contiguous()
+        self.valence = (valence_labels if valence_labels is not None else labels).long().contiguous()
         self.batch_size, self.fmt, self.shuffle, self.drop_last = batch_size, fmt, shuffle, drop_last
         self._gen = torch.Generator().manual_seed(seed)
+        self._staging = []
+        for _ in range(max(1, n_staging)):
+            bufs = []
+            for src in (self.text, self.image, self.third, self.labels, self.valence):
+                b = torch.empty((batch_size,) + tuple(src.shape[1:]), dtype=src.dtype)
+                bufs.append(b.pin_memory() if self.pinned else b)
+            self._staging.append(bufs)
+        self._turn = 0
 
     def __len__(self) -> int:
         n = self.text.shape[0]
@@ -60,8 +70,12 @@ class FeatureBatches:
         order = torch.randperm(n, generator=self._gen) if self.shuffle else torch.arange(n)
         for i in range(len(self)):
             idx = order[i * self.batch_size:(i + 1) * self.batch_size]
-            t, im, th = self.text[idx], self.image[idx], self.third[idx]
+            bufs = self._staging[self._turn]
+            self._turn = (self._turn + 1) % len(self._staging)
+            k = idx.numel()
+            t, im, th, la, va = (torch.index_select(src, 0, idx, out=buf[:k])
+                                 for src, buf in zip((self.text, self.image, self.third, self.labels, self.valence), bufs))
             if self.fmt == "dict":
-                yield {"eeg": t, "eye": im, "pps": th}, self.labels[idx]
+                yield {"eeg": t, "eye": im, "pps": th}, la
             else:
-                yield t, im, th, self.labels[idx], self.valence[idx]
+                yield t, im, th, la, va

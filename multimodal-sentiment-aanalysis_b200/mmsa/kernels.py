@@ -23,8 +23,13 @@ def dt(t_or_dtype) -> int:
     raise TypeError(f"mmsa: unsupported dtype {d}")
 
 
+_DEV = None      # device of the tensors of the call being marshalled (set by _check)
+
+
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    """current stream of the device the call's tensors live on (kernels launch on the CURRENT device, which _check has
+    verified to be that device)."""
+    return torch.cuda.current_stream(_DEV).cuda_stream
 
 
 def _p(t: Optional[Tensor]) -> Optional[int]:
@@ -32,9 +37,22 @@ def _p(t: Optional[Tensor]) -> Optional[int]:
 
 
 def _check(*ts: Optional[Tensor]):
+    global _DEV
+    dev = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise _lib.MmsaError("mmsa: tensors must live on a CUDA device (no CPU fallback)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise _lib.MmsaError(f"mmsa: operands on different devices ({dev} and {t.device})")
+    if dev is not None:
+        if dev.index != torch.cuda.current_device():
+            raise _lib.MmsaError(f"mmsa: tensors live on {dev} but the current CUDA device is "
+                                 f"cuda:{torch.cuda.current_device()}; wrap the call in torch.cuda.device({dev.index})")
+        _DEV = dev
 
 
 def cast(x: Tensor, dtype: torch.dtype) -> Tensor:
@@ -289,7 +307,7 @@ def act_bwd(x: Tensor, dy: Tensor, act: int, out_dtype: torch.dtype) -> Tensor:
 
 def bn_act_fwd(x: Tensor, gamma, beta, running_mean, running_var, momentum: float, eps: float, training: bool,
                order: int, dropout_p: float, keep_mask: Optional[Tensor], seed: int, offset: int,
-               out_dtype: torch.dtype):
+               out_dtype: torch.dtype, rng_state: Optional[Tensor] = None):
     _check(x, gamma, beta)
     assert x.dtype == torch.float32
     B, N = x.shape
@@ -301,7 +319,7 @@ def bn_act_fwd(x: Tensor, gamma, beta, running_mean, running_var, momentum: floa
         keep_mask = torch.empty((B, N), device=x.device, dtype=torch.uint8)
     call("mmsa_bn_act_fwd", dt(out_dtype), B, N, order, x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _p(running_mean),
          _p(running_var), float(momentum), float(eps), int(training), float(dropout_p), _p(keep_mask),
-         int(mask_given), seed, offset, y.data_ptr(), save_mean.data_ptr(), save_rstd.data_ptr(), _stream())
+         int(mask_given), seed, offset, _p(rng_state), y.data_ptr(), save_mean.data_ptr(), save_rstd.data_ptr(), _stream())
     return y, save_mean, save_rstd, keep_mask
 
 
@@ -321,15 +339,22 @@ def bn_act_bwd(x, dy, gamma, beta, save_mean, save_rstd, training: bool, order: 
 
 
 def dropout(x: Tensor, p: float, keep_mask: Optional[Tensor], mask_given: bool, seed: int, offset: int,
-            out_dtype: torch.dtype):
+            out_dtype: torch.dtype, rng_state: Optional[Tensor] = None):
     _check(x, keep_mask)
     assert x.dtype == torch.float32
     y = torch.empty(x.shape, device=x.device, dtype=out_dtype)
     if keep_mask is None:
         keep_mask = torch.empty(x.shape, device=x.device, dtype=torch.uint8)
     call("mmsa_dropout", dt(out_dtype), x.numel(), x.data_ptr(), float(p), keep_mask.data_ptr(), int(mask_given), seed,
-         offset, y.data_ptr(), _stream())
+         offset, _p(rng_state), y.data_ptr(), _stream())
     return y, keep_mask
+
+
+def rng_advance(rng_state: Tensor, n: int) -> None:
+    """rng_state[1] += n on the current stream (a kernel node: replays of a captured graph keep advancing)."""
+    _check(rng_state)
+    assert rng_state.dtype == torch.int64 and rng_state.numel() >= 2
+    call("mmsa_rng_advance", rng_state.data_ptr(), int(n), _stream())
 
 
 def ce_fwd(logits: Tensor, labels: Tensor):

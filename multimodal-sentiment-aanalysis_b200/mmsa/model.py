@@ -96,6 +96,7 @@ class Subnetwork(nn.Module):
             h = ops.encoder_layer(h, layer, self._drop, f"transformer.layers.{i}", cd)
         h = ops.add_layer_norm(h, None, self.norm)
         h = ops.cast(h, torch.float32)
+        self._drop.commit(h.device)
         return h.squeeze(1) if squeeze else h
 
 
@@ -222,6 +223,11 @@ class MultimodalTransformerModel(nn.Module):
 
     # -- forward ------------------------------------------------------------------------------------
     def forward(self, eeg: Tensor, eye: Tensor, pps: Optional[Tensor] = None, labels=None):
+        out = self._forward(eeg, eye, pps, labels)
+        self._drop.commit(self.temperature.device)       # one kernel node: the Philox position moves on every (re)play
+        return out
+
+    def _forward(self, eeg: Tensor, eye: Tensor, pps: Optional[Tensor] = None, labels=None):
         if labels is not None and self.contract == "multitask":
             con_labels = labels[0]                                   # MultimodalModel.py:273
         else:
@@ -324,7 +330,9 @@ class MultiModalEncoder(nn.Module):
         if self.variant == "mean":
             return ops.cast(ops.mean_pool(y), torch.float32)         # ME-MHACL/model.py:73
         fused = ops.max_pool(y)                                      # MultimodalModel.py:401
-        return run_sequential(fused, self.fusion_mlp, self._drop, "fusion_mlp", cd)
+        out = run_sequential(fused, self.fusion_mlp, self._drop, "fusion_mlp", cd)
+        self._drop.commit(out.device)
+        return out
 
 
 class ProjectionHead(nn.Module):
@@ -341,7 +349,9 @@ class ProjectionHead(nn.Module):
         self._drop = _DropoutState()
 
     def forward(self, x: Tensor) -> Tensor:
-        return run_sequential(x, self.net, self._drop, "net", self.compute_dtype)
+        out = run_sequential(x, self.net, self._drop, "net", self.compute_dtype)
+        self._drop.commit(out.device)
+        return out
 
 
 class Classifier(nn.Module):
@@ -361,4 +371,5 @@ class Classifier(nn.Module):
         h = run_sequential(x, self.shared, self._drop, "shared", cd)
         out_a = ops.linear(h, self.fc_arousal.weight, self.fc_arousal.bias, out_fp32=True, cd=cd)
         out_v = ops.linear(h, self.fc_valence.weight, self.fc_valence.bias, out_fp32=True, cd=cd)
+        self._drop.commit(out_a.device)
         return out_a, out_v

@@ -24,8 +24,11 @@ Tensor = torch.Tensor
 # ------------------------------------------------------------------------------------------ weight copies
 # fp32 master weight -> bf16 operand copy.  prepare_weights() refreshes every copy of a model in ONE
 # launch (call it once per step, after the optimiser update); _w() falls back to a single cast when a
-# parameter was modified since (tensor._version) or never prepared.
-_WCACHE: Dict[int, Tuple[int, int, Tensor]] = {}      # id(param) -> (param._version, weights epoch, operand copy)
+# parameter was modified since (tensor._version), re-homed (data_ptr) or never prepared.
+# The copy is an attribute OF THE PARAMETER (`_mmsa_wc` = (version, epoch, data_ptr, copy)): it dies with the
+# parameter and can never be served to another tensor that happens to reuse a Python id.  Writes through `p.data`
+# (dist.broadcast(p.data), an optimiser kernel) bump neither the version nor the address: optimisers call
+# bump_weights_epoch(), and model.prepare_step() re-casts every copy unconditionally once per step.
 _WEPOCH = 0
 
 
@@ -37,6 +40,13 @@ def bump_weights_epoch() -> None:
     _WEPOCH += 1
 
 
+def _wc_get(p: Tensor, dtype: torch.dtype):
+    ent = getattr(p, "_mmsa_wc", None)
+    if ent is None or ent[3].shape != p.shape or ent[3].device != p.device or ent[3].dtype != dtype:
+        return None
+    return ent
+
+
 def prepare_weights(params: Sequence[Tensor], dtype: torch.dtype) -> None:
     if dtype == torch.float32:
         return
@@ -44,12 +54,11 @@ def prepare_weights(params: Sequence[Tensor], dtype: torch.dtype) -> None:
     for p in params:
         if p.ndim < 2 or not p.is_cuda:
             continue
-        ent = _WCACHE.get(id(p))
-        if ent is None or ent[2].shape != p.shape or ent[2].device != p.device or ent[2].dtype != dtype:
-            ent = (-1, -1, torch.empty(p.shape, device=p.device, dtype=dtype))
+        ent = _wc_get(p, dtype)
+        buf = ent[3] if ent is not None else torch.empty(p.shape, device=p.device, dtype=dtype)
         srcs.append(p.detach())
-        dsts.append(ent[2])
-        _WCACHE[id(p)] = (p._version, _WEPOCH, ent[2])
+        dsts.append(buf)
+        p._mmsa_wc = (p._version, _WEPOCH, p.data_ptr(), buf)
     K.cast_multi(srcs, dsts)
 
 
@@ -58,16 +67,15 @@ def _w(w: Tensor, dtype: torch.dtype) -> Tensor:
     if dtype == torch.float32:
         wd = w.detach()
         return wd if wd.is_contiguous() else wd.contiguous()
-    ent = _WCACHE.get(id(w))
-    fits = ent is not None and ent[2].shape == w.shape and ent[2].dtype == dtype and ent[2].device == w.device
-    if fits and ent[0] == w._version and ent[1] == _WEPOCH:
-        return ent[2]
+    ent = _wc_get(w, dtype)
+    if ent is not None and ent[0] == w._version and ent[1] == _WEPOCH and ent[2] == w.data_ptr():
+        return ent[3]
     wd = w.detach()
     wd = wd if wd.is_contiguous() else wd.contiguous()
-    if fits:                                      # stale: refresh in place (stable address)
-        K.cast_multi([wd], [ent[2]])
-        _WCACHE[id(w)] = (w._version, _WEPOCH, ent[2])
-        return ent[2]
+    if ent is not None:                           # stale: refresh in place (stable address)
+        K.cast_multi([wd], [ent[3]])
+        w._mmsa_wc = (w._version, _WEPOCH, w.data_ptr(), ent[3])
+        return ent[3]
     return K.cast(wd, dtype)
 
 
@@ -470,12 +478,32 @@ def modal_concat(logits, slots: Sequence[Tensor]):
 
 # ------------------------------------------------------------------------------------------ nn.Sequential chains
 class _DropoutState:
-    """Seeds for the in-kernel Philox dropout; parity tests may inject explicit keep masks."""
+    """Philox stream of the in-kernel dropout of one module; parity tests may inject explicit keep masks.
+
+    The stream POSITION lives in device memory (`state(device)` = int64 {seed, position}): the kernels add it to the
+    relative offset they are launched with, and `commit()` -- called by the owning module at the end of every forward --
+    enqueues one mmsa_rng_advance that moves the position past what the pass drew.  Both are kernel nodes, so a CUDA
+    graph captured around the pass draws a new mask on every replay, from the same stream an eager loop would draw
+    (seed/offset passed by value alone would be frozen into the captured nodes)."""
 
     def __init__(self, seed: int = 0x5EED):
         self.seed = seed
-        self.offset = 0
+        self.offset = 0                      # draws since the last commit (relative to the device position)
         self.mask_provider = None
+        self._state: Dict[torch.device, Tensor] = {}
+
+    def state(self, device) -> Tensor:
+        device = torch.device(device)
+        st = self._state.get(device)
+        if st is None:
+            st = torch.tensor([self.seed, 0], dtype=torch.int64, device=device)
+            self._state[device] = st
+        return st
+
+    def reseed(self, seed: int, position: int = 0) -> None:
+        self.seed, self.offset = int(seed), 0
+        for st in self._state.values():
+            st.copy_(torch.tensor([self.seed, int(position)], dtype=torch.int64))
 
     def next(self, name: str, shape) -> Tuple[Optional[Tensor], int, int]:
         mask = self.mask_provider(name, tuple(shape)) if self.mask_provider else None
@@ -485,6 +513,12 @@ class _DropoutState:
             n *= int(s)
         self.offset += n
         return mask, self.seed, off
+
+    def commit(self, device) -> None:
+        """end of a forward pass: move the device-resident position past this pass's draws"""
+        if self.offset and torch.device(device).type == "cuda":
+            K.rng_advance(self.state(device), self.offset)
+            self.offset = 0
 
 
 def _plan(seq: nn.Sequential):
@@ -567,7 +601,8 @@ class SeqFn(Function):
                     bn.num_batches_tracked += 1
                 y, mean, rstd, mask = K.bn_act_fwd(cur, gamma.detach(), beta.detach(), bn.running_mean, bn.running_var,
                                                    0.1 if bn.momentum is None else bn.momentum, bn.eps, training, order,
-                                                   p, mask, seed, off, out_dt)
+                                                   p, mask, seed, off, out_dt,
+                                                   rng_state=(drop.state(cur.device) if (p > 0 and mask is None) else None))
                 tape.append(("bn_act", cur, gamma.detach(), beta.detach(), mean, rstd, training, order, p, mask, pidx))
                 cur, a = (None, y) if nxt_is_linear else (y, None)
             elif kind == "act":
@@ -578,7 +613,8 @@ class SeqFn(Function):
                 dmod, didx = st[1], st[2]
                 if training and dmod.p > 0:
                     mask, seed, off = drop.next(f"{name}.{didx}", cur.shape)
-                    y, mask = K.dropout(cur, dmod.p, mask, mask is not None, seed, off, out_dt)
+                    y, mask = K.dropout(cur, dmod.p, mask, mask is not None, seed, off, out_dt,
+                                        rng_state=(drop.state(cur.device) if mask is None else None))
                     tape.append(("dropout", dmod.p, mask))
                     cur, a = (None, y) if nxt_is_linear else (y, None)
                 elif nxt_is_linear:
@@ -855,7 +891,8 @@ class ActDropFn(Function):
         if p_eff > 0:
             h = K.act_fwd(z, act, torch.float32)
             mask, seed, off = drop.next(name, z.shape)
-            y, mask = K.dropout(h, p_eff, mask, mask is not None, seed, off, cd)
+            y, mask = K.dropout(h, p_eff, mask, mask is not None, seed, off, cd,
+                                rng_state=(drop.state(h.device) if mask is None else None))
         else:
             y, mask = K.act_fwd(z, act, cd), None
         ctx.save_for_backward(z, mask)
@@ -879,7 +916,8 @@ class DropFn(Function):
     @staticmethod
     def forward(ctx, x, p: float, drop: _DropoutState, name: str):
         mask, seed, off = drop.next(name, x.shape)
-        y, mask = K.dropout(K.cast(_c(x), torch.float32), p, mask, mask is not None, seed, off, x.dtype)
+        y, mask = K.dropout(K.cast(_c(x), torch.float32), p, mask, mask is not None, seed, off, x.dtype,
+                            rng_state=(drop.state(x.device) if mask is None else None))
         ctx.save_for_backward(mask)
         ctx.p = p
         return y

@@ -21,6 +21,56 @@ for p in (ROOT, PKG):
 from oracle import fusion_oracle as O  # noqa: E402
 
 
+# ---------------------------------------------------------------------------------------- strict-bar exceptions report
+# north_star's bars are 1e-5 (fp32) and 2e-2 (bf16) relative.  A few quantities are ill-conditioned enough that the
+# REFERENCE'S OWN evaluation at the working precision misses its float64 value by more than that (InfoNCE at T = 0.01,
+# tiny-batch BatchNorm); those pass through the documented noise-floor clause  err <= noise_mult x reference deviation.
+# Every such pass (and every fixed softer bar in the kernel tests) is LOGGED here, so the softness is never silent:
+# one JSON line per tensor in $MMSA_PARITY_REPORT (default gpurun_out/parity_report.jsonl), turned into
+# profiles/rNN_parity_report.md by scripts/make_parity_report.py.
+import json as _json
+
+REPORT_PATH = os.environ.get("MMSA_PARITY_REPORT", os.path.join(ROOT, "gpurun_out", "parity_report.jsonl"))
+
+
+def _report(rec: Dict) -> None:
+    try:
+        os.makedirs(os.path.dirname(REPORT_PATH), exist_ok=True)
+        with open(REPORT_PATH, "a") as f:
+            f.write(_json.dumps(rec) + "\n")
+    except OSError:
+        pass
+
+
+def report_summary(test: str, strict: float, errs: Dict[str, float], noise: Optional[Dict[str, float]] = None,
+                   bar: Optional[Dict[str, float]] = None, full: bool = False, note: str = "") -> None:
+    """log one test case: how many tensors were checked, the worst error, and every tensor above the strict bar"""
+    noise = noise or {}
+    bar = bar or {}
+    worst = max(errs, key=lambda k: errs[k]) if errs else None
+    _report({"kind": "summary", "test": test, "strict": strict, "checked": len(errs), "worst": worst,
+             "worst_err": errs.get(worst), "over_strict": sum(1 for v in errs.values() if v > strict), "note": note})
+    for k, e in errs.items():
+        if e > strict or full:
+            _report({"kind": "tensor", "test": test, "tensor": k, "err": e, "strict": strict, "noise": noise.get(k),
+                     "bar": bar.get(k), "over_strict": e > strict})
+
+
+def check_close(test: str, name: str, got: torch.Tensor, want64: torch.Tensor, strict: float,
+                want_same_precision: Optional[torch.Tensor] = None, noise_mult: float = 3.0,
+                fixed_bar: Optional[float] = None, why: str = "") -> float:
+    """assert rel_err(got, want64) <= max(strict, noise_mult x rel_err(reference at the same precision, want64)) (or
+    <= fixed_bar when given); whenever the strict bar alone would not have passed, the exception is logged."""
+    err = rel_err(got, want64)
+    noise = rel_err(want_same_precision, want64) if want_same_precision is not None else None
+    bar = fixed_bar if fixed_bar is not None else max(strict, noise_mult * (noise or 0.0))
+    if err > strict:
+        _report({"kind": "tensor", "test": test, "tensor": name, "err": err, "strict": strict, "noise": noise, "bar": bar,
+                 "over_strict": True, "why": why})
+    assert err <= bar, f"{test}: {name}: err {err:.3e} > bar {bar:.3e} (strict {strict:.1e}, reference noise {noise})"
+    return err
+
+
 def rel_err(x: torch.Tensor, r: torch.Tensor, floor: float = 1e-12) -> float:
     x = x.detach().double().cpu().reshape(-1)
     r = r.detach().double().cpu().reshape(-1)
@@ -92,7 +142,7 @@ def build_model(cfg: O.FusionConfig, params, buffers, compute_dtype, device):
 def run_fusion_parity(batch: int = 4, L: int = 64, R: int = 49, dtype: str = "fp32", tol: float = 1e-5,
                       device: str = "cuda:0", embed_dim: int = 768, num_heads: int = 12, text_dim: int = 768,
                       image_dim: int = 2048, seed: int = 0, noise_mult: float = 3.0,
-                      temperature: Optional[float] = None) -> Dict:
+                      temperature: Optional[float] = None, name: Optional[str] = None, full_report: bool = False) -> Dict:
     """Bidirectional (text+image) fusion step on the GPU vs the CPU oracle on identical inputs.
 
     The yardstick is the oracle evaluated in float64.  A tensor passes when its error against that is
@@ -133,9 +183,21 @@ def run_fusion_parity(batch: int = 4, L: int = 64, R: int = 49, dtype: str = "fp
         noise["grad:" + k] = grad_err(k, n_grads[k], o_grads[k], o_grads, zero_keys)
     excess = {k: errs[k] / max(tol, noise_mult * noise[k]) for k in errs}
     worst = max(excess, key=lambda k: excess[k])
+    report_summary(name or f"fusion_step[{dtype},B={batch},L={L},T={temperature}]", tol, errs, noise,
+                   {k: max(tol, noise_mult * noise[k]) for k in errs}, full=full_report,
+                   note=f"noise = the oracle's own {'bf16-autocast' if dtype == 'bf16' else 'fp32'} deviation from float64; bar = max(strict, {noise_mult} x noise)")
     labels_equal = bool(torch.equal(logits.argmax(1).cpu(), o_out.arousal.argmax(1)))
     top2 = o_out.arousal.detach().topk(2, dim=1).values
-    return {"ok": excess[worst] <= 1.0 and labels_equal, "max_rel": errs[worst], "worst": worst, "errs": errs,
+    # labels: bit-exact wherever the oracle's own top-2 margin exceeds the precision bar on the logits (a sample whose
+    # two best logits differ by less than the allowed logit error has no defined label at that precision)
+    margin = (top2[:, 0] - top2[:, 1])
+    sure = margin > tol * float(o_out.arousal.detach().abs().max())
+    pred, want = logits.argmax(1).cpu(), o_out.arousal.argmax(1)
+    labels_equal_sure = bool(torch.equal(pred[sure], want[sure]))
+    _report({"kind": "labels", "test": name or f"fusion_step[{dtype},B={batch},L={L},T={temperature}]",
+             "samples": int(batch), "mismatches": int((pred != want).sum()), "below_margin": int((~sure).sum()),
+             "mismatches_above_margin": int((pred[sure] != want[sure]).sum()), "min_margin": float(margin.min())})
+    return {"ok": excess[worst] <= 1.0 and labels_equal_sure, "labels_equal_sure": labels_equal_sure, "max_rel": errs[worst], "worst": worst, "errs": errs,
             "noise": noise, "excess": excess[worst],
             "failing": {k: (errs[k], noise[k]) for k in errs if excess[k] > 1.0},
             "loss": float(loss.detach()), "oracle_loss": float(o_loss), "labels_equal": labels_equal,

@@ -8,7 +8,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from parity_util import rel_err
+from parity_util import check_close, rel_err, report_summary
 
 pytestmark = pytest.mark.gpu
 
@@ -246,7 +246,10 @@ def test_gate_ln(cuda_device, dtype, M, E, L):
     tol = TOL[dtype]
     assert rel_err(dq_part, du_q + extra) <= tol
     assert rel_err(da_part, ins[2].grad) <= tol
-    assert rel_err(dgp, ins[0].grad) <= (tol if dtype == torch.float32 else 4e-2)
+    why_dgate = ("bf16 storage: the gate g is ROUNDED to bf16 before g(1-g) and (q-attn) are formed (so that forward and "
+                 "backward see the same g); g(1-g) near saturation carries that 2^-9 relative error of g at full size")
+    check_close(f"gate_ln[{dtype}]", "dgate_pre (un-pooled bwd)", dgp, ins[0].grad, tol,
+                fixed_bar=(tol if dtype == torch.float32 else 4e-2), why=why_dgate)
     assert rel_err(dgamma, ins[3].grad) <= (1e-5 if dtype == torch.float32 else 2e-2)
     assert rel_err(dbeta, ins[4].grad) <= (1e-5 if dtype == torch.float32 else 2e-2)
     # fused forward/backward with the token mean-pool (no y in HBM, fp32 pooled outputs and gradients)
@@ -259,7 +262,8 @@ def test_gate_ln(cuda_device, dtype, M, E, L):
         assert pq_lp.dtype == dtype and rel_err(pq_lp, pq) <= 4e-3
     dq2, da2, dgp2, dgamma2, dbeta2 = k.gate_ln_pool_bwd(dyp.float(), dqb.float(), dqa, g, q, a, gamma, mean, rstd, B, L)
     assert rel_err(dq2, du_q + extra) <= tol and rel_err(da2, ins[2].grad) <= tol
-    assert rel_err(dgp2, ins[0].grad) <= (tol if dtype == torch.float32 else 4e-2)
+    check_close(f"gate_ln[{dtype}]", "dgate_pre (pooled bwd)", dgp2, ins[0].grad, tol,
+                fixed_bar=(tol if dtype == torch.float32 else 4e-2), why=why_dgate)
     assert rel_err(dgamma2, ins[3].grad) <= (1e-5 if dtype == torch.float32 else 2e-2)
     assert rel_err(dbeta2, ins[4].grad) <= (1e-5 if dtype == torch.float32 else 2e-2)
     # plain form
@@ -419,11 +423,18 @@ def test_infonce_op(cuda_device, B, E, same, T):
     tg = temp.clone().to(cuda_device).requires_grad_(True)
     out = ops.infonce(x, y, labels.to(cuda_device), tg)
     out.backward()
+    # the reference's own fp32 evaluation: exp(s/T) at T = 0.01 amplifies the fp32 rounding of a cosine 100x, so its
+    # gradients sit up to ~1e-4 from their float64 values; bar = max(1e-5, 3 x that), every excess over 1e-5 is logged
+    a32 = f1.clone().requires_grad_(True)
+    b32 = a32 if same else f2.clone().requires_grad_(True)
+    t32 = temp.clone().requires_grad_(True)
+    O.infonce(a32, b32, labels, t32).backward()
+    name = f"infonce_op[B={B},E={E},same={same},T={T}]"
     assert rel_err(out, ref) <= 1e-5
-    assert rel_err(x.grad, a.grad) <= 2e-4      # fp32 exp(s/T) at T=0.01 amplifies cosine rounding 100x
+    check_close(name, "d feat1", x.grad, a.grad, 1e-5, a32.grad)
     if not same:
-        assert rel_err(y.grad, b.grad) <= 2e-4
-    assert rel_err(tg.grad, tt.grad) <= 2e-4
+        check_close(name, "d feat2", y.grad, b.grad, 1e-5, b32.grad)
+    check_close(name, "d temperature", tg.grad, tt.grad, 1e-5, t32.grad)
 
 
 @pytest.mark.parametrize("B,Bg,E,T", [(64, 64, 768, 0.01), (256, 256, 768, 0.07), (128, 512, 768, 0.01), (40, 40, 128, 0.2)])
@@ -450,6 +461,47 @@ def test_infonce_split_bf16_tensor_core(cuda_device, B, Bg, E, T):
     assert rel_err(out, ref) <= 1e-4
     assert rel_err(x.grad, a.grad) <= 2e-3 and rel_err(y.grad, b.grad) <= 2e-3
     assert rel_err(tg.grad, tt.grad) <= 2e-3
+
+
+@pytest.mark.parametrize("B,Bg,row_offset,T", [(4096, 4096, 0, 0.01), (2048, 4096, 2048, 0.07), (1024, 8192, 3072, 0.01),
+                                               (1024, 8192, 7168, 0.07), (8192, 8192, 0, 0.01)])
+def test_infonce_global_batch_sizes(cuda_device, B, Bg, row_offset, T):
+    """BASELINE.json configs[2] / configs[3]: InfoNCE over a GLOBAL batch of 4096 / 8192 (E_c = 768), as the whole square
+    on one GPU and as the row block one rank owns (2048 of 4096 = N=2; 1024 of 8192 = N=8, global diagonal at
+    row_offset + i), in both engines -- split-bf16 tcgen05 GEMMs (`fast`, the bf16-mode path that bench.py runs) and the
+    exact-fp32 CUDA-core GEMMs (parity mode) -- against the float64 oracle (MultimodalModel.py:232-260): loss, d feat1,
+    d feat2 (the gathered side), d temperature.  Strict bar 1e-5 for the exact engine (noise-floor clause against the
+    oracle's own fp32 evaluation, logged), 2e-3 for the split-bf16 engine (bf16-mode bar is 2e-2)."""
+    from mmsa import ops
+    O = _oracle()
+    E = 768
+    g = torch.Generator().manual_seed(B + Bg + row_offset)
+    f2 = torch.randn(Bg, E, generator=g)
+    f1 = 0.7 * f2[row_offset:row_offset + B] + 0.3 * torch.randn(B, E, generator=g)      # positives correlate with their pair
+    lab_c = torch.randint(0, 3, (Bg,), generator=g)
+    lab_r = lab_c[row_offset:row_offset + B].clone()
+    refs = {}
+    for dt in (torch.float64, torch.float32):
+        a, b = f1.clone().to(dt).requires_grad_(True), f2.clone().to(dt).requires_grad_(True)
+        tt = torch.tensor(T, dtype=dt, requires_grad=True)
+        loss = O.infonce(a, b, lab_r, tt, labels2=lab_c, row_offset=row_offset)
+        loss.backward()
+        refs[dt] = (loss.detach(), a.grad, b.grad, tt.grad)
+    r64, r32 = refs[torch.float64], refs[torch.float32]
+    for fast in (True, False):
+        x, y = f1.clone().to(cuda_device).requires_grad_(True), f2.clone().to(cuda_device).requires_grad_(True)
+        tg = torch.tensor(T, device=cuda_device, requires_grad=True)
+        out = ops.infonce(x, y, lab_r.to(cuda_device), tg, labels_cols=lab_c.to(cuda_device), row_offset=row_offset, fast=fast)
+        out.backward()
+        name = f"infonce_global[B={B},Bg={Bg},off={row_offset},T={T},{'split-bf16 tcgen05' if fast else 'exact fp32'}]"
+        got = (out, x.grad, y.grad, tg.grad)
+        errs = {}
+        for nm, gt, w64, w32 in zip(("loss", "d feat1", "d feat2 (gathered)", "d temperature"), got, r64, r32):
+            strict = 1e-5 if (not fast or nm == "loss") else 2e-3
+            if fast and nm == "loss":
+                strict = 1e-4
+            errs[nm] = check_close(name, nm, gt, w64, strict, w32)
+        report_summary(name, 1e-5 if not fast else 2e-3, errs, note="float64 oracle; noise = the oracle's own fp32 evaluation")
 
 
 def test_split3_layout(cuda_device):
@@ -555,9 +607,12 @@ def test_not_sm100_message():
 
 
 def test_fused_clip_adamw_optimizer(cuda_device):
-    """mmsa.FusedClipAdamW (flat arenas, one clip+AdamW kernel per group) vs clip_grad_norm_ + torch.optim.AdamW on the
-    same multi-tensor parameter set: two groups (Trainer.py:24-26 adds the trainer's own weight as a second group), a
-    parameter without gradient, an lr change through param_groups (ReduceLROnPlateau, Trainer.py:28)."""
+    """mmsa.FusedClipAdamW (flat arenas, one clip+AdamW kernel per run of parameters) vs the reference's own call pattern
+    (Trainer.py:19-26,80-81): torch.optim.AdamW over the model parameters + add_param_group(the trainer's weight), and
+    clip_grad_norm_ over the MODEL parameters only (the added group is neither counted in the norm nor scaled).  A parameter
+    whose grad is None is skipped on both sides (no weight decay, no moment decay, no step count), an lr change goes
+    through param_groups (ReduceLROnPlateau, Trainer.py:28), and the state round-trips through state_dict() in both
+    directions between the two optimisers."""
     import mmsa
     g = torch.Generator().manual_seed(5)
     shapes = [(256, 768), (768,), (3, 128), (128, 128), (1,), ()]
@@ -569,31 +624,59 @@ def test_fused_clip_adamw_optimizer(cuda_device):
     opt_r = torch.optim.AdamW(ref, lr=1e-3, weight_decay=0.01)
     opt_o.add_param_group({"params": [extra_o], "lr": 1e-3})
     opt_r.add_param_group({"params": [extra_r], "lr": 1e-3})
+    assert opt_o.param_groups[0]["clip"] is True and opt_o.param_groups[1]["clip"] is False
     ids = [id(p) for p in ours]
-    for step in range(1, 6):
-        for i, (po, pr) in enumerate(zip(ours + [extra_o], ref + [extra_r])):
-            if i == 2 and step % 2 == 0:           # a parameter without gradient this step
-                po.grad, pr.grad = None, torch.zeros_like(pr)
+
+    def one_step(step, oo, orr, po_all, pr_all, model_ref):
+        for i, (po, pr) in enumerate(zip(po_all, pr_all)):
+            if (i == 2 and step % 2 == 0) or (i == 3 and step < 3):     # parameters without a gradient this step
+                po.grad, pr.grad = None, None
                 continue
-            gr = torch.randn(po.shape, generator=g).to(cuda_device) * (0.5 * step)
+            scale = 40.0 if i == len(po_all) - 1 else 0.5 * step        # the trainer's weight: a large gradient (the loss value)
+            gr = torch.randn(po.shape, generator=g).to(cuda_device) * scale
             po.grad, pr.grad = gr.clone(), gr.clone()
+        torch.nn.utils.clip_grad_norm_(model_ref, 1.0)                  # Trainer.py:80: model.parameters() only
+        orr.step()
+        oo.step()
+        for k, (po, pr) in enumerate(zip(po_all, pr_all)):
+            assert rel_err(po, pr) <= 2e-6, (step, k)
+
+    for step in range(1, 6):
         if step == 4:
             for grp in opt_o.param_groups + opt_r.param_groups:
                 grp["lr"] *= 0.1
-        torch.nn.utils.clip_grad_norm_(ref + [extra_r], 1.0)
-        opt_r.step()
-        opt_o.step()
-        for po, pr in zip(ours + [extra_o], ref + [extra_r]):
-            assert rel_err(po, pr) <= 2e-6, step
+        one_step(step, opt_o, opt_r, ours + [extra_o], ref + [extra_r], ref)
     assert [id(p) for p in ours] == ids            # Parameter identity survives the re-homing into the arena
+    # per-parameter step counts as torch keeps them (parameter 3 skipped two steps, parameter 2 every other one)
+    sd_o, sd_r = opt_o.state_dict(), opt_r.state_dict()
+    assert sorted(sd_o["state"].keys()) == sorted(sd_r["state"].keys())
+    for k in sd_r["state"]:
+        assert float(sd_o["state"][k]["step"]) == float(sd_r["state"][k]["step"]), k
+        assert rel_err(sd_o["state"][k]["exp_avg"], sd_r["state"][k]["exp_avg"]) <= 2e-6
+        assert rel_err(sd_o["state"][k]["exp_avg_sq"], sd_r["state"][k]["exp_avg_sq"]) <= 2e-6
+    # resume: fresh optimisers over clones of the parameters, each loading the OTHER implementation's state_dict
+    ours2 = [torch.nn.Parameter(p.detach().clone()) for p in ours + [extra_o]]
+    ref2 = [torch.nn.Parameter(p.detach().clone()) for p in ours + [extra_o]]
+    opt_o2 = mmsa.FusedClipAdamW(ours2[:-1], lr=1e-3, weight_decay=0.01, max_norm=1.0)
+    opt_o2.add_param_group({"params": [ours2[-1]], "lr": 1e-3})
+    opt_r2 = torch.optim.AdamW(ref2[:-1], lr=1e-3, weight_decay=0.01)
+    opt_r2.add_param_group({"params": [ref2[-1]], "lr": 1e-3})
+    opt_o2.load_state_dict(sd_r)
+    opt_r2.load_state_dict(sd_o)
+    assert opt_o2.param_groups[0]["lr"] == pytest.approx(1e-4) and opt_o2.param_groups[1].get("clip") is False
+    for step in range(6, 9):
+        one_step(step, opt_o2, opt_r2, ours2, ref2, ref2[:-1])
     # gradients that already live in one flat buffer in parameter order (GradAllReducer) are used in place
     from mmsa.optim import arena_layout
     offs, total = arena_layout(ours)
     flat = torch.zeros(total, device=cuda_device)
     for p, off in zip(ours, offs):
         p.grad = flat[off:off + p.numel()].view_as(p)
-    a = opt_o._arena(opt_o.param_groups[0])
-    assert opt_o._flat_grad(a).data_ptr() == flat.data_ptr()
+    assert opt_o._flat_grad(opt_o._arenas[0])[0].data_ptr() == flat.data_ptr()
+    # a parameter moved out of its arena after construction is an error, not a silent stale update
+    ours[0].data = ours[0].data.clone()
+    with pytest.raises(mmsa._lib.MmsaError):
+        opt_o.step()
 
 
 def test_sharded_supcon_ntxent_rows(cuda_device):
