@@ -128,6 +128,23 @@ int mmsa_attn_bwd(int dtype, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64
                   float* delta, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
                   void* stream);
 
+/* Same core with dropout on the attention PROBABILITIES -- nn.MultiheadAttention(dropout=p) in training mode, as
+ * nn.TransformerEncoderLayer(dropout=0.3) builds it (MultimodalModel.py:89-95): O = (softmax(S) o M / (1-p)) V.
+ * keep_mask:[B,H,Lq,Lk] uint8 (explicit mask, parity tests) or NULL: the keep decision of element (b,h,i,j) is drawn
+ * from Philox at counter offset + ((b*H+h)*Lq+i)*Lk+j and RE-DRAWN by the backward (no B*H*Lq*Lk mask is stored), so fwd
+ * and bwd must be given the same seed / offset / rng_state contents.  rng_state: device {seed, position} or NULL (see
+ * mmsa_bn_act_fwd).  Runs on the CUDA-core engine (the encoder-tail shapes: L <= 100, 4 heads). */
+int mmsa_attn_dropout_fwd(int dtype, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t D,
+                          const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                          void* o, int64_t ldo, float* lse, float dropout_p, const uint8_t* keep_mask,
+                          uint64_t seed, uint64_t offset, const uint64_t* rng_state, void* stream);
+int mmsa_attn_dropout_bwd(int dtype, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t D,
+                          const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                          const void* o, int64_t ldo, const void* dout, int64_t lddo, const float* lse,
+                          float* delta, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
+                          float dropout_p, const uint8_t* keep_mask, uint64_t seed, uint64_t offset,
+                          const uint64_t* rng_state, void* stream);
+
 /* ---- sigmoid gate + blend + LayerNorm (MultimodalModel.py:147-149) --------------------------
  * gate_pre:[M,E] = Linear(2E,E)(cat[q,attn]) before the sigmoid; g_out = sigmoid(gate_pre);
  * u = g*q + (1-g)*attn; y = LayerNorm(u; gamma, beta, eps).  mean/rstd:[M] fp32 saved. */
@@ -268,7 +285,7 @@ int mmsa_contrastive_bwd(int kind, int64_t B, int64_t Bg, int64_t row_offset, co
  *      SURVEY.md section 8(f) rank 1) ----------------------------------------------------------- */
 int mmsa_sumsq(const float* x, int64_t n, float* partials, int64_t nblk, float* out, void* stream);
 int mmsa_clip_adamw(float* p, const float* g, float* m, float* v, int64_t n, const float* gradsq,
-                    float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay,
+                    float max_norm, double lr, double beta1, double beta2, double eps, double weight_decay,
                     int64_t step, void* stream);
 
 #ifdef __cplusplus

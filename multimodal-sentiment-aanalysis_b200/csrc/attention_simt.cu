@@ -11,14 +11,52 @@ namespace mmsa {
 constexpr int kAttnWarps = 8;   // rows per block
 constexpr int kChunk = 32;      // keys (or queries) staged per shared-memory chunk
 
+// Dropout on the attention PROBABILITIES (nn.MultiheadAttention(dropout=0.3) in training mode, as nn.TransformerEncoderLayer
+// builds it: MultimodalModel.py:89-95): O = (P o M / (1-p)) V with P the soft-max over keys.  The keep decision of element
+// (b, h, i, j) is either read from an explicit uint8 mask [B,H,Lq,Lk] (parity tests) or drawn from Philox4x32-10 at counter
+// offset + ((b*H + h)*Lq + i)*Lk + j, so the backward kernels re-draw the same mask instead of storing B*H*Lq*Lk bytes.
+// rng_state (device {seed, position}) makes the stream position graph-replay safe (see mmsa_rng_advance).
+struct AttnDrop {
+  float p;                  // 0: no dropout
+  const uint8_t* mask;      // explicit keep mask or null
+  uint64_t seed, offset;
+  const uint64_t* rng_state;
+};
+
+__device__ __forceinline__ uint32_t attn_philox(uint64_t seed, uint64_t ctr) {
+  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0u, c3 = 0u;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return c0;
+}
+// keep / (1-p) of probability element `idx` (flat [B,H,Lq,Lk] index); 1 when dropout is off
+__device__ __forceinline__ float attn_keep_scale(const AttnDrop& d, uint64_t seed, uint64_t base, int64_t idx) {
+  if (d.p <= 0.f) return 1.f;
+  bool keep;
+  if (d.mask != nullptr) keep = d.mask[idx] != 0;
+  else keep = ((float)(attn_philox(seed, base + (uint64_t)idx) >> 8) * (1.f / 16777216.f)) >= d.p;
+  return keep ? 1.f / (1.f - d.p) : 0.f;
+}
+#define MMSA_ATTN_DROP_PROLOGUE(d)                                                   \
+  uint64_t dseed = (d).seed, dbase = (d).offset;                                     \
+  if ((d).rng_state != nullptr) { dseed = (d).rng_state[0]; dbase += (d).rng_state[1]; }
+
 template <typename T, int D>
 __global__ void __launch_bounds__(kAttnWarps * 32)
 attn_fwd_simt_kernel(int H, int Lq, int Lk, const T* __restrict__ q, int64_t ldq, const T* __restrict__ k,
                      int64_t ldk, const T* __restrict__ v, int64_t ldv, T* __restrict__ o, int64_t ldo,
-                     float* __restrict__ lse, float scale) {
+                     float* __restrict__ lse, float scale, AttnDrop drop) {
   constexpr int DL = D / 32;
   __shared__ float Ks[kChunk][D + 1];
   __shared__ float Vs[kChunk][D + 1];
+  MMSA_ATTN_DROP_PROLOGUE(drop)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int bh = blockIdx.y, b = bh / H, h = bh % H;
   const int i = blockIdx.x * kAttnWarps + warp;
@@ -58,7 +96,8 @@ attn_fwd_simt_kernel(int H, int Lq, int Lk, const T* __restrict__ q, int64_t ldq
     float mn = fmaxf(m, warp_max(s));
     float p = (j < Lk) ? expf(s - mn) : 0.f;
     float alpha = expf(m - mn);          // m = -inf on the first chunk -> alpha = 0
-    l = l * alpha + warp_sum(p);
+    l = l * alpha + warp_sum(p);            // the soft-max normaliser sees every key; dropout applies to P afterwards
+    if (drop.p > 0.f && j < Lk && row_ok) p *= attn_keep_scale(drop, dseed, dbase, ((int64_t)bh * Lq + i) * Lk + j);
 #pragma unroll
     for (int t = 0; t < DL; ++t) acc[t] *= alpha;
     for (int jj = 0; jj < kChunk; ++jj) {
@@ -118,10 +157,11 @@ __global__ void __launch_bounds__(kAttnWarps * 32)
 attn_bwd_dq_simt_kernel(int H, int Lq, int Lk, const T* __restrict__ q, int64_t ldq, const T* __restrict__ k,
                         int64_t ldk, const T* __restrict__ v, int64_t ldv, const T* __restrict__ dout, int64_t lddo,
                         const float* __restrict__ lse, const float* __restrict__ delta, T* __restrict__ dq,
-                        int64_t lddq, float scale) {
+                        int64_t lddq, float scale, AttnDrop drop) {
   constexpr int DL = D / 32;
   __shared__ float Ks[kChunk][D + 1];
   __shared__ float Vs[kChunk][D + 1];
+  MMSA_ATTN_DROP_PROLOGUE(drop)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int bh = blockIdx.y, b = bh / H, h = bh % H;
   const int i = blockIdx.x * kAttnWarps + warp;
@@ -162,6 +202,7 @@ attn_bwd_dq_simt_kernel(int H, int Lq, int Lk, const T* __restrict__ q, int64_t 
 #pragma unroll
       for (int d = 0; d < D; ++d) { s = fmaf(qr[d], Ks[lane][d], s); dp = fmaf(dor[d], Vs[lane][d], dp); }
       float p = expf(s - lse_i);
+      if (drop.p > 0.f) dp *= attn_keep_scale(drop, dseed, dbase, ((int64_t)bh * Lq + i) * Lk + j);   // dP = dP' o M/(1-p)
       ds = p * (dp - del_i);
     }
     for (int jj = 0; jj < kChunk; ++jj) {
@@ -183,8 +224,9 @@ __global__ void __launch_bounds__(kAttnWarps * 32)
 attn_bwd_dkv_simt_kernel(int H, int Lq, int Lk, const T* __restrict__ q, int64_t ldq, const T* __restrict__ k,
                          int64_t ldk, const T* __restrict__ v, int64_t ldv, const T* __restrict__ dout, int64_t lddo,
                          const float* __restrict__ lse, const float* __restrict__ delta, T* __restrict__ dk,
-                         int64_t lddk, T* __restrict__ dv, int64_t lddv, float scale) {
+                         int64_t lddk, T* __restrict__ dv, int64_t lddv, float scale, AttnDrop drop) {
   constexpr int DL = D / 32;
+  MMSA_ATTN_DROP_PROLOGUE(drop)
   __shared__ float Qs[kChunk][D + 1];
   __shared__ float Os[kChunk][D + 1];
   __shared__ float Ls[kChunk], Ds[kChunk];
@@ -230,7 +272,14 @@ attn_bwd_dkv_simt_kernel(int H, int Lq, int Lk, const T* __restrict__ q, int64_t
 #pragma unroll
       for (int d = 0; d < D; ++d) { s = fmaf(Qs[lane][d], kr[d], s); dp = fmaf(Os[lane][d], vr[d], dp); }
       p = expf(s - Ls[lane]);
-      ds = p * (dp - Ds[lane]);
+      if (drop.p > 0.f) {
+        const float ks = attn_keep_scale(drop, dseed, dbase, ((int64_t)bh * Lq + i) * Lk + j);
+        dp *= ks;                       // dP = dP' o M/(1-p)
+        ds = p * (dp - Ds[lane]);
+        p *= ks;                        // dV accumulates the DROPPED probabilities
+      } else {
+        ds = p * (dp - Ds[lane]);
+      }
     }
     for (int ii = 0; ii < kChunk; ++ii) {
       float pi = __shfl_sync(0xffffffffu, p, ii);
@@ -251,14 +300,19 @@ attn_bwd_dkv_simt_kernel(int H, int Lq, int Lk, const T* __restrict__ q, int64_t
 }
 
 template <typename T, int D>
-int attn_fwd_simt(int64_t B, int64_t H, int64_t Lq, int64_t Lk, const void* q, int64_t ldq, const void* k, int64_t ldk,
-                  const void* v, int64_t ldv, void* o, int64_t ldo, float* lse, cudaStream_t s) {
+int attn_fwd_simt_drop(int64_t B, int64_t H, int64_t Lq, int64_t Lk, const void* q, int64_t ldq, const void* k, int64_t ldk,
+                       const void* v, int64_t ldv, void* o, int64_t ldo, float* lse, AttnDrop drop, cudaStream_t s) {
   dim3 grid((unsigned)ceil_div(Lq, kAttnWarps), (unsigned)(B * H));
   ProfScope prof("attn_fwd_simt", s, (double)sizeof(T) * D * (double)B * H * (2.0 * Lq + 2.0 * Lk));
   attn_fwd_simt_kernel<T, D><<<grid, kAttnWarps * 32, 0, s>>>((int)H, (int)Lq, (int)Lk, (const T*)q, ldq, (const T*)k, ldk,
-                                                             (const T*)v, ldv, (T*)o, ldo, lse, 1.f / sqrtf((float)D));
+                                                             (const T*)v, ldv, (T*)o, ldo, lse, 1.f / sqrtf((float)D), drop);
   MMSA_LAUNCH_CHECK("attn_fwd_simt_kernel");
   return MMSA_OK;
+}
+template <typename T, int D>
+int attn_fwd_simt(int64_t B, int64_t H, int64_t Lq, int64_t Lk, const void* q, int64_t ldq, const void* k, int64_t ldk,
+                  const void* v, int64_t ldv, void* o, int64_t ldo, float* lse, cudaStream_t s) {
+  return attn_fwd_simt_drop<T, D>(B, H, Lq, Lk, q, ldq, k, ldk, v, ldv, o, ldo, lse, AttnDrop{0.f, nullptr, 0, 0, nullptr}, s);
 }
 
 template <typename T, int D>
@@ -276,9 +330,10 @@ int attn_delta(int64_t B, int64_t H, int64_t Lq, const void* o, int64_t ldo, con
 }
 
 template <typename T, int D>
-int attn_bwd_simt(int64_t B, int64_t H, int64_t Lq, int64_t Lk, const void* q, int64_t ldq, const void* k, int64_t ldk,
-                  const void* v, int64_t ldv, const void* o, int64_t ldo, const void* dout, int64_t lddo, const float* lse,
-                  float* delta, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, cudaStream_t s) {
+int attn_bwd_simt_drop(int64_t B, int64_t H, int64_t Lq, int64_t Lk, const void* q, int64_t ldq, const void* k, int64_t ldk,
+                       const void* v, int64_t ldv, const void* o, int64_t ldo, const void* dout, int64_t lddo, const float* lse,
+                       float* delta, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, AttnDrop drop,
+                       cudaStream_t s) {
   int rc = attn_delta<T, D>(B, H, Lq, o, ldo, dout, lddo, delta, s);
   if (rc) return rc;
   const float scale = 1.f / sqrtf((float)D);
@@ -287,16 +342,23 @@ int attn_bwd_simt(int64_t B, int64_t H, int64_t Lq, int64_t Lk, const void* q, i
   ProfScope prof("attn_bwd_dq_simt", s, (double)sizeof(T) * D * (double)B * H * (3.0 * Lq + 2.0 * Lk));
   attn_bwd_dq_simt_kernel<T, D><<<g1, kAttnWarps * 32, 0, s>>>((int)H, (int)Lq, (int)Lk, (const T*)q, ldq, (const T*)k, ldk,
                                                               (const T*)v, ldv, (const T*)dout, lddo, lse, delta, (T*)dq,
-                                                              lddq, scale);
+                                                              lddq, scale, drop);
   }
   MMSA_LAUNCH_CHECK("attn_bwd_dq_simt_kernel");
   dim3 g2((unsigned)ceil_div(Lk, kAttnWarps), (unsigned)(B * H));
   ProfScope prof("attn_bwd_dkv_simt", s, (double)sizeof(T) * D * (double)B * H * (2.0 * Lq + 4.0 * Lk));
   attn_bwd_dkv_simt_kernel<T, D><<<g2, kAttnWarps * 32, 0, s>>>((int)H, (int)Lq, (int)Lk, (const T*)q, ldq, (const T*)k,
                                                                ldk, (const T*)v, ldv, (const T*)dout, lddo, lse, delta,
-                                                               (T*)dk, lddk, (T*)dv, lddv, scale);
+                                                               (T*)dk, lddk, (T*)dv, lddv, scale, drop);
   MMSA_LAUNCH_CHECK("attn_bwd_dkv_simt_kernel");
   return MMSA_OK;
+}
+template <typename T, int D>
+int attn_bwd_simt(int64_t B, int64_t H, int64_t Lq, int64_t Lk, const void* q, int64_t ldq, const void* k, int64_t ldk,
+                  const void* v, int64_t ldv, const void* o, int64_t ldo, const void* dout, int64_t lddo, const float* lse,
+                  float* delta, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv, cudaStream_t s) {
+  return attn_bwd_simt_drop<T, D>(B, H, Lq, Lk, q, ldq, k, ldk, v, ldv, o, ldo, dout, lddo, lse, delta, dq, lddq, dk, lddk, dv,
+                                  lddv, AttnDrop{0.f, nullptr, 0, 0, nullptr}, s);
 }
 
 // explicit instantiations used by attention.cu
@@ -311,3 +373,51 @@ template int attn_bwd_simt<bf16, 64>(int64_t, int64_t, int64_t, int64_t, const v
 template int attn_delta<bf16, 64>(int64_t, int64_t, int64_t, const void*, int64_t, const void*, int64_t, float*, cudaStream_t);
 
 }  // namespace mmsa
+
+using namespace mmsa;
+
+extern "C" {
+
+int mmsa_attn_dropout_fwd(int dtype, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t D, const void* q, int64_t ldq,
+                          const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo, float* lse,
+                          float dropout_p, const uint8_t* keep_mask, uint64_t seed, uint64_t offset,
+                          const uint64_t* rng_state, void* stream) {
+  MMSA_REQUIRE_DEVICE();
+  MMSA_REQUIRE(D == 32 || D == 64, "mmsa_attn_dropout_fwd: head dim %lld not in {32,64}", (long long)D);
+  MMSA_REQUIRE(B >= 0 && H > 0 && Lq > 0 && Lk > 0, "mmsa_attn_dropout_fwd: bad shape");
+  MMSA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "mmsa_attn_dropout_fwd: dropout_p out of [0,1)");
+  if (B == 0) return MMSA_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  AttnDrop dr{dropout_p, keep_mask, seed, offset, rng_state};
+  if (dtype == MMSA_F32)
+    return D == 64 ? attn_fwd_simt_drop<float, 64>(B, H, Lq, Lk, q, ldq, k, ldk, v, ldv, o, ldo, lse, dr, s)
+                   : attn_fwd_simt_drop<float, 32>(B, H, Lq, Lk, q, ldq, k, ldk, v, ldv, o, ldo, lse, dr, s);
+  if (dtype == MMSA_BF16)
+    return D == 64 ? attn_fwd_simt_drop<bf16, 64>(B, H, Lq, Lk, q, ldq, k, ldk, v, ldv, o, ldo, lse, dr, s)
+                   : attn_fwd_simt_drop<bf16, 32>(B, H, Lq, Lk, q, ldq, k, ldk, v, ldv, o, ldo, lse, dr, s);
+  set_error("mmsa_attn_dropout_fwd: bad dtype %d", dtype);
+  return MMSA_ERR_ARG;
+}
+
+int mmsa_attn_dropout_bwd(int dtype, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t D, const void* q, int64_t ldq,
+                          const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o, int64_t ldo,
+                          const void* dout, int64_t lddo, const float* lse, float* delta, void* dq, int64_t lddq, void* dk,
+                          int64_t lddk, void* dv, int64_t lddv, float dropout_p, const uint8_t* keep_mask, uint64_t seed,
+                          uint64_t offset, const uint64_t* rng_state, void* stream) {
+  MMSA_REQUIRE_DEVICE();
+  MMSA_REQUIRE(D == 32 || D == 64, "mmsa_attn_dropout_bwd: head dim %lld not in {32,64}", (long long)D);
+  MMSA_REQUIRE(B >= 0 && H > 0 && Lq > 0 && Lk > 0, "mmsa_attn_dropout_bwd: bad shape");
+  MMSA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "mmsa_attn_dropout_bwd: dropout_p out of [0,1)");
+  if (B == 0) return MMSA_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  AttnDrop dr{dropout_p, keep_mask, seed, offset, rng_state};
+#define MMSA_ADB(T_, D_) attn_bwd_simt_drop<T_, D_>(B, H, Lq, Lk, q, ldq, k, ldk, v, ldv, o, ldo, dout, lddo, lse, delta, dq, \
+                                                    lddq, dk, lddk, dv, lddv, dr, s)
+  if (dtype == MMSA_F32) return D == 64 ? MMSA_ADB(float, 64) : MMSA_ADB(float, 32);
+  if (dtype == MMSA_BF16) return D == 64 ? MMSA_ADB(bf16, 64) : MMSA_ADB(bf16, 32);
+#undef MMSA_ADB
+  set_error("mmsa_attn_dropout_bwd: bad dtype %d", dtype);
+  return MMSA_ERR_ARG;
+}
+
+}  // extern "C"

@@ -370,19 +370,21 @@ __global__ void sumsq_partial_kernel(const float* __restrict__ x, int64_t n, flo
 // torch.nn.utils.clip_grad_norm_(params, max_norm) then AdamW (decoupled weight decay), Trainer.py:19-21,80-81
 __global__ void clip_adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                   float* __restrict__ v, int64_t n, const float* __restrict__ gradsq,
-                                  float max_norm, float lr, float beta1, float beta2, float eps, float wd,
-                                  float bc1, float bc2) {
+                                  float max_norm, float decay, float beta1, float omb1, float beta2, float omb2,
+                                  float eps, float step_size, float bc2_sqrt) {
+  // every derived scalar (1 - lr*wd, 1 - beta, lr / bias_correction1, sqrt(bias_correction2)) is formed in DOUBLE on
+  // the host and rounded once, as torch.optim.AdamW does with its Python floats: 1.f - 0.999f is 4.7e-5 off 0.001
   float total = sqrtf(gradsq[0]);
   float coef = max_norm / (total + 1e-6f);
   coef = coef < 1.f ? coef : 1.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float gi = g[i] * coef;
-    float pi = p[i] * (1.f - lr * wd);
-    float mi = beta1 * m[i] + (1.f - beta1) * gi;
-    float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    float pi = p[i] * decay;
+    float mi = m[i] + (gi - m[i]) * omb1;                 // exp_avg.lerp_(grad, 1 - beta1)
+    float vi = beta2 * v[i] + omb2 * (gi * gi);           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
     m[i] = mi; v[i] = vi;
-    float denom = sqrtf(vi) / sqrtf(bc2) + eps;
-    p[i] = pi - (lr / bc1) * (mi / denom);
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - step_size * (mi / denom);
   }
 }
 
@@ -510,18 +512,19 @@ int mmsa_sumsq(const float* x, int64_t n, float* partials, int64_t nblk, float* 
 }
 
 int mmsa_clip_adamw(float* p, const float* g, float* m, float* v, int64_t n, const float* gradsq,
-                    float max_norm, float lr, float beta1, float beta2, float eps, float weight_decay,
+                    float max_norm, double lr, double beta1, double beta2, double eps, double weight_decay,
                     int64_t step, void* stream) {
   MMSA_REQUIRE_DEVICE();
   MMSA_REQUIRE(step >= 1, "mmsa_clip_adamw: step starts at 1");
   if (n == 0) return MMSA_OK;
   cudaStream_t s = (cudaStream_t)stream;
   ProfScope prof("clip_adamw", s, (double)n * 28.0);
-  float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
   int64_t blocks = ceil_div(n, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  clip_adamw_kernel<<<(unsigned)blocks, 256, 0, s>>>(p, g, m, v, n, gradsq, max_norm, lr, beta1, beta2, eps,
-                                                    weight_decay, bc1, bc2);
+  clip_adamw_kernel<<<(unsigned)blocks, 256, 0, s>>>(p, g, m, v, n, gradsq, max_norm, (float)(1.0 - lr * weight_decay),
+                                                    (float)beta1, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
+                                                    (float)eps, (float)(lr / bc1), (float)sqrt(bc2));
   MMSA_LAUNCH_CHECK("clip_adamw_kernel");
   return MMSA_OK;
 }

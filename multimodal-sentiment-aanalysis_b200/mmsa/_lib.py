@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes
 import os
 import re
-from ctypes import c_float, c_int, c_int64, c_uint64, c_void_p
+from ctypes import c_double, c_float, c_int, c_int64, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmmsa.so")
@@ -18,7 +18,7 @@ ACT_NONE, ACT_SIGMOID, ACT_GELU, ACT_RELU = 0, 1, 2, 3
 BN_THEN_GELU, RELU_THEN_BN, BN_ONLY = 0, 1, 2
 LOSS_INFONCE, LOSS_SUPCON, LOSS_NTXENT = 0, 1, 2
 
-P, I, L, F, U = c_void_p, c_int, c_int64, c_float, c_uint64
+P, I, L, F, U, Dbl = c_void_p, c_int, c_int64, c_float, c_uint64, c_double
 
 # name -> (restype, argtypes); must cover every symbol include/mmsa.h declares
 _PROTOS = {
@@ -41,6 +41,8 @@ _PROTOS = {
     "mmsa_debug_gemm_engine": (None, [I]),
     "mmsa_attn_fwd": (I, [I, L, L, L, L, L, P, L, P, L, P, L, P, L, P, P]),
     "mmsa_attn_bwd": (I, [I, L, L, L, L, L, P, L, P, L, P, L, P, L, P, L, P, P, P, L, P, L, P, L, P]),
+    "mmsa_attn_dropout_fwd": (I, [I, L, L, L, L, L, P, L, P, L, P, L, P, L, P, F, P, U, U, P, P]),
+    "mmsa_attn_dropout_bwd": (I, [I, L, L, L, L, L, P, L, P, L, P, L, P, L, P, L, P, P, P, L, P, L, P, L, F, P, U, U, P, P]),
     "mmsa_gate_ln_fwd": (I, [I, L, L, P, P, P, P, P, F, P, P, P, P, P]),
     "mmsa_gate_ln_bwd_blocks": (L, [L]),
     "mmsa_gate_ln_bwd": (I, [I, L, L, P, L, P, P, P, P, P, P, P, L, P, P, P, P, P, P, P, P]),
@@ -66,7 +68,7 @@ _PROTOS = {
     "mmsa_contrastive_fwd": (I, [I, L, L, L, P, P, P, P, F, L, P, P, P, P]),
     "mmsa_contrastive_bwd": (I, [I, L, L, L, P, P, P, P, F, L, P, P, P, I, P, P, P]),
     "mmsa_sumsq": (I, [P, L, P, L, P, P]),
-    "mmsa_clip_adamw": (I, [P, P, P, P, L, P, F, F, F, F, F, F, L, P]),
+    "mmsa_clip_adamw": (I, [P, P, P, P, L, P, F, Dbl, Dbl, Dbl, Dbl, Dbl, L, P]),
 }
 
 _lib = None

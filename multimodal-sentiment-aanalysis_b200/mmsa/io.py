@@ -61,6 +61,12 @@ class FeatureBatches:
             self._staging.append(bufs)
         self._turn = 0
 
+    @property
+    def dataset(self):
+        """`len(loader.dataset)` = number of samples, as MultiTaskTrainer.py:225,281,337,398,459,504 reads it off a
+        torch DataLoader."""
+        return range(self.text.shape[0])
+
     def __len__(self) -> int:
         n = self.text.shape[0]
         return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size

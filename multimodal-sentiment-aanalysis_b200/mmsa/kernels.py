@@ -156,6 +156,28 @@ def attn_bwd(q, k, v, o, dout, lse, B, H, Lq, Lk, D, dq: Tensor, dk: Tensor, dv:
          _stream())
 
 
+def attn_dropout_fwd(q: Tensor, k: Tensor, v: Tensor, B: int, H: int, Lq: int, Lk: int, D: int, p: float,
+                     keep_mask: Optional[Tensor], seed: int, offset: int, rng_state: Optional[Tensor]):
+    """attention core with dropout on the probabilities (mmsa_attn_dropout_fwd); keep_mask uint8 [B,H,Lq,Lk] or None (Philox)."""
+    _check(q, k, v, keep_mask, rng_state)
+    o = torch.empty((B * Lq, H * D), device=q.device, dtype=q.dtype)
+    lse = torch.empty((B, H, Lq), device=q.device, dtype=torch.float32)
+    call("mmsa_attn_dropout_fwd", dt(q), B, H, Lq, Lk, D, q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0),
+         v.data_ptr(), v.stride(0), o.data_ptr(), o.stride(0), lse.data_ptr(), float(p), _p(keep_mask), seed, offset,
+         _p(rng_state), _stream())
+    return o, lse
+
+
+def attn_dropout_bwd(q, k, v, o, dout, lse, B, H, Lq, Lk, D, dq: Tensor, dk: Tensor, dv: Tensor, p: float,
+                     keep_mask: Optional[Tensor], seed: int, offset: int, rng_state: Optional[Tensor]):
+    _check(q, k, v, o, dout, lse, dq, dk, dv, keep_mask, rng_state)
+    delta = torch.empty((B, H, Lq), device=q.device, dtype=torch.float32)
+    call("mmsa_attn_dropout_bwd", dt(q), B, H, Lq, Lk, D, q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0),
+         v.data_ptr(), v.stride(0), o.data_ptr(), o.stride(0), dout.data_ptr(), dout.stride(0), lse.data_ptr(),
+         delta.data_ptr(), dq.data_ptr(), dq.stride(0), dk.data_ptr(), dk.stride(0), dv.data_ptr(), dv.stride(0),
+         float(p), _p(keep_mask), seed, offset, _p(rng_state), _stream())
+
+
 def gate_ln_fwd(gate_pre: Tensor, q: Tensor, attn: Tensor, gamma: Tensor, beta: Tensor, eps: float,
                 want_y: bool = True):
     _check(gate_pre, q, attn, gamma, beta)

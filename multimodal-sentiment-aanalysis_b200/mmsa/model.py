@@ -64,7 +64,8 @@ class PositionalEncoding(nn.Module):
 class Subnetwork(nn.Module):
     """Drop-in for MultimodalModel.Subnetwork (MultimodalModel.py:83-105), the encoder tail in front of the fusion path
     (SURVEY.md section 8(f) rank 2): proj -> + positional table -> num_layers x post-norm TransformerEncoderLayer(d, nhead,
-    ff = 3d, ReLU, dropout 0.3) -> LayerNorm.  Same attribute names and state_dict keys.  The reference feeds [B, input_dim]
+    ff = 3d, ReLU, dropout 0.3) -> LayerNorm.  Same attribute names and state_dict keys.  Train mode applies all four
+    dropouts of a layer (attention probabilities, dropout1, dropout, dropout2) with in-kernel Philox masks.  The reference feeds [B, input_dim]
     (one token); [B, L, input_dim] runs the same layers over L tokens (text tokens get a self-attention stage before the
     cross-attention).  torch modules are parameter containers only; every op runs the sm_100a kernels."""
 
@@ -79,6 +80,15 @@ class Subnetwork(nn.Module):
         self.transformer = nn.TransformerEncoder(layer, num_layers, enable_nested_tensor=False)
         self.norm = nn.LayerNorm(feat_dim)
         self._drop = _DropoutState()
+
+    def set_dropout(self, p: float) -> "Subnetwork":
+        """every dropout of the encoder tail: the layers' three nn.Dropout modules and the attention-probability rate"""
+        for m in self.modules():
+            if isinstance(m, nn.Dropout):
+                m.p = p
+            if isinstance(m, nn.MultiheadAttention):
+                m.dropout = p
+        return self
 
     def forward(self, x: Tensor) -> Tensor:
         cd = self.compute_dtype
@@ -101,8 +111,9 @@ class Subnetwork(nn.Module):
 
 
 class CrossModalTransformer(nn.Module):
-    """MultimodalModel.py:108-149.  forward(query, key, value) with 2-D [B,E] or 3-D [B,L,E] inputs;
-    the gate concat runs on the feature axis, so Lq > 1 works (identical to the reference for Lq == 1)."""
+    """MultimodalModel.py:108-149.  forward(query, key, value) with 2-D [B,E] or 3-D [B,L,E] inputs (key and value may be
+    one tensor, as at every reference call site, or two); the gate concat runs on the feature axis, so Lq > 1 works
+    (identical to the reference for Lq == 1)."""
 
     def __init__(self, embed_dim: int = 256, num_heads: int = 4):
         super().__init__()
@@ -118,15 +129,17 @@ class CrossModalTransformer(nn.Module):
                 self.gate[0].weight, self.gate[0].bias, self.norm.weight, self.norm.bias)
 
     def forward(self, query: Tensor, key: Tensor, value: Tensor) -> Tensor:
-        if key is not value and key.data_ptr() != value.data_ptr():
-            raise NotImplementedError("mmsa: CrossModalTransformer kernels take key and value from one tensor, "
-                                      "as every reference call site does (MultimodalModel.py:287-297)")
         squeeze = query.ndim == 2
         if squeeze:
             query = query.unsqueeze(1)
         if key.ndim == 2:
             key = key.unsqueeze(1)
-        out = ops.cross_block(query, key, *self.kernel_params(), self.num_heads)
+        if value.ndim == 2:
+            value = value.unsqueeze(1)
+        # every reference call site passes ONE tensor as key and value (MultimodalModel.py:287-297): K and V then come out
+        # of one packed N = 2E GEMM; a distinct value tensor takes two N = E GEMMs into the same packed buffer
+        same = key.data_ptr() == value.data_ptr() and key.shape == value.shape and key.stride() == value.stride()
+        out = ops.cross_block(query, key, *self.kernel_params(), self.num_heads, value=None if same else value)
         return out.squeeze(1) if squeeze else out
 
 

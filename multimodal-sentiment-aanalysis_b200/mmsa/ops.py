@@ -184,15 +184,17 @@ def linear(x: Tensor, w: Tensor, b: Optional[Tensor], x2: Optional[Tensor] = Non
 # ------------------------------------------------------------------------------------------ cross block
 class _BlockState:
     """Tensors one CrossModalTransformer block keeps between forward and backward."""
-    __slots__ = ("q_in", "kv_in", "Qp", "KVp", "O", "lse", "A", "G", "mean", "rstd", "w_in", "w_out", "w_gate",
+    __slots__ = ("q_in", "kv_in", "v_in", "Qp", "KVp", "O", "lse", "A", "G", "mean", "rstd", "w_in", "w_out", "w_gate",
                  "gamma", "B", "Lq", "Lk", "E", "H", "pooled")
 
 
 def _block_fwd(q_in: Tensor, kv_in: Tensor, B: int, Lq: int, Lk: int, H: int, in_w, in_b, out_w, out_b, gate_w,
-               gate_b, ln_w, ln_b, eps: float = 1e-5, pooled: bool = False):
+               gate_b, ln_w, ln_b, eps: float = 1e-5, pooled: bool = False, v_in: Optional[Tensor] = None):
     """CrossModalTransformer.forward (MultimodalModel.py:124-149) on flattened [B*L, E] activations.
     MHA in-projection (q rows of in_proj_weight; packed k,v rows), attention core, out-projection,
     gate GEMM over the two operands [q | attn] (no concat), fused sigmoid/blend/LayerNorm.
+    v_in: the `value` tensor when it is not the `key` tensor (forward(query, key, value), MultimodalModel.py:124): K and V
+    are then projected by two N = E GEMMs into the two halves of the same packed buffer instead of one N = 2E GEMM.
     pooled=False -> (y [B*Lq,E], state); pooled=True -> ((mean_l y, mean_l q) fp32 [B,E] each, state)."""
     cd = q_in.dtype
     E = q_in.shape[1]
@@ -200,7 +202,12 @@ def _block_fwd(q_in: Tensor, kv_in: Tensor, B: int, Lq: int, Lk: int, H: int, in
     st.w_in, st.w_out, st.w_gate = _w(in_w, cd), _w(out_w, cd), _w(gate_w, cd)
     in_b = in_b.detach()
     st.Qp = K.linear_fwd(q_in, st.w_in[:E], in_b[:E])
-    st.KVp = K.linear_fwd(kv_in, st.w_in[E:], in_b[E:])
+    if v_in is None:
+        st.KVp = K.linear_fwd(kv_in, st.w_in[E:], in_b[E:])
+    else:
+        st.KVp = torch.empty((kv_in.shape[0], 2 * E), device=kv_in.device, dtype=cd)
+        K.linear_fwd(kv_in, st.w_in[E:2 * E], in_b[E:2 * E], out=st.KVp[:, :E])
+        K.linear_fwd(v_in, st.w_in[2 * E:], in_b[2 * E:], out=st.KVp[:, E:])
     st.O, st.lse = K.attn_fwd(st.Qp, st.KVp[:, :E], st.KVp[:, E:], B, H, Lq, Lk, E // H)
     st.A = K.linear_fwd(st.O, st.w_out, out_b.detach())
     gate_pre = K.linear_fwd(q_in, st.w_gate, gate_b.detach(), x2=st.A)
@@ -212,7 +219,7 @@ def _block_fwd(q_in: Tensor, kv_in: Tensor, B: int, Lq: int, Lk: int, H: int, in
         out = (py, pq)
     else:
         st.G, out, st.mean, st.rstd = K.gate_ln_fwd(gate_pre, q_in, st.A, st.gamma, ln_b.detach(), eps)
-    st.q_in, st.kv_in = q_in, kv_in
+    st.q_in, st.kv_in, st.v_in = q_in, kv_in, v_in
     st.B, st.Lq, st.Lk, st.E, st.H = B, Lq, Lk, E, H
     return out, st
 
@@ -222,6 +229,7 @@ def _block_bwd(st: _BlockState, dy: Tensor, *, dpooled_q: Optional[Tensor] = Non
                wgrad_stream=None, keep: Optional[list] = None):
     """Backward of _block_fwd.  dy is [B*Lq,E] (cd) for a plain block, or the fp32 [B,E] gradient of the
     pooled output for a pooled block (dpooled_q: fp32 [B,E] gradient of the pooled query stream).
+    For a block with a separate value tensor (st.v_in) dkv is the pair (dkey, dvalue).
     Returns (dq, dkv, grads) with grads = (d_in_w, d_in_b, d_out_w, d_out_b, d_gate_w, d_gate_b, d_ln_w, d_ln_b).
     Every accumulation of gradients w.r.t. q and kv happens in GEMM residual epilogues / the LN kernel;
     bias gradients fall out of the wgrad GEMMs (ones-tile MMA)."""
@@ -272,24 +280,34 @@ def _block_bwd(st: _BlockState, dy: Tensor, *, dpooled_q: Optional[Tensor] = Non
 
         def in_wgrads():
             K.linear_wgrad(dQp, st.q_in, dw=d_in_w[:E], db=d_in_b[:E])
-            K.linear_wgrad(dKVp, st.kv_in, dw=d_in_w[E:], db=d_in_b[E:])
+            if st.v_in is None:
+                K.linear_wgrad(dKVp, st.kv_in, dw=d_in_w[E:], db=d_in_b[E:])
+            else:
+                K.linear_wgrad(dKVp[:, :E], st.kv_in, dw=d_in_w[E:2 * E], db=d_in_b[E:2 * E])
+                K.linear_wgrad(dKVp[:, E:], st.v_in, dw=d_in_w[2 * E:], db=d_in_b[2 * E:])
         on_side(in_wgrads)
     dq = K.linear_dgrad(dQp, st.w_in[:E], residual=dq_acc) if need_dq else None
-    dkv = K.linear_dgrad(dKVp, st.w_in[E:], residual=dkv_residual) if need_dkv else None
+    if st.v_in is None:
+        dkv = K.linear_dgrad(dKVp, st.w_in[E:], residual=dkv_residual) if need_dkv else None
+    else:
+        dkv = (K.linear_dgrad(dKVp[:, :E], st.w_in[E:2 * E]) if need_dkv else None,
+               K.linear_dgrad(dKVp[:, E:], st.w_in[2 * E:]) if need_dkv else None)
     if keep is not None:
         keep.extend((dgate, dA, dQp, dKVp, r0, r1))     # read by the side stream: alive until the join
     return dq, dkv, (d_in_w, d_in_b, d_out_w, d_out_b, d_gate_w, d_gate_b, d_ln_w, d_ln_b)
 
 
 class CrossBlockFn(Function):
-    """One CrossModalTransformer block, query [B,Lq,E] x key/value [B,Lk,E] -> [B,Lq,E]."""
+    """One CrossModalTransformer block, query [B,Lq,E] x key [B,Lk,E] (x value [B,Lk,E], None = the key tensor)
+    -> [B,Lq,E]."""
 
     @staticmethod
-    def forward(ctx, query, kv, in_w, in_b, out_w, out_b, gate_w, gate_b, ln_w, ln_b, num_heads: int):
+    def forward(ctx, query, kv, value, in_w, in_b, out_w, out_b, gate_w, gate_b, ln_w, ln_b, num_heads: int):
         B, Lq, E = query.shape
         Lk = kv.shape[1]
+        v2d = None if value is None else _c(value).view(B * Lk, E)
         y, st = _block_fwd(_c(query).view(B * Lq, E), _c(kv).view(B * Lk, E), B, Lq, Lk, num_heads,
-                           in_w, in_b, out_w, out_b, gate_w, gate_b, ln_w, ln_b)
+                           in_w, in_b, out_w, out_b, gate_w, gate_b, ln_w, ln_b, v_in=v2d)
         ctx.st = st
         return y.view(B, Lq, E)
 
@@ -297,18 +315,26 @@ class CrossBlockFn(Function):
     @once_differentiable
     def backward(ctx, dy):
         st = ctx.st
-        need_w = any(ctx.needs_input_grad[2:10])
+        need_w = any(ctx.needs_input_grad[3:11])
+        need_kv = ctx.needs_input_grad[1] or (st.v_in is not None and ctx.needs_input_grad[2])
         dq, dkv, g = _block_bwd(st, K.cast(_c(dy), st.q_in.dtype).view(st.B * st.Lq, st.E),
-                                need_dq=ctx.needs_input_grad[0], need_dkv=ctx.needs_input_grad[1], need_w=need_w)
+                                need_dq=ctx.needs_input_grad[0], need_dkv=need_kv, need_w=need_w)
         ctx.st = None
         dq = None if dq is None else dq.view(st.B, st.Lq, st.E)
+        dval = None
+        if st.v_in is not None:
+            dkv, dval = dkv
+            dval = None if (dval is None or not ctx.needs_input_grad[2]) else dval.view(st.B, st.Lk, st.E)
+            if not ctx.needs_input_grad[1]:
+                dkv = None
         dkv = None if dkv is None else dkv.view(st.B, st.Lk, st.E)
-        g = tuple(gi if need else None for gi, need in zip(g, ctx.needs_input_grad[2:10]))
-        return (dq, dkv) + g + (None,)
+        g = tuple(gi if need else None for gi, need in zip(g, ctx.needs_input_grad[3:11]))
+        return (dq, dkv, dval) + g + (None,)
 
 
-def cross_block(query, kv, in_w, in_b, out_w, out_b, gate_w, gate_b, ln_w, ln_b, num_heads: int) -> Tensor:
-    return CrossBlockFn.apply(query, kv, in_w, in_b, out_w, out_b, gate_w, gate_b, ln_w, ln_b, num_heads)
+def cross_block(query, kv, in_w, in_b, out_w, out_b, gate_w, gate_b, ln_w, ln_b, num_heads: int,
+                value: Optional[Tensor] = None) -> Tensor:
+    return CrossBlockFn.apply(query, kv, value, in_w, in_b, out_w, out_b, gate_w, gate_b, ln_w, ln_b, num_heads)
 
 
 class FusionCoreFn(Function):
@@ -391,12 +417,44 @@ class AttnFn(Function):
         return dq, dk, dv, None, None, None, None
 
 
-def self_attention(x: Tensor, in_w, in_b, out_w, out_b, num_heads: int) -> Tensor:
+class AttnDropFn(Function):
+    """Attention core with dropout on the PROBABILITIES (nn.MultiheadAttention(dropout=p) in training mode --
+    nn.TransformerEncoderLayer(dropout=0.3), MultimodalModel.py:89-95).  The mask is not stored: the backward re-draws it
+    from the same Philox position, a snapshot of the module's device-resident stream state taken at forward time (the
+    state itself moves on at the end of the forward pass); parity tests inject an explicit [B,H,Lq,Lk] mask instead."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, B, H, Lq, Lk, p: float, drop, name: str):
+        D = q.shape[1] // H
+        mask, seed, off = drop.next(name, (B, H, Lq, Lk))
+        state = None if mask is not None else drop.state(q.device).clone()
+        o, lse = K.attn_dropout_fwd(q, k, v, B, H, Lq, Lk, D, p, mask, seed, off, state)
+        ctx.save_for_backward(q, k, v, o, lse, mask, state)
+        ctx.cfg = (B, H, Lq, Lk, D, p, seed, off)
+        return o
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, do):
+        q, k, v, o, lse, mask, state = ctx.saved_tensors
+        B, H, Lq, Lk, D, p, seed, off = ctx.cfg
+        dq = torch.empty((B * Lq, H * D), device=q.device, dtype=q.dtype)
+        dk = torch.empty((B * Lk, H * D), device=q.device, dtype=q.dtype)
+        dv = torch.empty((B * Lk, H * D), device=q.device, dtype=q.dtype)
+        K.attn_dropout_bwd(q, k, v, o, K.cast(_c(do), q.dtype), lse, B, H, Lq, Lk, D, dq, dk, dv, p, mask, seed, off, state)
+        return dq, dk, dv, None, None, None, None, None, None, None
+
+
+def self_attention(x: Tensor, in_w, in_b, out_w, out_b, num_heads: int, dropout_p: float = 0.0,
+                   drop: Optional["_DropoutState"] = None, name: str = "self_attn") -> Tensor:
     """nn.MultiheadAttention self-attention on x:[B,S,E] (batch-major), packed in-projection
-    (ME-MHACL/model.py:71, MultimodalModel.py:397)."""
+    (ME-MHACL/model.py:71, MultimodalModel.py:397); dropout_p > 0: dropout on the attention probabilities."""
     B, S, E = x.shape
     qkv = linear(x.reshape(B * S, E), in_w, in_b)
-    o = AttnFn.apply(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], B, num_heads, S, S)
+    if dropout_p > 0.0:
+        o = AttnDropFn.apply(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], B, num_heads, S, S, dropout_p, drop, name)
+    else:
+        o = AttnFn.apply(qkv[:, :E], qkv[:, E:2 * E], qkv[:, 2 * E:], B, num_heads, S, S)
     return linear(o, out_w, out_b).view(B, S, E)
 
 
@@ -937,11 +995,13 @@ def token_dropout(x: Tensor, p: float, training: bool, drop: _DropoutState, name
 def encoder_layer(x: Tensor, layer: nn.TransformerEncoderLayer, drop: _DropoutState, name: str, cd) -> Tensor:
     """One post-norm nn.TransformerEncoderLayer (norm_first=False, ReLU) on x:[B,S,E] in the compute dtype:
         x = norm1(x + dropout1(self_attn(x)));  x = norm2(x + dropout2(linear2(dropout(relu(linear1(x))))))
-    Dropout on the attention PROBABILITIES (MultiheadAttention(dropout=0.3) in training mode) is not implemented."""
+    In training mode the self-attention also drops attention PROBABILITIES (MultiheadAttention(dropout=0.3)), as torch's
+    scaled_dot_product_attention(dropout_p=...) does inside TransformerEncoderLayer._sa_block."""
     a = layer.self_attn
     training = layer.training
     B, S, E = x.shape
-    sa = self_attention(x, a.in_proj_weight, a.in_proj_bias, a.out_proj.weight, a.out_proj.bias, a.num_heads)
+    sa = self_attention(x, a.in_proj_weight, a.in_proj_bias, a.out_proj.weight, a.out_proj.bias, a.num_heads,
+                        dropout_p=(float(a.dropout) if training else 0.0), drop=drop, name=name + ".self_attn.dropout")
     sa = token_dropout(sa, layer.dropout1.p, training, drop, name + ".dropout1")
     x = add_layer_norm(x, sa, layer.norm1)
     z = linear(x.reshape(B * S, E), layer.linear1.weight, layer.linear1.bias, out_fp32=True, cd=cd)

@@ -38,8 +38,11 @@ Params = Dict[str, Tensor]
 # (third-party: torch/nn/functional.py multi_head_attention_forward, reached from
 #  MultimodalModel.py:139-143 and ME-MHACL/model.py:71 / MultimodalModel.py:397)
 # --------------------------------------------------------------------------
-def mha_core(q: Tensor, k: Tensor, v: Tensor, num_heads: int) -> Tensor:
-    """q:[Lq,B,E] k,v:[Lk,B,E] (already projected, seq-first) -> [Lq*B, E] pre-out-proj."""
+def mha_core(q: Tensor, k: Tensor, v: Tensor, num_heads: int, prob_mask: Optional[Tensor] = None) -> Tensor:
+    """q:[Lq,B,E] k,v:[Lk,B,E] (already projected, seq-first) -> [Lq*B, E] pre-out-proj.
+    prob_mask: pre-scaled keep mask [B*H, Lq, Lk] multiplied onto the soft-max probabilities (training-mode
+    MultiheadAttention(dropout=p): torch applies dropout to the attention weights, functional.py
+    multi_head_attention_forward -> scaled_dot_product_attention(dropout_p))."""
     Lq, B, E = q.shape
     Lk = k.shape[0]
     d = E // num_heads
@@ -50,6 +53,8 @@ def mha_core(q: Tensor, k: Tensor, v: Tensor, num_heads: int) -> Tensor:
     q_scaled = qh * math.sqrt(1.0 / float(d))
     w = torch.bmm(q_scaled, kh.transpose(-2, -1))
     w = torch.softmax(w, dim=-1)
+    if prob_mask is not None:
+        w = w * prob_mask
     o = torch.bmm(w, vh)
     return o.transpose(0, 1).contiguous().view(Lq * B, E)
 
@@ -75,25 +80,27 @@ def mha_cross(query: Tensor, key: Tensor, value: Tensor, in_w: Tensor, in_b: Ten
 
 
 def mha_self_seq_first(x: Tensor, in_w: Tensor, in_b: Tensor, out_w: Tensor, out_b: Tensor,
-                       num_heads: int) -> Tensor:
+                       num_heads: int, prob_mask: Optional[Tensor] = None) -> Tensor:
     """self attention, seq-first [L,B,E] (ME-MHACL/model.py:71, MultimodalModel.py:397):
     packed in-projection `linear(x, W, b)` then split in q,k,v order."""
     L, B, E = x.shape
     proj = F.linear(x, in_w, in_b)
     proj = proj.unflatten(-1, (3, E)).unsqueeze(0).transpose(0, -2).squeeze(-2).contiguous()
-    o = mha_core(proj[0], proj[1], proj[2], num_heads)
+    o = mha_core(proj[0], proj[1], proj[2], num_heads, prob_mask)
     return F.linear(o, out_w, out_b).view(L, B, E)
 
 
 # --------------------------------------------------------------------------
 # CrossModalTransformer (MultimodalModel.py:108-149)
 # --------------------------------------------------------------------------
-def cross_block(query: Tensor, kv: Tensor, p: Params, prefix: str, num_heads: int) -> Tensor:
-    """query:[B,Lq,E] kv:[B,Lk,E] -> [B,Lq,E].
+def cross_block(query: Tensor, kv: Tensor, p: Params, prefix: str, num_heads: int,
+                value: Optional[Tensor] = None) -> Tensor:
+    """query:[B,Lq,E] kv:[B,Lk,E] -> [B,Lq,E]  (value: a separate value tensor, forward(query, key, value) :124;
+    every reference call site passes the key tensor again, :287-297).
     MHA (:139-143) -> gate = sigmoid(Linear(2E,E)(cat[q, attn])) (:147, restated with the
     concat on the LAST dim so Lq > 1 works; identical when Lq == 1) ->
     g*q + (1-g)*attn (:148) -> LayerNorm(E) (:149)."""
-    attn = mha_cross(query, kv, kv,
+    attn = mha_cross(query, kv, kv if value is None else value,
                      p[prefix + "multihead_attn.in_proj_weight"], p[prefix + "multihead_attn.in_proj_bias"],
                      p[prefix + "multihead_attn.out_proj.weight"], p[prefix + "multihead_attn.out_proj.bias"],
                      num_heads)
@@ -469,23 +476,36 @@ def positional_table(d_model: int, max_len: int = 100, dtype=torch.float32) -> T
     return pe.to(dtype)
 
 
-def encoder_layer(x: Tensor, p: Params, prefix: str, num_heads: int) -> Tensor:
-    """One nn.TransformerEncoderLayer as Subnetwork builds it (MultimodalModel.py:89-95: post-norm, ReLU, batch_first),
-    dropout off: x = norm1(x + self_attn(x)); x = norm2(x + linear2(relu(linear1(x)))).  (third-party torch
-    nn/modules/transformer.py TransformerEncoderLayer._sa_block / _ff_block, norm_first=False branch.)"""
+def encoder_layer(x: Tensor, p: Params, prefix: str, num_heads: int,
+                  masks: Optional[Dict[str, Tensor]] = None) -> Tensor:
+    """One nn.TransformerEncoderLayer as Subnetwork builds it (MultimodalModel.py:89-95: post-norm, ReLU, batch_first):
+        x = norm1(x + dropout1(self_attn(x)));  x = norm2(x + dropout2(linear2(dropout(relu(linear1(x))))))
+    (third-party torch nn/modules/transformer.py TransformerEncoderLayer._sa_block / _ff_block, norm_first=False branch).
+    masks=None: dropout off.  Training mode: `masks` holds PRE-SCALED keep masks for the four dropouts of the layer --
+    "attn" [B,H,L,L] on the attention probabilities (MultiheadAttention(dropout=0.3)), "dropout1" [B,L,E], "dropout"
+    [B,L,3E], "dropout2" [B,L,E]; tests/test_cpu_oracle_and_abi.py pins these four positions against torch's own layer."""
     B, L, E = x.shape
+    m = masks or {}
+    pm = m["attn"].reshape(B * num_heads, L, L) if "attn" in m else None
     sa = mha_self_seq_first(x.transpose(0, 1), p[prefix + "self_attn.in_proj_weight"], p[prefix + "self_attn.in_proj_bias"],
                             p[prefix + "self_attn.out_proj.weight"], p[prefix + "self_attn.out_proj.bias"],
-                            num_heads).transpose(0, 1)
+                            num_heads, pm).transpose(0, 1)
+    if "dropout1" in m:
+        sa = sa * m["dropout1"]
     x = F.layer_norm(x + sa, (E,), p[prefix + "norm1.weight"], p[prefix + "norm1.bias"], 1e-5)
-    ff = F.linear(torch.relu(F.linear(x, p[prefix + "linear1.weight"], p[prefix + "linear1.bias"])),
-                  p[prefix + "linear2.weight"], p[prefix + "linear2.bias"])
+    h = torch.relu(F.linear(x, p[prefix + "linear1.weight"], p[prefix + "linear1.bias"]))
+    if "dropout" in m:
+        h = h * m["dropout"]
+    ff = F.linear(h, p[prefix + "linear2.weight"], p[prefix + "linear2.bias"])
+    if "dropout2" in m:
+        ff = ff * m["dropout2"]
     return F.layer_norm(x + ff, (E,), p[prefix + "norm2.weight"], p[prefix + "norm2.bias"], 1e-5)
 
 
-def subnetwork(x: Tensor, p: Params, num_heads: int = 4, num_layers: int = 2) -> Tensor:
-    """Subnetwork.forward (MultimodalModel.py:99-105) with dropout off; x:[B,D] (one token, as the reference feeds it) or
-    [B,L,D] (generalised to L tokens)."""
+def subnetwork(x: Tensor, p: Params, num_heads: int = 4, num_layers: int = 2,
+               masks: Optional[Sequence[Dict[str, Tensor]]] = None) -> Tensor:
+    """Subnetwork.forward (MultimodalModel.py:99-105); x:[B,D] (one token, as the reference feeds it) or [B,L,D]
+    (generalised to L tokens).  masks: per-layer dropout masks (see encoder_layer) for training mode, None = dropout off."""
     squeeze = x.ndim == 2
     if squeeze:
         x = x.unsqueeze(1)                                           # :102
@@ -493,6 +513,6 @@ def subnetwork(x: Tensor, p: Params, num_heads: int = 4, num_layers: int = 2) ->
     pe = p["pos_encoder.pe"] if "pos_encoder.pe" in p else positional_table(h.shape[-1], 100, h.dtype).unsqueeze(0)
     h = h + pe[:, :h.shape[1]].to(h.dtype)                           # :103 (PositionalEncoding.forward :19-20)
     for i in range(num_layers):
-        h = encoder_layer(h, p, f"transformer.layers.{i}.", num_heads)     # :104
+        h = encoder_layer(h, p, f"transformer.layers.{i}.", num_heads, None if masks is None else masks[i])     # :104
     h = F.layer_norm(h, (h.shape[-1],), p["norm.weight"], p["norm.bias"], 1e-5)   # :105
     return h.squeeze(1) if squeeze else h

@@ -250,6 +250,68 @@ def test_oracle_subnetwork_bit_identical_to_reference():
     assert rel_err(got, want) <= 1e-6
 
 
+def test_oracle_subnetwork_train_mode_dropout_positions(monkeypatch):
+    """TRAIN mode of the encoder tail: torch's nn.TransformerEncoderLayer(dropout=0.3) (what Subnetwork builds,
+    MultimodalModel.py:89-95) drops in four places per layer -- the attention probabilities, dropout1, dropout, dropout2.
+    torch draws those masks from its own generator, so the pin intercepts the two functions the third-party layer calls
+    (F.dropout and F.scaled_dot_product_attention) and feeds them recorded masks; the oracle given the same masks must
+    reproduce the layer's output and gradients.  (The imported reference Subnetwork is used when the tree is mounted.)"""
+    import torch.nn as nn
+    import torch.nn.functional as Fn
+    torch.manual_seed(11)
+    E, H, L, Bn, p_drop = 64, 4, 5, 3, 0.3
+    layer = nn.TransformerEncoderLayer(d_model=E, nhead=H, dim_feedforward=3 * E, dropout=p_drop, batch_first=True)
+    enc = nn.TransformerEncoder(layer, 2, enable_nested_tensor=False).train()
+    proj, norm = nn.Linear(10, E), nn.LayerNorm(E)
+    g = torch.Generator().manual_seed(2)
+    masks = []
+    for _ in range(2):
+        masks.append({"attn": (torch.rand(Bn, H, L, L, generator=g) >= p_drop).float() / (1 - p_drop),
+                      "dropout1": (torch.rand(Bn, L, E, generator=g) >= p_drop).float() / (1 - p_drop),
+                      "dropout": (torch.rand(Bn, L, 3 * E, generator=g) >= p_drop).float() / (1 - p_drop),
+                      "dropout2": (torch.rand(Bn, L, E, generator=g) >= p_drop).float() / (1 - p_drop)})
+    calls = {"drop": [], "sdpa": 0}
+    order = ["dropout1", "dropout", "dropout2"]          # _sa_block's dropout1, then _ff_block's dropout and dropout2
+
+    def fake_dropout(x, p=0.5, training=True, inplace=False):
+        if not training or p == 0:
+            return x
+        i = len(calls["drop"])
+        # call order inside one layer: dropout1 (after self_attn), dropout (after relu(linear1)), dropout2 (after linear2)
+        name = {0: "dropout1", 1: "dropout", 2: "dropout2"}[i % 3]
+        calls["drop"].append(name)
+        return x * masks[i // 3][name].to(x.dtype)
+
+    def fake_sdpa(q, k, v, attn_mask=None, dropout_p=0.0, is_causal=False, **kw):
+        i = calls["sdpa"]
+        calls["sdpa"] += 1
+        assert abs(dropout_p - p_drop) < 1e-12 and attn_mask is None        # training mode hands the rate to SDPA
+        w = torch.softmax(q @ k.transpose(-2, -1) / math.sqrt(q.shape[-1]), dim=-1)
+        return (w * masks[i]["attn"].to(w.dtype)) @ v
+
+    import math
+    monkeypatch.setattr(Fn, "dropout", fake_dropout)
+    monkeypatch.setattr(Fn, "scaled_dot_product_attention", fake_sdpa)
+    xs = torch.randn(Bn, L, 10).requires_grad_(True)
+    wgt = torch.randn(Bn, L, E)
+    want = norm(enc(proj(xs) + O.positional_table(E, 100)[:L]))
+    (want * wgt).sum().backward()
+    monkeypatch.undo()
+    assert calls["sdpa"] == 2 and calls["drop"] == order * 2
+    sd = {"proj.weight": proj.weight, "proj.bias": proj.bias, "norm.weight": norm.weight, "norm.bias": norm.bias}
+    sd.update({"transformer." + k: v for k, v in enc.state_dict().items()})
+    pp = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    x2 = xs.detach().clone().requires_grad_(True)
+    got = O.subnetwork(x2, pp, num_heads=H, masks=masks)
+    (got * wgt).sum().backward()
+    assert rel_err(got, want.detach()) <= 1e-5
+    assert rel_err(x2.grad, xs.grad) <= 1e-5
+    named = dict(proj.named_parameters(prefix="proj")) | dict(norm.named_parameters(prefix="norm")) | \
+        dict(enc.named_parameters(prefix="transformer"))
+    for k, prm in named.items():
+        assert rel_err(pp[k].grad, prm.grad) <= 2e-5, k
+
+
 def test_oracle_sharded_supcon_ntxent_equal_global():
     """row-block forms (two ranks, rows sharded, both views gathered) reproduce train.py:16-40 / ME-MHACL/train.py:47-66."""
     g = torch.Generator().manual_seed(4)

@@ -447,3 +447,136 @@ def test_bn_act_dropout_keep_rate(cuda_device):
     assert torch.allclose(y1[kept], y0[kept] / (1 - p), rtol=1e-6, atol=1e-7) and float(y1[~kept].abs().max()) == 0.0
     col_rate = m1.float().mean(0)                                 # no column (feature unit) is systematically dropped
     assert float((col_rate - (1 - p)).abs().max()) <= 6 * (p * (1 - p) / B) ** 0.5
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+def test_subnetwork_train_mode_dropout(cuda_device, dtype, tol):
+    """TRAIN mode of mmsa.Subnetwork (MultimodalModel.py:89-95, TransformerEncoderLayer(dropout=0.3)): all four dropouts of
+    a layer -- attention probabilities, dropout1, dropout, dropout2 -- with explicit keep masks, against the float64 oracle
+    given the same masks (the oracle's mask positions are pinned against torch's own layer on the CPU)."""
+    import mmsa
+    torch.manual_seed(31)
+    E, H, B, L, p = 256, 4, 5, 12, 0.3
+    m = mmsa.Subnetwork(768, feat_dim=E, num_layers=2, nhead=H, compute_dtype=dtype)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.to(cuda_device).train()
+    g = torch.Generator().manual_seed(8)
+    keep = {}
+    for i in range(2):
+        pre = f"transformer.layers.{i}."
+        keep[pre + "self_attn.dropout"] = torch.rand(B, H, L, L, generator=g) >= p
+        keep[pre + "dropout1"] = torch.rand(B, L, E, generator=g) >= p
+        keep[pre + "dropout"] = torch.rand(B * L, 3 * E, generator=g) >= p
+        keep[pre + "dropout2"] = torch.rand(B, L, E, generator=g) >= p
+    seen = []
+
+    def provider(name, shape):
+        seen.append(name)
+        k = keep[name]
+        assert tuple(k.shape) == tuple(shape) or k.numel() == int(torch.tensor(shape).prod()), (name, shape)
+        return k.reshape(shape).to(torch.uint8).to(cuda_device).contiguous()
+    m._drop.mask_provider = provider
+    x = torch.randn(B, L, 768)
+    wgt = torch.randn(B, L, E)
+    xg = x.to(cuda_device).requires_grad_(True)
+    y = m(xg)
+    (y * wgt.to(cuda_device)).sum().backward()
+    assert len(seen) == 8, seen
+    sc = 1.0 / (1.0 - p)
+    masks = [{"attn": keep[f"transformer.layers.{i}.self_attn.dropout"].double() * sc,
+              "dropout1": keep[f"transformer.layers.{i}.dropout1"].double() * sc,
+              "dropout": keep[f"transformer.layers.{i}.dropout"].double().view(B, L, 3 * E) * sc,
+              "dropout2": keep[f"transformer.layers.{i}.dropout2"].double() * sc} for i in range(2)]
+    p64 = {k: v.double().requires_grad_(k != "pos_encoder.pe") for k, v in sd.items()}
+    x64 = x.double().requires_grad_(True)
+    want = O.subnetwork(x64, p64, num_heads=H, masks=masks)
+    (want * wgt.double()).sum().backward()
+    assert rel_err(y, want.detach()) <= tol
+
+    def ok(got, ref):
+        if dtype == torch.float32:
+            return rel_err(got, ref) <= 5e-5
+        n_got, n_ref = float(got.double().norm()), float(ref.double().norm())
+        return abs(n_got - n_ref) <= 5e-2 * n_ref and rel_err(got, ref) <= 2e-1
+    assert ok(xg.grad, x64.grad)
+    for k, prm in m.named_parameters():
+        assert ok(prm.grad, p64[k].grad), k
+
+
+def test_subnetwork_train_mode_philox_masks_consistent(cuda_device):
+    """in-kernel Philox masks (no provider): the attention backward RE-DRAWS the probability mask from the stream position
+    snapshotted at forward time.  With the stream reset to the same position before every forward the module is a fixed
+    function of x, so a central finite difference along a random direction must match <grad, direction>; two forwards
+    WITHOUT the reset differ (the position moves on); the keep rate of the output is sane."""
+    import mmsa
+    torch.manual_seed(7)
+    m = mmsa.Subnetwork(64, feat_dim=64, num_layers=1, nhead=2).to(cuda_device).train()
+    x = torch.randn(6, 9, 64, device=cuda_device, dtype=torch.float32)
+    wgt = torch.randn(6, 9, 64, device=cuda_device)
+
+    def f(xx):
+        m._drop.reseed(99, position=5)
+        return (m(xx) * wgt).sum()
+    xg = x.clone().requires_grad_(True)
+    f(xg).backward()
+    d = torch.randn_like(x)
+    d /= d.norm()
+    eps = 1e-2
+    with torch.no_grad():
+        fd = (f(x + eps * d).double() - f(x - eps * d).double()) / (2 * eps)
+    an = float((xg.grad.double() * d.double()).sum())
+    assert abs(float(fd) - an) <= 2e-2 * max(abs(an), 1.0), (float(fd), an)
+    with torch.no_grad():
+        y1 = m(x)
+        y2 = m(x)
+    assert not torch.equal(y1, y2)
+    m.eval()
+    with torch.no_grad():
+        assert torch.equal(m(x), m(x))
+
+
+@pytest.mark.parametrize("E,H,Lq,Lk,dtype,tol", [(256, 4, 1, 1, torch.float32, 1e-5), (768, 12, 20, 49, torch.float32, 1e-5),
+                                                  (768, 12, 20, 49, torch.bfloat16, 2e-2)])
+def test_cross_modal_transformer_distinct_key_value(cuda_device, E, H, Lq, Lk, dtype, tol):
+    """CrossModalTransformer.forward(query, key, value) with key IS NOT value (MultimodalModel.py:124; the signature allows
+    it even though every reference call site passes one tensor): output and all gradients, incl. separate dkey / dvalue and
+    the k / v row blocks of in_proj_weight, against the float64 oracle.  Native shape [B,E] (Lq = Lk = 1) and token shapes."""
+    import mmsa
+    torch.manual_seed(E + Lq)
+    blk = mmsa.CrossModalTransformer(E, H)
+    with torch.no_grad():
+        blk.multihead_attn.in_proj_bias.normal_(0, 0.1)
+    sd = {k: v.clone() for k, v in blk.state_dict().items()}
+    blk = blk.to(cuda_device)
+    B = 6
+    shp = (lambda L: (B, E) if (Lq == 1 and Lk == 1) else (B, L, E))
+    q, k, v = torch.randn(shp(Lq)), torch.randn(shp(Lk)), torch.randn(shp(Lk))
+    wgt = torch.randn(shp(Lq))
+    xs = [ops_cast(t, dtype, cuda_device) for t in (q, k, v)]
+    y = blk(*xs)
+    (y.float() * wgt.to(cuda_device)).sum().backward()
+    p64 = {"b." + kk: vv.double().requires_grad_(True) for kk, vv in sd.items()}
+    x64 = [t.to(dtype).double().requires_grad_(True) for t in (q, k, v)]          # the same (storage-rounded) inputs
+    u = [t if t.ndim == 3 else t.unsqueeze(1) for t in x64]
+    want = O.cross_block(u[0], u[1], p64, "b.", H, value=u[2])
+    want = want if q.ndim == 3 else want.squeeze(1)
+    (want * wgt.double()).sum().backward()
+    assert rel_err(y, want.detach()) <= tol
+
+    def ok(got, ref):
+        if dtype == torch.float32:
+            return rel_err(got, ref) <= 5e-5
+        return rel_err(got, ref) <= 5e-2
+    for name, a, b in zip(("dquery", "dkey", "dvalue"), xs, x64):
+        assert ok(a.grad, b.grad), name
+    for kk, prm in blk.named_parameters():
+        assert ok(prm.grad, p64["b." + kk].grad), kk
+    # the one-tensor call (key is value) still takes the packed K/V path and agrees with passing an equal COPY as value
+    blk.zero_grad()
+    y_same = blk(xs[0].detach(), xs[1].detach(), xs[1].detach())
+    y_copy = blk(xs[0].detach(), xs[1].detach(), xs[1].detach().clone())
+    assert rel_err(y_copy, y_same) <= (1e-6 if dtype == torch.float32 else 1e-2)
+
+
+def ops_cast(t, dtype, device):
+    return t.to(device).to(dtype).requires_grad_(True)
