@@ -248,11 +248,13 @@ def torch_eager_baseline(B: int, L: int, dev, steps: int = 5) -> dict:
     return out
 
 
-def cublas_matmul_tflops(prof: dict, dev, reps: int = 20) -> dict:
+def cublas_matmul_tflops(prof: dict, dev, prof_steps: int, reps: int = 20) -> dict:
     """torch.matmul (cuBLAS, bf16 in / fp32 accumulate) on every tcgen05 GEMM shape the step launched, same operand majors
-    (kk: X W^T, km: dY W, mm: dY^T X), timed back to back with CUDA events; next to it this library's TFLOP/s on that
-    shape from the per-launch profile."""
+    (kk: X W^T, km: dY W, mm: dY^T X), timed back to back with CUDA events over operand sets larger than L2; next to it this
+    library's kernel on that shape timed the SAME way through the C ABI (mmsa_b2b_tflops; bf16 output, no bias) and its
+    TFLOP/s inside the profiled step (mmsa_in_step_tflops: per-launch events, includes the launch gap)."""
     import torch
+    from mmsa import kernels as K
     out = {}
     for name, v in prof.items():
         if not name.startswith("gemm_tc_"):
@@ -275,10 +277,35 @@ def cublas_matmul_tflops(prof: dict, dev, reps: int = 20) -> dict:
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
-        del As, Bs
+        # the same product through this library (fwd: x W^T; dgrad: dy W; wgrad: dy^T x), same rotation
+        raw_a = [a.t() if maj[0] == "m" else a for a in As]          # storage as allocated: [K,M] or [M,K]
+        raw_b = [b if maj[1] == "m" else b.t() for b in Bs]          # [K,N] or [N,K]
+
+        def ours(i):
+            a, b = raw_a[i % nset], raw_b[i % nset]
+            if maj == "kk":
+                K.linear_fwd(a, b, None)
+            elif maj == "km":
+                K.linear_dgrad(a, b)
+            else:
+                K.linear_wgrad(a, b, want_bias=False)
+        ms_o = None
+        try:
+            for i in range(3):
+                ours(i)
+            e0.record()
+            for i in range(reps):
+                ours(i)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_o = e0.elapsed_time(e1) / reps
+        except Exception:
+            pass
+        del As, Bs, raw_a, raw_b
         out[name[len("gemm_tc_"):]] = {"cublas_tflops": 2.0 * M * N * K / (ms * 1e-3) / 1e12,
-                                       "mmsa_tflops": v["work"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else None,
-                                       "launches_per_step": v["count"]}
+                                       "mmsa_b2b_tflops": (2.0 * M * N * K / (ms_o * 1e-3) / 1e12) if ms_o else None,
+                                       "mmsa_in_step_tflops": v["work"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else None,
+                                       "launches_per_step": v["count"] / prof_steps}
     return out
 
 
@@ -580,9 +607,10 @@ def run_ours(args) -> None:
         if not args.no_torch_eager:
             try:
                 eager = torch_eager_baseline(B, L, dev)
-                eager["gemm_shapes"] = cublas_matmul_tflops(prof, dev)
-                eager["gemm_shapes_note"] = ("cublas_tflops: torch.matmul bf16 back to back over operand sets > L2, CUDA events; "
-                                             "mmsa_tflops: this library's launch of the same shape inside the profiled step")
+                eager["gemm_shapes"] = cublas_matmul_tflops(prof, dev, prof_steps)
+                eager["gemm_shapes_note"] = ("cublas_tflops / mmsa_b2b_tflops: torch.matmul bf16 and this library's kernel, each back "
+                                             "to back over operand sets > L2, CUDA events; mmsa_in_step_tflops: the same shape "
+                                             "inside the profiled step (per-launch events)")
             except Exception as ex:
                 eager = {"error": f"{type(ex).__name__}: {ex}"}
         try:      # the CPU baseline is an N = 1 figure (torchrun also pins OMP_NUM_THREADS=1 on the ranks)

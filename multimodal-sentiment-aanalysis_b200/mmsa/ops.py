@@ -549,17 +549,18 @@ class _DropoutState:
         self.offset = 0                      # draws since the last commit (relative to the device position)
         self.mask_provider = None
         self._state: Dict[torch.device, Tensor] = {}
+        self._position0 = 0                  # where a state tensor created later (first use on a device) starts
 
     def state(self, device) -> Tensor:
         device = torch.device(device)
         st = self._state.get(device)
         if st is None:
-            st = torch.tensor([self.seed, 0], dtype=torch.int64, device=device)
+            st = torch.tensor([self.seed, self._position0], dtype=torch.int64, device=device)
             self._state[device] = st
         return st
 
     def reseed(self, seed: int, position: int = 0) -> None:
-        self.seed, self.offset = int(seed), 0
+        self.seed, self.offset, self._position0 = int(seed), 0, int(position)
         for st in self._state.values():
             st.copy_(torch.tensor([self.seed, int(position)], dtype=torch.int64))
 

@@ -735,3 +735,37 @@ def test_sharded_two_view_losses_single_rank_group(cuda_device, tmp_path):
     finally:
         if created:
             dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("D", [32, 64])
+def test_attention_probability_dropout_philox_redraw(cuda_device, D):
+    """mmsa_attn_dropout_fwd/bwd: the backward RE-DRAWS the Philox keep mask of the probabilities instead of storing it.
+    With V = per-head identity rows the forward output IS the dropped probability matrix, which yields the mask the kernel
+    drew; the Philox backward must equal the explicit-mask backward given that mask, the kept probabilities must be the
+    undropped ones scaled by 1/(1-p), and the keep rate must be 1-p within 4 sigma."""
+    k = _k()
+    B, H, Lq, Lk, p = 4, 2, 16, 16, 0.3
+    E = H * D
+    q, kk = _rand((B * Lq, E), torch.float32, cuda_device, 1), _rand((B * Lk, E), torch.float32, cuda_device, 2)
+    v = torch.zeros(B * Lk, E, device=cuda_device)
+    for j in range(Lk):
+        for h in range(H):
+            v[j::Lk, h * D + j] = 1.0
+    state = torch.tensor([99, 5], dtype=torch.int64, device=cuda_device)
+    o, lse = k.attn_dropout_fwd(q, kk, v, B, H, Lq, Lk, D, p, None, 0, 7, state)
+    o0, _ = k.attn_dropout_fwd(q, kk, v, B, H, Lq, Lk, D, 0.0, None, 0, 0, None)
+    o_val, _ = k.attn_dropout_fwd(q, kk, v, B, H, Lq, Lk, D, p, None, 99, 12, None)      # by-value (seed, offset) = state + 7
+    assert torch.equal(o, o_val)
+    Pd = o.view(B, Lq, H, D)[..., :Lk].permute(0, 2, 1, 3)
+    P0 = o0.view(B, Lq, H, D)[..., :Lk].permute(0, 2, 1, 3)
+    mask = (Pd != 0).to(torch.uint8).contiguous()
+    n = mask.numel()
+    assert abs(float(mask.float().mean()) - (1 - p)) <= 4 * (p * (1 - p) / n) ** 0.5
+    assert float((Pd - P0 * mask / (1 - p)).abs().max()) <= 1e-6
+    do = _rand((B * Lq, E), torch.float32, cuda_device, 3)
+    got = [torch.empty_like(t) for t in (q, kk, v)]
+    want = [torch.empty_like(t) for t in (q, kk, v)]
+    k.attn_dropout_bwd(q, kk, v, o, do, lse, B, H, Lq, Lk, D, *got, p, None, 0, 7, state)
+    k.attn_dropout_bwd(q, kk, v, o, do, lse, B, H, Lq, Lk, D, *want, p, mask, 0, 0, None)
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)

@@ -568,9 +568,18 @@ def test_cross_modal_transformer_distinct_key_value(cuda_device, E, H, Lq, Lk, d
             return rel_err(got, ref) <= 5e-5
         return rel_err(got, ref) <= 5e-2
     for name, a, b in zip(("dquery", "dkey", "dvalue"), xs, x64):
+        if Lk == 1 and name == "dkey":      # soft-max over ONE key is 1 whatever the score: dL/dkey is exactly zero
+            assert float(b.grad.abs().max()) == 0.0 and float(a.grad.abs().max()) <= 1e-6 * float(x64[2].grad.abs().max())
+            continue
         assert ok(a.grad, b.grad), name
     for kk, prm in blk.named_parameters():
-        assert ok(prm.grad, p64["b." + kk].grad), kk
+        ref = p64["b." + kk].grad
+        if Lk == 1 and kk.startswith("multihead_attn.in_proj"):     # the q and k row blocks get exactly-zero gradients
+            n3 = ref.shape[0] // 3
+            assert float(prm.grad[:2 * n3].abs().max()) <= 1e-6 * float(ref.abs().max())
+            assert ok(prm.grad[2 * n3:], ref[2 * n3:]), kk
+            continue
+        assert ok(prm.grad, ref), kk
     # the one-tensor call (key is value) still takes the packed K/V path and agrees with passing an equal COPY as value
     blk.zero_grad()
     y_same = blk(xs[0].detach(), xs[1].detach(), xs[1].detach())
