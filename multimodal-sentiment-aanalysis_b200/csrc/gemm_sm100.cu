@@ -20,6 +20,7 @@
 // distributed shared memory in split order -- deterministic, no workspace, no second launch.  In wgrad the bias gradient (column sums of dY) comes
 // from one extra 128x16x16 MMA per k-step against a constant tile of ones (A = dY is already staged).
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace mmsa {
@@ -68,6 +69,11 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(leader_bar)
       : "memory");
+}
+// L2 prefetch of a tensor-map box (no shared-memory destination, no barrier): pulls an operand tile from HBM into L2
+// ahead of the cp.async.bulk.tensor that will stage it
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -142,6 +148,11 @@ struct GemmParams {
   // wgrad bias gradient: colsum[m] = sum_k A[m,k] (A = dY^T), from the ones-tile MMA of the n0 == 0 tiles
   float* colsum;
   int tma_epi;              // 1: C (and the residual) go through shared-memory slabs and TMA (tmC / tmR)
+  // workspace split-K (wgrad with 2-CTA tiles): the work units are (output tile, K-slice) pairs, ksplit slices per tile;
+  // slice ks of a tile writes its fp32 partial to rows [ks*M, (ks+1)*M) of the output (a [ksplit*M, N] workspace) and
+  // its bias-gradient partial to colsum[ks*M + m]; a second kernel sums the slices in slice order (deterministic).
+  int ksplit;
+  int prefetch;             // 1: the producer L2-prefetches the A tile of its NEXT work unit while it stages the current one
 };
 
 // PAIR: 2-CTA mode (tcgen05 cta_group::2).  Two CTAs on the SMs of one TPC compute a 256 x BN tile together: each stages
@@ -258,6 +269,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   auto peer_of = [&](int sp) { return (uint32_t)(PAIR ? 2 * sp + pair_rank : sp); };   // same rows, K-slice sp
   const int unit0 = blockIdx.x / CS, unit_stride = gridDim.x / CS;   // output tiles are dealt to clusters
   const int tiles_mn = p.tiles_m * p.tiles_n;
+  const int KS = p.ksplit > 1 ? p.ksplit : 1;               // workspace split-K: (tile, K-slice) work units
+  const int units_total = tiles_mn * KS;
   const int kb0 = split * p.kb_per_split;
   const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
 
@@ -292,14 +305,34 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // ===================== TMA producer =====================
       int stage = 0; uint32_t phase = 0;
       uint32_t cl_phase = 0;
-      for (int unit = unit0; unit < tiles_mn; unit += unit_stride) {
-        const int m0 = (unit / p.tiles_n) * TILE_M + pair_rank * BM;           // this CTA's 128 rows of A
-        const int n0 = (unit % p.tiles_n) * BN + pair_rank * Cfg::CTA_N;       // this CTA's share of the B tile
+      for (int unit = unit0; unit < units_total; unit += unit_stride) {
+        const int tile = unit % tiles_mn;
+        const int m0 = (tile / p.tiles_n) * TILE_M + pair_rank * BM;           // this CTA's 128 rows of A
+        const int n0 = (tile % p.tiles_n) * BN + pair_rank * Cfg::CTA_N;       // this CTA's share of the B tile
         if (S > 1 && unit != unit0) {     // the stage buffers held the previous tile's partial: wait until read
           mbar_wait_cluster(read_done_bar, cl_phase);
           cl_phase ^= 1u;
         }
-        for (int kb = kb0; kb < kb1; ++kb) {
+        const int ukb0 = KS > 1 ? (unit / tiles_mn) * p.kb_per_split : kb0;
+        const int ukb1 = KS > 1 ? min(p.kb_total, ukb0 + p.kb_per_split) : kb1;
+        // probe (MMSA_GEMM_PREFETCH=1, off by default): L2-prefetch the A tile of this CTA's NEXT unit one tile ahead.
+        // Measured neutral to -3 % on every configs[1] shape: the ring is not DRAM-latency bound
+        const int next_unit = unit + unit_stride;
+        const bool pf = p.prefetch != 0 && KS == 1 && S == 1 && next_unit < units_total;
+        const int pf_m0 = pf ? ((next_unit % tiles_mn) / p.tiles_n) * TILE_M + pair_rank * BM : 0;
+        const bool pf_new_rows = pf && pf_m0 != m0;             // same rows (next n-tile): already on their way
+        for (int kb = ukb0; kb < ukb1; ++kb) {
+          if (pf_new_rows) {
+            const bool sec = kb >= p.kb_a1;
+            const CUtensorMap* pm = sec ? &tmA2 : &tmA;
+            const int pk = (sec ? kb - p.kb_a1 : kb) * BK;
+            if (A_MN) {
+#pragma unroll
+              for (int c = 0; c < BM / 64; ++c) tma_prefetch_2d(pm, pf_m0 + c * 64, pk);
+            } else {
+              tma_prefetch_2d(pm, pk, pf_m0);
+            }
+          }
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + Cfg::A_BYTES;
@@ -353,14 +386,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint64_t ones_desc = make_sdesc(ones_base, 0, 1024);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int unit = unit0; unit < tiles_mn; unit += unit_stride) {
-        const bool cs = colsum_on && (unit % p.tiles_n) == 0;
+      for (int unit = unit0; unit < units_total; unit += unit_stride) {
+        const bool cs = colsum_on && ((unit % tiles_mn) % p.tiles_n) == 0;
         if (PAIR) mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);     // local + remote epilogue warps
         else mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         const uint32_t cs_tmem = tmem_base + (uint32_t)(Cfg::NACC * BN + acc * 16);
-        for (int kb = kb0; kb < kb1; ++kb) {
+        const int ukb0 = KS > 1 ? (unit / tiles_mn) * p.kb_per_split : kb0;
+        const int ukb1 = KS > 1 ? min(p.kb_total, ukb0 + p.kb_per_split) : kb1;
+        for (int kb = ukb0; kb < ukb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
@@ -370,19 +405,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // K-major: advance 32 bytes inside the 128B swizzle row; MN-major: advance 16 rows of 128B
             const uint64_t ad = A_MN ? make_sdesc(sa + k * (UMMA_K * 128), 8192, 1024) : make_sdesc(sa + k * (UMMA_K * 2), 0, 1024);
             const uint64_t bd = B_MN ? make_sdesc(sb + k * (UMMA_K * 128), 8192, 1024) : make_sdesc(sb + k * (UMMA_K * 2), 0, 1024);
-            if (PAIR) tc_mma_bf16_pair(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else tc_mma_bf16(d_tmem, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (PAIR) tc_mma_bf16_pair(d_tmem, ad, bd, idesc, (kb > ukb0 || k > 0) ? 1u : 0u);
+            else tc_mma_bf16(d_tmem, ad, bd, idesc, (kb > ukb0 || k > 0) ? 1u : 0u);
             if (cs) {
-              if (PAIR) tc_mma_bf16_pair(cs_tmem, ad, ones_desc, idesc_ones, (kb > kb0 || k > 0) ? 1u : 0u);
-              else tc_mma_bf16(cs_tmem, ad, ones_desc, idesc_ones, (kb > kb0 || k > 0) ? 1u : 0u);
+              if (PAIR) tc_mma_bf16_pair(cs_tmem, ad, ones_desc, idesc_ones, (kb > ukb0 || k > 0) ? 1u : 0u);
+              else tc_mma_bf16(cs_tmem, ad, ones_desc, idesc_ones, (kb > ukb0 || k > 0) ? 1u : 0u);
             }
           }
           if (PAIR) {                                    // both CTAs' slots / accumulators are released together
             tc_commit_pair(empty_bar(stage), pair_mask);
-            if (kb == kb1 - 1) tc_commit_pair(tfull_bar(acc), pair_mask);
+            if (kb == ukb1 - 1) tc_commit_pair(tfull_bar(acc), pair_mask);
           } else {
             tc_commit(empty_bar(stage));                 // frees the smem slot when these MMAs retire
-            if (kb == kb1 - 1) tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+            if (kb == ukb1 - 1) tc_commit(tfull_bar(acc));  // accumulator complete -> epilogue
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -402,8 +437,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t epi_it = 0, res_it = 0;                   // chunks / residual slabs this warp has pushed through its staging
     float* part = reinterpret_cast<float*>(smem_al);   // [BM][PART_LD] fp32 + [BM] colsum (split-K only)
     float* part_cs = part + BM * Cfg::PART_LD;
-    for (int unit = unit0; unit < tiles_mn; unit += unit_stride) {
-      const int m0 = (unit / p.tiles_n) * TILE_M + pair_rank * BM, n0 = (unit % p.tiles_n) * BN;
+    for (int unit = unit0; unit < units_total; unit += unit_stride) {
+      const int tile = unit % tiles_mn;
+      const int ks_row = KS > 1 ? (unit / tiles_mn) * p.M : 0;       // workspace split-K: row offset of this slice's slab
+      const int m0 = (tile / p.tiles_n) * TILE_M + pair_rank * BM, n0 = (tile % p.tiles_n) * BN;
       // stage this tile's bias slice in shared memory while the main loop is still running
       float* bs = bias_s + acc * BN;
       if (p.bias) {
@@ -501,7 +538,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t out_slab0 = epi_base + (uint32_t)ew * Cfg::OUT_SLAB;
         const uint32_t res_slab = epi_base + (uint32_t)kEpiWarps * Cfg::OUT_SLAB + (uint32_t)ew * Cfg::RES_SLAB;
         const bool has_res = p.residual != nullptr;
-        const int row0 = m0 + quad * 32;
+        const int row0 = ks_row + m0 + quad * 32;
         const int nc = min(BN / 32, (p.N - n0 + 31) / 32);
         if (has_res && lane == 0 && hh < nc) {
           mbar_expect_tx(res_bar(ew), Cfg::RES_SLAB);
@@ -590,7 +627,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(cv)
                        : "r"(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(Cfg::NACC * BN + acc * 16)) : "memory");
           tmem_ld_wait();
-          if (row_ok) p.colsum[row] = __uint_as_float(cv);
+          if (row_ok) p.colsum[ks_row + row] = __uint_as_float(cv);
         }
         tc_fence_before();
         __syncwarp();
@@ -805,7 +842,7 @@ bool gemm_bf16_sm100_supported(const GemmDesc& d) {
 int gemm_tc_max_clusters(int size);
 
 template <int BN, bool A_MN, bool B_MN, bool PAIR = false>
-static int launch_gemm(const GemmDesc& d, int splits_req, cudaStream_t s) {
+static int launch_gemm(const GemmDesc& d, int splits_req, cudaStream_t s, int ksplit = 1) {
   using Cfg = GemmCfg<BN, A_MN, B_MN, PAIR>;
   constexpr int TILE_M = PAIR ? 2 * BM : BM;
   CUtensorMap tmA, tmA2, tmB;
@@ -831,6 +868,20 @@ static int launch_gemm(const GemmDesc& d, int splits_req, cudaStream_t s) {
   if (d.out_dtype != MMSA_F32 || d.residual || d.act != MMSA_ACT_NONE || d.alpha != 1.f) splits = 1;
   p.kb_per_split = (int)ceil_div(p.kb_total, splits);
   p.splits = (int)ceil_div(p.kb_total, p.kb_per_split);
+  p.ksplit = 1;
+  {
+    static int pf_env = -1;
+    if (pf_env < 0) { const char* e = getenv("MMSA_GEMM_PREFETCH"); pf_env = e ? atoi(e) : 0; }      // measured: no gain on B200 (profiles/r02), kept as a probe
+    p.prefetch = pf_env;
+  }
+  if (ksplit > 1) {        // workspace split-K: d.C is a [ksplit * M, N] fp32 workspace, d.colsum a [ksplit * M] one
+    if (!PAIR || p.splits != 1 || d.out_dtype != MMSA_F32 || d.M % TILE_M != 0) {
+      set_error("mmsa: internal: workspace split-K needs 2-CTA tiles, fp32 output and M %% 256 == 0");
+      return MMSA_ERR_ARG;
+    }
+    p.kb_per_split = (int)ceil_div(p.kb_total, ksplit);
+    p.ksplit = (int)ceil_div(p.kb_total, p.kb_per_split);
+  }
   p.bias = d.bias; p.residual = d.residual; p.ldr = d.ldr; p.res_is_f32 = 0;
   p.C = d.C; p.ldc = d.ldc; p.out_is_f32 = (d.out_dtype == MMSA_F32);
   p.act = d.act; p.alpha = d.alpha;
@@ -841,10 +892,11 @@ static int launch_gemm(const GemmDesc& d, int splits_req, cudaStream_t s) {
     bool ok = p.splits == 1 && ((uintptr_t)d.C % 16 == 0) && ((d.ldc * esz) % 16 == 0);
     if (d.residual) ok = ok && ((uintptr_t)d.residual % 16 == 0) && ((d.ldr * 2) % 16 == 0);
     if (ok) {
-      if (!make_epi_map(&tmC, d.C, p.out_is_f32, d.N, d.M, d.ldc)) return MMSA_ERR_CUDA;
+      if (!make_epi_map(&tmC, d.C, p.out_is_f32, d.N, d.M * p.ksplit, d.ldc)) return MMSA_ERR_CUDA;
       if (d.residual && !make_epi_map(&tmR, d.residual, false, d.N, d.M, d.ldr)) return MMSA_ERR_CUDA;
     }
     p.tma_epi = ok ? 1 : 0;
+    if (p.ksplit > 1 && !ok) { set_error("mmsa: internal: workspace split-K needs a 16-byte aligned workspace"); return MMSA_ERR_ARG; }
   }
   p.colsum = nullptr;
   if (d.colsum != nullptr) {
@@ -871,7 +923,8 @@ static int launch_gemm(const GemmDesc& d, int splits_req, cudaStream_t s) {
     cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = s;
     cfg.attrs = attr; cfg.numAttrs = 1;
     const int max_cl = gemm_tc_max_clusters(csize);
-    const int ncl = tiles_mn < max_cl ? tiles_mn : max_cl;
+    const int units = tiles_mn * p.ksplit;
+    const int ncl = units < max_cl ? units : max_cl;
     cfg.gridDim = dim3((unsigned)(ncl * csize));
     ProfScope prof(nm, s, 2.0 * (double)d.M * (double)d.N * (double)Kt);
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmB, tmC, tmR, p);
@@ -976,6 +1029,24 @@ int gemm_bf16_sm100_splits(const GemmDesc& d, int splits, int bn, cudaStream_t s
 }
 
 int gemm_bf16_sm100(const GemmDesc& d, cudaStream_t s) { return gemm_bf16_sm100_splits(d, 1, 0, s); }
+
+// wgrad with 2-CTA 256 x 256 tiles and a WORKSPACE split-K: d.C is a [ksplit * M, N] fp32 workspace (row stride ldc),
+// d.colsum (or null) a [ksplit * M] one; returns the number of K-slices actually written through *real_ksplit.
+// Why: the output of a weight gradient has 9-24 tiles, so the K range must be split ~8x to fill the chip; a DSMEM
+// cluster split (<= 8 CTAs) cannot combine with CTA pairs, and 128 x 256 1-CTA tiles pull 48 KB of operands per k-block
+// and SM through L2 against 32 KB for a pair tile -- under full load the kernel is L2->SM bound, so bytes are time.
+int gemm_bf16_sm100_wgrad_pair(const GemmDesc& d, int ksplit, int* real_ksplit, cudaStream_t s) {
+  if (!gemm_bf16_sm100_supported(d) || !d.a_mn_major || !d.b_mn_major) {
+    set_error("mmsa: internal: gemm_bf16_sm100_wgrad_pair needs aligned MN-major operands");
+    return MMSA_ERR_ARG;
+  }
+  const int64_t kb_total = ceil_div(d.K, BK);
+  if (ksplit > kb_total) ksplit = (int)kb_total;
+  if (ksplit < 1) ksplit = 1;
+  const int64_t per = ceil_div(kb_total, ksplit);
+  if (real_ksplit) *real_ksplit = (int)ceil_div(kb_total, per);
+  return launch_gemm<256, true, true, true>(d, 1, s, ksplit);
+}
 
 int gemm_num_sms() { return num_sms(); }
 

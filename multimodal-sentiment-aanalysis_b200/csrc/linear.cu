@@ -13,6 +13,7 @@ int gemm_simt_f32(const GemmDesc& d, int splits, cudaStream_t s);
 int gemm_simt_bf16(const GemmDesc& d, int splits, cudaStream_t s);
 int gemm_simt_real_splits(int64_t Kt, int splits);
 int gemm_bf16_sm100_splits(const GemmDesc& d, int splits, int bn, cudaStream_t s);
+int gemm_bf16_sm100_wgrad_pair(const GemmDesc& d, int ksplit, int* real_ksplit, cudaStream_t s);
 int gemm_tc_max_clusters(int size);
 int gemm_tc_bn(int64_t N, bool need_colsum);
 int gemm_num_sms();
@@ -21,6 +22,8 @@ int gemm_bf16_small(const GemmDesc& d, cudaStream_t s);
 
 static int g_gemm_engine = 0;     // test hook: 1 = keep small products on the tcgen05 / CUDA-core engines
 static bool small_ok(int dtype, const GemmDesc& d) { return dtype == MMSA_BF16 && g_gemm_engine != 1 && gemm_bf16_small_ok(d); }
+
+constexpr int kMaxSplitsWs = 16;       // K-slices of the workspace split-K (mmsa_linear_wgrad_workspace reserves 16 slabs)
 
 static int tc_real_splits(int64_t Kt, int splits) {
   int64_t kb = ceil_div(Kt, 64);
@@ -124,6 +127,48 @@ __global__ void reduce_splits_kernel(const float* __restrict__ partials, int spl
     for (int k = 0; k < splits; ++k) s += partials[(int64_t)k * stride + r * ldp + c];
     out[r * ldo + c] = s;
   }
+}
+
+// Finish of the 2-CTA weight gradient (gemm_bf16_sm100_wgrad_pair): dw[r, c] = sum_ks ws[ks][r][c] in slice order
+// (deterministic), 16-byte vectors; the last blocks sum the bias-gradient partials the same way.  The workspace was
+// written microseconds earlier and is L2-resident (<= 16 x 2.4 MB against 126 MB).
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ ws, int ksplit, int64_t rows, int64_t cols, float* __restrict__ dw,
+                    int64_t lddw, const float* __restrict__ ws_colsum, float* __restrict__ db, int mat_blocks) {
+  if ((int)blockIdx.x >= mat_blocks) {
+    if (db == nullptr) return;
+    const int64_t r = (int64_t)(blockIdx.x - mat_blocks) * blockDim.x + threadIdx.x;
+    if (r < rows) {
+      float s = 0.f;
+      for (int k = 0; k < ksplit; ++k) s += ws_colsum[(int64_t)k * rows + r];
+      db[r] = s;
+    }
+    return;
+  }
+  const int64_t c4n = cols >> 2, total = rows * c4n, slab = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)mat_blocks * blockDim.x) {
+    const int64_t r = i / c4n, c = (i % c4n) << 2;
+    const float* src = ws + r * cols + c;
+    float4 a = *reinterpret_cast<const float4*>(src);
+    for (int k = 1; k < ksplit; ++k) {
+      const float4 b = *reinterpret_cast<const float4*>(src + (int64_t)k * slab);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    *reinterpret_cast<float4*>(dw + r * lddw + c) = a;
+  }
+}
+
+// 2-CTA 256 x 256 tiles + workspace split-K for the big weight gradients: output rows a multiple of 256, a reduction long
+// enough to give every K-slice >= 8 k-blocks, a 16-byte addressable dW.  Returns the K-slice count (0: not eligible).
+static int wgrad_pair_ksplit(int64_t Nw, int64_t Kw, int64_t tokens, const float* dw, int64_t lddw) {
+  if (Nw % 256 != 0 || Kw % 4 != 0 || Kw < 512 || tokens < 4096 || lddw % 4 != 0 || ((uintptr_t)dw % 16) != 0) return 0;
+  const int64_t tiles = (Nw / 256) * ceil_div(Kw, 256);
+  const int pairs = gemm_tc_max_clusters(2);
+  int ks = (int)(pairs / tiles);
+  if (ks > kMaxSplitsWs) ks = kMaxSplitsWs;
+  const int64_t kb = ceil_div(tokens, 64);
+  while (ks > 1 && kb / ks < 8) --ks;
+  return ks < 1 ? 1 : ks;
 }
 
 // ------------------------------------------------------------------ skinny Linear (N <= 8 output features)
@@ -325,6 +370,27 @@ int mmsa_linear_wgrad(int dtype, int64_t M, int64_t N, int64_t K, const void* dy
       d.colsum = db;                                  // bias gradient from the ones-fragment MMA of the same launch
       int rc = gemm_bf16_small(d, s);
       if (rc) return rc;
+      db_done = true;
+    } else if (use_tc(dtype, d) && getenv("MMSA_WGRAD_PAIR_OFF") == nullptr && wgrad_pair_ksplit(N, K, M, dw, lddw) > 0) {
+      // 2-CTA 256 x 256 tiles, (tile, K-slice) work units filling the 74 CTA pairs, fp32 partials into the (L2-resident)
+      // workspace, bias-gradient partials from the ones-tile MMA, then one small kernel sums the slices in order
+      const int ks_req = wgrad_pair_ksplit(N, K, M, dw, lddw);
+      int ks = 1;
+      GemmDesc dp = d;
+      dp.C = ks_req > 1 ? (void*)ws : (void*)dw;
+      dp.ldc = ks_req > 1 ? K : lddw;
+      dp.colsum = db ? (ks_req > 1 ? ws_colsum : db) : nullptr;
+      int rc = gemm_bf16_sm100_wgrad_pair(dp, ks_req, &ks, s);
+      if (rc) return rc;
+      if (ks_req > 1) {
+        const int64_t total4 = N * (K / 4);
+        int mat_blocks = (int)ceil_div(total4, 256);
+        if (mat_blocks > 148 * 4) mat_blocks = 148 * 4;
+        const int cs_blocks = db ? (int)ceil_div(N, 256) : 0;
+        ProfScope prof("wgrad_reduce", s, 4.0 * (double)N * K * (ks + 1));
+        wgrad_reduce_kernel<<<(unsigned)(mat_blocks + cs_blocks), 256, 0, s>>>(ws, ks, N, K, dw, lddw, ws_colsum, db, mat_blocks);
+        MMSA_LAUNCH_CHECK("wgrad_reduce_kernel");
+      }
       db_done = true;
     } else if (use_tc(dtype, d)) {
       // one launch: split-K partials are summed by the last CTA of each tile, and the bias gradient

@@ -103,7 +103,10 @@ def test_linear_dgrad(cuda_device, gemm_engine, dtype, M, N, K):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("M,N,K", [(1024, 768, 768), (392, 768, 2048), (5000, 1536, 768), (300, 3, 128), (64, 256, 2304),
-                                   (256, 256, 2304), (100, 24, 40)])
+                                   (256, 256, 2304), (100, 24, 40),
+                                   # 2-CTA 256x256 tiles + workspace split-K (tokens >= 4096, dW rows % 256 == 0): ragged token
+                                   # count (TMA zero fill of the last k-block), ragged dW columns, the configs[1] shape
+                                   (4100, 768, 2048), (8192, 256, 520), (32768, 768, 768)])
 def test_linear_wgrad(cuda_device, gemm_engine, dtype, M, N, K):
     if dtype == torch.float32 and gemm_engine:
         pytest.skip("engine switch only affects bf16 storage")
@@ -118,6 +121,8 @@ def test_linear_wgrad(cuda_device, gemm_engine, dtype, M, N, K):
     assert rel_err(dw, ref_w) <= tol
     assert rel_err(db, ref_b) <= tol
     assert float(dwfull[:, :8].abs().max()) == 0.0
+    dw2, db2 = k.linear_wgrad(dy, x)                   # deterministic: slice-ordered sums, no atomics
+    assert torch.equal(dw2, dw) and torch.equal(db2, db)
 
 
 @pytest.mark.parametrize("M,N,K,K2", [(100, 256, 2304, 0), (256, 64, 768, 768), (100, 37, 72, 0), (33, 130, 8, 0),
