@@ -254,7 +254,7 @@ def cublas_matmul_tflops(prof: dict, dev, prof_steps: int, reps: int = 20) -> di
     library's kernel on that shape timed the SAME way through the C ABI (mmsa_b2b_tflops; bf16 output, no bias) and its
     TFLOP/s inside the profiled step (mmsa_in_step_tflops: per-launch events, includes the launch gap)."""
     import torch
-    from mmsa import kernels as K
+    from mmsa import kernels as mk
     out = {}
     for name, v in prof.items():
         if not name.startswith("gemm_tc_"):
@@ -284,11 +284,11 @@ def cublas_matmul_tflops(prof: dict, dev, prof_steps: int, reps: int = 20) -> di
         def ours(i):
             a, b = raw_a[i % nset], raw_b[i % nset]
             if maj == "kk":
-                K.linear_fwd(a, b, None)
+                mk.linear_fwd(a, b, None)
             elif maj == "km":
-                K.linear_dgrad(a, b)
+                mk.linear_dgrad(a, b)
             else:
-                K.linear_wgrad(a, b, want_bias=False)
+                mk.linear_wgrad(a, b, want_bias=False)
         ms_o = None
         try:
             for i in range(3):
@@ -329,6 +329,9 @@ def run_ours(args) -> None:
     numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # the gradient all-reduces run as graph branches BESIDE the persistent GEMM CTAs: cap NCCL's CTAs so that it takes
+        # a few SMs instead of evicting a wave of tiles (40 MB per step needs nowhere near the default channel count)
+        os.environ.setdefault("NCCL_MAX_CTAS", "8")
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
     if _lib.load().mmsa_check_device() != 0:
@@ -350,7 +353,12 @@ def run_ours(args) -> None:
         if "shard" not in ablate:
             mdist.shard_contrastive(model)
         if "reduce" not in ablate:
-            reducer = mdist.GradAllReducer(model.parameters())
+            # default: gradients land in the flat arena and leave in buckets under the backward (ArenaGradReducer);
+            # MMSA_DP_REDUCER=flat selects the one-bucket pack-and-reduce form for an A/B
+            if os.environ.get("MMSA_DP_REDUCER", "arena") == "flat":
+                reducer = mdist.GradAllReducer(model.parameters())
+            else:
+                reducer = mdist.ArenaGradReducer(model.parameters())
     peaks = load_peaks()
 
     def barrier():
@@ -632,6 +640,7 @@ def run_ours(args) -> None:
                                    f"(projections, 2 cross-attention blocks, pool, fusion MLP, 3-class CE, InfoNCE), "
                                    f"L={L}, R={R}, E={E}, per-GPU batch {B}, global batch {B * world}",
                        "parallelism": f"dp{world}", "cuda_graph": graph_ok,
+                       **({"grad_reducer": type(reducer).__name__, "nccl_max_ctas": os.environ.get("NCCL_MAX_CTAS")} if reducer is not None else {}),
                        **({"optimizer": "mmsa.FusedClipAdamW after every step (eager: pack + sumsq + clip_adamw), lr 1e-4, wd 0.01, clip 1.0"} if opt is not None else {}),
                        **({"ablate": os.environ["MMSA_BENCH_ABLATE"]} if os.environ.get("MMSA_BENCH_ABLATE") else {}),
                        "dropout": "train mode, in-kernel Philox; stream position in device memory, advanced by a graph node "

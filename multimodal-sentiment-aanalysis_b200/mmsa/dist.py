@@ -350,6 +350,146 @@ class GradAllReducer:
                 p.grad.copy_(g).div_(world)
 
 
+class ArenaGradReducer:
+    """Parameter-gradient mean all-reduce with the gradients LANDING IN the communication arena and leaving in buckets
+    under the rest of the backward (the default reducer of bench.py at N > 1).
+
+    * One flat fp32 arena in PARAMETER order (mmsa.optim.arena_layout, the layout FusedClipAdamW consumes in place), built
+      up front.  It is registered as the kernels' gradient SINK (mmsa.ops.set_grad_sink): the fusion core's backward has
+      its weight-gradient GEMMs / LayerNorm reductions write straight into the arena views and returns no tensor for
+      those parameters -- the 81 MB multi-tensor pack of the one-bucket form disappears (the ~0.8 M parameters of the [B,*]
+      tail still arrive through autograd and are packed, 3 MB).
+    * The core reports each group of gradients the moment its kernels are ENQUEUED (`bucket_done(params, stream)`: tail
+      first, then block e2p, block p2e, the input projections).  A group is a contiguous arena range, so it is ONE
+      ncclAllReduce (op AVG), issued on a communication stream that waits for the producing stream -- inside the captured
+      graph it is a parallel branch under the remaining dgrad / attention / wgrad kernels.  `step()` reduces what is left
+      (normally only the projection weights, 8.7 MB of the 40.7 MB), joins, and points `.grad` at the arena views.
+    * NCCL's kernels are capped (NCCL_MAX_CTAS, set by bench.py before the communicator exists) so that they do not evict
+      the persistent GEMM CTAs they run beside.
+    Results equal the one-bucket form (same element-wise mean).  Gradient ACCUMULATION over several backwards is not
+    supported in this mode (a second backward overwrites the arena): use GradAllReducer for that."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], group=None, register_sink: bool = True):
+        from .optim import arena_layout
+        self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        self.group = group
+        dev = self.params[0].device
+        self.offs, total = arena_layout(self.params)
+        self._flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.views = [self._flat[o:o + p.numel()].view_as(p) for p, o in zip(self.params, self.offs)]
+        self._index = {id(p): i for i, p in enumerate(self.params)}
+        self._ends = self.offs[1:] + [total]
+        self._reduced = [False] * len(self.params)      # this step: already inside an all-reduce that was launched
+        self._direct = [False] * len(self.params)       # this step: written into the arena by the kernels
+        self._comm = None
+        self.launched: List[Tuple[int, int]] = []       # arena ranges all-reduced this step, in launch order (tests)
+        self.early_bytes = 0                            # bytes that went out before step() in the last step (tests)
+        if register_sink:
+            from . import ops
+            ops.set_grad_sink(self)
+        if self._flat.is_cuda:      # autograd may accumulate a gradient on a side stream: the communication stream waits for it
+            for p in self.params:
+                p.register_post_accumulate_grad_hook(self._on_accumulate)
+
+    def _on_accumulate(self, p) -> None:
+        self._comm_stream().wait_stream(torch.cuda.current_stream(p.device))
+
+    # ---- sink protocol (called by mmsa.ops) ----
+    def sink(self, p) -> Optional[Tensor]:
+        i = self._index.get(id(p))
+        if i is None:
+            return None
+        self._direct[i] = True
+        return self.views[i]
+
+    def _comm_stream(self):
+        if self._comm is None and self._flat.is_cuda:
+            self._comm = torch.cuda.Stream(device=self._flat.device, priority=-1)
+        return self._comm
+
+    def _all_reduce(self, lo: int, hi: int):
+        seg = self._flat if (lo == 0 and hi == self._flat.numel()) else self._flat[lo:hi]
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_reduce(seg, op=dist.ReduceOp.AVG, group=self.group)
+        else:                                           # gloo (CPU tests): no AVG
+            dist.all_reduce(seg, group=self.group)
+            seg.div_(dist.get_world_size(self.group))
+        self.launched.append((lo, hi))
+
+    @torch.no_grad()
+    def _flush(self, idx: List[int], streams) -> None:
+        """all-reduce the arena ranges of parameters `idx` (sorted; neighbours merge into one call) on the communication
+        stream, after everything enqueued so far on `streams`; autograd-delivered gradients among them are packed first"""
+        idx = [i for i in idx if not self._reduced[i]]
+        if not idx:
+            return
+        comm = self._comm_stream()
+        if comm is not None:
+            for st in streams:
+                if st is not None:
+                    comm.wait_stream(st)
+        ctx = torch.cuda.stream(comm) if comm is not None else _NullCtx()
+        with ctx:
+            src, dst = [], []
+            for i in idx:
+                g = self.params[i].grad
+                if not self._direct[i]:
+                    if g is None:
+                        self.views[i].zero_()           # a parameter without gradient on this rank counts as zero
+                    elif g.data_ptr() != self.views[i].data_ptr():
+                        src.append(g); dst.append(self.views[i])
+            if src:
+                torch._foreach_copy_(dst, src)
+            lo, hi = self.offs[idx[0]], self._ends[idx[0]]
+            for a, b in zip(idx, idx[1:]):
+                if b == a + 1:
+                    hi = self._ends[b]
+                else:
+                    self._all_reduce(lo, hi)
+                    lo, hi = self.offs[b], self._ends[b]
+            self._all_reduce(lo, hi)
+        for i in idx:
+            self._reduced[i] = True
+
+    def bucket_done(self, params, stream=None) -> None:
+        """the gradients of `params` have just been enqueued (on `stream`, default: the current stream): send their arena
+        range(s) off.  Every parameter BEFORE them in landing order whose gradient autograd has already delivered (the
+        tail) rides along on the first call."""
+        idx = sorted({self._index[id(p)] for p in params if id(p) in self._index})
+        cur = torch.cuda.current_stream(self._flat.device) if self._flat.is_cuda else None
+        if not self.launched:                           # first call of the step: the autograd-delivered tail goes too
+            tail = [i for i, p in enumerate(self.params) if not self._direct[i] and p.grad is not None]
+            self._flush(sorted(tail), (cur,))
+        before = len(self.launched)
+        self._flush(idx, (stream, cur))
+        self.early_bytes += sum((hi - lo) * 4 for lo, hi in self.launched[before:])
+
+    @torch.no_grad()
+    def step(self):
+        cur = torch.cuda.current_stream(self._flat.device) if self._flat.is_cuda else None
+        early = sum((hi - lo) * 4 for lo, hi in self.launched)
+        rest = [i for i in range(len(self.params)) if not self._reduced[i] and (self._direct[i] or self.params[i].grad is not None)]
+        self._flush(rest, (cur,))
+        if self._comm is not None:
+            cur.wait_stream(self._comm)
+        for i, p in enumerate(self.params):
+            if self._reduced[i]:
+                p.grad = self.views[i]
+        self.early_bytes = early
+        self.last_launched = list(self.launched)
+        self.launched = []
+        self._reduced = [False] * len(self.params)
+        self._direct = [False] * len(self.params)
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 # --------------------------------------------------------------------------------------------- parity yardstick
 def emulate_data_parallel_step(model, text_all: Tensor, image_all: Tensor, labels_all: Tensor, world: int):
     """The N-rank data-parallel step evaluated on ONE device with the same kernels -- the yardstick `bench.py` (dp_parity)

@@ -192,14 +192,15 @@ def gate_ln_fwd(gate_pre: Tensor, q: Tensor, attn: Tensor, gamma: Tensor, beta: 
 
 
 def gate_ln_bwd(dy: Tensor, rows_per_sample: int, g, q, attn, gamma, mean, rstd, *,
-                dq_bcast: Optional[Tensor] = None, bcast_rows: int = 0, dq_add: Optional[Tensor] = None):
+                dq_bcast: Optional[Tensor] = None, bcast_rows: int = 0, dq_add: Optional[Tensor] = None,
+                dgamma: Optional[Tensor] = None, dbeta: Optional[Tensor] = None):
     _check(dy, g, q, attn)
     M, E = q.shape
     dq_part = torch.empty_like(q)
     dattn_part = torch.empty_like(q)
     dgate_pre = torch.empty_like(q)
-    dgamma = torch.empty((E,), device=q.device, dtype=torch.float32)
-    dbeta = torch.empty((E,), device=q.device, dtype=torch.float32)
+    dgamma = dgamma if dgamma is not None else torch.empty((E,), device=q.device, dtype=torch.float32)
+    dbeta = dbeta if dbeta is not None else torch.empty((E,), device=q.device, dtype=torch.float32)
     nblk = _lib.load().mmsa_gate_ln_bwd_blocks(M)
     partials = torch.empty((nblk, 2, E), device=q.device, dtype=torch.float32)
     call("mmsa_gate_ln_bwd", dt(q), M, E, dy.data_ptr(), rows_per_sample, g.data_ptr(), q.data_ptr(), attn.data_ptr(),
@@ -229,15 +230,15 @@ def gate_ln_pool_fwd(gate_pre: Tensor, q: Tensor, attn: Tensor, gamma: Tensor, b
 
 
 def gate_ln_pool_bwd(dpy: Tensor, dpq: Optional[Tensor], dq_add: Optional[Tensor], g, q, attn, gamma, mean, rstd,
-                     B: int, L: int):
+                     B: int, L: int, dgamma: Optional[Tensor] = None, dbeta: Optional[Tensor] = None):
     _check(dpy, dpq, dq_add, g, q, attn)
     M, E = q.shape
     assert dpy.dtype == torch.float32 and (dpq is None or dpq.dtype == torch.float32)
     dq_part = torch.empty_like(q)
     dattn_part = torch.empty_like(q)
     dgate_pre = torch.empty_like(q)
-    dgamma = torch.empty((E,), device=q.device, dtype=torch.float32)
-    dbeta = torch.empty((E,), device=q.device, dtype=torch.float32)
+    dgamma = dgamma if dgamma is not None else torch.empty((E,), device=q.device, dtype=torch.float32)
+    dbeta = dbeta if dbeta is not None else torch.empty((E,), device=q.device, dtype=torch.float32)
     nblk = _lib.load().mmsa_gate_ln_bwd_blocks(M)
     partials = torch.empty((nblk, 2, E), device=q.device, dtype=torch.float32)
     call("mmsa_gate_ln_pool_bwd", dt(q), B, L, E, dpy.data_ptr(), _p(dpq), _p(dq_add), g.data_ptr(), q.data_ptr(),

@@ -79,6 +79,19 @@ def _w(w: Tensor, dtype: torch.dtype) -> Tensor:
     return K.cast(wd, dtype)
 
 
+# Gradient sink (data parallelism, mmsa.dist.ArenaGradReducer): when set, the fusion core's backward asks it for a
+# preallocated fp32 destination per parameter (`sink(p)` -> tensor or None), has its kernels write the gradient THERE,
+# returns no tensor for that parameter (autograd leaves p.grad alone; the sink's step() points it at the arena view)
+# and reports each finished group with `bucket_done(params, stream)` so that the all-reduce can start under the rest of
+# the backward.
+_GRAD_SINK = None
+
+
+def set_grad_sink(sink) -> None:
+    global _GRAD_SINK
+    _GRAD_SINK = sink
+
+
 OVERLAP_WGRAD = True      # block weight gradients on a second stream (FusionCoreFn.backward)
 OVERLAP_TAIL = True       # tail weight gradients (SeqFn.backward) and the contrastive branch (model.forward) on a second stream
 
@@ -226,21 +239,27 @@ def _block_fwd(q_in: Tensor, kv_in: Tensor, B: int, Lq: int, Lk: int, H: int, in
 
 def _block_bwd(st: _BlockState, dy: Tensor, *, dpooled_q: Optional[Tensor] = None, dq_add: Optional[Tensor] = None,
                dkv_residual: Optional[Tensor] = None, need_dq: bool = True, need_dkv: bool = True, need_w: bool = True,
-               wgrad_stream=None, keep: Optional[list] = None):
+               wgrad_stream=None, keep: Optional[list] = None, sinks: Optional[Sequence[Optional[Tensor]]] = None):
     """Backward of _block_fwd.  dy is [B*Lq,E] (cd) for a plain block, or the fp32 [B,E] gradient of the
     pooled output for a pooled block (dpooled_q: fp32 [B,E] gradient of the pooled query stream).
     For a block with a separate value tensor (st.v_in) dkv is the pair (dkey, dvalue).
     Returns (dq, dkv, grads) with grads = (d_in_w, d_in_b, d_out_w, d_out_b, d_gate_w, d_gate_b, d_ln_w, d_ln_b).
     Every accumulation of gradients w.r.t. q and kv happens in GEMM residual epilogues / the LN kernel;
-    bias gradients fall out of the wgrad GEMMs (ones-tile MMA)."""
+    bias gradients fall out of the wgrad GEMMs (ones-tile MMA).
+    sinks: optional preallocated fp32 destinations for the eight parameter gradients (same order as `grads`; None
+    entries are allocated here) -- the data-parallel gradient arena (set_grad_sink)."""
     E, B, Lq, Lk, H = st.E, st.B, st.Lq, st.Lk, st.H
     dev = dy.device
+    sk = list(sinks) if sinks is not None else [None] * 8
+
+    def buf(i, shape):
+        return sk[i] if sk[i] is not None else torch.empty(shape, device=dev, dtype=torch.float32)
     if st.pooled:
         r0, r1, dgate, d_ln_w, d_ln_b = K.gate_ln_pool_bwd(dy, dpooled_q, dq_add, st.G, st.q_in, st.A, st.gamma,
-                                                           st.mean, st.rstd, B, Lq)
+                                                           st.mean, st.rstd, B, Lq, dgamma=sk[6], dbeta=sk[7])
     else:
         r0, r1, dgate, d_ln_w, d_ln_b = K.gate_ln_bwd(dy, 0, st.G, st.q_in, st.A, st.gamma, st.mean, st.rstd,
-                                                      dq_add=dq_add)
+                                                      dq_add=dq_add, dgamma=sk[6], dbeta=sk[7])
     d_gate_w = d_gate_b = d_out_w = d_out_b = d_in_w = d_in_b = None
     # The weight-gradient GEMMs are leaves of the backward chain and their split-K clusters cover 108 of the 148 SMs:
     # they are enqueued on a second stream (joined by the caller, `wgrad_stream` is not None then), so the dgrad /
@@ -256,8 +275,8 @@ def _block_bwd(st: _BlockState, dy: Tensor, *, dpooled_q: Optional[Tensor] = Non
             fn()
 
     if need_w:
-        d_gate_w = torch.empty((E, 2 * E), device=dev, dtype=torch.float32)
-        d_gate_b = torch.empty((E,), device=dev, dtype=torch.float32)
+        d_gate_w = buf(4, (E, 2 * E))
+        d_gate_b = buf(5, (E,))
 
         def gate_wgrads():
             K.linear_wgrad(dgate, st.q_in, dw=d_gate_w[:, :E], db=d_gate_b)
@@ -266,8 +285,8 @@ def _block_bwd(st: _BlockState, dy: Tensor, *, dpooled_q: Optional[Tensor] = Non
     dA = K.linear_dgrad(dgate, st.w_gate[:, E:], residual=r1)
     dq_acc = K.linear_dgrad(dgate, st.w_gate[:, :E], residual=r0) if need_dq else None
     if need_w:
-        d_out_w = torch.empty((E, E), device=dev, dtype=torch.float32)
-        d_out_b = torch.empty((E,), device=dev, dtype=torch.float32)
+        d_out_w = buf(2, (E, E))
+        d_out_b = buf(3, (E,))
         on_side(lambda: K.linear_wgrad(dA, st.O, dw=d_out_w, db=d_out_b))
     dO = K.linear_dgrad(dA, st.w_out)
     dQp = torch.empty_like(st.Qp)
@@ -275,8 +294,8 @@ def _block_bwd(st: _BlockState, dy: Tensor, *, dpooled_q: Optional[Tensor] = Non
     K.attn_bwd(st.Qp, st.KVp[:, :E], st.KVp[:, E:], st.O, dO, st.lse, B, H, Lq, Lk, E // H,
                dQp, dKVp[:, :E], dKVp[:, E:])
     if need_w:
-        d_in_w = torch.empty((3 * E, E), device=dev, dtype=torch.float32)
-        d_in_b = torch.empty((3 * E,), device=dev, dtype=torch.float32)
+        d_in_w = buf(0, (3 * E, E))
+        d_in_b = buf(1, (3 * E,))
 
         def in_wgrads():
             K.linear_wgrad(dQp, st.q_in, dw=d_in_w[:E], db=d_in_b[:E])
@@ -360,6 +379,7 @@ class FusionCoreFn(Function):
         (e2, fv), st2 = _block_fwd(v, t, B, R, L, num_heads, *p2, pooled=True)
         ctx.st = (st1, st2, text2d, image2d)
         ctx.dims = (B, L, R)
+        ctx.plist = (wt, bt, wi, bi) + tuple(bp)          # the Parameter objects: keys of the gradient sink
         return f0, fv, e1, e2
 
     @staticmethod
@@ -370,23 +390,44 @@ class FusionCoreFn(Function):
         df0, dfv, de1, de2 = (K.cast(_c(x), torch.float32) for x in (df0, dfv, de1, de2))
         need_w1 = any(ctx.needs_input_grad[7:15])
         need_w2 = any(ctx.needs_input_grad[15:23])
+        # data-parallel gradient arena: destinations for the parameter gradients (None: allocate and hand to autograd)
+        sink = _GRAD_SINK
+        plist = ctx.plist
+        ctx.plist = None
+        need_p = (ctx.needs_input_grad[2:6]) + tuple(ctx.needs_input_grad[7:23])
+
+        def dst(j):
+            return sink.sink(plist[j]) if (sink is not None and need_p[j] and plist[j].is_leaf) else None
+        d_proj = [dst(j) for j in range(4)]
+        d_b1 = [dst(4 + j) for j in range(8)] if need_w1 else [None] * 8
+        d_b2 = [dst(12 + j) for j in range(8)] if need_w2 else [None] * 8
         # block e2p: grad wrt t (as query, + pooled f0 broadcast), grad wrt v (as key/value)
         main = torch.cuda.current_stream(df0.device)
         side = _side_stream(df0.device) if OVERLAP_WGRAD else None
         keep: list = []
-        dt1, dv1, g1 = _block_bwd(st1, de1, dpooled_q=df0, need_w=need_w1, wgrad_stream=side, keep=keep)
+        dt1, dv1, g1 = _block_bwd(st1, de1, dpooled_q=df0, need_w=need_w1, wgrad_stream=side, keep=keep, sinks=d_b1)
+        if sink is not None and need_w1:
+            sink.bucket_done(plist[4:12], side)           # block e2p's gradients are enqueued: their all-reduce may start
         # block p2e: grad wrt v (as query, + pooled fv broadcast + dv1), grad wrt t (as kv, + dt1)
         dv_tot, dt_tot, g2 = _block_bwd(st2, de2, dpooled_q=dfv, dq_add=dv1, dkv_residual=dt1, need_w=need_w2,
-                                        wgrad_stream=side, keep=keep)
+                                        wgrad_stream=side, keep=keep, sinks=d_b2)
+        if sink is not None and need_w2:
+            sink.bucket_done(plist[12:20], side)
         dwt = dbt = dwi = dbi = None
         if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
-            dwt, dbt = K.linear_wgrad(dt_tot, text2d)
+            dwt, dbt = K.linear_wgrad(dt_tot, text2d, dw=d_proj[0], db=d_proj[1])
         if ctx.needs_input_grad[4] or ctx.needs_input_grad[5]:
-            dwi, dbi = K.linear_wgrad(dv_tot, image2d)
+            dwi, dbi = K.linear_wgrad(dv_tot, image2d, dw=d_proj[2], db=d_proj[3])
         if side is not None:
             main.wait_stream(side)
         keep.clear()
-        return (None, None, dwt, dbt, dwi, dbi, None) + g1 + g2
+        if sink is not None:
+            sink.bucket_done(plist[0:4], main)
+        # gradients that went into the sink are not handed to autograd (the sink's step() publishes them as .grad)
+        proj_g = [None if d is not None else g for d, g in zip(d_proj, (dwt, dbt, dwi, dbi))]
+        g1 = tuple(None if d is not None else g for d, g in zip(d_b1, g1))
+        g2 = tuple(None if d is not None else g for d, g in zip(d_b2, g2))
+        return (None, None) + tuple(proj_g) + (None,) + g1 + g2
 
 
 def fusion_core(text, image, wt, bt, wi, bi, num_heads, block1: Sequence[Tensor], block2: Sequence[Tensor]):

@@ -141,3 +141,68 @@ def test_overlapped_two_bucket_grad_allreduce_gloo():
     for p in procs:
         p.join(timeout=30)
     assert all(ok for _, ok in results), results
+
+
+def _arena_worker(rank, world, port, q):
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mmsa import dist as mdist
+        torch.manual_seed(0)
+        shapes = [(6, 5), (6,), (4, 6), (4,), (3, 4), (3,), (2, 3), (1,)]        # "proj", "block1", "block2", "tail" pairs
+        params = [torch.nn.Parameter(torch.zeros(s)) for s in shapes]
+        red = mdist.ArenaGradReducer(params, register_sink=False)
+        ok = True
+        for it in range(3):
+            g = torch.Generator().manual_seed(50 + it)
+            grads = [[torch.randn(s, generator=g) for s in shapes] for _ in range(world)]      # every rank knows every shard
+            for p_ in params:
+                p_.grad = None
+            # tail (last two parameters) arrives through autograd BEFORE the core's backward starts
+            params[6].grad = grads[rank][6].clone()
+            if it != 1:                                   # one step without a gradient for the last parameter
+                params[7].grad = grads[rank][7].clone()
+            # the kernels write block1 / block2 / proj straight into the arena views and report them group by group
+            for grp in ((2, 3), (4, 5), (0, 1)):
+                for i in grp:
+                    red.sink(params[i]).copy_(grads[rank][i])
+                red.bucket_done([params[i] for i in grp])
+            red.step()
+            for i, p_ in enumerate(params):
+                if i == 7 and it == 1:
+                    ok &= p_.grad is None
+                    continue
+                want = sum(grads[r][i] for r in range(world)) / world
+                ok &= bool(torch.allclose(p_.grad, want, rtol=1e-6, atol=1e-7))
+                ok &= p_.grad.data_ptr() == red.views[i].data_ptr()        # .grad IS the arena view (optimiser in-place path)
+            # launch order: tail rides with the first report, then block1, block2, proj; nothing is left for step()
+            first = red.last_launched[0]
+            ok &= first[0] == red.offs[6]
+            ok &= red.early_bytes == sum((hi - lo) * 4 for lo, hi in red.last_launched)
+            ok &= len(red.last_launched) == 4
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_arena_grad_reducer_buckets_gloo():
+    """ArenaGradReducer: gradients written straight into the arena (sink protocol), groups all-reduced as they are reported
+    in landing order (tail, block e2p, block p2e, projections), autograd-delivered tail packed, a missing gradient left
+    alone, .grad pointed at the arena views; equal to the mean of the per-rank gradients."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 35000 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_arena_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=100) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+    assert all(ok for _, ok in results), results

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "multimodal-sentiment-aanalysis_b200")
 
 
-def _worker(rank: int, world: int, port: int, dtype_name: str, q):
+def _worker(rank: int, world: int, port: int, dtype_name: str, reducer_kind: str, q):
     for p in (ROOT, PKG, os.path.join(ROOT, "tests")):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -41,7 +41,7 @@ def _worker(rank: int, world: int, port: int, dtype_name: str, q):
         sl = slice(rank * B, (rank + 1) * B)
         model = build_model(cfg, params, buffers, cd, dev)
         mdist.shard_contrastive(model)
-        reducer = mdist.GradAllReducer(model.parameters())
+        reducer = (mdist.GradAllReducer if reducer_kind == "flat" else mdist.ArenaGradReducer)(model.parameters())
         text, image = inputs[0][sl].to(dev), inputs[1][sl].to(dev)
         lab = labels[sl].to(dev)
         logits, closs = model(text, image, None, lab)
@@ -94,8 +94,9 @@ def _worker(rank: int, world: int, port: int, dtype_name: str, q):
 
 
 @pytest.mark.timeout(600)
+@pytest.mark.parametrize("reducer_kind", ["arena", "flat"])
 @pytest.mark.parametrize("dtype_name", ["fp32", "bf16"])
-def test_two_rank_sharded_step_against_oracle(dtype_name):
+def test_two_rank_sharded_step_against_oracle(dtype_name, reducer_kind):
     if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     import torch.multiprocessing as mp
@@ -103,7 +104,7 @@ def test_two_rank_sharded_step_against_oracle(dtype_name):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 33000 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, world, port, dtype_name, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, dtype_name, reducer_kind, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=500) for _ in range(world)]
