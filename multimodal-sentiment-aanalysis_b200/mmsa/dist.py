@@ -456,6 +456,8 @@ class ArenaGradReducer:
         range(s) off.  Every parameter BEFORE them in landing order whose gradient autograd has already delivered (the
         tail) rides along on the first call."""
         idx = sorted({self._index[id(p)] for p in params if id(p) in self._index})
+        if not idx:                                     # another model's backward (e.g. a single-GPU yardstick): not ours
+            return
         cur = torch.cuda.current_stream(self._flat.device) if self._flat.is_cuda else None
         if not self.launched:                           # first call of the step: the autograd-delivered tail goes too
             tail = [i for i, p in enumerate(self.params) if not self._direct[i] and p.grad is not None]
