@@ -329,9 +329,8 @@ def run_ours(args) -> None:
     numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # the gradient all-reduces run as graph branches BESIDE the persistent GEMM CTAs: cap NCCL's CTAs so that it takes
-        # a few SMs instead of evicting a wave of tiles (40 MB per step needs nowhere near the default channel count)
-        os.environ.setdefault("NCCL_MAX_CTAS", "8")
+        # (NCCL_MAX_CTAS is deliberately left alone: capping NCCL's CTAs to 4 / 8 / 16 made the step 12 / 6 / 1.5 % slower
+        #  at N = 2 and 7 % slower at N = 8 with 16 -- profiles/r02_dp_matrix.md)
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
     if _lib.load().mmsa_check_device() != 0:
@@ -353,12 +352,14 @@ def run_ours(args) -> None:
         if "shard" not in ablate:
             mdist.shard_contrastive(model)
         if "reduce" not in ablate:
-            # default: gradients land in the flat arena and leave in buckets under the backward (ArenaGradReducer);
-            # MMSA_DP_REDUCER=flat selects the one-bucket pack-and-reduce form for an A/B
+            # default: gradients land in the flat arena (no pack) and leave in ONE all-reduce after the last weight gradient;
+            # MMSA_DP_BUCKETS=1 sends them in landing-order buckets under the backward instead (measured slower on this
+            # fabric: the NCCL kernels take SMs from the persistent GEMMs), MMSA_DP_REDUCER=flat is round 1's pack-and-reduce
             if os.environ.get("MMSA_DP_REDUCER", "arena") == "flat":
                 reducer = mdist.GradAllReducer(model.parameters())
             else:
-                reducer = mdist.ArenaGradReducer(model.parameters())
+                reducer = mdist.ArenaGradReducer(model.parameters(),
+                                                 early_buckets=os.environ.get("MMSA_DP_BUCKETS", "0") == "1")
     peaks = load_peaks()
 
     def barrier():

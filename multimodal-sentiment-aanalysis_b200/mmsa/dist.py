@@ -369,8 +369,13 @@ class ArenaGradReducer:
     Results equal the one-bucket form (same element-wise mean).  Gradient ACCUMULATION over several backwards is not
     supported in this mode (a second backward overwrites the arena): use GradAllReducer for that."""
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], group=None, register_sink: bool = True):
+    def __init__(self, params: Iterable[torch.nn.Parameter], group=None, register_sink: bool = True,
+                 early_buckets: Optional[bool] = None):
         from .optim import arena_layout
+        # early_buckets=False (MMSA_DP_BUCKETS=0): gradients still land in the arena (no pack), but everything leaves in
+        # ONE all-reduce from step() -- for fabrics / world sizes where NCCL kernels beside the GEMMs cost more than the
+        # exposed tail saves
+        self.early_buckets = (os.environ.get("MMSA_DP_BUCKETS", "1") != "0") if early_buckets is None else bool(early_buckets)
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.group = group
         dev = self.params[0].device
@@ -457,6 +462,8 @@ class ArenaGradReducer:
         tail) rides along on the first call."""
         idx = sorted({self._index[id(p)] for p in params if id(p) in self._index})
         if not idx:                                     # another model's backward (e.g. a single-GPU yardstick): not ours
+            return
+        if not self.early_buckets:
             return
         cur = torch.cuda.current_stream(self._flat.device) if self._flat.is_cuda else None
         if not self.launched:                           # first call of the step: the autograd-delivered tail goes too
