@@ -213,6 +213,19 @@ int mmsa_modal_concat_fwd(int dtype, int64_t B, int64_t E, int S, const void* lo
 int mmsa_modal_concat_bwd(int dtype, int64_t B, int64_t E, int S, const void* dfused, const float* w,
                           const void* const* slots_host, void* const* dslots_host, void* dlogits, void* stream);
 
+/* ---- modality head: the rest of `attention_weights` behind its first Linear + the weighted concat, one kernel
+ *      (MultimodalModel.py:173-175 GELU, Linear(64,3), Softmax(dim=1); :299-306 weights x features, cat) --------------
+ * h_pre:[B,Hd] fp32 (output of attention_weights.0), w2:[S,Hd] in `dtype` (operand copy of attention_weights.2.weight),
+ * b2:[S] fp32; slots as in mmsa_modal_concat_fwd.  Outputs: hg:[B,Hd] `dtype` = GELU(h_pre) (operand of the W2 weight
+ * gradient), w:[B,S] fp32 softmax weights, fused:[B,S*E] fp32, fused_lp:[B,S*E] `dtype` or NULL (bf16 operand copy for the
+ * next Linear; ignored when dtype is fp32).  Backward: dfused:[B,S*E] fp32 -> dslots (fp32, NULL entries skipped),
+ * dlogits:[B,S] and dh_pre:[B,Hd] in `dtype` (GEMM operands of the two Linear backward products). */
+int mmsa_modal_head_fwd(int dtype, int64_t B, int64_t E, int S, int64_t Hd, const float* h_pre, const void* w2, const float* b2,
+                        const void* const* slots_host, void* hg, float* w, float* fused, void* fused_lp, void* stream);
+int mmsa_modal_head_bwd(int dtype, int64_t B, int64_t E, int S, int64_t Hd, const float* dfused, const float* w,
+                        const void* const* slots_host, void* const* dslots_host, const float* h_pre, const void* w2,
+                        void* dlogits, void* dh_pre, void* stream);
+
 /* ---- activation (nn.GELU exact-erf, MultimodalModel.py:173; ReLU, ME-MHACL/model.py:108) ----
  * x (and dy) fp32, y / dx in `dtype`. */
 int mmsa_act_fwd(int dtype, int64_t n, const void* x, int act, void* y, void* stream);
@@ -226,12 +239,13 @@ int mmsa_act_bwd(int dtype, int64_t n, const void* x, const void* dy, int act, v
  * rng_state (device, {seed, position}) or NULL: when given, the kernel reads the seed from it and adds its
  * position to `offset` -- the stream position then lives in device memory and moves with mmsa_rng_advance, so a
  * captured CUDA graph draws a new mask on every replay (by-value seed/offset are frozen at capture).
- * save_mean/save_rstd:[N] fp32.  x (and dy in bwd) are fp32 GEMM outputs; y / dx are written in `dtype`. */
+ * save_mean/save_rstd:[N] fp32.  x (and dy in bwd) are fp32 GEMM outputs; y / dx are written in `dtype`; y_lp (or NULL):
+ * an additional bf16 copy of y when `dtype` is fp32 (the autograd-boundary output that is also the next Linear's operand). */
 int mmsa_bn_act_fwd(int dtype, int64_t B, int64_t N, int order, const void* x,
                     const float* gamma, const float* beta, float* running_mean, float* running_var,
                     float momentum, float eps, int training,
                     float dropout_p, uint8_t* keep_mask, int mask_given, uint64_t seed, uint64_t offset,
-                    const uint64_t* rng_state, void* y, float* save_mean, float* save_rstd, void* stream);
+                    const uint64_t* rng_state, void* y, void* y_lp, float* save_mean, float* save_rstd, void* stream);
 int mmsa_bn_act_bwd(int dtype, int64_t B, int64_t N, int order, const void* x, const void* dy,
                     const float* gamma, const float* beta, const float* save_mean, const float* save_rstd, int training,
                     float dropout_p, const uint8_t* keep_mask,

@@ -876,6 +876,120 @@ modal_concat_bwd_kernel(int64_t B, int E, int S, const float* __restrict__ dfuse
   }
 }
 
+
+// ------------------------------------------------------------------ modality head: GELU -> Linear(Hd, S) -> softmax -> weighted concat
+// One kernel for the rest of `attention_weights` behind its first Linear and the weighted concat that consumes it
+// (MultimodalModel.py:173-175, 299-306): h = GELU(h_pre) [Hd <= 256], logits = W2 h + b2 [S <= 4], w = softmax(logits),
+// fused = [slot_0 * w_0 | ... | slot_{S-1} * w_{S-1}].  Replaces act_fwd + skinny_fwd + modal_concat_fwd + a cast on the
+// (latency-bound) critical path of the [B,*] tail.  One block per sample.  Storage type T: h and W2 are the GEMM-operand
+// copies (h is rounded to T before the dot product, as the unfused path does); fused is written in fp32 (autograd
+// boundary) and, when fused_lp != null, also in T (the next Linear's operand).
+template <typename T>
+__global__ void __launch_bounds__(256)
+modal_head_fwd_kernel(int64_t B, int E, int S, int Hd, const float* __restrict__ h_pre, const T* __restrict__ w2,
+                      const float* __restrict__ b2, SlotPtrs sp, T* __restrict__ hg_out, float* __restrict__ w_out,
+                      float* __restrict__ fused, T* __restrict__ fused_lp) {
+  __shared__ float hs[256];
+  __shared__ float red[4][8];
+  __shared__ float wsm[4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t b = blockIdx.x;
+  float hv = 0.f;
+  if ((int)threadIdx.x < Hd) {
+    hv = round_to<T>(gelu_erf(h_pre[b * Hd + threadIdx.x]));
+    hg_out[b * Hd + threadIdx.x] = from_f<T>(hv);
+  }
+  hs[threadIdx.x] = hv;
+  float part[4] = {0.f, 0.f, 0.f, 0.f};
+  if ((int)threadIdx.x < Hd)
+    for (int s = 0; s < S; ++s) part[s] = hv * to_f(w2[(int64_t)s * Hd + threadIdx.x]);
+#pragma unroll
+  for (int s = 0; s < 4; ++s) { const float r = warp_sum(part[s]); if (lane == 0) red[s][warp] = r; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float lg[4], mx = -INFINITY, den = 0.f;
+    for (int s = 0; s < S; ++s) {
+      float a = 0.f;
+      for (int k = 0; k < 8; ++k) a += red[s][k];
+      a += b2 ? b2[s] : 0.f;                 // bias last, as the GEMM epilogue of the unfused path adds it
+      lg[s] = a; mx = fmaxf(mx, a);
+    }
+    for (int s = 0; s < S; ++s) { lg[s] = expf(lg[s] - mx); den += lg[s]; }
+    for (int s = 0; s < S; ++s) { lg[s] /= den; wsm[s] = lg[s]; w_out[b * S + s] = lg[s]; }
+  }
+  __syncthreads();
+  const int ev = E / 4;
+  for (int v = threadIdx.x; v < S * ev; v += blockDim.x) {
+    const int sl = v / ev, c = (v - sl * ev) * 4;
+    float x[4];
+    load_vec<float>(reinterpret_cast<const float*>(sp.p[sl]) + b * (int64_t)E + c, x);
+    const float ws = wsm[sl];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) x[t] *= ws;
+    const int64_t o = b * (int64_t)S * E + (int64_t)sl * E + c;
+    store_vec<float>(fused + o, x);
+    if (fused_lp != nullptr) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) fused_lp[o + t] = from_f<T>(x[t]);
+    }
+  }
+}
+
+// backward of the above: dslot_s = dfused_s * w_s, dw_s = <slot_s, dfused_s>, dlogits = w * (dw - <w, dw>) (rounded to T: the
+// operand of the W2 weight gradient), dh_pre = (W2^T dlogits) * GELU'(h_pre) (T: the operand of the first Linear's gradients)
+template <typename T>
+__global__ void __launch_bounds__(256)
+modal_head_bwd_kernel(int64_t B, int E, int S, int Hd, const float* __restrict__ dfused, const float* __restrict__ w,
+                      SlotPtrs sp, const float* __restrict__ h_pre, const T* __restrict__ w2, T* __restrict__ dlogits,
+                      T* __restrict__ dh_pre) {
+  __shared__ float red[4][8];
+  __shared__ float dl[4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t b = blockIdx.x;
+  float ws[4], acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int s = 0; s < S; ++s) ws[s] = w[b * S + s];
+  const int ev = E / 4;
+  for (int v = threadIdx.x; v < S * ev; v += blockDim.x) {
+    const int sl = v / ev, c = (v - sl * ev) * 4;
+    float x[4], d[4];
+    load_vec<float>(reinterpret_cast<const float*>(sp.p[sl]) + b * (int64_t)E + c, x);
+    load_vec<float>(dfused + b * (int64_t)S * E + (int64_t)sl * E + c, d);
+    float wsl = ws[0];
+#pragma unroll
+    for (int t = 1; t < 4; ++t) if (sl == t) wsl = ws[t];
+    float dot = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { dot += x[t] * d[t]; d[t] *= wsl; }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) if (sl == t) acc[t] += dot;
+    float* dslot = reinterpret_cast<float*>(sp.d[sl]);
+    if (dslot != nullptr) store_vec<float>(dslot + b * (int64_t)E + c, d);
+  }
+#pragma unroll
+  for (int t = 0; t < 4; ++t) { const float r = warp_sum(acc[t]); if (lane == 0) red[t][warp] = r; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float dw[4], dot = 0.f;
+    for (int s = 0; s < S; ++s) {
+      float a = 0.f;
+      for (int k = 0; k < 8; ++k) a += red[s][k];
+      dw[s] = a;
+      dot += ws[s] * a;
+    }
+    for (int s = 0; s < S; ++s) {
+      const float g = round_to<T>(ws[s] * (dw[s] - dot));
+      dl[s] = g;
+      dlogits[b * S + s] = from_f<T>(g);
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < Hd) {
+    float a = 0.f;
+    for (int s = 0; s < S; ++s) a += dl[s] * to_f(w2[(int64_t)s * Hd + threadIdx.x]);
+    dh_pre[b * Hd + threadIdx.x] = from_f<T>(a * gelu_erf_grad(h_pre[b * Hd + threadIdx.x]));
+  }
+}
+
 // ------------------------------------------------------------------ activations
 template <typename T>
 __global__ void act_fwd_kernel(int64_t n, const float* __restrict__ x, int act, T* __restrict__ y) {
@@ -1182,6 +1296,39 @@ int mmsa_modal_concat_bwd(int dtype, int64_t B, int64_t E, int S, const void* df
   MMSA_DISPATCH_DTYPE(dtype, T, (modal_concat_bwd_kernel<T><<<(unsigned)B, 256, 0, s>>>(
       B, (int)E, S, (const float*)dfused, w, sp, (T*)dlogits)));
   MMSA_LAUNCH_CHECK("modal_concat_bwd_kernel");
+  return MMSA_OK;
+}
+
+int mmsa_modal_head_fwd(int dtype, int64_t B, int64_t E, int S, int64_t Hd, const float* h_pre, const void* w2, const float* b2,
+                        const void* const* slots_host, void* hg, float* w, float* fused, void* fused_lp, void* stream) {
+  MMSA_REQUIRE_DEVICE();
+  MMSA_REQUIRE(S >= 1 && S <= 4, "mmsa_modal_head_fwd: S=%d out of [1,4]", S);
+  MMSA_REQUIRE(E % 4 == 0 && Hd >= 1 && Hd <= 256, "mmsa_modal_head_fwd: E must be a multiple of 4 and Hd in [1,256]");
+  if (B == 0) return MMSA_OK;
+  SlotPtrs sp{};
+  for (int i = 0; i < S; ++i) sp.p[i] = slots_host[i];
+  cudaStream_t s = (cudaStream_t)stream;
+  ProfScope prof("modal_head_fwd", s, (double)B * E * S * (8.0 + (fused_lp ? 2.0 : 0.0)));
+  MMSA_DISPATCH_DTYPE(dtype, T, (modal_head_fwd_kernel<T><<<(unsigned)B, 256, 0, s>>>(
+      B, (int)E, S, (int)Hd, h_pre, (const T*)w2, b2, sp, (T*)hg, w, fused, (T*)(dtype == MMSA_F32 ? nullptr : fused_lp))));
+  MMSA_LAUNCH_CHECK("modal_head_fwd_kernel");
+  return MMSA_OK;
+}
+
+int mmsa_modal_head_bwd(int dtype, int64_t B, int64_t E, int S, int64_t Hd, const float* dfused, const float* w,
+                        const void* const* slots_host, void* const* dslots_host, const float* h_pre, const void* w2,
+                        void* dlogits, void* dh_pre, void* stream) {
+  MMSA_REQUIRE_DEVICE();
+  MMSA_REQUIRE(S >= 1 && S <= 4, "mmsa_modal_head_bwd: S=%d out of [1,4]", S);
+  MMSA_REQUIRE(E % 4 == 0 && Hd >= 1 && Hd <= 256, "mmsa_modal_head_bwd: E must be a multiple of 4 and Hd in [1,256]");
+  if (B == 0) return MMSA_OK;
+  SlotPtrs sp{};
+  for (int i = 0; i < S; ++i) { sp.p[i] = slots_host[i]; sp.d[i] = dslots_host[i]; }
+  cudaStream_t s = (cudaStream_t)stream;
+  ProfScope prof("modal_head_bwd", s, (double)B * E * S * 12.0);
+  MMSA_DISPATCH_DTYPE(dtype, T, (modal_head_bwd_kernel<T><<<(unsigned)B, 256, 0, s>>>(
+      B, (int)E, S, (int)Hd, dfused, w, sp, h_pre, (const T*)w2, (T*)dlogits, (T*)dh_pre)));
+  MMSA_LAUNCH_CHECK("modal_head_bwd_kernel");
   return MMSA_OK;
 }
 

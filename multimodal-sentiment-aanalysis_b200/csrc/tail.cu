@@ -34,7 +34,7 @@ bn_act_fwd_kernel(int64_t B, int N, int order, const float* __restrict__ x, cons
                   const float* __restrict__ beta, float* __restrict__ running_mean,
                   float* __restrict__ running_var, float momentum, float eps, int training,
                   float dropout_p, uint8_t* __restrict__ keep_mask, int mask_given, uint64_t seed,
-                  uint64_t offset, const uint64_t* __restrict__ rng_state, T* __restrict__ y,
+                  uint64_t offset, const uint64_t* __restrict__ rng_state, T* __restrict__ y, bf16* __restrict__ y_lp,
                   float* __restrict__ save_mean, float* __restrict__ save_rstd) {
   __shared__ float red[kBnRows][kBnCols + 1];
   if (rng_state != nullptr) { seed = rng_state[0]; offset += rng_state[1]; }   // device-resident stream position
@@ -103,6 +103,7 @@ bn_act_fwd_kernel(int64_t B, int N, int order, const float* __restrict__ x, cons
       z = keep ? z * keep_scale : 0.f;
     }
     y[r * N + col] = from_f<T>(z);
+    if (y_lp != nullptr) y_lp[r * N + col] = __float2bfloat16_rn(z);
   }
 }
 
@@ -397,7 +398,7 @@ extern "C" {
 int mmsa_bn_act_fwd(int dtype, int64_t B, int64_t N, int order, const void* x, const float* gamma,
                     const float* beta, float* running_mean, float* running_var, float momentum, float eps,
                     int training, float dropout_p, uint8_t* keep_mask, int mask_given, uint64_t seed,
-                    uint64_t offset, const uint64_t* rng_state, void* y, float* save_mean, float* save_rstd,
+                    uint64_t offset, const uint64_t* rng_state, void* y, void* y_lp, float* save_mean, float* save_rstd,
                     void* stream) {
   MMSA_REQUIRE_DEVICE();
   MMSA_REQUIRE(B > 0 && N > 0, "mmsa_bn_act_fwd: empty input");
@@ -409,7 +410,7 @@ int mmsa_bn_act_fwd(int dtype, int64_t B, int64_t N, int order, const void* x, c
   dim3 block(kBnCols, kBnRows);
   MMSA_DISPATCH_DTYPE(dtype, T, (bn_act_fwd_kernel<T><<<(unsigned)ceil_div(N, kBnCols), block, 0, s>>>(
       B, (int)N, order, (const float*)x, gamma, beta, running_mean, running_var, momentum, eps, training, dropout_p,
-      keep_mask, mask_given, seed, offset, rng_state, (T*)y, save_mean, save_rstd)));
+      keep_mask, mask_given, seed, offset, rng_state, (T*)y, (bf16*)(dtype == MMSA_F32 ? y_lp : nullptr), save_mean, save_rstd)));
   MMSA_LAUNCH_CHECK("bn_act_fwd_kernel");
   return MMSA_OK;
 }

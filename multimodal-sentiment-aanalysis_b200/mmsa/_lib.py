@@ -55,9 +55,11 @@ _PROTOS = {
     "mmsa_pool_bwd": (I, [I, L, L, L, P, I, P, P, P]),
     "mmsa_modal_concat_fwd": (I, [I, L, L, I, P, P, P, P, P]),
     "mmsa_modal_concat_bwd": (I, [I, L, L, I, P, P, P, P, P, P]),
+    "mmsa_modal_head_fwd": (I, [I, L, L, I, L, P, P, P, P, P, P, P, P, P]),
+    "mmsa_modal_head_bwd": (I, [I, L, L, I, L, P, P, P, P, P, P, P, P, P]),
     "mmsa_act_fwd": (I, [I, L, P, I, P, P]),
     "mmsa_act_bwd": (I, [I, L, P, P, I, P, P]),
-    "mmsa_bn_act_fwd": (I, [I, L, L, I, P, P, P, P, P, F, F, I, F, P, I, U, U, P, P, P, P, P]),
+    "mmsa_bn_act_fwd": (I, [I, L, L, I, P, P, P, P, P, F, F, I, F, P, I, U, U, P, P, P, P, P, P]),
     "mmsa_bn_act_bwd": (I, [I, L, L, I, P, P, P, P, P, P, I, F, P, P, P, P, P, P]),
     "mmsa_dropout": (I, [I, L, P, F, P, I, U, U, P, P, P]),
     "mmsa_rng_advance": (I, [P, U, P]),

@@ -516,7 +516,7 @@ def emulate_data_parallel_step(model, text_all: Tensor, image_all: Tensor, label
     model.zero_grad(set_to_none=True)
     model.prepare_step()
     fast = model.compute_dtype == torch.bfloat16
-    f0, fv, e1, e2 = ops.fusion_core(model._cd(text_all), model._cd(image_all), model.eeg_net.proj.weight,
+    f0, fv, e1, e2, _, _ = ops.fusion_core(model._cd(text_all), model._cd(image_all), model.eeg_net.proj.weight,
                                      model.eeg_net.proj.bias, model.eye_net.proj.weight, model.eye_net.proj.bias,
                                      model.num_heads, model.cross_attn_e2p.kernel_params(),
                                      model.cross_attn_p2e.kernel_params())

@@ -312,6 +312,40 @@ def modal_concat_bwd(dfused: Tensor, w: Tensor, slots: Sequence[Tensor], need: S
     return dslots, dlogits
 
 
+def modal_head_fwd(h_pre: Tensor, w2: Tensor, b2: Optional[Tensor], slots: Sequence[Tensor], cd: torch.dtype):
+    """GELU -> Linear(Hd,S) -> softmax -> weighted concat in one launch (mmsa_modal_head_fwd).
+    h_pre [B,Hd] fp32, w2 [S,Hd] in `cd`, slots S x [B,E] fp32 -> hg [B,Hd] cd, w [B,S] fp32, fused [B,S*E] fp32,
+    fused_lp [B,S*E] cd (None in fp32 mode)."""
+    _check(h_pre, w2, b2, *slots)
+    assert h_pre.dtype == torch.float32 and w2.dtype == cd and w2.is_contiguous() and all(s.dtype == torch.float32 for s in slots)
+    B, Hd = h_pre.shape
+    E, S = slots[0].shape[1], len(slots)
+    hg = torch.empty((B, Hd), device=h_pre.device, dtype=cd)
+    w = torch.empty((B, S), device=h_pre.device, dtype=torch.float32)
+    fused = torch.empty((B, S * E), device=h_pre.device, dtype=torch.float32)
+    fused_lp = torch.empty((B, S * E), device=h_pre.device, dtype=cd) if cd != torch.float32 else None
+    arr = _ptr_array(slots)
+    call("mmsa_modal_head_fwd", dt(cd), B, E, S, Hd, h_pre.data_ptr(), w2.data_ptr(), _p(b2), ctypes.cast(arr, ctypes.c_void_p),
+         hg.data_ptr(), w.data_ptr(), fused.data_ptr(), _p(fused_lp), _stream())
+    return hg, w, fused, fused_lp
+
+
+def modal_head_bwd(dfused: Tensor, w: Tensor, slots: Sequence[Tensor], need: Sequence[bool], h_pre: Tensor, w2: Tensor,
+                   cd: torch.dtype):
+    """-> dslots (fp32 where needed), dlogits [B,S] cd, dh_pre [B,Hd] cd (mmsa_modal_head_bwd)."""
+    _check(dfused, w, h_pre, w2, *slots)
+    assert dfused.dtype == torch.float32
+    B, Hd = h_pre.shape
+    E, S = slots[0].shape[1], len(slots)
+    dslots = [torch.empty_like(s) if n else None for s, n in zip(slots, need)]
+    dlogits = torch.empty((B, S), device=dfused.device, dtype=cd)
+    dh = torch.empty((B, Hd), device=dfused.device, dtype=cd)
+    a1, a2 = _ptr_array(slots), _ptr_array(dslots)
+    call("mmsa_modal_head_bwd", dt(cd), B, E, S, Hd, dfused.data_ptr(), w.data_ptr(), ctypes.cast(a1, ctypes.c_void_p),
+         ctypes.cast(a2, ctypes.c_void_p), h_pre.data_ptr(), w2.data_ptr(), dlogits.data_ptr(), dh.data_ptr(), _stream())
+    return dslots, dlogits, dh
+
+
 def act_fwd(x: Tensor, act: int, out_dtype: torch.dtype) -> Tensor:
     _check(x)
     assert x.dtype == torch.float32
@@ -330,11 +364,13 @@ def act_bwd(x: Tensor, dy: Tensor, act: int, out_dtype: torch.dtype) -> Tensor:
 
 def bn_act_fwd(x: Tensor, gamma, beta, running_mean, running_var, momentum: float, eps: float, training: bool,
                order: int, dropout_p: float, keep_mask: Optional[Tensor], seed: int, offset: int,
-               out_dtype: torch.dtype, rng_state: Optional[Tensor] = None):
+               out_dtype: torch.dtype, rng_state: Optional[Tensor] = None, want_lp: bool = False):
+    """-> y, save_mean, save_rstd, keep_mask[, y_lp]; want_lp (fp32 out only): also a bf16 copy of y from the same launch."""
     _check(x, gamma, beta)
     assert x.dtype == torch.float32
     B, N = x.shape
     y = torch.empty((B, N), device=x.device, dtype=out_dtype)
+    y_lp = torch.empty((B, N), device=x.device, dtype=torch.bfloat16) if (want_lp and out_dtype == torch.float32) else None
     save_mean = torch.empty((N,), device=x.device, dtype=torch.float32)
     save_rstd = torch.empty((N,), device=x.device, dtype=torch.float32)
     mask_given = keep_mask is not None
@@ -342,7 +378,10 @@ def bn_act_fwd(x: Tensor, gamma, beta, running_mean, running_var, momentum: floa
         keep_mask = torch.empty((B, N), device=x.device, dtype=torch.uint8)
     call("mmsa_bn_act_fwd", dt(out_dtype), B, N, order, x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _p(running_mean),
          _p(running_var), float(momentum), float(eps), int(training), float(dropout_p), _p(keep_mask),
-         int(mask_given), seed, offset, _p(rng_state), y.data_ptr(), save_mean.data_ptr(), save_rstd.data_ptr(), _stream())
+         int(mask_given), seed, offset, _p(rng_state), y.data_ptr(), _p(y_lp), save_mean.data_ptr(), save_rstd.data_ptr(),
+         _stream())
+    if want_lp:
+        return y, save_mean, save_rstd, keep_mask, y_lp
     return y, save_mean, save_rstd, keep_mask
 
 

@@ -221,17 +221,25 @@ class MultimodalTransformerModel(nn.Module):
         one cast per weight, whenever a parameter's version changed."""
         _prepare(self, self.compute_dtype)
 
-    def _tail(self, raw_a: Tensor, raw_b: Optional[Tensor], slots: Sequence[Tensor]):
+    def _tail(self, raw_a: Tensor, raw_b: Optional[Tensor], slots: Sequence[Tensor], a_lp: Optional[Tensor] = None,
+              b_lp: Optional[Tensor] = None):
         """modality weights (:171-176, :299-301) -> weighted concat (:302-306) -> fusion (:309) -> heads (:312-313).
-        Everything here is [B,*]: fp32 at the autograd boundaries, `compute_dtype` GEMM operands inside."""
+        Everything here is [B,*]: fp32 at the autograd boundaries, `compute_dtype` GEMM operands inside.  The chain is
+        latency-bound (a few dozen launches of a few microseconds each), so operand copies in the compute dtype are passed
+        from producer to consumer (a_lp / b_lp: the pooled features as the LayerNorm kernel wrote them) instead of being
+        re-cast, and the modality-weight MLP tail + softmax + concat run as one kernel."""
         cd = self.compute_dtype
-        logits3 = run_sequential(raw_a, self.attention_weights, self._drop, "attention_weights", cd, x2=raw_b)
-        fused, w = ops.modal_concat(logits3, slots)
-        fused = run_sequential(fused, self.fusion, self._drop, "fusion", cd)
-        arousal = run_sequential(fused, self.arousal_head, self._drop, "arousal_head", cd)
+        if ops.is_modal_head(self.attention_weights) and len(slots) <= 4:
+            fused, fused_lp, w = ops.modal_head(raw_a, raw_b, self.attention_weights, slots, cd, a_lp=a_lp, b_lp=b_lp)
+        else:
+            logits3 = run_sequential(raw_a, self.attention_weights, self._drop, "attention_weights", cd, x2=raw_b)
+            fused, w = ops.modal_concat(logits3, slots)
+            fused_lp = None
+        fused, fused2_lp = ops.sequential(fused, self.fusion, self._drop, "fusion", cd, x_lp=fused_lp, want_lp=True)
+        arousal = ops.sequential(fused, self.arousal_head, self._drop, "arousal_head", cd, x_lp=fused2_lp)
         valence = None
         if self.valence_head is not None and self.contract == "multitask":
-            valence = run_sequential(fused, self.valence_head, self._drop, "valence_head", cd)
+            valence = ops.sequential(fused, self.valence_head, self._drop, "valence_head", cd, x_lp=fused2_lp)
         return arousal, valence
 
     # -- forward ------------------------------------------------------------------------------------
@@ -263,9 +271,10 @@ class MultimodalTransformerModel(nn.Module):
             slots = (ops.cast(f0, f32), ops.cast(e1, f32), ops.cast(e2, f32))
         else:
             text, image = self._cd(eeg), self._cd(eye)
-            f0, fv, e1, e2 = ops.fusion_core(text, image, self.eeg_net.proj.weight, self.eeg_net.proj.bias,
-                                             self.eye_net.proj.weight, self.eye_net.proj.bias, self.num_heads,
-                                             self.cross_attn_e2p.kernel_params(), self.cross_attn_p2e.kernel_params())
+            f0, fv, e1, e2, f0_lp, fv_lp = ops.fusion_core(
+                text, image, self.eeg_net.proj.weight, self.eeg_net.proj.bias, self.eye_net.proj.weight,
+                self.eye_net.proj.bias, self.num_heads, self.cross_attn_e2p.kernel_params(),
+                self.cross_attn_p2e.kernel_params())
             raw_a, raw_b = f0, fv
             slots = (f0, e1, e2)
             if con_labels is not None:
@@ -291,7 +300,7 @@ class MultimodalTransformerModel(nn.Module):
                         contrastive.append(ops.infonce(e2, e1, con_labels, self.temperature, fast=fast))
                     contrastive = [self.contrastive_weight * c for c in contrastive]     # :315-317 -> shape (1,)
                     weighted = True
-        arousal, valence = self._tail(raw_a, raw_b, slots)
+        arousal, valence = self._tail(raw_a, raw_b, slots, *((f0_lp, fv_lp) if self.wiring == "bidirectional" else ()))
         if side is not None:                                         # join the contrastive branch
             cur = torch.cuda.current_stream(arousal.device)
             cur.wait_stream(side)

@@ -227,9 +227,9 @@ def _block_fwd(q_in: Tensor, kv_in: Tensor, B: int, Lq: int, Lk: int, H: int, in
     st.gamma = ln_w.detach()
     st.pooled = pooled
     if pooled:
-        st.G, st.mean, st.rstd, py, pq, _ = K.gate_ln_pool_fwd(gate_pre, q_in, st.A, st.gamma, ln_b.detach(), eps, B, Lq,
-                                                               want_q_lp=False)
-        out = (py, pq)
+        st.G, st.mean, st.rstd, py, pq, pq_lp = K.gate_ln_pool_fwd(gate_pre, q_in, st.A, st.gamma, ln_b.detach(), eps, B, Lq,
+                                                                   want_q_lp=True)
+        out = (py, pq, pq_lp)      # pq_lp: the pooled query in the compute dtype (operand copy for the tail's first Linear)
     else:
         st.G, out, st.mean, st.rstd = K.gate_ln_fwd(gate_pre, q_in, st.A, st.gamma, ln_b.detach(), eps)
     st.q_in, st.kv_in, st.v_in = q_in, kv_in, v_in
@@ -361,6 +361,7 @@ class FusionCoreFn(Function):
         t = Linear(text), v = Linear(image)                         (Subnetwork.proj pattern, :86)
         t2 = Block_e2p(query=t, kv=v), v2 = Block_p2e(query=v, kv=t) (:287-297, bidirectional)
         returns mean_tokens(t), mean_tokens(v), mean_tokens(t2), mean_tokens(v2)   each fp32 [B,E]
+        (+ the first two again in the compute dtype -- operand copies for the tail's first Linear; None in fp32 mode)
     Keeping it one node lets every gradient accumulation on the big [B,L,E] tensors happen inside
     GEMM epilogues instead of autograd's add kernels; t2 / v2 are never written (the LayerNorm kernel
     pools them in fp32 registers) and the pooled-output backward never materialises a [B,L,E] broadcast."""
@@ -375,16 +376,18 @@ class FusionCoreFn(Function):
         wtc, wic = _w(wt, cd), _w(wi, cd)
         t = K.linear_fwd(text2d, wtc, bt.detach())
         v = K.linear_fwd(image2d, wic, bi.detach())
-        (e1, f0), st1 = _block_fwd(t, v, B, L, R, num_heads, *p1, pooled=True)
-        (e2, fv), st2 = _block_fwd(v, t, B, R, L, num_heads, *p2, pooled=True)
+        (e1, f0, f0_lp), st1 = _block_fwd(t, v, B, L, R, num_heads, *p1, pooled=True)
+        (e2, fv, fv_lp), st2 = _block_fwd(v, t, B, R, L, num_heads, *p2, pooled=True)
         ctx.st = (st1, st2, text2d, image2d)
         ctx.dims = (B, L, R)
         ctx.plist = (wt, bt, wi, bi) + tuple(bp)          # the Parameter objects: keys of the gradient sink
-        return f0, fv, e1, e2
+        if f0_lp is not None:
+            ctx.mark_non_differentiable(f0_lp, fv_lp)
+        return f0, fv, e1, e2, f0_lp, fv_lp
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, df0, dfv, de1, de2):
+    def backward(ctx, df0, dfv, de1, de2, _df0_lp=None, _dfv_lp=None):
         st1, st2, text2d, image2d = ctx.st
         ctx.st = None
         df0, dfv, de1, de2 = (K.cast(_c(x), torch.float32) for x in (df0, dfv, de1, de2))
@@ -575,6 +578,80 @@ def modal_concat(logits, slots: Sequence[Tensor]):
     return ModalConcatFn.apply(logits, *slots)
 
 
+class ModalHeadFn(Function):
+    """`attention_weights` (Linear(K,Hd) - GELU - Linear(Hd,S) - Softmax, MultimodalModel.py:171-176) applied to the raw
+    features [raw_a | raw_b], and the weighted concat of the S feature slots (:299-306), as ONE autograd node over three
+    kernels: the first Linear (GEMM, two A operands, no concat), then GELU + second Linear + softmax + weighting + concat in
+    one launch (mmsa_modal_head_fwd), which also writes the fused vector in the compute dtype for the fusion MLP's first
+    GEMM.  Backward: one launch for d(slots), d(logits), d(h_pre) (mmsa_modal_head_bwd), then the weight gradients (second
+    stream) and the two input gradients of the first Linear."""
+
+    @staticmethod
+    def forward(ctx, raw_a, raw_b, a_lp, b_lp, w1, b1, w2, b2, cd, *slots):
+        xa = a_lp if (a_lp is not None and a_lp.dtype == cd) else K.cast(K.cast(_c(raw_a), torch.float32), cd)
+        xb = None
+        if raw_b is not None:
+            xb = b_lp if (b_lp is not None and b_lp.dtype == cd) else K.cast(K.cast(_c(raw_b), torch.float32), cd)
+        w1c, w2c = _w(w1, cd), _w(w2, cd)
+        h_pre = K.linear_fwd(xa, w1c, None if b1 is None else b1.detach(), x2=xb, out_dtype=torch.float32)
+        slots32 = [K.cast(_c(s), torch.float32) for s in slots]
+        hg, w, fused, fused_lp = K.modal_head_fwd(h_pre, _c(w2c), None if b2 is None else b2.detach(), slots32, cd)
+        ctx.save_for_backward(xa, xb, w1c, w2c, h_pre, hg, w, *slots32)
+        ctx.cfg = (cd, raw_a.shape, None if raw_b is None else raw_b.shape, b1 is not None, b2 is not None)
+        ctx.mark_non_differentiable(w)
+        if fused_lp is not None:
+            ctx.mark_non_differentiable(fused_lp)
+        return fused, fused_lp, w
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dfused, _dlp, _dw):
+        xa, xb, w1c, w2c, h_pre, hg, w, *slots32 = ctx.saved_tensors
+        cd, shp_a, shp_b, has_b1, has_b2 = ctx.cfg
+        need_slots = list(ctx.needs_input_grad[9:])
+        dslots, dlogits, dh = K.modal_head_bwd(K.cast(_c(dfused), torch.float32), w, slots32, need_slots, h_pre, _c(w2c), cd)
+        main = torch.cuda.current_stream(dfused.device)
+        side = _side_stream(dfused.device) if OVERLAP_TAIL else None
+        Ka = xa.shape[1]
+        dw1 = db1 = dw2 = db2 = None
+        want_w1, want_b1 = ctx.needs_input_grad[4], has_b1 and ctx.needs_input_grad[5]
+        want_w2, want_b2 = ctx.needs_input_grad[6], has_b2 and ctx.needs_input_grad[7]
+        if side is not None:
+            side.wait_stream(main)
+        with torch.cuda.stream(side if side is not None else main):        # leaves of the backward chain
+            if want_w2 or want_b2:
+                dw2, db2 = K.linear_wgrad(dlogits, hg, want_bias=want_b2, want_weight=want_w2)
+            if want_w1 or want_b1:
+                dw1 = torch.empty(w1c.shape, device=dh.device, dtype=torch.float32)
+                _, db1 = K.linear_wgrad(dh, xa, dw=dw1[:, :Ka], want_bias=want_b1, want_weight=True)
+                if xb is not None:
+                    K.linear_wgrad(dh, xb, dw=dw1[:, Ka:], want_bias=False, want_weight=True)
+                if not want_w1:
+                    dw1 = None
+        da = db = None
+        if ctx.needs_input_grad[0]:
+            da = K.linear_dgrad(dh, w1c[:, :Ka], out_dtype=torch.float32).view(shp_a)
+        if xb is not None and ctx.needs_input_grad[1]:
+            db = K.linear_dgrad(dh, w1c[:, Ka:], out_dtype=torch.float32).view(shp_b)
+        if side is not None:
+            main.wait_stream(side)
+        return (da, db, None, None, dw1, db1, dw2, db2, None) + tuple(dslots)
+
+
+def modal_head(raw_a: Tensor, raw_b: Optional[Tensor], seq: nn.Sequential, slots: Sequence[Tensor], cd: torch.dtype,
+               a_lp: Optional[Tensor] = None, b_lp: Optional[Tensor] = None):
+    """-> (fused fp32 [B,S*E], fused in the compute dtype or None, softmax weights [B,S]); `seq` must be
+    Linear - GELU - Linear - Softmax (the reference's attention_weights)."""
+    l1, l2 = seq[0], seq[2]
+    return ModalHeadFn.apply(raw_a, raw_b, a_lp, b_lp, l1.weight, l1.bias, l2.weight, l2.bias, cd, *slots)
+
+
+def is_modal_head(seq: nn.Sequential) -> bool:
+    m = list(seq.children())
+    return (len(m) == 4 and isinstance(m[0], nn.Linear) and isinstance(m[1], nn.GELU) and isinstance(m[2], nn.Linear)
+            and isinstance(m[3], nn.Softmax) and m[2].out_features <= 4 and m[0].out_features <= 256)
+
+
 # ------------------------------------------------------------------------------------------ nn.Sequential chains
 class _DropoutState:
     """Philox stream of the in-kernel dropout of one module; parity tests may inject explicit keep masks.
@@ -666,13 +743,17 @@ class SeqFn(Function):
     `cd`, GEMM outputs fp32, and the elementwise kernel that feeds the next GEMM writes `cd` directly."""
 
     @staticmethod
-    def forward(ctx, x, x2, seq, steps, drop: _DropoutState, name: str, cd, *params):
+    def forward(ctx, x, x2, seq, steps, drop: _DropoutState, name: str, cd, x_lp, x2_lp, want_lp: bool, *params):
+        # x_lp / x2_lp: the same values already in the compute dtype (written by the producing kernel): no cast launch;
+        # want_lp: also return the output in the compute dtype (from the last kernel of the chain) for the next chain
         training = seq.training
         pi = 0
         tape = []
         cur = K.cast(_c(x), torch.float32)
-        a = K.cast(cur, cd)
-        a2 = None if x2 is None else K.cast(K.cast(_c(x2), torch.float32), cd)
+        a = x_lp if (x_lp is not None and x_lp.dtype == cd) else K.cast(cur, cd)
+        a2 = None if x2 is None else (x2_lp if (x2_lp is not None and x2_lp.dtype == cd)
+                                      else K.cast(K.cast(_c(x2), torch.float32), cd))
+        out_lp = None
         n = len(steps)
         for si, st in enumerate(steps):
             last = si == n - 1
@@ -699,10 +780,14 @@ class SeqFn(Function):
                 mask, seed, off = drop.next(f"{name}.{didx}", cur.shape) if p > 0 else (None, 0, 0)
                 if training and bn.track_running_stats and bn.num_batches_tracked is not None:
                     bn.num_batches_tracked += 1
-                y, mean, rstd, mask = K.bn_act_fwd(cur, gamma.detach(), beta.detach(), bn.running_mean, bn.running_var,
-                                                   0.1 if bn.momentum is None else bn.momentum, bn.eps, training, order,
-                                                   p, mask, seed, off, out_dt,
-                                                   rng_state=(drop.state(cur.device) if (p > 0 and mask is None) else None))
+                lp_here = want_lp and last and out_dt == torch.float32 and cd == torch.bfloat16
+                res = K.bn_act_fwd(cur, gamma.detach(), beta.detach(), bn.running_mean, bn.running_var,
+                                   0.1 if bn.momentum is None else bn.momentum, bn.eps, training, order,
+                                   p, mask, seed, off, out_dt,
+                                   rng_state=(drop.state(cur.device) if (p > 0 and mask is None) else None), want_lp=lp_here)
+                y, mean, rstd, mask = res[:4]
+                if lp_here:
+                    out_lp = res[4]
                 tape.append(("bn_act", cur, gamma.detach(), beta.detach(), mean, rstd, training, order, p, mask, pidx))
                 cur, a = (None, y) if nxt_is_linear else (y, None)
             elif kind == "act":
@@ -725,15 +810,21 @@ class SeqFn(Function):
         ctx.has_x2 = x2 is not None
         ctx.in_dtypes = (x.dtype, None if x2 is None else x2.dtype)
         ctx.in_shapes = (x.shape, None if x2 is None else x2.shape)
+        if want_lp:
+            if out_lp is None and cd != torch.float32:
+                out_lp = K.cast(cur, cd)
+            if out_lp is not None:
+                ctx.mark_non_differentiable(out_lp)
+            return cur, out_lp
         return cur
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dlp=None):
         tape, cd = ctx.tape, ctx.cd
         ctx.tape = None
         grads: List[Optional[Tensor]] = [None] * ctx.n_params
-        need = ctx.needs_input_grad[7:]
+        need = ctx.needs_input_grad[10:]
         d = K.cast(_c(dy), torch.float32)          # fp32 unless an elementwise backward wrote cd for a GEMM
         main = torch.cuda.current_stream(dy.device)
         side = _side_stream(dy.device)
@@ -804,12 +895,15 @@ class SeqFn(Function):
             dx = K.cast(dx, ctx.in_dtypes[0]).view(ctx.in_shapes[0])
         if dx2 is not None:
             dx2 = K.cast(dx2, ctx.in_dtypes[1]).view(ctx.in_shapes[1])
-        return (dx, dx2, None, None, None, None, None) + tuple(grads)
+        return (dx, dx2, None, None, None, None, None, None, None, None) + tuple(grads)
 
 
 def sequential(x: Tensor, seq: nn.Sequential, drop: _DropoutState, name: str, cd: torch.dtype,
-               x2: Optional[Tensor] = None) -> Tensor:
-    """Run an nn.Sequential (parameter container) on the CUDA kernels; fp32 in, fp32 out."""
+               x2: Optional[Tensor] = None, x_lp: Optional[Tensor] = None, x2_lp: Optional[Tensor] = None,
+               want_lp: bool = False):
+    """Run an nn.Sequential (parameter container) on the CUDA kernels; fp32 in, fp32 out.
+    x_lp / x2_lp: optional copies of x / x2 in the compute dtype (saves the cast launch); want_lp: return
+    (out, out in the compute dtype or None) -- the copy comes out of the chain's last kernel."""
     steps = getattr(seq, "_mmsa_plan", None)
     if steps is None:
         steps = _plan(seq)
@@ -822,7 +916,7 @@ def sequential(x: Tensor, seq: nn.Sequential, drop: _DropoutState, name: str, cd
                 params.append(st[1].bias)
         elif st[0] == "bn_act":
             params.extend([st[1].weight, st[1].bias])
-    return SeqFn.apply(x, x2, seq, steps, drop, name, cd, *params)
+    return SeqFn.apply(x, x2, seq, steps, drop, name, cd, x_lp, x2_lp, want_lp, *params)
 
 
 # ------------------------------------------------------------------------------------------ losses

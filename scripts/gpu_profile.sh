@@ -4,17 +4,17 @@
 # scripts/summarize_ncu.py distils them into profiles/ on the CPU box.
 mkdir -p gpurun_out
 rm -f gpurun_out/*.ncu-rep
-CMD="python bench.py --steps 2 --warmup 1 --no-graph"
+CMD="python bench.py --steps 2 --warmup 1 --no-graph --sustained-seconds 0 --no-extra-configs --no-torch-eager"
 $CMD > gpurun_out/plain.log 2> gpurun_out/plain.err || { echo "plain run failed"; tail -5 gpurun_out/plain.err; exit 1; }
-# 96 launches per step; skip TrainStep.warmup (2 iterations x 2 slots) and take about 3 steps
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 300 --csv \
+# ~110 library launches (+ ~40 torch plumbing kernels) per step; skip TrainStep.warmup (2 iterations x 2 slots) and take about 3 steps
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 600 -c 450 --csv \
     --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo "launch list exit=$?"
 # DRAM bytes of the 38 tcgen05 GEMM launches of one step (after the 4 warm-up steps)
 timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
     -k regex:gemm_tcgen05 -s 152 -c 38 --csv --log-file gpurun_out/gemm_traffic.csv $CMD > gpurun_out/ncu_traffic.log 2>&1
 echo "gemm traffic exit=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 152 -c 14 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 152 -c 38 \
     -f -o gpurun_out/prof_gemm $CMD > gpurun_out/ncu_gemm.log 2>&1
 echo "gemm capture exit=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:gate_ln_pool|attn_" -s 16 -c 8 \
