@@ -135,7 +135,8 @@ def test_native_against_reference_goldens(cuda_device, case):
     for k, b in model.named_buffers():
         if b.is_floating_point():
             want32 = c["buffers_after"][k].float()
-            assert rel_err(b.float(), b64[k]) <= max(1e-5, 3.0 * rel_err(want32, b64[k])), k
+            check_close(f"native_goldens[{case}]", "buffer:" + k, b.float(), b64[k], 1e-5, want32, noise_mult=nm,
+                        why="tiny-batch BatchNorm stack" if c["B"] < 8 else "")
         else:
             assert torch.equal(b.cpu(), c["buffers_after"][k]), k
     model.eval()
@@ -143,7 +144,7 @@ def test_native_against_reference_goldens(cuda_device, case):
         ea, ev = model(*xs)
     # eval mode reads the running statistics written by the train step above; with B = 2 those carry
     # the amplified noise of the 2-sample variance
-    etol = 1e-5 if c["B"] >= 8 else 3.0 * max(rel_err(c["arousal"], r64["arousal"]), 1e-5)
+    etol = 1e-5 if c["B"] >= 8 else nm * max(rel_err(c["arousal"], r64["arousal"]), rel_err(c["valence"], r64["valence"]), 1e-5)
     assert rel_err(ea, c["eval_arousal"]) <= etol and rel_err(ev, c["eval_valence"]) <= etol
 
 
