@@ -22,7 +22,13 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar) { asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar) { asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__global__ void fill_kernel(uint32_t* p, size_t n, uint32_t seed) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t x = (uint32_t)i * 2654435761u + seed; x ^= x >> 15; x *= 2246822519u; x ^= x >> 13;
+    p[i] = (x & 0x3FFF3FFFu) | 0x3C003C00u;     // two finite bf16 values with random mantissas
+  }
+}
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) { uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r; }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -103,11 +109,13 @@ int main() {
   void* fnp = nullptr; cudaDriverEntryPointQueryResult q;
   CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fnp, cudaEnableDefault, &q));
   EncodeTiledFn fn = (EncodeTiledFn)fnp;
-  const int kblocks = 12, rows_a = 32768;                    // K = 768: the E x E GEMM family
+  const int kblocks = 12, rows_a = 262144;                   // A = 403 MB: far beyond the 126 MB L2, streams from HBM                    // K = 768: the E x E GEMM family
   const uint64_t K = 64ull * kblocks;
   __nv_bfloat16 *A, *B;
   CK(cudaMalloc(&A, (size_t)rows_a * K * 2)); CK(cudaMalloc(&B, (size_t)128 * K * 2));
-  CK(cudaMemset(A, 0, (size_t)rows_a * K * 2)); CK(cudaMemset(B, 0, (size_t)128 * K * 2));
+  fill_kernel<<<1024, 256>>>((uint32_t*)A, (size_t)rows_a * K / 2, 1u);       // incompressible operands (zeros would be)
+  fill_kernel<<<64, 256>>>((uint32_t*)B, (size_t)128 * K / 2, 2u);
+  CK(cudaDeviceSynchronize());
   const int smem = STAGES * STAGE_BYTES + 1024 + 256;
   CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   CK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));

@@ -62,6 +62,8 @@ KEYS = [
     ("dram__bytes_write.sum", "dram wr"),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
     ("lts__t_sector_hit_rate.pct", "L2 hit %"),
+    ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 thr %"),
+    ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "L1/smem thr %"),
     ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor %"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps %"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"),
