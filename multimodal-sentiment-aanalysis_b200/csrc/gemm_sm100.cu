@@ -110,6 +110,29 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uin
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand from TENSOR MEMORY (lane = row of A, every 32-bit column holds two consecutive K elements), B from shared memory
+__device__ __forceinline__ void tc_mma_bf16_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return (uint32_t)v;
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -159,7 +182,12 @@ struct GemmParams {
 // its own 128 rows of A and HALF of the B tile (BN/2 rows), the leader's MMA reads both halves, and each CTA's TMEM
 // receives its 128 accumulator rows.  Operand bytes pulled from L2 per FLOP drop by a third against 128 x 256 tiles --
 // the L2->SM path (~6.3 KB/clk chip-wide), not the tensor pipe, is what bounds the 1-CTA kernel.
-template <int BN, bool A_MN, bool B_MN, bool PAIR = false>
+// A_TM (probe for the 2-CTA weight gradients, MMSA_WGRAD_A_TMEM=1): the MN-major A tile staged by TMA is TRANSPOSED INTO
+// TENSOR MEMORY by the (otherwise idle) epilogue warps -- ld.shared.u16 down the K axis, two elements per 32-bit column,
+// tcgen05.st -- and the MMAs take A from TMEM.  Motivation: an MN-major A read from shared memory costs this tensor core
+// ~905-960 cycles per 64-deep k-block against ~646 for a K-major one (scripts/mma_rate_probe.py); A in TMEM has no major.
+// Measured: correct, but slower than the shared-memory descriptor (see gemm_bf16_sm100_wgrad_pair), so it is off by default.
+template <int BN, bool A_MN, bool B_MN, bool PAIR = false, bool A_TM = false>
 struct GemmCfg {
   static constexpr int CTA_N = PAIR ? BN / 2 : BN;    // B rows (output columns) staged by one CTA
   static constexpr int A_BYTES = BM * BK * 2;
@@ -169,18 +197,22 @@ struct GemmCfg {
   // alternately) and one residual slab 32 x 32 bf16 (2 KB), all moved by TMA so that global traffic is line-granular
   static constexpr int OUT_SLAB = 4096, RES_SLAB = 2048;
   static constexpr int EPI_BYTES = kEpiWarps * (OUT_SLAB + RES_SLAB);
-  static constexpr int STAGE_BUDGET = 227 * 1024 - EPI_BYTES - 2048 /*ones*/ - 2048 /*align*/ - 256 - 2 * BN * 4;
+  static constexpr int BAR_BYTES = 384;           // mbarriers (8 B each) + the TMEM base pointer
+  static constexpr int STAGE_BUDGET = 227 * 1024 - EPI_BYTES - 2048 /*ones*/ - 2048 /*align*/ - BAR_BYTES - 2 * BN * 4;
   static constexpr int STAGES = STAGE_BUDGET / STAGE_BYTES > 8 ? 8 : STAGE_BUDGET / STAGE_BYTES;
   // accumulator buffers in TMEM: two, so the epilogue of tile i overlaps the main loop of tile i+1 --
   // except the 256-wide wgrad tile (A MN-major), which runs one tile per CTA under split-K anyway and
   // needs the columns for the bias-gradient accumulator
   static constexpr int NACC = (A_MN && BN == 256) ? 1 : 2;
   static constexpr bool COLSUM_OK = A_MN && (NACC * (BN + 16) <= 512);
-  static constexpr int TMEM_NEED = NACC * BN + (COLSUM_OK ? NACC * 16 : 0);
+  static constexpr int A_SLOTS = 6, A_SLOT_COLS = BK / 2;       // A_TM: ring of A k-blocks in TMEM (32 columns each)
+  static constexpr int A_COL0 = 320;                            // behind the accumulator (256) and the bias-gradient columns
+  static_assert(!A_TM || (BN == 256 && NACC == 1 && PAIR && A_MN), "A_TM is the 2-CTA 256-wide weight-gradient configuration");
+  static constexpr int TMEM_NEED = A_TM ? A_COL0 + A_SLOTS * A_SLOT_COLS : NACC * BN + (COLSUM_OK ? NACC * 16 : 0);
   static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
   static constexpr int ONES_BYTES = 2048;         // 16 rows x 128 B of bf16 1.0 (any swizzle of ones is ones)
   static constexpr int BIAS_BYTES = 2 * BN * 4;   // double-buffered bias tile for the epilogue warps
-  static constexpr int AUX_BYTES = ((256 + BIAS_BYTES + 1023) / 1024) * 1024;    // barriers + bias, padded to 1 KB
+  static constexpr int AUX_BYTES = ((BAR_BYTES + BIAS_BYTES + 1023) / 1024) * 1024;    // barriers + bias, padded to 1 KB
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + ONES_BYTES + AUX_BYTES + EPI_BYTES + 1024 /*align*/;
   // split-K finish: each CTA parks its fp32 partial tile in the (then idle) stage buffers
   static constexpr int PART_LD = BN + 4;          // padded row (floats): conflict-free 16-byte row writes
@@ -225,12 +257,12 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template <int BN, bool A_MN, bool B_MN, bool PAIR>
+template <int BN, bool A_MN, bool B_MN, bool PAIR, bool A_TM = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                     const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
                     const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
-  using Cfg = GemmCfg<BN, A_MN, B_MN, PAIR>;
+  using Cfg = GemmCfg<BN, A_MN, B_MN, PAIR, A_TM>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int TILE_M = PAIR ? 2 * BM : BM;          // rows of the output tile a work unit covers
   extern __shared__ uint8_t smem_raw[];
@@ -247,10 +279,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t part_full_bar = bar_base + 8u * (2 * STAGES + 4);
   const uint32_t read_done_bar = bar_base + 8u * (2 * STAGES + 5);
   auto res_bar = [&](int w) { return bar_base + 8u * (2 * STAGES + 6 + w); };   // per epilogue warp
+  // A_TM: afull[STAGES] (this CTA's A tile has landed), aready[A_SLOTS] (leader: both CTAs' warps have written the TMEM slot),
+  //       afree[A_SLOTS] (the MMAs that read the slot have retired)
+  auto afull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 15 + s); };
+  auto aready_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + 15 + a); };
+  auto afree_bar = [&](int a) { return bar_base + 8u * (3 * STAGES + 15 + Cfg::A_SLOTS + a); };
+  static_assert(8 * (3 * STAGES + 15 + 2 * Cfg::A_SLOTS) <= Cfg::BAR_BYTES, "barrier area too small");
   uint8_t* aux = smem_al + STAGES * Cfg::STAGE_BYTES + Cfg::ONES_BYTES;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(aux + 8 * (2 * STAGES + 14));
   const uint32_t epi_base = bar_base + Cfg::AUX_BYTES;      // 1024-aligned: [warp][buf] out slabs, then res slabs
-  float* bias_s = reinterpret_cast<float*>(aux + 256);   // [2][BN]
+  float* bias_s = reinterpret_cast<float*>(aux + Cfg::BAR_BYTES);   // [2][BN]
   const bool colsum_on = Cfg::COLSUM_OK && p.colsum != nullptr;
   if (colsum_on) {   // constant tile of ones (generic-proxy writes, made visible to the tensor core below)
     uint32_t* o = reinterpret_cast<uint32_t*>(smem_al + STAGES * Cfg::STAGE_BYTES);
@@ -283,6 +321,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     mbar_init(part_full_bar, (uint32_t)S);
     mbar_init(read_done_bar, (uint32_t)S);
     for (int w = 0; w < kEpiWarps; ++w) mbar_init(res_bar(w), 1);
+    if (A_TM) {
+      for (int s = 0; s < STAGES; ++s) mbar_init(afull_bar(s), 1);
+      for (int a = 0; a < Cfg::A_SLOTS; ++a) { mbar_init(aready_bar(a), 2 * kEpiWarps); mbar_init(afree_bar(a), 1); }
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -339,11 +381,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           // PAIR: both CTAs' copies complete on the LEADER's barrier, which expects the bytes of both
           const uint32_t fbar = PAIR ? mapa_u32(full_bar(stage), leader) : full_bar(stage);
           if (!PAIR) mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-          else if (pair_rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+          else if (pair_rank == 0) mbar_expect_tx(full_bar(stage), A_TM ? 2 * Cfg::B_BYTES : 2 * Cfg::STAGE_BYTES);
           const bool second = kb >= p.kb_a1;
           const CUtensorMap* ma = second ? &tmA2 : &tmA;
           const int ka = (second ? kb - p.kb_a1 : kb) * BK;
-          if (PAIR) {
+          if (A_TM) {
+            // A lands on THIS CTA's afull barrier (its own warps transpose it into TMEM); B on the leader's full barrier
+            mbar_expect_tx(afull_bar(stage), Cfg::A_BYTES);
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * 8192, ma, m0 + c * 64, ka, afull_bar(stage));
+#pragma unroll
+            for (int c = 0; c < Cfg::CTA_N / 64; ++c) tma_load_2d_pair(sb + c * 8192, &tmB, n0 + c * 64, kb * BK, fbar);
+          } else if (PAIR) {
             if (A_MN) {
 #pragma unroll
               for (int c = 0; c < BM / 64; ++c) tma_load_2d_pair(sa + c * 8192, ma, m0 + c * 64, ka, fbar);
@@ -386,6 +435,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint64_t ones_desc = make_sdesc(ones_base, 0, 1024);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+      int aslot = 0; uint32_t aphase = 0;                  // A_TM: TMEM ring position
+      constexpr uint32_t idesc_ts = (1u << 4) | (1u << 7) | (1u << 10) | ((B_MN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+                                    ((uint32_t)(TILE_M >> 4) << 24);
+      constexpr uint32_t idesc_ones_ts = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
       for (int unit = unit0; unit < units_total; unit += unit_stride) {
         const bool cs = colsum_on && ((unit % tiles_mn) % p.tiles_n) == 0;
         if (PAIR) mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);     // local + remote epilogue warps
@@ -397,9 +450,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int ukb1 = KS > 1 ? min(p.kb_total, ukb0 + p.kb_per_split) : kb1;
         for (int kb = ukb0; kb < ukb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
+          if (A_TM) mbar_wait_cluster(aready_bar(aslot), aphase);      // both CTAs' warps have written this k-block of A to TMEM
           tc_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sb = sa + Cfg::A_BYTES;
+          if (A_TM) {
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint32_t at = tmem_base + (uint32_t)(Cfg::A_COL0 + aslot * Cfg::A_SLOT_COLS + k * (UMMA_K / 2));
+              const uint64_t bd = make_sdesc(sb + k * (UMMA_K * 128), 8192, 1024);
+              tc_mma_bf16_ts_pair(d_tmem, at, bd, idesc_ts, (kb > ukb0 || k > 0) ? 1u : 0u);
+              if (cs) tc_mma_bf16_ts_pair(cs_tmem, at, ones_desc, idesc_ones_ts, (kb > ukb0 || k > 0) ? 1u : 0u);
+            }
+            tc_commit_pair(afree_bar(aslot), pair_mask);                // the TMEM slot may be rewritten once these retire
+            if (++aslot == Cfg::A_SLOTS) { aslot = 0; aphase ^= 1u; }
+          } else
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // K-major: advance 32 bytes inside the 128B swizzle row; MN-major: advance 16 rows of 128B
@@ -437,8 +502,43 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t epi_it = 0, res_it = 0;                   // chunks / residual slabs this warp has pushed through its staging
     float* part = reinterpret_cast<float*>(smem_al);   // [BM][PART_LD] fp32 + [BM] colsum (split-K only)
     float* part_cs = part + BM * Cfg::PART_LD;
+    int tstage = 0; uint32_t tphase = 0, aslot = 0, aphase = 0;       // A_TM: smem stage / TMEM slot this warp transposes next
     for (int unit = unit0; unit < units_total; unit += unit_stride) {
       const int tile = unit % tiles_mn;
+      if (A_TM) {
+        // ---- A tile (MN-major in shared memory: [64-row chunk][k][64 rows], 128B-swizzled) -> TMEM, K-major by construction.
+        // Thread = row m of the tile (TMEM lane), warps w / w+4 take the k ranges [0,32) / [32,64): 32 ld.shared.u16 down the
+        // K axis (the 32 lanes of a warp read 64 contiguous bytes: conflict-free), packed two per column, one tcgen05.st.
+        const int ukb0 = KS > 1 ? (unit / tiles_mn) * p.kb_per_split : kb0;
+        const int ukb1 = KS > 1 ? min(p.kb_total, ukb0 + p.kb_per_split) : kb1;
+        const int m = quad * 32 + lane;
+        const uint32_t row_off = (uint32_t)((m >> 6) * 8192 + (m & 7) * 2);
+        const uint32_t unit16 = (uint32_t)((m & 63) >> 3);
+        for (int kb = ukb0; kb < ukb1; ++kb) {
+          mbar_wait(afull_bar(tstage), tphase);
+          mbar_wait(afree_bar((int)aslot), aphase ^ 1u);
+          tc_fence_after();
+          const uint32_t sa = smem_base + tstage * Cfg::STAGE_BYTES + row_off;
+          uint32_t r[16], e[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {        // all 32 loads in flight before the first use (a warp issues in order)
+            const int k = hh * 32 + j;
+            e[j] = lds_u16(sa + (uint32_t)(k * 128) + ((unit16 ^ (uint32_t)(k & 7)) << 4));
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] = e[2 * j] | (e[2 * j + 1] << 16);
+          tmem_st16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(Cfg::A_COL0 + aslot * Cfg::A_SLOT_COLS + hh * 16), r);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (pair_rank == 0) mbar_arrive(aready_bar((int)aslot));
+            else mbar_arrive_remote_relaxed(mapa_u32(aready_bar((int)aslot), leader));
+          }
+          if (++tstage == STAGES) { tstage = 0; tphase ^= 1u; }
+          if (++aslot == (uint32_t)Cfg::A_SLOTS) { aslot = 0; aphase ^= 1u; }
+        }
+      }
       const int ks_row = KS > 1 ? (unit / tiles_mn) * p.M : 0;       // workspace split-K: row offset of this slice's slab
       const int m0 = (tile / p.tiles_n) * TILE_M + pair_rank * BM, n0 = (tile % p.tiles_n) * BN;
       // stage this tile's bias slice in shared memory while the main loop is still running
@@ -841,9 +941,9 @@ bool gemm_bf16_sm100_supported(const GemmDesc& d) {
 
 int gemm_tc_max_clusters(int size);
 
-template <int BN, bool A_MN, bool B_MN, bool PAIR = false>
+template <int BN, bool A_MN, bool B_MN, bool PAIR = false, bool A_TM = false>
 static int launch_gemm(const GemmDesc& d, int splits_req, cudaStream_t s, int ksplit = 1) {
-  using Cfg = GemmCfg<BN, A_MN, B_MN, PAIR>;
+  using Cfg = GemmCfg<BN, A_MN, B_MN, PAIR, A_TM>;
   constexpr int TILE_M = PAIR ? 2 * BM : BM;
   CUtensorMap tmA, tmA2, tmB;
   // K-major operand [rows, K]: inner = K, outer = rows, box = {64, rows_tile}
@@ -903,7 +1003,7 @@ static int launch_gemm(const GemmDesc& d, int splits_req, cudaStream_t s, int ks
     if (!Cfg::COLSUM_OK) { set_error("mmsa: internal: colsum requested on a tile shape without TMEM room (BN=%d)", BN); return MMSA_ERR_ARG; }
     p.colsum = d.colsum;
   }
-  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, PAIR>;
+  auto kern = gemm_tcgen05_kernel<BN, A_MN, B_MN, PAIR, A_TM>;
   static PerDeviceOnce attr_set;
   if (attr_set.pending()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -1045,6 +1145,13 @@ int gemm_bf16_sm100_wgrad_pair(const GemmDesc& d, int ksplit, int* real_ksplit, 
   if (ksplit < 1) ksplit = 1;
   const int64_t per = ceil_div(kb_total, ksplit);
   if (real_ksplit) *real_ksplit = (int)ceil_div(kb_total, per);
+  // MMSA_WGRAD_A_TMEM=1 (probe, off by default): transpose the A tile into TENSOR MEMORY and issue A-from-TMEM MMAs.
+  // Correct (tests/test_gpu_kernels.py::test_wgrad_a_from_tmem_probe) but 11-17 % SLOWER than the MN-major shared-memory
+  // descriptor on every configs[1] weight gradient: the extra hop (TMA -> warps -> TMEM -> MMA) lengthens the time a stage
+  // stays occupied, and the ring is latency-bound
+  static int a_tm = -1;
+  if (a_tm < 0) { const char* e = getenv("MMSA_WGRAD_A_TMEM"); a_tm = e ? atoi(e) : 0; }
+  if (a_tm) return launch_gemm<256, true, true, true, true>(d, 1, s, ksplit);
   return launch_gemm<256, true, true, true>(d, 1, s, ksplit);
 }
 

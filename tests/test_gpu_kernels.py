@@ -774,3 +774,28 @@ def test_attention_probability_dropout_philox_redraw(cuda_device, D):
     k.attn_dropout_bwd(q, kk, v, o, do, lse, B, H, Lq, Lk, D, *want, p, mask, 0, 0, None)
     for a, b in zip(got, want):
         assert torch.equal(a, b)
+
+
+def test_wgrad_a_from_tmem_probe(cuda_device):
+    """MMSA_WGRAD_A_TMEM=1 (probe, off by default): the 2-CTA weight gradient with its A tile transposed into tensor memory by
+    the epilogue warps (tcgen05.st) and A-from-TMEM MMAs.  The switch is read once per process, so the check runs in a child
+    process: result against a float64 product, incl. the bias gradient of the ones-tile MMA and a ragged token count."""
+    import subprocess
+    import sys
+    code = r"""
+import sys, torch
+sys.path.insert(0, %r)
+from mmsa import kernels as K
+dev = torch.device("cuda:0")
+g = torch.Generator().manual_seed(3)
+for (T, N, Kd) in ((4100, 768, 768), (8192, 256, 520)):
+    dy = torch.randn(T, N, generator=g).to(dev).bfloat16(); x = torch.randn(T, Kd, generator=g).to(dev).bfloat16()
+    dw, db = K.linear_wgrad(dy, x)
+    rw = dy.double().T @ x.double(); rb = dy.double().sum(0)
+    ew = float((dw.double() - rw).abs().max() / rw.abs().max()); eb = float((db.double() - rb).abs().max() / rb.abs().max())
+    assert ew <= 2e-3 and eb <= 2e-3, (T, N, Kd, ew, eb)
+print("ok")
+""" % os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "multimodal-sentiment-aanalysis_b200")
+    env = dict(os.environ, MMSA_WGRAD_A_TMEM="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
