@@ -199,7 +199,10 @@ struct GemmCfg {
   static constexpr int EPI_BYTES = kEpiWarps * (OUT_SLAB + RES_SLAB);
   static constexpr int BAR_BYTES = 384;           // mbarriers (8 B each) + the TMEM base pointer
   static constexpr int STAGE_BUDGET = 227 * 1024 - EPI_BYTES - 2048 /*ones*/ - 2048 /*align*/ - BAR_BYTES - 2 * BN * 4;
-  static constexpr int STAGES = STAGE_BUDGET / STAGE_BYTES > 8 ? 8 : STAGE_BUDGET / STAGE_BYTES;
+#ifndef MMSA_STAGE_CUT
+#define MMSA_STAGE_CUT 0          // probe: build with -DMMSA_STAGE_CUT=1 to see how sensitive a GEMM is to ring depth
+#endif
+  static constexpr int STAGES = (STAGE_BUDGET / STAGE_BYTES > 8 ? 8 : STAGE_BUDGET / STAGE_BYTES) - MMSA_STAGE_CUT;
   // accumulator buffers in TMEM: two, so the epilogue of tile i overlaps the main loop of tile i+1 --
   // except the 256-wide wgrad tile (A MN-major), which runs one tile per CTA under split-K anyway and
   // needs the columns for the bias-gradient accumulator
@@ -217,7 +220,7 @@ struct GemmCfg {
   // split-K finish: each CTA parks its fp32 partial tile in the (then idle) stage buffers
   static constexpr int PART_LD = BN + 4;          // padded row (floats): conflict-free 16-byte row writes
   static constexpr int PART_BYTES = BM * PART_LD * 4 + BM * 4;
-  static_assert(PART_BYTES <= STAGES * STAGE_BYTES, "partial tile must fit in the stage buffers");
+  static_assert(MMSA_STAGE_CUT != 0 || PART_BYTES <= STAGES * STAGE_BYTES, "partial tile must fit in the stage buffers");
 };
 
 // ---- cluster helpers (split-K over a thread-block cluster, reduction through distributed shared memory)

@@ -10,7 +10,7 @@ import re
 from ctypes import c_double, c_float, c_int, c_int64, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmmsa.so")
+LIB_PATH = os.environ.get("MMSA_LIB_PATH") or os.path.join(_HERE, "libmmsa.so")      # override: A/B builds of the library (probes)
 HEADER_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "include", "mmsa.h"))
 
 F32, BF16 = 0, 1
