@@ -163,7 +163,12 @@ wgrad_reduce_kernel(const float* __restrict__ ws, int ksplit, int64_t rows, int6
 static int wgrad_pair_ksplit(int64_t Nw, int64_t Kw, int64_t tokens, const float* dw, int64_t lddw) {
   if (Nw % 256 != 0 || Kw % 4 != 0 || Kw < 512 || tokens < 4096 || lddw % 4 != 0 || ((uintptr_t)dw % 16) != 0) return 0;
   const int64_t tiles = (Nw / 256) * ceil_div(Kw, 256);
-  const int pairs = gemm_tc_max_clusters(2);
+  int pairs = gemm_tc_max_clusters(2);
+  // MMSA_WGRAD_PAIRS (tuning probe): CTA pairs a weight gradient may occupy.  The weight gradients run on a helper stream
+  // beside the main backward chain; leaving some SMs free lets main-chain kernels start without waiting for a 45 us unit.
+  static int pairs_env = -1;
+  if (pairs_env < 0) { const char* e = getenv("MMSA_WGRAD_PAIRS"); pairs_env = e ? atoi(e) : 0; }
+  if (pairs_env > 0 && pairs_env < pairs) pairs = pairs_env;
   int ks = (int)(pairs / tiles);
   if (ks > kMaxSplitsWs) ks = kMaxSplitsWs;
   const int64_t kb = ceil_div(tokens, 64);

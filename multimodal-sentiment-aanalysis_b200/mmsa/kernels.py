@@ -23,13 +23,15 @@ def dt(t_or_dtype) -> int:
     raise TypeError(f"mmsa: unsupported dtype {d}")
 
 
-_DEV = None      # device of the tensors of the call being marshalled (set by _check)
+import threading
+
+_TLS = threading.local()      # .dev: device of the tensors of the call being marshalled on THIS thread (set by _check)
 
 
 def _stream() -> int:
     """current stream of the device the call's tensors live on (kernels launch on the CURRENT device, which _check has
-    verified to be that device)."""
-    return torch.cuda.current_stream(_DEV).cuda_stream
+    verified to be that device).  Thread-local: nn.DataParallel drives one replica per thread."""
+    return torch.cuda.current_stream(getattr(_TLS, "dev", None)).cuda_stream
 
 
 def _p(t: Optional[Tensor]) -> Optional[int]:
@@ -37,7 +39,6 @@ def _p(t: Optional[Tensor]) -> Optional[int]:
 
 
 def _check(*ts: Optional[Tensor]):
-    global _DEV
     dev = None
     for t in ts:
         if t is None:
@@ -52,7 +53,7 @@ def _check(*ts: Optional[Tensor]):
         if dev.index != torch.cuda.current_device():
             raise _lib.MmsaError(f"mmsa: tensors live on {dev} but the current CUDA device is "
                                  f"cuda:{torch.cuda.current_device()}; wrap the call in torch.cuda.device({dev.index})")
-        _DEV = dev
+        _TLS.dev = dev
 
 
 def cast(x: Tensor, dtype: torch.dtype) -> Tensor:
