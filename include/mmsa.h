@@ -108,6 +108,12 @@ int mmsa_linear_wgrad(int dtype, int64_t M, int64_t N, int64_t K,
                       const void* dy, int64_t lddy, const void* x, int64_t ldx,
                       float* dw, int64_t lddw, float* db, void* workspace, void* stream);
 
+/* dw[N, K+K2] = dy^T [x | x2] (+ db): weight gradient of a Linear over the feature-axis concat of two tensors (the gate's
+ * cat[q, attn], MultimodalModel.py:147) without the concat.  workspace: mmsa_linear_wgrad_workspace(dtype, M, N, K + K2). */
+int mmsa_linear_wgrad2(int dtype, int64_t M, int64_t N, int64_t K, int64_t K2,
+                       const void* dy, int64_t lddy, const void* x, int64_t ldx, const void* x2, int64_t ldx2,
+                       float* dw, int64_t lddw, float* db, void* workspace, void* stream);
+
 /* ---- multi-head attention core (torch F.multi_head_attention_forward need_weights branch,
  *      reached from MultimodalModel.py:139-143, ME-MHACL/model.py:71) ------------------------
  * q:[B,Lq,H*D] row stride ldq, k/v:[B,Lk,H*D] row strides ldk/ldv (K and V may alias one packed
@@ -163,8 +169,11 @@ int mmsa_gate_ln_bwd(int dtype, int64_t M, int64_t E, const void* dy, int64_t dy
                      const void* g, const void* q, const void* attn,
                      const float* gamma, const float* mean, const float* rstd,
                      const void* dq_bcast, int64_t bcast_rows, const void* dq_add,
-                     void* dq_part, void* dattn_part, void* dgate_pre,
+                     void* dq_part, void* dattn_part, int64_t ld_parts, void* dgate_pre,
                      float* dgamma, float* dbeta, float* partials, void* stream);
+/* ld_parts: row stride (elements; 0 = E) of dq_part and dattn_part -- they may be the two column halves of ONE [M, 2E]
+ * buffer, so that the gate's two input gradients dgate W[:, :E] + dq_part and dgate W[:, E:] + dattn_part come out of a
+ * single N = 2E GEMM with that buffer as its residual. */
 
 /* Fused form for a block whose output only feeds a token mean-pool (the text+image path pools t' and
  * v' straight away): y is never written; pooled_y[b,:] = mean over the L rows of sample b of LN(u)
@@ -179,7 +188,7 @@ int mmsa_gate_ln_pool_fwd(int dtype, int64_t B, int64_t L, int64_t E, const void
 int mmsa_gate_ln_pool_bwd(int dtype, int64_t B, int64_t L, int64_t E, const float* dpooled_y,
                           const float* dpooled_q, const void* dq_add, const void* g, const void* q,
                           const void* attn, const float* gamma, const float* mean, const float* rstd,
-                          void* dq_part, void* dattn_part, void* dgate_pre, float* dgamma, float* dbeta,
+                          void* dq_part, void* dattn_part, int64_t ld_parts, void* dgate_pre, float* dgamma, float* dbeta,
                           float* partials, void* stream);
 
 /* ---- residual add + LayerNorm, positional table (the encoder tail in front of the path: Subnetwork,

@@ -173,6 +173,8 @@ struct GemmDesc {
   const void* A; int64_t lda; bool a_mn_major;   // a_mn_major: A stored [K,M] (element (m,k) at A[k*lda+m])
   const void* A2; int64_t lda2;                   // optional second K-segment of A (K-major only)
   const void* B; int64_t ldb; bool b_mn_major;   // K-major: B[n*ldb+k]; MN-major: B[k*ldb+n]
+  const void* B2; int64_t ldb2; int64_t N1;       // optional second N-segment of an MN-major B (output columns >= N1 read B2):
+                                                  // the weight gradient of a Linear over cat[x, x2] without the concat
   const float* bias;                              // [N] or null
   const void* residual; int64_t ldr;              // [M,N] out dtype family (in dtype), or null
   int act;

@@ -176,6 +176,7 @@ struct GemmParams {
   // its bias-gradient partial to colsum[ks*M + m]; a second kernel sums the slices in slice order (deterministic).
   int ksplit;
   int prefetch;             // 1: the producer L2-prefetches the A tile of its NEXT work unit while it stages the current one
+  int n_split;              // > 0: output columns >= n_split take their B operand from the second tensor map (tmB2)
 };
 
 // PAIR: 2-CTA mode (tcgen05 cta_group::2).  Two CTAs on the SMs of one TPC compute a 256 x BN tile together: each stages
@@ -263,8 +264,8 @@ __device__ __forceinline__ void cluster_sync_all() {
 template <int BN, bool A_MN, bool B_MN, bool PAIR, bool A_TM = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-                    const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
-                    const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmB2,
+                    const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const GemmParams p) {
   using Cfg = GemmCfg<BN, A_MN, B_MN, PAIR, A_TM>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int TILE_M = PAIR ? 2 * BM : BM;          // rows of the output tile a work unit covers
@@ -360,6 +361,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         const int ukb0 = KS > 1 ? (unit / tiles_mn) * p.kb_per_split : kb0;
         const int ukb1 = KS > 1 ? min(p.kb_total, ukb0 + p.kb_per_split) : kb1;
+        // B from two tensors along N (weight gradient over cat[x, x2]): tiles right of n_split read the second one
+        const bool b_second = B_MN && p.n_split > 0 && (tile % p.tiles_n) * BN >= p.n_split;
+        const CUtensorMap* mb = b_second ? &tmB2 : &tmB;
+        const int nb0 = n0 - (b_second ? p.n_split : 0);
         // probe (MMSA_GEMM_PREFETCH=1, off by default): L2-prefetch the A tile of this CTA's NEXT unit one tile ahead.
         // Measured neutral to -3 % on every configs[1] shape: the ring is not DRAM-latency bound
         const int next_unit = unit + unit_stride;
@@ -394,7 +399,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * 8192, ma, m0 + c * 64, ka, afull_bar(stage));
 #pragma unroll
-            for (int c = 0; c < Cfg::CTA_N / 64; ++c) tma_load_2d_pair(sb + c * 8192, &tmB, n0 + c * 64, kb * BK, fbar);
+            for (int c = 0; c < Cfg::CTA_N / 64; ++c) tma_load_2d_pair(sb + c * 8192, mb, nb0 + c * 64, kb * BK, fbar);
           } else if (PAIR) {
             if (A_MN) {
 #pragma unroll
@@ -404,7 +409,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             if (B_MN) {
 #pragma unroll
-              for (int c = 0; c < Cfg::CTA_N / 64; ++c) tma_load_2d_pair(sb + c * 8192, &tmB, n0 + c * 64, kb * BK, fbar);
+              for (int c = 0; c < Cfg::CTA_N / 64; ++c) tma_load_2d_pair(sb + c * 8192, mb, nb0 + c * 64, kb * BK, fbar);
             } else {
               tma_load_2d_pair(sb, &tmB, kb * BK, n0, fbar);
             }
@@ -417,7 +422,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             if (B_MN) {
 #pragma unroll
-              for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * 8192, &tmB, n0 + c * 64, kb * BK, full_bar(stage));
+              for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * 8192, mb, nb0 + c * 64, kb * BK, full_bar(stage));
             } else {
               tma_load_2d(sb, &tmB, kb * BK, n0, full_bar(stage));
             }
@@ -956,8 +961,16 @@ static int launch_gemm(const GemmDesc& d, int splits_req, cudaStream_t s, int ks
   if (d.A2) { if (!make_map(&tmA2, d.A2, d.K2, d.M, d.lda2, BK, BM)) return MMSA_ERR_CUDA; }
   else tmA2 = tmA;
   const int64_t Kt = d.K + (d.A2 ? d.K2 : 0);
-  if (B_MN) { if (!make_map(&tmB, d.B, d.N, Kt, d.ldb, 64, BK)) return MMSA_ERR_CUDA; }
+  const bool two_b = d.B2 != nullptr;
+  if (two_b && (!B_MN || d.N1 <= 0 || d.N1 >= d.N || d.N1 % BN != 0)) {
+    set_error("mmsa: internal: a two-tensor B needs an MN-major B and a split on a tile boundary (N1=%lld, BN=%d)", (long long)d.N1, BN);
+    return MMSA_ERR_ARG;
+  }
+  CUtensorMap tmB2;
+  if (B_MN) { if (!make_map(&tmB, d.B, two_b ? d.N1 : d.N, Kt, d.ldb, 64, BK)) return MMSA_ERR_CUDA; }
   else      { if (!make_map(&tmB, d.B, Kt, d.N, d.ldb, BK, Cfg::CTA_N)) return MMSA_ERR_CUDA; }
+  if (two_b) { if (!make_map(&tmB2, d.B2, d.N - d.N1, Kt, d.ldb2, 64, BK)) return MMSA_ERR_CUDA; }
+  else tmB2 = tmB;
 
   GemmParams p{};
   p.M = (int)d.M; p.N = (int)d.N;
@@ -972,6 +985,7 @@ static int launch_gemm(const GemmDesc& d, int splits_req, cudaStream_t s, int ks
   p.kb_per_split = (int)ceil_div(p.kb_total, splits);
   p.splits = (int)ceil_div(p.kb_total, p.kb_per_split);
   p.ksplit = 1;
+  p.n_split = two_b ? (int)d.N1 : 0;
   {
     static int pf_env = -1;
     if (pf_env < 0) { const char* e = getenv("MMSA_GEMM_PREFETCH"); pf_env = e ? atoi(e) : 0; }      // measured: no gain on B200 (profiles/r02), kept as a probe
@@ -1030,12 +1044,12 @@ static int launch_gemm(const GemmDesc& d, int splits_req, cudaStream_t s, int ks
     const int ncl = units < max_cl ? units : max_cl;
     cfg.gridDim = dim3((unsigned)(ncl * csize));
     ProfScope prof(nm, s, 2.0 * (double)d.M * (double)d.N * (double)Kt);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmB, tmC, tmR, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmB, tmB2, tmC, tmR, p);
     if (e != cudaSuccess) { set_error("mmsa: 2-CTA launch of gemm_tcgen05_kernel failed: %s", cudaGetErrorString(e)); return MMSA_ERR_CUDA; }
   } else if (p.splits == 1) {
     int grid = tiles_mn < num_sms() ? tiles_mn : num_sms();
     ProfScope prof(nm, s, 2.0 * (double)d.M * (double)d.N * (double)Kt);
-    kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, s>>>(tmA, tmA2, tmB, tmC, tmR, p);
+    kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, s>>>(tmA, tmA2, tmB, tmB2, tmC, tmR, p);
   } else {
     // one cluster of `splits` CTAs per output tile (co-scheduled by the hardware, so the in-kernel
     // cross-CTA reduction cannot deadlock); clusters loop over tiles when there are more tiles than slots
@@ -1049,7 +1063,7 @@ static int launch_gemm(const GemmDesc& d, int splits_req, cudaStream_t s, int ks
     const int nclusters = tiles_mn < max_clusters ? tiles_mn : max_clusters;
     cfg.gridDim = dim3((unsigned)(nclusters * p.splits));
     ProfScope prof(nm, s, 2.0 * (double)d.M * (double)d.N * (double)Kt);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmB, tmC, tmR, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmA2, tmB, tmB2, tmC, tmR, p);
     if (e != cudaSuccess) { set_error("mmsa: cluster launch of gemm_tcgen05_kernel (cluster %d) failed: %s", p.splits, cudaGetErrorString(e)); return MMSA_ERR_CUDA; }
   }
   MMSA_LAUNCH_CHECK("gemm_tcgen05_kernel");
@@ -1139,7 +1153,8 @@ int gemm_bf16_sm100(const GemmDesc& d, cudaStream_t s) { return gemm_bf16_sm100_
 // cluster split (<= 8 CTAs) cannot combine with CTA pairs, and 128 x 256 1-CTA tiles pull 48 KB of operands per k-block
 // and SM through L2 against 32 KB for a pair tile -- under full load the kernel is L2->SM bound, so bytes are time.
 int gemm_bf16_sm100_wgrad_pair(const GemmDesc& d, int ksplit, int* real_ksplit, cudaStream_t s) {
-  if (!gemm_bf16_sm100_supported(d) || !d.a_mn_major || !d.b_mn_major) {
+  if (!gemm_bf16_sm100_supported(d) || !d.a_mn_major || !d.b_mn_major ||
+      (d.B2 && (((uintptr_t)d.B2 % 16) != 0 || d.ldb2 % 8 != 0))) {
     set_error("mmsa: internal: gemm_bf16_sm100_wgrad_pair needs aligned MN-major operands");
     return MMSA_ERR_ARG;
   }

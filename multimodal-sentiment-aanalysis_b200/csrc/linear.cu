@@ -341,6 +341,45 @@ int mmsa_linear_dgrad(int dtype, int64_t M, int64_t N, int64_t K, const void* dy
   return run_gemm(dtype, d, 1, (cudaStream_t)stream);
 }
 
+}  // extern "C"
+
+// 2-CTA weight gradient (+ ordered slice reduction) of dy^T [x | x2]; x2 may be null.  Returns MMSA_OK, or -1 when the shape is
+// not eligible (the caller then takes the generic path).
+static int wgrad_pair_path(int64_t M, int64_t N, int64_t K, int64_t K2, const void* dy, int64_t lddy, const void* x, int64_t ldx,
+                           const void* x2, int64_t ldx2, float* dw, int64_t lddw, float* db, float* ws, float* ws_colsum,
+                           cudaStream_t s) {
+  const int64_t Kt = K + (x2 ? K2 : 0);
+  if (getenv("MMSA_WGRAD_PAIR_OFF") != nullptr) return -1;
+  if (x2 && (K % 256 != 0 || ((uintptr_t)x2 % 16) != 0 || ldx2 % 8 != 0)) return -1;
+  const int ks_req = wgrad_pair_ksplit(N, Kt, M, dw, lddw);
+  if (ks_req <= 0) return -1;
+  GemmDesc d{};
+  d.M = N; d.N = Kt; d.K = M; d.K2 = 0;
+  d.A = dy; d.lda = lddy; d.a_mn_major = true; d.A2 = nullptr;
+  d.B = x; d.ldb = ldx; d.b_mn_major = true;
+  d.B2 = x2; d.ldb2 = ldx2; d.N1 = x2 ? K : 0;
+  d.bias = nullptr; d.residual = nullptr; d.act = MMSA_ACT_NONE; d.alpha = 1.f; d.out_dtype = MMSA_F32;
+  if (!gemm_bf16_sm100_supported(d)) return -1;
+  d.C = ks_req > 1 ? (void*)ws : (void*)dw;
+  d.ldc = ks_req > 1 ? Kt : lddw;
+  d.colsum = db ? (ks_req > 1 ? ws_colsum : db) : nullptr;
+  int ks = 1;
+  int rc = gemm_bf16_sm100_wgrad_pair(d, ks_req, &ks, s);
+  if (rc) return rc;
+  if (ks_req > 1) {
+    const int64_t total4 = N * (Kt / 4);
+    int mat_blocks = (int)ceil_div(total4, 256);
+    if (mat_blocks > 148 * 4) mat_blocks = 148 * 4;
+    const int cs_blocks = db ? (int)ceil_div(N, 256) : 0;
+    ProfScope prof("wgrad_reduce", s, 4.0 * (double)N * Kt * (ks + 1));
+    wgrad_reduce_kernel<<<(unsigned)(mat_blocks + cs_blocks), 256, 0, s>>>(ws, ks, N, Kt, dw, lddw, ws_colsum, db, mat_blocks);
+    MMSA_LAUNCH_CHECK("wgrad_reduce_kernel");
+  }
+  return MMSA_OK;
+}
+
+extern "C" {
+
 int64_t mmsa_linear_wgrad_workspace(int dtype, int64_t M, int64_t N, int64_t K) {
   (void)dtype; (void)M;
   return (int64_t)sizeof(float) * (kMaxSplits * N * K + (int64_t)(kColsumRowSplits > kMaxSplits ? kColsumRowSplits : kMaxSplits) * N);
@@ -376,26 +415,9 @@ int mmsa_linear_wgrad(int dtype, int64_t M, int64_t N, int64_t K, const void* dy
       int rc = gemm_bf16_small(d, s);
       if (rc) return rc;
       db_done = true;
-    } else if (use_tc(dtype, d) && getenv("MMSA_WGRAD_PAIR_OFF") == nullptr && wgrad_pair_ksplit(N, K, M, dw, lddw) > 0) {
+    } else if (use_tc(dtype, d) && wgrad_pair_path(M, N, K, 0, dy, lddy, x, ldx, nullptr, 0, dw, lddw, db, ws, ws_colsum, s) == MMSA_OK) {
       // 2-CTA 256 x 256 tiles, (tile, K-slice) work units filling the 74 CTA pairs, fp32 partials into the (L2-resident)
       // workspace, bias-gradient partials from the ones-tile MMA, then one small kernel sums the slices in order
-      const int ks_req = wgrad_pair_ksplit(N, K, M, dw, lddw);
-      int ks = 1;
-      GemmDesc dp = d;
-      dp.C = ks_req > 1 ? (void*)ws : (void*)dw;
-      dp.ldc = ks_req > 1 ? K : lddw;
-      dp.colsum = db ? (ks_req > 1 ? ws_colsum : db) : nullptr;
-      int rc = gemm_bf16_sm100_wgrad_pair(dp, ks_req, &ks, s);
-      if (rc) return rc;
-      if (ks_req > 1) {
-        const int64_t total4 = N * (K / 4);
-        int mat_blocks = (int)ceil_div(total4, 256);
-        if (mat_blocks > 148 * 4) mat_blocks = 148 * 4;
-        const int cs_blocks = db ? (int)ceil_div(N, 256) : 0;
-        ProfScope prof("wgrad_reduce", s, 4.0 * (double)N * K * (ks + 1));
-        wgrad_reduce_kernel<<<(unsigned)(mat_blocks + cs_blocks), 256, 0, s>>>(ws, ks, N, K, dw, lddw, ws_colsum, db, mat_blocks);
-        MMSA_LAUNCH_CHECK("wgrad_reduce_kernel");
-      }
       db_done = true;
     } else if (use_tc(dtype, d)) {
       // one launch: split-K partials are summed by the last CTA of each tile, and the bias gradient
@@ -450,6 +472,32 @@ int mmsa_linear_wgrad(int dtype, int64_t M, int64_t N, int64_t K, const void* dy
     MMSA_LAUNCH_CHECK("reduce_splits_kernel");
   }
   return MMSA_OK;
+}
+
+/* dw[N, K + K2] = dy^T [x | x2], db = column sums of dy: the weight gradient of a Linear whose input is the feature-axis
+ * concat of two tensors (the gate, MultimodalModel.py:147), without materialising the concat.  Eligible shapes run as ONE
+ * 2-CTA launch (B operand from two tensor maps); others as two mmsa_linear_wgrad calls on the column blocks of dw. */
+int mmsa_linear_wgrad2(int dtype, int64_t M, int64_t N, int64_t K, int64_t K2, const void* dy, int64_t lddy, const void* x,
+                       int64_t ldx, const void* x2, int64_t ldx2, float* dw, int64_t lddw, float* db, void* workspace,
+                       void* stream) {
+  MMSA_REQUIRE_DEVICE();
+  MMSA_REQUIRE(dtype == MMSA_F32 || dtype == MMSA_BF16, "mmsa_linear_wgrad2: bad dtype");
+  MMSA_REQUIRE(M > 0 && N > 0 && K > 0 && K2 > 0 && x2 != nullptr && dw != nullptr, "mmsa_linear_wgrad2: bad arguments");
+  MMSA_REQUIRE(workspace != nullptr, "mmsa_linear_wgrad2: workspace required (mmsa_linear_wgrad_workspace(dtype, M, N, K + K2))");
+  float* ws = reinterpret_cast<float*>(workspace);
+  float* ws_colsum = ws + (int64_t)kMaxSplits * N * (K + K2);
+  if (dtype == MMSA_BF16) {
+    GemmDesc probe{};
+    probe.M = N; probe.N = K + K2; probe.K = M; probe.A = dy; probe.lda = lddy; probe.a_mn_major = true;
+    probe.B = x; probe.ldb = ldx; probe.b_mn_major = true;
+    if (use_tc(dtype, probe)) {
+      int rc = wgrad_pair_path(M, N, K, K2, dy, lddy, x, ldx, x2, ldx2, dw, lddw, db, ws, ws_colsum, (cudaStream_t)stream);
+      if (rc != -1) return rc;
+    }
+  }
+  int rc = mmsa_linear_wgrad(dtype, M, N, K, dy, lddy, x, ldx, dw, lddw, db, workspace, stream);
+  if (rc) return rc;
+  return mmsa_linear_wgrad(dtype, M, N, K2, dy, lddy, x2, ldx2, dw + K, lddw, nullptr, workspace, stream);
 }
 
 }  // extern "C"

@@ -83,8 +83,8 @@ gate_ln_bwd_kernel(int64_t M, int E, const T* __restrict__ dy, int64_t dy_rows_p
                    const T* __restrict__ g, const T* __restrict__ q, const T* __restrict__ attn,
                    const float* __restrict__ gamma, const float* __restrict__ mean,
                    const float* __restrict__ rstd, const T* __restrict__ dq_bcast, int64_t bcast_rows,
-                   const T* __restrict__ dq_add, T* __restrict__ dq_part, T* __restrict__ dattn_part, T* __restrict__ dgate_pre,
-                   float* __restrict__ partials /* [gridDim.x, 2, E] */) {
+                   const T* __restrict__ dq_add, T* __restrict__ dq_part, T* __restrict__ dattn_part, int64_t ldp,
+                   T* __restrict__ dgate_pre, float* __restrict__ partials /* [gridDim.x, 2, E] */) {
   constexpr int VN = VecN<T>::N;
   constexpr int NV = kMaxRowFloats / VN;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -158,8 +158,8 @@ gate_ln_bwd_kernel(int64_t M, int E, const T* __restrict__ dy, int64_t dy_rows_p
           o2[j] = du * (1.f - gv[j]);
           o3[j] = du * (qv[j] - av[j]) * gv[j] * (1.f - gv[j]);
         }
-        store_vec<T>(dq_part + base + v * VN, o1);
-        store_vec<T>(dattn_part + base + v * VN, o2);
+        store_vec<T>(dq_part + row * ldp + v * VN, o1);          // ldp: row stride of the two partial-gradient outputs (they
+        store_vec<T>(dattn_part + row * ldp + v * VN, o2);       // may be the two column halves of one [M, 2E] buffer)
         store_vec<T>(dgate_pre + base + v * VN, o3);
       }
     }
@@ -536,7 +536,7 @@ gate_ln_pool_bwd_kernel(int64_t M, int L, int E, int64_t rows_per_warp, const fl
                         const float* __restrict__ dpooled_q, const T* __restrict__ dq_add,
                         const T* __restrict__ g, const T* __restrict__ q, const T* __restrict__ attn,
                         const float* __restrict__ gamma, const float* __restrict__ mean,
-                        const float* __restrict__ rstd, T* __restrict__ dq_part, T* __restrict__ dattn_part,
+                        const float* __restrict__ rstd, T* __restrict__ dq_part, T* __restrict__ dattn_part, int64_t ldp,
                         T* __restrict__ dgate_pre, float* __restrict__ partials /* [gridDim.x, 2, E] */) {
   constexpr int VN = VecN<T>::N;
   constexpr int NV = F / VN;
@@ -673,8 +673,8 @@ gate_ln_pool_bwd_kernel(int64_t M, int L, int E, int64_t rows_per_warp, const fl
           o2[j] = du * (1.f - gg);
           o3[j] = du * (q8[j] - a8[j]) * gg * (1.f - gg);
         }
-        store_vec<T>(dq_part + base + v * VN, o1);
-        store_vec<T>(dattn_part + base + v * VN, o2);
+        store_vec<T>(dq_part + row * ldp + v * VN, o1);          // ldp: row stride of the two partial-gradient outputs (they
+        store_vec<T>(dattn_part + row * ldp + v * VN, o2);       // may be the two column halves of one [M, 2E] buffer)
         store_vec<T>(dgate_pre + base + v * VN, o3);
       }
     }
@@ -1088,18 +1088,20 @@ int64_t mmsa_gate_ln_bwd_blocks(int64_t M) {
 int mmsa_gate_ln_bwd(int dtype, int64_t M, int64_t E, const void* dy, int64_t dy_rows_per_sample,
                      const void* g, const void* q, const void* attn, const float* gamma,
                      const float* mean, const float* rstd, const void* dq_bcast, int64_t bcast_rows,
-                     const void* dq_add, void* dq_part, void* dattn_part, void* dgate_pre,
+                     const void* dq_add, void* dq_part, void* dattn_part, int64_t ld_parts, void* dgate_pre,
                      float* dgamma, float* dbeta, float* partials, void* stream) {
   MMSA_REQUIRE_DEVICE();
   MMSA_REQUIRE(E % 8 == 0 && E <= 1024 && E > 0, "mmsa_gate_ln_bwd: E=%lld must be a multiple of 8 and <= 1024", (long long)E);
   MMSA_REQUIRE(dq_bcast == nullptr || bcast_rows > 0, "mmsa_gate_ln_bwd: dq_bcast needs bcast_rows > 0");
+  if (ld_parts <= 0) ld_parts = E;
+  MMSA_REQUIRE(ld_parts >= E && ld_parts % 8 == 0, "mmsa_gate_ln_bwd: ld_parts must be >= E and a multiple of 8");
   if (M == 0) return MMSA_OK;
   cudaStream_t s = (cudaStream_t)stream;
   ProfScope prof("gate_ln_bwd", s, (double)M * E * (dtype == MMSA_F32 ? 4 : 2) * (dy_rows_per_sample > 0 ? 6.0 : 7.0));
   int64_t nblk = mmsa_gate_ln_bwd_blocks(M);
   MMSA_DISPATCH_DTYPE(dtype, T, (gate_ln_bwd_kernel<T><<<(unsigned)nblk, kRowWarps * 32, 0, s>>>(
       M, (int)E, (const T*)dy, dy_rows_per_sample, (const T*)g, (const T*)q, (const T*)attn, gamma, mean, rstd,
-      (const T*)dq_bcast, bcast_rows, (const T*)dq_add, (T*)dq_part, (T*)dattn_part, (T*)dgate_pre, partials)));
+      (const T*)dq_bcast, bcast_rows, (const T*)dq_add, (T*)dq_part, (T*)dattn_part, ld_parts, (T*)dgate_pre, partials)));
   MMSA_LAUNCH_CHECK("gate_ln_bwd_kernel");
   reduce_partials_kernel<<<(unsigned)ceil_div(E, 32), 256, 0, s>>>(partials, nblk, (int)E, nullptr, 0, dgamma, dbeta);
   MMSA_LAUNCH_CHECK("reduce_partials_kernel");
@@ -1186,11 +1188,13 @@ int mmsa_gate_ln_pool_fwd(int dtype, int64_t B, int64_t L, int64_t E, const void
 int mmsa_gate_ln_pool_bwd(int dtype, int64_t B, int64_t L, int64_t E, const float* dpooled_y,
                           const float* dpooled_q, const void* dq_add, const void* g, const void* q,
                           const void* attn, const float* gamma, const float* mean, const float* rstd,
-                          void* dq_part, void* dattn_part, void* dgate_pre, float* dgamma, float* dbeta,
+                          void* dq_part, void* dattn_part, int64_t ld_parts, void* dgate_pre, float* dgamma, float* dbeta,
                           float* partials, void* stream) {
   MMSA_REQUIRE_DEVICE();
   MMSA_REQUIRE(E % 8 == 0 && E <= 1024 && E > 0, "mmsa_gate_ln_pool_bwd: E=%lld must be a multiple of 8 and <= 1024", (long long)E);
   MMSA_REQUIRE(L > 0 && L < (1 << 30) && dpooled_y != nullptr, "mmsa_gate_ln_pool_bwd: bad arguments");
+  if (ld_parts <= 0) ld_parts = E;
+  MMSA_REQUIRE(ld_parts >= E && ld_parts % 8 == 0, "mmsa_gate_ln_pool_bwd: ld_parts must be >= E and a multiple of 8");
   MMSA_REQUIRE(((uintptr_t)g | (uintptr_t)q | (uintptr_t)attn | (uintptr_t)dq_add | (uintptr_t)dq_part | (uintptr_t)dattn_part |
                 (uintptr_t)dgate_pre | (uintptr_t)dpooled_y | (uintptr_t)dpooled_q) % 16 == 0,
                "mmsa_gate_ln_pool_bwd: operands must be 16-byte aligned");
@@ -1211,7 +1215,7 @@ int mmsa_gate_ln_pool_bwd(int dtype, int64_t B, int64_t L, int64_t E, const floa
     cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
     kfn<<<(unsigned)nblk, kRowWarps * 32, smem, s>>>(                                                           \
       M, (int)L, (int)E, rpw, dpooled_y, dpooled_q, (const T*)dq_add, (const T*)g, (const T*)q, (const T*)attn, gamma, \
-      mean, rstd, (T*)dq_part, (T*)dattn_part, (T*)dgate_pre, partials);                                        \
+      mean, rstd, (T*)dq_part, (T*)dattn_part, ld_parts, (T*)dgate_pre, partials);                              \
   })
     if (E <= 256) MMSA_GLP_BWD(8);
     else if (E <= 512) MMSA_GLP_BWD(16);

@@ -36,6 +36,7 @@ _PROTOS = {
     "mmsa_linear_dgrad": (I, [I, L, L, L, P, L, P, L, P, L, P, L, I, P]),
     "mmsa_linear_wgrad_workspace": (L, [I, L, L, L]),
     "mmsa_linear_wgrad": (I, [I, L, L, L, P, L, P, L, P, L, P, P, P]),
+    "mmsa_linear_wgrad2": (I, [I, L, L, L, L, P, L, P, L, P, L, P, L, P, P, P]),
     "mmsa_debug_force_simt_attention": (None, [I]),
     "mmsa_debug_attention_engine": (None, [I]),
     "mmsa_debug_gemm_engine": (None, [I]),
@@ -45,9 +46,9 @@ _PROTOS = {
     "mmsa_attn_dropout_bwd": (I, [I, L, L, L, L, L, P, L, P, L, P, L, P, L, P, L, P, P, P, L, P, L, P, L, F, P, U, U, P, P]),
     "mmsa_gate_ln_fwd": (I, [I, L, L, P, P, P, P, P, F, P, P, P, P, P]),
     "mmsa_gate_ln_bwd_blocks": (L, [L]),
-    "mmsa_gate_ln_bwd": (I, [I, L, L, P, L, P, P, P, P, P, P, P, L, P, P, P, P, P, P, P, P]),
+    "mmsa_gate_ln_bwd": (I, [I, L, L, P, L, P, P, P, P, P, P, P, L, P, P, P, L, P, P, P, P, P]),
     "mmsa_gate_ln_pool_fwd": (I, [I, L, L, L, P, P, P, P, P, F, P, P, P, P, P, P, P]),
-    "mmsa_gate_ln_pool_bwd": (I, [I, L, L, L, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P, P]),
+    "mmsa_gate_ln_pool_bwd": (I, [I, L, L, L, P, P, P, P, P, P, P, P, P, P, P, L, P, P, P, P, P]),
     "mmsa_add_ln_fwd": (I, [I, L, L, P, P, P, P, F, P, P, P, P]),
     "mmsa_add_ln_bwd": (I, [I, L, L, P, P, P, P, P, P, P, P, P, P, P]),
     "mmsa_add_rows": (I, [I, L, L, L, P, P, P, P]),

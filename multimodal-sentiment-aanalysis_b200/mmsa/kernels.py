@@ -138,6 +138,26 @@ def linear_wgrad(dy: Tensor, x: Tensor, *, dw: Optional[Tensor] = None, db: Opti
     return (dw if want_weight else None), db
 
 
+def linear_wgrad2(dy: Tensor, x: Tensor, x2: Tensor, *, dw: Optional[Tensor] = None, db: Optional[Tensor] = None,
+                  want_bias: bool = True) -> Tuple[Tensor, Optional[Tensor]]:
+    """dw[N, K+K2] = dy.T @ cat[x, x2] (fp32) without the concat; db[N] = dy.sum(0) (mmsa_linear_wgrad2)."""
+    _check(dy, x, x2, dw, db)
+    M, N = dy.shape
+    K1, K2 = x.shape[1], x2.shape[1]
+    assert x.shape[0] == M and x2.shape[0] == M and dy.stride(1) == 1 and x.stride(1) == 1 and x2.stride(1) == 1
+    if dw is None:
+        dw = torch.empty((N, K1 + K2), device=dy.device, dtype=torch.float32)
+    if want_bias and db is None:
+        db = torch.empty((N,), device=dy.device, dtype=torch.float32)
+    if not want_bias:
+        db = None
+    nbytes = _lib.load().mmsa_linear_wgrad_workspace(dt(dy), M, N, K1 + K2)
+    ws = torch.empty((nbytes // 4,), device=dy.device, dtype=torch.float32)
+    call("mmsa_linear_wgrad2", dt(dy), M, N, K1, K2, dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), x2.data_ptr(),
+         x2.stride(0), dw.data_ptr(), dw.stride(0), _p(db), ws.data_ptr(), _stream())
+    return dw, db
+
+
 def attn_fwd(q: Tensor, k: Tensor, v: Tensor, B: int, H: int, Lq: int, Lk: int, D: int) -> Tuple[Tensor, Tensor]:
     """q:[B*Lq, >=H*D] views, k/v:[B*Lk, ...] views (row strides may differ) -> o:[B*Lq,H*D], lse:[B,H,Lq]."""
     _check(q, k, v)
@@ -194,11 +214,16 @@ def gate_ln_fwd(gate_pre: Tensor, q: Tensor, attn: Tensor, gamma: Tensor, beta: 
 
 def gate_ln_bwd(dy: Tensor, rows_per_sample: int, g, q, attn, gamma, mean, rstd, *,
                 dq_bcast: Optional[Tensor] = None, bcast_rows: int = 0, dq_add: Optional[Tensor] = None,
-                dgamma: Optional[Tensor] = None, dbeta: Optional[Tensor] = None):
+                dgamma: Optional[Tensor] = None, dbeta: Optional[Tensor] = None, packed_parts: bool = False):
+    """packed_parts: dq_part and dattn_part are returned as the two column halves of ONE [M, 2E] buffer (row stride 2E)."""
     _check(dy, g, q, attn)
     M, E = q.shape
-    dq_part = torch.empty_like(q)
-    dattn_part = torch.empty_like(q)
+    if packed_parts:
+        parts = torch.empty((M, 2 * E), device=q.device, dtype=q.dtype)
+        dq_part, dattn_part = parts[:, :E], parts[:, E:]
+    else:
+        dq_part = torch.empty_like(q)
+        dattn_part = torch.empty_like(q)
     dgate_pre = torch.empty_like(q)
     dgamma = dgamma if dgamma is not None else torch.empty((E,), device=q.device, dtype=torch.float32)
     dbeta = dbeta if dbeta is not None else torch.empty((E,), device=q.device, dtype=torch.float32)
@@ -206,7 +231,7 @@ def gate_ln_bwd(dy: Tensor, rows_per_sample: int, g, q, attn, gamma, mean, rstd,
     partials = torch.empty((nblk, 2, E), device=q.device, dtype=torch.float32)
     call("mmsa_gate_ln_bwd", dt(q), M, E, dy.data_ptr(), rows_per_sample, g.data_ptr(), q.data_ptr(), attn.data_ptr(),
          gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _p(dq_bcast), bcast_rows, _p(dq_add),
-         dq_part.data_ptr(), dattn_part.data_ptr(), dgate_pre.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+         dq_part.data_ptr(), dattn_part.data_ptr(), dq_part.stride(0), dgate_pre.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
          partials.data_ptr(), _stream())
     return dq_part, dattn_part, dgate_pre, dgamma, dbeta
 
@@ -231,12 +256,17 @@ def gate_ln_pool_fwd(gate_pre: Tensor, q: Tensor, attn: Tensor, gamma: Tensor, b
 
 
 def gate_ln_pool_bwd(dpy: Tensor, dpq: Optional[Tensor], dq_add: Optional[Tensor], g, q, attn, gamma, mean, rstd,
-                     B: int, L: int, dgamma: Optional[Tensor] = None, dbeta: Optional[Tensor] = None):
+                     B: int, L: int, dgamma: Optional[Tensor] = None, dbeta: Optional[Tensor] = None,
+                     packed_parts: bool = False):
     _check(dpy, dpq, dq_add, g, q, attn)
     M, E = q.shape
     assert dpy.dtype == torch.float32 and (dpq is None or dpq.dtype == torch.float32)
-    dq_part = torch.empty_like(q)
-    dattn_part = torch.empty_like(q)
+    if packed_parts:
+        parts = torch.empty((M, 2 * E), device=q.device, dtype=q.dtype)
+        dq_part, dattn_part = parts[:, :E], parts[:, E:]
+    else:
+        dq_part = torch.empty_like(q)
+        dattn_part = torch.empty_like(q)
     dgate_pre = torch.empty_like(q)
     dgamma = dgamma if dgamma is not None else torch.empty((E,), device=q.device, dtype=torch.float32)
     dbeta = dbeta if dbeta is not None else torch.empty((E,), device=q.device, dtype=torch.float32)
@@ -244,7 +274,7 @@ def gate_ln_pool_bwd(dpy: Tensor, dpq: Optional[Tensor], dq_add: Optional[Tensor
     partials = torch.empty((nblk, 2, E), device=q.device, dtype=torch.float32)
     call("mmsa_gate_ln_pool_bwd", dt(q), B, L, E, dpy.data_ptr(), _p(dpq), _p(dq_add), g.data_ptr(), q.data_ptr(),
          attn.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dq_part.data_ptr(), dattn_part.data_ptr(),
-         dgate_pre.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), partials.data_ptr(), _stream())
+         dq_part.stride(0), dgate_pre.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), partials.data_ptr(), _stream())
     return dq_part, dattn_part, dgate_pre, dgamma, dbeta
 
 

@@ -799,3 +799,23 @@ print("ok")
     env = dict(os.environ, MMSA_WGRAD_A_TMEM="1")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K1,K2", [(4352, 768, 768, 768),      # one 2-CTA launch, B operand from two tensor maps
+                                       (4100, 256, 512, 256),      # ragged tokens, unequal segments (split on a tile boundary)
+                                       (300, 768, 768, 768),       # too few tokens for the pair path: two launches on dw's column blocks
+                                       (4352, 768, 264, 768)])     # first segment not a multiple of the tile width: fallback
+def test_linear_wgrad_two_inputs(cuda_device, dtype, M, N, K1, K2):
+    """mmsa_linear_wgrad2: dW = dy^T [x | x2] without materialising the concat (the gate's Linear(2E, E), MultimodalModel.py:147)."""
+    k = _k()
+    dy = _rand((M, N), dtype, cuda_device, 1)
+    x = _rand((M, K1), dtype, cuda_device, 2)
+    x2 = _rand((M, K2), dtype, cuda_device, 3)
+    dw, db = k.linear_wgrad2(dy, x, x2)
+    ref_w = dy.double().T @ torch.cat([x, x2], 1).double()
+    tol = 1e-5 if dtype == torch.float32 else 2e-3
+    assert rel_err(dw, ref_w) <= tol
+    assert rel_err(db, dy.double().sum(0)) <= tol
+    dw2, _ = k.linear_wgrad2(dy, x, x2, want_bias=False)
+    assert torch.equal(dw2, dw)
