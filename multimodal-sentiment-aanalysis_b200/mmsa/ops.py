@@ -93,6 +93,7 @@ def set_grad_sink(sink) -> None:
 
 
 OVERLAP_WGRAD = True      # block weight gradients on a second stream (FusionCoreFn.backward)
+OVERLAP_BLOCKS = os.environ.get("MMSA_OVERLAP_BLOCKS", "0") == "1"     # forward of block p2e beside block e2p (probe)
 OVERLAP_TAIL = True       # tail weight gradients (SeqFn.backward) and the contrastive branch (model.forward) on a second stream
 
 
@@ -202,7 +203,8 @@ class _BlockState:
 
 
 def _block_fwd(q_in: Tensor, kv_in: Tensor, B: int, Lq: int, Lk: int, H: int, in_w, in_b, out_w, out_b, gate_w,
-               gate_b, ln_w, ln_b, eps: float = 1e-5, pooled: bool = False, v_in: Optional[Tensor] = None):
+               gate_b, ln_w, ln_b, eps: float = 1e-5, pooled: bool = False, v_in: Optional[Tensor] = None,
+               keep: Optional[list] = None):
     """CrossModalTransformer.forward (MultimodalModel.py:124-149) on flattened [B*L, E] activations.
     MHA in-projection (q rows of in_proj_weight; packed k,v rows), attention core, out-projection,
     gate GEMM over the two operands [q | attn] (no concat), fused sigmoid/blend/LayerNorm.
@@ -234,6 +236,8 @@ def _block_fwd(q_in: Tensor, kv_in: Tensor, B: int, Lq: int, Lk: int, H: int, in
         st.G, out, st.mean, st.rstd = K.gate_ln_fwd(gate_pre, q_in, st.A, st.gamma, ln_b.detach(), eps)
     st.q_in, st.kv_in, st.v_in = q_in, kv_in, v_in
     st.B, st.Lq, st.Lk, st.E, st.H = B, Lq, Lk, E, H
+    if keep is not None:
+        keep.append(gate_pre)          # temporaries of a block run on a helper stream stay alive until the caller joins
     return out, st
 
 
@@ -385,8 +389,21 @@ class FusionCoreFn(Function):
         wtc, wic = _w(wt, cd), _w(wi, cd)
         t = K.linear_fwd(text2d, wtc, bt.detach())
         v = K.linear_fwd(image2d, wic, bi.detach())
+        # The two blocks only share their inputs: block p2e (image queries: 12 544 rows, GEMMs of two waves each) runs on the
+        # helper stream beside block e2p (32 768 rows), so one kernel's partial last wave and launch gap fill with the other's CTAs
+        main = torch.cuda.current_stream(text.device)
+        side = _side_stream(text.device) if (OVERLAP_BLOCKS and OVERLAP_WGRAD) else None
+        keep: list = []
+        if side is not None:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                (e2, fv, fv_lp), st2 = _block_fwd(v, t, B, R, L, num_heads, *p2, pooled=True, keep=keep)
         (e1, f0, f0_lp), st1 = _block_fwd(t, v, B, L, R, num_heads, *p1, pooled=True)
-        (e2, fv, fv_lp), st2 = _block_fwd(v, t, B, R, L, num_heads, *p2, pooled=True)
+        if side is not None:
+            main.wait_stream(side)
+            keep.clear()
+        else:
+            (e2, fv, fv_lp), st2 = _block_fwd(v, t, B, R, L, num_heads, *p2, pooled=True)
         ctx.st = (st1, st2, text2d, image2d)
         ctx.dims = (B, L, R)
         ctx.plist = (wt, bt, wi, bi) + tuple(bp)          # the Parameter objects: keys of the gradient sink
