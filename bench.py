@@ -617,6 +617,20 @@ def run_ours(args) -> None:
             try:
                 eager = torch_eager_baseline(B, L, dev)
                 eager["gemm_shapes"] = cublas_matmul_tflops(prof, dev, prof_steps)
+                # the same launches weighted by their count per step, timed back to back (no launch gaps, cold operands):
+                # context for roofline.achieved, which brackets every launch of an eager pass with events
+                fl = tm = 0.0
+                for nm, v in eager["gemm_shapes"].items():
+                    if v.get("mmsa_b2b_tflops"):
+                        Mq, Nq, Kq = (int(x) for x in nm.split("_")[1].split("x"))
+                        f = 2.0 * Mq * Nq * Kq * v["launches_per_step"]
+                        fl += f
+                        tm += f / (v["mmsa_b2b_tflops"] * 1e12)
+                if roofline is not None and tm > 0:
+                    roofline["achieved_back_to_back"] = fl / tm / 1e12
+                    roofline["frac_back_to_back"] = fl / tm / 1e12 / burst_peak
+                    roofline["back_to_back_note"] = ("the step's big tcgen05 GEMM shapes weighted by launches per step, each timed back "
+                                                     "to back over operand sets > L2 (torch_eager.gemm_shapes.mmsa_b2b_tflops)")
                 eager["gemm_shapes_note"] = ("cublas_tflops / mmsa_b2b_tflops: torch.matmul bf16 and this library's kernel, each back "
                                              "to back over operand sets > L2, CUDA events; mmsa_in_step_tflops: the same shape "
                                              "inside the profiled step (per-launch events)")
