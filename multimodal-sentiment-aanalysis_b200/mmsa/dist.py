@@ -359,13 +359,15 @@ class ArenaGradReducer:
       its weight-gradient GEMMs / LayerNorm reductions write straight into the arena views and returns no tensor for
       those parameters -- the 81 MB multi-tensor pack of the one-bucket form disappears (the ~0.8 M parameters of the [B,*]
       tail still arrive through autograd and are packed, 3 MB).
-    * The core reports each group of gradients the moment its kernels are ENQUEUED (`bucket_done(params, stream)`: tail
-      first, then block e2p, block p2e, the input projections).  A group is a contiguous arena range, so it is ONE
-      ncclAllReduce (op AVG), issued on a communication stream that waits for the producing stream -- inside the captured
-      graph it is a parallel branch under the remaining dgrad / attention / wgrad kernels.  `step()` reduces what is left
-      (normally only the projection weights, 8.7 MB of the 40.7 MB), joins, and points `.grad` at the arena views.
-    * NCCL's kernels are capped (NCCL_MAX_CTAS, set by bench.py before the communicator exists) so that they do not evict
-      the persistent GEMM CTAs they run beside.
+    * Default (`early_buckets=False`): `step()` sends the whole arena in ONE ncclAllReduce (op AVG) after the last weight
+      gradient, joins, and points `.grad` at the arena views.
+    * `early_buckets=True` (MMSA_DP_BUCKETS=1): the core reports each group of gradients the moment its kernels are ENQUEUED
+      (`bucket_done(params, stream)`: tail first, then block e2p, block p2e, the input projections).  A group is a
+      contiguous arena range, so it is one all-reduce, issued on a communication stream that waits for the producing stream
+      -- inside the captured graph a parallel branch under the remaining dgrad / attention / wgrad kernels; `step()` then
+      reduces only what is left.  Measured SLOWER than the single all-reduce at N = 2 and N = 8 on B200 / NVSwitch
+      (profiles/r02_dp_matrix.md): the NCCL kernels take SMs from persistent GEMMs that own the whole chip, and capping
+      NCCL's CTAs costs more than it saves -- hence not the default.
     Results equal the one-bucket form (same element-wise mean).  Gradient ACCUMULATION over several backwards is not
     supported in this mode (a second backward overwrites the arena): use GradAllReducer for that."""
 
@@ -375,7 +377,7 @@ class ArenaGradReducer:
         # early_buckets=False (MMSA_DP_BUCKETS=0): gradients still land in the arena (no pack), but everything leaves in
         # ONE all-reduce from step() -- for fabrics / world sizes where NCCL kernels beside the GEMMs cost more than the
         # exposed tail saves
-        self.early_buckets = (os.environ.get("MMSA_DP_BUCKETS", "1") != "0") if early_buckets is None else bool(early_buckets)
+        self.early_buckets = (os.environ.get("MMSA_DP_BUCKETS", "0") == "1") if early_buckets is None else bool(early_buckets)
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         self.group = group
         dev = self.params[0].device

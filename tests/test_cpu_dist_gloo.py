@@ -156,7 +156,8 @@ def _arena_worker(rank, world, port, q):
         torch.manual_seed(0)
         shapes = [(6, 5), (6,), (4, 6), (4,), (3, 4), (3,), (2, 3), (1,)]        # "proj", "block1", "block2", "tail" pairs
         params = [torch.nn.Parameter(torch.zeros(s)) for s in shapes]
-        red = mdist.ArenaGradReducer(params, register_sink=False)
+        red = mdist.ArenaGradReducer(params, register_sink=False, early_buckets=True)
+        single = mdist.ArenaGradReducer([torch.nn.Parameter(torch.zeros(s)) for s in shapes], register_sink=False)   # default: one all-reduce
         ok = True
         for it in range(3):
             g = torch.Generator().manual_seed(50 + it)
@@ -185,6 +186,22 @@ def _arena_worker(rank, world, port, q):
             ok &= first[0] == red.offs[6]
             ok &= red.early_bytes == sum((hi - lo) * 4 for lo, hi in red.last_launched)
             ok &= len(red.last_launched) == 4
+            # default form: the same gradients, nothing leaves before step(), one all-reduce over the whole arena
+            for i, p_ in enumerate(single.params):
+                p_.grad = None
+                if i >= 6:
+                    if not (i == 7 and it == 1):
+                        p_.grad = grads[rank][i].clone()
+                else:
+                    single.sink(p_).copy_(grads[rank][i])
+            single.bucket_done(single.params[:6])
+            ok &= single.launched == []
+            single.step()
+            ok &= single.early_bytes == 0 and len(single.last_launched) == (1 if it != 1 else 1)
+            for i, p_ in enumerate(single.params):
+                if i == 7 and it == 1:
+                    continue
+                ok &= bool(torch.allclose(p_.grad, params[i].grad, rtol=0, atol=0))
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
