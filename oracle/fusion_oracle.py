@@ -2,8 +2,10 @@
 
 TEST INFRASTRUCTURE ONLY.  Nothing in the product package
 (`multimodal-sentiment-aanalysis_b200/`) may import this file; only `tests/`,
-`__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference` legs of
-`bench.py` use it, and only as the checker / CPU baseline.
+`__graft_entry__.smoke()` and the baseline legs of `bench.py` (`cpu_baseline`,
+`--impl reference`, and `torch_eager`: the same functions on `cuda`, i.e. PyTorch
+eager running the reference arithmetic on the B200 as the kernel-to-beat) use it,
+and only as the checker / baseline -- never on the measured product path.
 
 It is a plain-PyTorch (CPU, fp32 or fp64) functional restatement of the
 reference arithmetic, parametrised in (E, H, L, R, input widths, wiring) so
@@ -13,9 +15,12 @@ MultimodalModel.py:147, which is the feature axis only when Lq == 1).
 
 Parity pin: the reference holds no golden vectors or tests for this path
 (SURVEY.md section 4), so the oracle is pinned against the *imported reference itself*
-at the reference's native sizes (tests/test_oracle_vs_reference.py, run where
-/root/reference is mounted) and against committed fixtures generated from the
-imported reference by oracle/make_goldens.py (tests/golden/native_*.pt).
+at the reference's native sizes (tests/test_cpu_oracle_and_abi.py::
+test_oracle_bit_identical_to_reference, run where /root/reference is mounted),
+against committed fixtures generated from the imported reference by
+oracle/make_goldens.py (tests/golden/*.pt), and -- for the training-mode dropout
+positions of the encoder layer -- against torch's own nn.TransformerEncoderLayer
+with intercepted masks (test_oracle_subnetwork_train_mode_dropout_positions).
 
 Every function cites the reference lines it follows
 (paths relative to /root/reference/MML_ZYC/).

@@ -1,3 +1,5 @@
+"""Diagnostic (GPU box): mmsa_attn_dropout_fwd/bwd -- extract the Philox mask through V = identity rows and compare the
+re-drawn-mask backward with the explicit-mask backward."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "multimodal-sentiment-aanalysis_b200"))

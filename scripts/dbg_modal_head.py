@@ -1,3 +1,5 @@
+"""Diagnostic (GPU box): native-wiring golden cases with the fused modality-head kernel vs the unfused chain (B = 2 is
+chaotic through its two-sample BatchNorm stack; B = 20 agrees to 1e-7)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "multimodal-sentiment-aanalysis_b200")); sys.path.insert(0, ROOT)

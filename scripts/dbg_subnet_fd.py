@@ -1,3 +1,5 @@
+"""Diagnostic (GPU box): finite-difference check of mmsa.Subnetwork in train mode with the Philox stream reset before every
+forward, per dropout kind (attention probabilities / token dropouts)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "multimodal-sentiment-aanalysis_b200"))
