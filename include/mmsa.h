@@ -248,11 +248,13 @@ int mmsa_act_bwd(int dtype, int64_t n, const void* x, const void* dy, int act, v
  * rng_state (device, {seed, position}) or NULL: when given, the kernel reads the seed from it and adds its
  * position to `offset` -- the stream position then lives in device memory and moves with mmsa_rng_advance, so a
  * captured CUDA graph draws a new mask on every replay (by-value seed/offset are frozen at capture).
+ * num_batches_tracked (device int64 scalar or NULL): incremented by one in training mode (nn.BatchNorm1d's counter, kept
+ * by the kernel so that the step has no separate add launch).
  * save_mean/save_rstd:[N] fp32.  x (and dy in bwd) are fp32 GEMM outputs; y / dx are written in `dtype`; y_lp (or NULL):
  * an additional bf16 copy of y when `dtype` is fp32 (the autograd-boundary output that is also the next Linear's operand). */
 int mmsa_bn_act_fwd(int dtype, int64_t B, int64_t N, int order, const void* x,
                     const float* gamma, const float* beta, float* running_mean, float* running_var,
-                    float momentum, float eps, int training,
+                    int64_t* num_batches_tracked, float momentum, float eps, int training,
                     float dropout_p, uint8_t* keep_mask, int mask_given, uint64_t seed, uint64_t offset,
                     const uint64_t* rng_state, void* y, void* y_lp, float* save_mean, float* save_rstd, void* stream);
 int mmsa_bn_act_bwd(int dtype, int64_t B, int64_t N, int order, const void* x, const void* dy,
@@ -273,8 +275,10 @@ int mmsa_dropout(int dtype, int64_t n, const void* x, float p, uint8_t* keep_mas
 int mmsa_rng_advance(uint64_t* rng_state, uint64_t n, void* stream);
 
 /* ---- softmax cross-entropy, mean reduction (nn.CrossEntropyLoss, Trainer.py:17,68) ----------
- * logits:[B,C] fp32, labels:[B] int64; loss:[1] fp32, pred:[B] int64 (argmax, Trainer.py:87). */
-int mmsa_ce_fwd(int64_t B, int64_t C, const float* logits, const int64_t* labels,
+ * logits:[B,C] fp32, labels:[B] int64; loss:[1] fp32, pred:[B] int64 (argmax, Trainer.py:87).
+ * addend:[n_add] fp32 device values or NULL (n_add <= 64): loss = CE + sum(addend) -- the trainer's
+ * `CE + contrastive_weight * contrastive_loss` (Trainer.py:68-71) folded into the same launch. */
+int mmsa_ce_fwd(int64_t B, int64_t C, const float* logits, const int64_t* labels, const float* addend, int64_t n_add,
                 float* loss, int64_t* pred, float* row_loss, void* stream);
 /* dlogits:[B,C] in `dtype` (the operand type of the head's dgrad / wgrad GEMMs). */
 int mmsa_ce_bwd(int dtype, int64_t B, int64_t C, const float* logits, const int64_t* labels,

@@ -8,21 +8,6 @@
 
 namespace mmsa {
 
-// ------------------------------------------------------------------ Philox4x32-10 (dropout masks)
-__device__ __forceinline__ uint32_t philox_first(uint64_t seed, uint64_t ctr) {
-  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0u, c3 = 0u;
-  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-  return c0;
-}
-
 // ------------------------------------------------------------------ BatchNorm1d + act + dropout
 // block (kBnCols columns x kBnRows row lanes = 1024 threads); one block per kBnCols columns; three passes over the
 // (tiny, L1-resident) [B,N] input.  The [B,*] tail is latency-bound: the wide block keeps each thread's serial row walk to
@@ -32,7 +17,8 @@ template <typename T>
 __global__ void __launch_bounds__(kBnCols * kBnRows)
 bn_act_fwd_kernel(int64_t B, int N, int order, const float* __restrict__ x, const float* __restrict__ gamma,
                   const float* __restrict__ beta, float* __restrict__ running_mean,
-                  float* __restrict__ running_var, float momentum, float eps, int training,
+                  float* __restrict__ running_var, int64_t* __restrict__ num_batches_tracked, float momentum, float eps,
+                  int training,
                   float dropout_p, uint8_t* __restrict__ keep_mask, int mask_given, uint64_t seed,
                   uint64_t offset, const uint64_t* __restrict__ rng_state, T* __restrict__ y, bf16* __restrict__ y_lp,
                   float* __restrict__ save_mean, float* __restrict__ save_rstd) {
@@ -72,6 +58,7 @@ bn_act_fwd_kernel(int64_t B, int N, int order, const float* __restrict__ x, cons
 #pragma unroll
     for (int k = 0; k < kBnRows; ++k) q += red[k][tx];
     var = q / (float)B;
+    if (num_batches_tracked != nullptr && blockIdx.x == 0 && tx == 0 && ty == 0) *num_batches_tracked += 1;
     if (ok && ty == 0 && running_mean != nullptr) {
       float unbiased = B > 1 ? q / (float)(B - 1) : var;
       running_mean[col] = (1.f - momentum) * running_mean[col] + momentum * mean;
@@ -182,6 +169,48 @@ __global__ void ce_fwd_kernel(int64_t B, int C, const float* __restrict__ logits
   int64_t y = labels[r];
   row_loss[r] = (logf(s) + mx) - z[y];
   if (pred) pred[r] = am;
+}
+
+// One-launch form for the batch sizes of the path (B <= kCeOneMax): row losses, argmax, the ordered mean and the optional
+// addend (loss = CE + sum(addend): the trainer's `CE + w * contrastive`, Trainer.py:68-71, without an add kernel).
+constexpr int64_t kCeOneMax = 16384;
+__global__ void __launch_bounds__(1024)
+ce_fwd_one_kernel(int64_t B, int C, const float* __restrict__ logits, const int64_t* __restrict__ labels,
+                  int64_t* __restrict__ pred, float* __restrict__ row_loss, const float* __restrict__ addend, int n_add,
+                  float* __restrict__ loss) {
+  __shared__ float sm[32];
+  float acc = 0.f;
+  for (int64_t r = threadIdx.x; r < B; r += blockDim.x) {
+    const float* z = logits + r * C;
+    float mx = z[0]; int am = 0;
+    for (int c = 1; c < C; ++c) if (z[c] > mx) { mx = z[c]; am = c; }
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s += expf(z[c] - mx);
+    const float l = (logf(s) + mx) - z[labels[r]];
+    row_loss[r] = l;
+    if (pred) pred[r] = am;
+    acc += l;
+  }
+  acc = block_sum(acc, sm);
+  if (threadIdx.x == 0) {
+    float extra = 0.f;
+    for (int i = 0; i < n_add; ++i) extra += addend[i];
+    loss[0] = acc / (float)B + extra;
+  }
+}
+
+// deterministic single-block sum: out[0] = scale * sum(v[0..n)) (+ sum(addend[0..n_add)))
+__global__ void sum_scale_add_kernel(const float* __restrict__ v, int64_t n, float scale, const float* __restrict__ addend,
+                                     int n_add, float* __restrict__ out) {
+  __shared__ float sm[32];
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
+  s = block_sum(s, sm);
+  if (threadIdx.x == 0) {
+    float extra = 0.f;
+    for (int i = 0; i < n_add; ++i) extra += addend[i];
+    out[0] = s * scale + extra;
+  }
 }
 
 // deterministic single-block sum: out[0] = scale * sum(v[0..n))
@@ -396,7 +425,8 @@ using namespace mmsa;
 extern "C" {
 
 int mmsa_bn_act_fwd(int dtype, int64_t B, int64_t N, int order, const void* x, const float* gamma,
-                    const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                    const float* beta, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                    float momentum, float eps,
                     int training, float dropout_p, uint8_t* keep_mask, int mask_given, uint64_t seed,
                     uint64_t offset, const uint64_t* rng_state, void* y, void* y_lp, float* save_mean, float* save_rstd,
                     void* stream) {
@@ -409,7 +439,8 @@ int mmsa_bn_act_fwd(int dtype, int64_t B, int64_t N, int order, const void* x, c
   ProfScope prof("bn_act_fwd", s, (double)B * N * 2.0 * (dtype == MMSA_F32 ? 4 : 2));
   dim3 block(kBnCols, kBnRows);
   MMSA_DISPATCH_DTYPE(dtype, T, (bn_act_fwd_kernel<T><<<(unsigned)ceil_div(N, kBnCols), block, 0, s>>>(
-      B, (int)N, order, (const float*)x, gamma, beta, running_mean, running_var, momentum, eps, training, dropout_p,
+      B, (int)N, order, (const float*)x, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps,
+      training, dropout_p,
       keep_mask, mask_given, seed, offset, rng_state, (T*)y, (bf16*)(dtype == MMSA_F32 ? y_lp : nullptr), save_mean, save_rstd)));
   MMSA_LAUNCH_CHECK("bn_act_fwd_kernel");
   return MMSA_OK;
@@ -431,16 +462,23 @@ int mmsa_bn_act_bwd(int dtype, int64_t B, int64_t N, int order, const void* x, c
   return MMSA_OK;
 }
 
-int mmsa_ce_fwd(int64_t B, int64_t C, const float* logits, const int64_t* labels, float* loss, int64_t* pred,
-                float* row_loss, void* stream) {
+int mmsa_ce_fwd(int64_t B, int64_t C, const float* logits, const int64_t* labels, const float* addend, int64_t n_add,
+                float* loss, int64_t* pred, float* row_loss, void* stream) {
   MMSA_REQUIRE_DEVICE();
   MMSA_REQUIRE(B > 0 && C > 0 && C <= 64, "mmsa_ce_fwd: bad shape B=%lld C=%lld", (long long)B, (long long)C);
+  MMSA_REQUIRE(n_add >= 0 && n_add <= 64 && (n_add == 0 || addend != nullptr), "mmsa_ce_fwd: bad addend (n_add=%lld)",
+               (long long)n_add);
   cudaStream_t s = (cudaStream_t)stream;
   ProfScope prof("ce_fwd", s, (double)B * (C * 4.0 + 20.0));
+  if (B <= kCeOneMax) {
+    ce_fwd_one_kernel<<<1, 1024, 0, s>>>(B, (int)C, logits, labels, pred, row_loss, addend, (int)n_add, loss);
+    MMSA_LAUNCH_CHECK("ce_fwd_one_kernel");
+    return MMSA_OK;
+  }
   ce_fwd_kernel<<<(unsigned)ceil_div(B, 128), 128, 0, s>>>(B, (int)C, logits, labels, pred, row_loss);
   MMSA_LAUNCH_CHECK("ce_fwd_kernel");
-  sum_scale_kernel<<<1, 256, 0, s>>>(row_loss, B, 1.f / (float)B, loss);
-  MMSA_LAUNCH_CHECK("sum_scale_kernel");
+  sum_scale_add_kernel<<<1, 256, 0, s>>>(row_loss, B, 1.f / (float)B, addend, (int)n_add, loss);
+  MMSA_LAUNCH_CHECK("sum_scale_add_kernel");
   return MMSA_OK;
 }
 

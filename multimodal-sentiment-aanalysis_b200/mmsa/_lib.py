@@ -60,11 +60,11 @@ _PROTOS = {
     "mmsa_modal_head_bwd": (I, [I, L, L, I, L, P, P, P, P, P, P, P, P, P]),
     "mmsa_act_fwd": (I, [I, L, P, I, P, P]),
     "mmsa_act_bwd": (I, [I, L, P, P, I, P, P]),
-    "mmsa_bn_act_fwd": (I, [I, L, L, I, P, P, P, P, P, F, F, I, F, P, I, U, U, P, P, P, P, P, P]),
+    "mmsa_bn_act_fwd": (I, [I, L, L, I, P, P, P, P, P, P, F, F, I, F, P, I, U, U, P, P, P, P, P, P]),
     "mmsa_bn_act_bwd": (I, [I, L, L, I, P, P, P, P, P, P, I, F, P, P, P, P, P, P]),
     "mmsa_dropout": (I, [I, L, P, F, P, I, U, U, P, P, P]),
     "mmsa_rng_advance": (I, [P, U, P]),
-    "mmsa_ce_fwd": (I, [L, L, P, P, P, P, P, P]),
+    "mmsa_ce_fwd": (I, [L, L, P, P, P, L, P, P, P, P]),
     "mmsa_ce_bwd": (I, [I, L, L, P, P, P, P, P]),
     "mmsa_l2norm_fwd": (I, [I, L, L, P, P, P, P]),
     "mmsa_l2norm_bwd": (I, [I, L, L, P, P, P, P, P, P]),

@@ -395,9 +395,12 @@ def act_bwd(x: Tensor, dy: Tensor, act: int, out_dtype: torch.dtype) -> Tensor:
 
 def bn_act_fwd(x: Tensor, gamma, beta, running_mean, running_var, momentum: float, eps: float, training: bool,
                order: int, dropout_p: float, keep_mask: Optional[Tensor], seed: int, offset: int,
-               out_dtype: torch.dtype, rng_state: Optional[Tensor] = None, want_lp: bool = False):
-    """-> y, save_mean, save_rstd, keep_mask[, y_lp]; want_lp (fp32 out only): also a bf16 copy of y from the same launch."""
-    _check(x, gamma, beta)
+               out_dtype: torch.dtype, rng_state: Optional[Tensor] = None, want_lp: bool = False,
+               num_batches_tracked: Optional[Tensor] = None):
+    """-> y, save_mean, save_rstd, keep_mask[, y_lp]; want_lp (fp32 out only): also a bf16 copy of y from the same launch.
+    num_batches_tracked (int64 scalar on the device): incremented by the kernel in training mode."""
+    _check(x, gamma, beta, num_batches_tracked)
+    assert num_batches_tracked is None or num_batches_tracked.dtype == torch.int64
     assert x.dtype == torch.float32
     B, N = x.shape
     y = torch.empty((B, N), device=x.device, dtype=out_dtype)
@@ -408,7 +411,7 @@ def bn_act_fwd(x: Tensor, gamma, beta, running_mean, running_var, momentum: floa
     if training and dropout_p > 0 and keep_mask is None:
         keep_mask = torch.empty((B, N), device=x.device, dtype=torch.uint8)
     call("mmsa_bn_act_fwd", dt(out_dtype), B, N, order, x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _p(running_mean),
-         _p(running_var), float(momentum), float(eps), int(training), float(dropout_p), _p(keep_mask),
+         _p(running_var), _p(num_batches_tracked), float(momentum), float(eps), int(training), float(dropout_p), _p(keep_mask),
          int(mask_given), seed, offset, _p(rng_state), y.data_ptr(), _p(y_lp), save_mean.data_ptr(), save_rstd.data_ptr(),
          _stream())
     if want_lp:
@@ -450,14 +453,16 @@ def rng_advance(rng_state: Tensor, n: int) -> None:
     call("mmsa_rng_advance", rng_state.data_ptr(), int(n), _stream())
 
 
-def ce_fwd(logits: Tensor, labels: Tensor):
-    _check(logits, labels)
+def ce_fwd(logits: Tensor, labels: Tensor, addend: Optional[Tensor] = None):
+    """-> loss [1] (= mean CE + sum(addend)), pred [B]; addend: up to 64 fp32 device values."""
+    _check(logits, labels, addend)
+    assert addend is None or (addend.dtype == torch.float32 and addend.is_contiguous() and addend.numel() <= 64)
     B, C = logits.shape
     loss = torch.empty((1,), device=logits.device, dtype=torch.float32)
     pred = torch.empty((B,), device=logits.device, dtype=torch.int64)
     row = torch.empty((B,), device=logits.device, dtype=torch.float32)
-    call("mmsa_ce_fwd", B, C, logits.data_ptr(), labels.data_ptr(), loss.data_ptr(), pred.data_ptr(), row.data_ptr(),
-         _stream())
+    call("mmsa_ce_fwd", B, C, logits.data_ptr(), labels.data_ptr(), _p(addend), 0 if addend is None else addend.numel(),
+         loss.data_ptr(), pred.data_ptr(), row.data_ptr(), _stream())
     return loss, pred
 
 

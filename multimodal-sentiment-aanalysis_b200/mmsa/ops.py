@@ -407,6 +407,7 @@ class FusionCoreFn(Function):
         ctx.st = (st1, st2, text2d, image2d)
         ctx.dims = (B, L, R)
         ctx.plist = (wt, bt, wi, bi) + tuple(bp)          # the Parameter objects: keys of the gradient sink
+        ctx.set_materialize_grads(False)                  # the operand copies never have a gradient: no zero fills
         if f0_lp is not None:
             ctx.mark_non_differentiable(f0_lp, fv_lp)
         return f0, fv, e1, e2, f0_lp, fv_lp
@@ -416,7 +417,11 @@ class FusionCoreFn(Function):
     def backward(ctx, df0, dfv, de1, de2, _df0_lp=None, _dfv_lp=None):
         st1, st2, text2d, image2d = ctx.st
         ctx.st = None
-        df0, dfv, de1, de2 = (K.cast(_c(x), torch.float32) for x in (df0, dfv, de1, de2))
+        if df0 is None and dfv is None and de1 is None and de2 is None:
+            ctx.plist = None
+            return (None,) * 23
+        zero = lambda: torch.zeros((ctx.dims[0], st1.E), device=text2d.device, dtype=torch.float32)   # an unused output
+        df0, dfv, de1, de2 = (zero() if x is None else K.cast(_c(x), torch.float32) for x in (df0, dfv, de1, de2))
         need_w1 = any(ctx.needs_input_grad[7:15])
         need_w2 = any(ctx.needs_input_grad[15:23])
         # data-parallel gradient arena: destinations for the parameter gradients (None: allocate and hand to autograd)
@@ -588,6 +593,7 @@ class ModalConcatFn(Function):
         slots = [K.cast(_c(s), torch.float32) for s in slots]
         w, fused = K.modal_concat_fwd(K.cast(_c(logits), torch.float32), slots, torch.float32)
         ctx.save_for_backward(w, *slots)
+        ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(w)
         return fused, w
 
@@ -595,6 +601,8 @@ class ModalConcatFn(Function):
     @once_differentiable
     def backward(ctx, dfused, _dw):
         w, *slots = ctx.saved_tensors
+        if dfused is None:
+            return (None,) * (1 + len(slots))
         need = list(ctx.needs_input_grad[1:])
         dslots, dlogits = K.modal_concat_bwd(K.cast(_c(dfused), torch.float32), w, slots, need, torch.float32)
         return (dlogits,) + tuple(dslots)
@@ -624,6 +632,7 @@ class ModalHeadFn(Function):
         hg, w, fused, fused_lp = K.modal_head_fwd(h_pre, _c(w2c), None if b2 is None else b2.detach(), slots32, cd)
         ctx.save_for_backward(xa, xb, w1c, w2c, h_pre, hg, w, *slots32)
         ctx.cfg = (cd, raw_a.shape, None if raw_b is None else raw_b.shape, b1 is not None, b2 is not None)
+        ctx.set_materialize_grads(False)     # fused_lp / w never have a gradient: no zero fills for them
         ctx.mark_non_differentiable(w)
         if fused_lp is not None:
             ctx.mark_non_differentiable(fused_lp)
@@ -634,6 +643,8 @@ class ModalHeadFn(Function):
     def backward(ctx, dfused, _dlp, _dw):
         xa, xb, w1c, w2c, h_pre, hg, w, *slots32 = ctx.saved_tensors
         cd, shp_a, shp_b, has_b1, has_b2 = ctx.cfg
+        if dfused is None:
+            return (None,) * (9 + len(slots32))
         need_slots = list(ctx.needs_input_grad[9:])
         dslots, dlogits, dh = K.modal_head_bwd(K.cast(_c(dfused), torch.float32), w, slots32, need_slots, h_pre, _c(w2c), cd)
         main = torch.cuda.current_stream(dfused.device)
@@ -804,13 +815,13 @@ class SeqFn(Function):
                 pi += 2
                 p = dmod.p if (dmod is not None and training) else 0.0
                 mask, seed, off = drop.next(f"{name}.{didx}", cur.shape) if p > 0 else (None, 0, 0)
-                if training and bn.track_running_stats and bn.num_batches_tracked is not None:
-                    bn.num_batches_tracked += 1
+                nbt = bn.num_batches_tracked if (training and bn.track_running_stats) else None   # the kernel counts
                 lp_here = want_lp and last and out_dt == torch.float32 and cd == torch.bfloat16
                 res = K.bn_act_fwd(cur, gamma.detach(), beta.detach(), bn.running_mean, bn.running_var,
                                    0.1 if bn.momentum is None else bn.momentum, bn.eps, training, order,
                                    p, mask, seed, off, out_dt,
-                                   rng_state=(drop.state(cur.device) if (p > 0 and mask is None) else None), want_lp=lp_here)
+                                   rng_state=(drop.state(cur.device) if (p > 0 and mask is None) else None), want_lp=lp_here,
+                                   num_batches_tracked=nbt)
                 y, mean, rstd, mask = res[:4]
                 if lp_here:
                     out_lp = res[4]
@@ -832,6 +843,7 @@ class SeqFn(Function):
                     a, cur = K.cast(cur, cd), None
         ctx.tape = tape
         ctx.cd = cd
+        ctx.set_materialize_grads(False)     # the compute-dtype copy never has a gradient: no zero fill for it
         ctx.n_params = len(params)
         ctx.has_x2 = x2 is not None
         ctx.in_dtypes = (x.dtype, None if x2 is None else x2.dtype)
@@ -849,6 +861,8 @@ class SeqFn(Function):
     def backward(ctx, dy, _dlp=None):
         tape, cd = ctx.tape, ctx.cd
         ctx.tape = None
+        if dy is None:
+            return (None,) * (10 + ctx.n_params)
         grads: List[Optional[Tensor]] = [None] * ctx.n_params
         need = ctx.needs_input_grad[10:]
         d = K.cast(_c(dy), torch.float32)          # fp32 unless an elementwise backward wrote cd for a GEMM
@@ -950,22 +964,29 @@ class CrossEntropyFn(Function):
     """nn.CrossEntropyLoss() (mean) on fp32 logits (Trainer.py:17,68)."""
 
     @staticmethod
-    def forward(ctx, logits, labels):
+    def forward(ctx, logits, labels, extra):
         logits = _c(logits.float())
-        loss, pred = K.ce_fwd(logits, labels)
+        loss, pred = K.ce_fwd(logits, labels, None if extra is None else _c(extra.float()).view(-1))
         ctx.save_for_backward(logits, labels)
         ctx.pred = pred
+        ctx.extra_shape = None if extra is None else extra.shape
         return loss.view(())
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dloss):
         logits, labels = ctx.saved_tensors
-        return K.ce_bwd(logits, labels, _c(dloss.float()).view(1)), None
+        dloss = _c(dloss.float()).view(1)
+        dextra = None
+        if ctx.extra_shape is not None and ctx.needs_input_grad[2]:
+            dextra = dloss.expand(ctx.extra_shape) if len(ctx.extra_shape) else dloss.view(())
+        return K.ce_bwd(logits, labels, dloss), None, dextra
 
 
-def cross_entropy(logits, labels):
-    return CrossEntropyFn.apply(logits, labels)
+def cross_entropy(logits, labels, extra: Optional[Tensor] = None):
+    """mean softmax cross-entropy; extra (a few fp32 device values, e.g. the weighted contrastive loss of Trainer.py:68-71):
+    returns CE + extra.sum() from the same launch (d extra = d loss)."""
+    return CrossEntropyFn.apply(logits, labels, extra)
 
 
 class ContrastiveFn(Function):

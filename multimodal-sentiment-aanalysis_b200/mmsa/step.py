@@ -45,14 +45,15 @@ class TrainStep:
             s.grads = None
             self.slots.append(s)
         self._pool = None
+        self._one = torch.ones((), device=self.device, dtype=torch.float32)
         self.launches_per_step = 0
 
     # the arithmetic of one step; every op below is a kernel of libmmsa.so
     def _body(self, s: _Slot) -> None:
         self.model.prepare_step()                                            # bf16 operand copies of the weights
         logits, closs = self.model(s.text, s.image, None, s.labels)          # Trainer.py:60
-        loss = ops.cross_entropy(logits, s.labels) + closs.sum()             # Trainer.py:68-71
-        loss.backward()                                                      # Trainer.py:79
+        loss = ops.cross_entropy(logits, s.labels, extra=closs)              # Trainer.py:68-71 (CE + w * contrastive)
+        loss.backward(gradient=self._one)                                    # Trainer.py:79 (seed given: no fill launch)
         if self.post_backward is not None:
             self.post_backward()                                             # e.g. gradient all-reduce
         s.loss, s.logits = loss.detach(), logits.detach()

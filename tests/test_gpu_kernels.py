@@ -402,6 +402,31 @@ def test_cross_entropy(cuda_device):
     assert rel_err(dl, lr.grad) <= 1e-5
 
 
+@pytest.mark.parametrize("B", [1, 256, 20000])       # 20000: past the one-launch form (two launches, same arithmetic)
+def test_cross_entropy_with_addend(cuda_device, B):
+    """loss = CE + sum(addend) from the CE launch itself (the trainer's CE + w * contrastive, Trainer.py:68-71), and through
+    autograd: d addend = d loss."""
+    import mmsa
+    k = _k()
+    C = 3
+    logits = _rand((B, C), torch.float32, cuda_device, 3, 3.0)
+    labels = torch.randint(0, C, (B,), generator=torch.Generator().manual_seed(4)).to(cuda_device)
+    add = torch.tensor([0.75, -2.5], device=cuda_device)
+    loss, pred = k.ce_fwd(logits, labels, add)
+    ref = F.cross_entropy(logits.double(), labels) + add.double().sum()
+    assert rel_err(loss, ref) <= 1e-5
+    assert torch.equal(pred, logits.argmax(1))
+    lg = logits.clone().requires_grad_(True)
+    extra = add.clone().requires_grad_(True)
+    out = mmsa.cross_entropy(lg, labels, extra=extra)
+    assert rel_err(out, ref) <= 1e-5
+    (2.0 * out).backward()
+    lr = logits.double().requires_grad_(True)
+    (2.0 * F.cross_entropy(lr, labels)).backward()
+    assert rel_err(lg.grad, lr.grad) <= 1e-5
+    assert torch.equal(extra.grad, torch.full_like(add, 2.0))
+
+
 def _oracle():
     from oracle import fusion_oracle as O
     return O

@@ -65,9 +65,12 @@ def test_fusion_eval_and_contracts(cuda_device):
     text, image = (x.to(cuda_device) for x in inputs)
     out = model(text, image, None, labels.to(cuda_device))
     assert isinstance(out, tuple) and len(out) == 2 and out[0].shape == (6, 3) and out[1].shape == (1,)
+    bns = [m for m in model.modules() if isinstance(m, torch.nn.BatchNorm1d) and m in list(model.fusion) + list(model.arousal_head)]
+    assert bns and all(int(m.num_batches_tracked) == 1 for m in bns)      # counted by the BatchNorm kernel itself
     model.eval()
     with torch.no_grad():
         logits = model(text, image, None)
+    assert all(int(m.num_batches_tracked) == 1 for m in bns)              # eval mode does not count
     assert logits.shape == (6, 3) and logits.dtype == torch.float32
     p = {k: v for k, v in params.items()}
     p.update(model.state_dict())                       # running stats after the one train step
@@ -276,6 +279,35 @@ def _full_step(model, text, image, labels):
     loss = mmsa.cross_entropy(logits, labels) + closs.sum()
     loss.backward()
     return logits.detach(), loss.detach(), {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+
+
+def test_step_loss_assembly_matches_trainer_form(cuda_device):
+    """mmsa.TrainStep folds `CE + w * contrastive` (Trainer.py:68-71) into the CE launch and seeds backward with a static
+    one: same loss and same gradients as the trainer's own expression, and unused outputs of the fused nodes (logits only,
+    no contrastive term) still back-propagate."""
+    import mmsa
+    cfg = O.FusionConfig(embed_dim=256, num_heads=4, wiring="bidirectional", contract="single", valence=False)
+    params, buffers = O.init_params(cfg, seed=2)
+    inputs, labels = O.synth_inputs(cfg, 16, L=32, R=49, seed=6)
+    text, image = (x.to(cuda_device) for x in inputs)
+    labels = labels.to(cuda_device)
+    model = build_model(cfg, params, buffers, torch.float32, cuda_device).set_dropout(0.0)
+    _, loss_a, grads_a = _full_step(model, text, image, labels)
+    buffers2 = {k: v.clone() for k, v in buffers.items()}
+    model2 = build_model(cfg, params, buffers2, torch.float32, cuda_device).set_dropout(0.0)
+    logits, closs = model2(text, image, None, labels)
+    loss_b = mmsa.cross_entropy(logits, labels, extra=closs)
+    loss_b.backward(gradient=torch.ones((), device=cuda_device))
+    assert rel_err(loss_b, loss_a) <= 1e-6
+    for k, p in model2.named_parameters():
+        if k in grads_a:
+            assert rel_err(p.grad, grads_a[k]) <= 1e-5, k
+    # only the classifier output is used: the contrastive features' gradients are absent (None, not zero-filled)
+    model2.zero_grad(set_to_none=True)
+    logits = model2(text, image, None)
+    mmsa.cross_entropy(logits, labels).backward()
+    assert model2.eeg_net.proj.weight.grad is not None and torch.isfinite(model2.eeg_net.proj.weight.grad).all()
+    assert model2.temperature.grad is None
 
 
 @pytest.mark.parametrize("dtype,tol,noise_mult", [("fp32", 1e-5, 3.0), ("bf16", 2e-2, 1.0)])
