@@ -297,16 +297,19 @@ int mmsa_l2norm_bwd(int dtype, int64_t B, int64_t E, const void* y, const float*
  *   grad flows through the row max; dtemp accumulates dL/dtemperature);
  * kind SUPCON: train.py:24-40; kind NTXENT: ME-MHACL/train.py:55-65 (partner = (i+Bg/2) mod Bg).
  * fwd writes row_stats:[B,4] fp32 (max, all, pos, argmax-as-float bits) and loss:[1] = sum_i l_i/denominator.
- * bwd writes G:[B,Bg] (g_dtype) = dloss * dL/dsim (w.r.t. the UN-scaled cosine) and dtemp:[1]. */
+ * bwd writes G:[B,Bg] (g_dtype) = dloss * dL/dsim (w.r.t. the UN-scaled cosine) and dtemp:[1].
+ * weight (device scalar or NULL): the learnable loss weight of MultimodalModel.py:315-317 folded into the same launches --
+ *   fwd: loss = weight * mean, loss_raw:[1] (or NULL) = the unweighted mean; bwd: the upstream gradient becomes
+ *   dloss * weight, and dweight:[1] (or NULL) = dloss * loss_raw. */
 int mmsa_contrastive_fwd(int kind, int64_t B, int64_t Bg, int64_t row_offset, const float* sim,
                          const int64_t* labels_rows, const int64_t* labels_cols,
-                         const float* temperature, float temperature_const, int64_t denom,
-                         float* row_stats, float* row_loss, float* loss, void* stream);
+                         const float* temperature, float temperature_const, int64_t denom, const float* weight,
+                         float* row_stats, float* row_loss, float* loss, float* loss_raw, void* stream);
 int mmsa_contrastive_bwd(int kind, int64_t B, int64_t Bg, int64_t row_offset, const float* sim,
                          const int64_t* labels_rows, const int64_t* labels_cols,
                          const float* temperature, float temperature_const, int64_t denom,
-                         const float* row_stats, const float* dloss,
-                         void* G, int g_dtype, float* dtemp_rows, float* dtemp, void* stream);
+                         const float* row_stats, const float* dloss, const float* weight, const float* loss_raw,
+                         void* G, int g_dtype, float* dtemp_rows, float* dtemp, float* dweight, void* stream);
 
 /* ---- fused global-norm clip + AdamW over a flat fp32 parameter arena (Trainer.py:19-21,80-81;
  *      SURVEY.md section 8(f) rank 1) ----------------------------------------------------------- */

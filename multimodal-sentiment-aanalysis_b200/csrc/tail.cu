@@ -213,6 +213,35 @@ __global__ void sum_scale_add_kernel(const float* __restrict__ v, int64_t n, flo
   }
 }
 
+// tail launches of the contrastive losses: the ordered mean of the row losses, times the (device-resident) loss weight
+// when there is one (`contrastive_weight * loss`, MultimodalModel.py:315-317), and in the backward the temperature
+// gradient's ordered sum plus d weight = d loss * unweighted loss
+__global__ void contrastive_finish_kernel(const float* __restrict__ row_loss, int64_t n, float scale,
+                                          const float* __restrict__ weight, float* __restrict__ loss,
+                                          float* __restrict__ loss_raw) {
+  __shared__ float sm[32];
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += row_loss[i];
+  s = block_sum(s, sm);
+  if (threadIdx.x == 0) {
+    const float raw = s * scale;
+    if (loss_raw != nullptr) loss_raw[0] = raw;
+    loss[0] = weight != nullptr ? weight[0] * raw : raw;
+  }
+}
+__global__ void contrastive_bwd_finish_kernel(const float* __restrict__ dtemp_rows, int64_t n, float* __restrict__ dtemp,
+                                              const float* __restrict__ dloss, const float* __restrict__ loss_raw,
+                                              float* __restrict__ dweight) {
+  __shared__ float sm[32];
+  float s = 0.f;
+  if (dtemp_rows != nullptr && dtemp != nullptr) {
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += dtemp_rows[i];
+    s = block_sum(s, sm);
+    if (threadIdx.x == 0) dtemp[0] = s;
+  }
+  if (threadIdx.x == 0 && dweight != nullptr) dweight[0] = dloss[0] * loss_raw[0];
+}
+
 // deterministic single-block sum: out[0] = scale * sum(v[0..n))
 __global__ void sum_scale_kernel(const float* __restrict__ v, int64_t n, float scale, float* __restrict__ out) {
   __shared__ float sm[32];
@@ -318,12 +347,12 @@ contrastive_bwd_kernel(int kind, int64_t B, int64_t Bg, int64_t row_offset, cons
                        const int64_t* __restrict__ lab_r, const int64_t* __restrict__ lab_c,
                        const float* __restrict__ tptr, float tconst, float inv_denom,
                        const float* __restrict__ row_stats, const float* __restrict__ dloss,
-                       TG* __restrict__ G, float* __restrict__ dtemp_rows) {
+                       const float* __restrict__ weight, TG* __restrict__ G, float* __restrict__ dtemp_rows) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t i = (int64_t)blockIdx.x * 8 + warp;
   if (i >= B) return;
   const float T = load_temp(tptr, tconst);
-  const float up = dloss[0] * inv_denom;
+  const float up = (weight != nullptr ? dloss[0] * weight[0] : dloss[0]) * inv_denom;
   const float* row = sim + i * Bg;
   TG* grow = G + i * Bg;
   const int64_t gi = row_offset + i;
@@ -495,8 +524,8 @@ int mmsa_ce_bwd(int dtype, int64_t B, int64_t C, const float* logits, const int6
 
 int mmsa_contrastive_fwd(int kind, int64_t B, int64_t Bg, int64_t row_offset, const float* sim,
                          const int64_t* labels_rows, const int64_t* labels_cols, const float* temperature,
-                         float temperature_const, int64_t denom, float* row_stats, float* row_loss,
-                         float* loss, void* stream) {
+                         float temperature_const, int64_t denom, const float* weight, float* row_stats, float* row_loss,
+                         float* loss, float* loss_raw, void* stream) {
   MMSA_REQUIRE_DEVICE();
   MMSA_REQUIRE(kind >= 0 && kind <= 2, "mmsa_contrastive_fwd: bad kind %d", kind);
   MMSA_REQUIRE(B > 0 && Bg > 0 && denom > 0, "mmsa_contrastive_fwd: empty input");
@@ -507,33 +536,35 @@ int mmsa_contrastive_fwd(int kind, int64_t B, int64_t Bg, int64_t row_offset, co
                                                                   labels_cols, temperature, temperature_const,
                                                                   row_stats, row_loss);
   MMSA_LAUNCH_CHECK("contrastive_fwd_kernel");
-  sum_scale_kernel<<<1, 256, 0, s>>>(row_loss, B, 1.f / (float)denom, loss);
-  MMSA_LAUNCH_CHECK("sum_scale_kernel");
+  contrastive_finish_kernel<<<1, 256, 0, s>>>(row_loss, B, 1.f / (float)denom, weight, loss, loss_raw);
+  MMSA_LAUNCH_CHECK("contrastive_finish_kernel");
   return MMSA_OK;
 }
 
 int mmsa_contrastive_bwd(int kind, int64_t B, int64_t Bg, int64_t row_offset, const float* sim,
                          const int64_t* labels_rows, const int64_t* labels_cols, const float* temperature,
                          float temperature_const, int64_t denom, const float* row_stats, const float* dloss,
-                         void* G, int g_dtype, float* dtemp_rows, float* dtemp, void* stream) {
+                         const float* weight, const float* loss_raw, void* G, int g_dtype, float* dtemp_rows, float* dtemp,
+                         float* dweight, void* stream) {
   MMSA_REQUIRE_DEVICE();
   MMSA_REQUIRE(kind >= 0 && kind <= 2, "mmsa_contrastive_bwd: bad kind %d", kind);
   MMSA_REQUIRE(B > 0 && Bg > 0 && denom > 0, "mmsa_contrastive_bwd: empty input");
+  MMSA_REQUIRE(dweight == nullptr || loss_raw != nullptr, "mmsa_contrastive_bwd: dweight needs the unweighted loss");
   cudaStream_t s = (cudaStream_t)stream;
   ProfScope prof("contrastive_bwd", s, (double)B * Bg * (4.0 + (g_dtype == MMSA_F32 ? 4 : 2)));
   float inv_denom = 1.f / (float)denom;
   if (g_dtype == MMSA_F32)
     contrastive_bwd_kernel<float><<<(unsigned)ceil_div(B, 8), 256, 0, s>>>(
         kind, B, Bg, row_offset, sim, labels_rows, labels_cols, temperature, temperature_const, inv_denom,
-        row_stats, dloss, (float*)G, dtemp_rows);
+        row_stats, dloss, weight, (float*)G, dtemp_rows);
   else
     contrastive_bwd_kernel<bf16><<<(unsigned)ceil_div(B, 8), 256, 0, s>>>(
         kind, B, Bg, row_offset, sim, labels_rows, labels_cols, temperature, temperature_const, inv_denom,
-        row_stats, dloss, (bf16*)G, dtemp_rows);
+        row_stats, dloss, weight, (bf16*)G, dtemp_rows);
   MMSA_LAUNCH_CHECK("contrastive_bwd_kernel");
-  if (dtemp_rows && dtemp) {
-    sum_scale_kernel<<<1, 256, 0, s>>>(dtemp_rows, B, 1.f, dtemp);
-    MMSA_LAUNCH_CHECK("sum_scale_kernel");
+  if ((dtemp_rows && dtemp) || dweight) {
+    contrastive_bwd_finish_kernel<<<1, 256, 0, s>>>(dtemp_rows, B, dtemp, dloss, loss_raw, dweight);
+    MMSA_LAUNCH_CHECK("contrastive_bwd_finish_kernel");
   }
   return MMSA_OK;
 }

@@ -68,8 +68,8 @@ _PROTOS = {
     "mmsa_ce_bwd": (I, [I, L, L, P, P, P, P, P]),
     "mmsa_l2norm_fwd": (I, [I, L, L, P, P, P, P]),
     "mmsa_l2norm_bwd": (I, [I, L, L, P, P, P, P, P, P]),
-    "mmsa_contrastive_fwd": (I, [I, L, L, L, P, P, P, P, F, L, P, P, P, P]),
-    "mmsa_contrastive_bwd": (I, [I, L, L, L, P, P, P, P, F, L, P, P, P, I, P, P, P]),
+    "mmsa_contrastive_fwd": (I, [I, L, L, L, P, P, P, P, F, L, P, P, P, P, P, P]),
+    "mmsa_contrastive_bwd": (I, [I, L, L, L, P, P, P, P, F, L, P, P, P, P, P, I, P, P, P, P]),
     "mmsa_sumsq": (I, [P, L, P, L, P, P]),
     "mmsa_clip_adamw": (I, [P, P, P, P, L, P, F, Dbl, Dbl, Dbl, Dbl, Dbl, L, P]),
 }

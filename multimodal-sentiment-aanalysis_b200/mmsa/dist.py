@@ -56,7 +56,8 @@ def gather_labels(labels: Tensor, group=None) -> Tensor:
     return out
 
 
-def sharded_infonce(f1: Tensor, f2: Tensor, labels: Tensor, temperature, group=None, fast: bool = False) -> Tensor:
+def sharded_infonce(f1: Tensor, f2: Tensor, labels: Tensor, temperature, group=None, fast: bool = False,
+                    weight: Optional[Tensor] = None) -> Tensor:
     """InfoNCE (MultimodalModel.py:232-260) over the GLOBAL batch with rows sharded by rank:
     this rank owns rows [rank*B, (rank+1)*B) of the B_g x B_g similarity matrix and all its columns.
     Returns the local mean over this rank's rows; averaging parameter gradients over ranks then
@@ -65,7 +66,8 @@ def sharded_infonce(f1: Tensor, f2: Tensor, labels: Tensor, temperature, group=N
     rank = dist.get_rank(group)
     f2_all = all_gather_rows(f2, group)
     labels_all = gather_labels(labels, group)
-    return ops.infonce(f1, f2_all, labels, temperature, labels_cols=labels_all, row_offset=rank * f1.shape[0], fast=fast)
+    return ops.infonce(f1, f2_all, labels, temperature, labels_cols=labels_all, row_offset=rank * f1.shape[0], fast=fast,
+                       weight=weight)
 
 
 def _sharded_two_view(z1: Tensor, z2: Tensor, labels: Optional[Tensor], temperature: float, kind: int, group=None) -> Tensor:
@@ -86,8 +88,10 @@ def _sharded_two_view(z1: Tensor, z2: Tensor, labels: Optional[Tensor], temperat
         lab_rows = labels.view(-1)
     else:
         lab_cols = lab_rows = None
-    a = ops.ContrastiveFn.apply(z1, z_all, lab_rows, lab_cols, None, float(temperature), kind, rank * B, 2 * B, False, False)
-    b = ops.ContrastiveFn.apply(z2, z_all, lab_rows, lab_cols, None, float(temperature), kind, Bg + rank * B, 2 * B, False, False)
+    a = ops.ContrastiveFn.apply(z1, z_all, lab_rows, lab_cols, None, float(temperature), kind, rank * B, 2 * B, False, False,
+                                None)
+    b = ops.ContrastiveFn.apply(z2, z_all, lab_rows, lab_cols, None, float(temperature), kind, Bg + rank * B, 2 * B, False,
+                                False, None)
     return a + b
 
 

@@ -494,30 +494,37 @@ def l2norm_bwd(y: Tensor, norm: Tensor, dy1: Tensor, dy2: Optional[Tensor]) -> T
 
 
 def contrastive_fwd(kind: int, sim: Tensor, labels_rows, labels_cols, temperature: Optional[Tensor],
-                    temperature_const: float, row_offset: int, denom: int):
-    _check(sim, labels_rows, labels_cols, temperature)
+                    temperature_const: float, row_offset: int, denom: int, weight: Optional[Tensor] = None):
+    """-> loss [1], row stats [B,4], unweighted loss [1] or None.  weight (fp32 device scalar): loss = weight * mean, from
+    the same launch; the unweighted mean is kept for d weight."""
+    _check(sim, labels_rows, labels_cols, temperature, weight)
+    assert weight is None or (weight.dtype == torch.float32 and weight.numel() == 1)
     B, Bg = sim.shape
     stats = torch.empty((B, 4), device=sim.device, dtype=torch.float32)
     row_loss = torch.empty((B,), device=sim.device, dtype=torch.float32)
     loss = torch.empty((1,), device=sim.device, dtype=torch.float32)
+    raw = torch.empty((1,), device=sim.device, dtype=torch.float32) if weight is not None else None
     call("mmsa_contrastive_fwd", kind, B, Bg, row_offset, sim.data_ptr(), _p(labels_rows), _p(labels_cols),
-         _p(temperature), float(temperature_const), denom, stats.data_ptr(), row_loss.data_ptr(), loss.data_ptr(),
-         _stream())
-    return loss, stats
+         _p(temperature), float(temperature_const), denom, _p(weight), stats.data_ptr(), row_loss.data_ptr(), loss.data_ptr(),
+         _p(raw), _stream())
+    return loss, stats, raw
 
 
 def contrastive_bwd(kind: int, sim: Tensor, labels_rows, labels_cols, temperature: Optional[Tensor],
                     temperature_const: float, row_offset: int, denom: int, stats: Tensor, dloss: Tensor,
-                    g_dtype: torch.dtype):
-    _check(sim, stats, dloss)
+                    g_dtype: torch.dtype, weight: Optional[Tensor] = None, loss_raw: Optional[Tensor] = None,
+                    want_dweight: bool = False):
+    """-> G [B,Bg], dtemp [1], dweight [1] or None (weight / loss_raw as in contrastive_fwd)."""
+    _check(sim, stats, dloss, weight, loss_raw)
     B, Bg = sim.shape
     G = torch.empty((B, Bg), device=sim.device, dtype=g_dtype)
     dtemp_rows = torch.empty((B,), device=sim.device, dtype=torch.float32)
     dtemp = torch.empty((1,), device=sim.device, dtype=torch.float32)
+    dweight = torch.empty((1,), device=sim.device, dtype=torch.float32) if (want_dweight and weight is not None) else None
     call("mmsa_contrastive_bwd", kind, B, Bg, row_offset, sim.data_ptr(), _p(labels_rows), _p(labels_cols),
-         _p(temperature), float(temperature_const), denom, stats.data_ptr(), dloss.data_ptr(), G.data_ptr(),
-         dt(g_dtype), dtemp_rows.data_ptr(), dtemp.data_ptr(), _stream())
-    return G, dtemp
+         _p(temperature), float(temperature_const), denom, stats.data_ptr(), dloss.data_ptr(), _p(weight), _p(loss_raw),
+         G.data_ptr(), dt(g_dtype), dtemp_rows.data_ptr(), dtemp.data_ptr(), _p(dweight), _stream())
+    return G, dtemp, dweight
 
 
 # ---- encoder tail: residual add + LayerNorm, positional table (SURVEY.md section 8(f) rank 2) ----

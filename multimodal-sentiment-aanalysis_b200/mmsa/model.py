@@ -256,14 +256,14 @@ class MultimodalTransformerModel(nn.Module):
         if con_labels is not None:
             con_labels = con_labels.contiguous().long()
         contrastive: List[Tensor] = []
-        side, weighted = None, False
+        side = None
         if self.wiring == "native":
             f0 = self._cd(self.eeg_net(eeg))
             f1 = self._cd(self.eye_net(eye))
             f2 = self._cd(self.pps_net(pps))
             if con_labels is not None:                               # :271-284
-                for f in (f0, f1, f2):
-                    contrastive.append(ops.infonce(f, f, con_labels, self.temperature))
+                for f in (f0, f1, f2):                               # weighted (:315-317) inside the loss kernels
+                    contrastive.append(ops.infonce(f, f, con_labels, self.temperature, weight=self.contrastive_weight))
             e1 = self.cross_attn_e2p(f0, f1, f1)                     # :287
             e2 = self.cross_attn_p2e(f0, f2, f2)                     # :293
             f32 = torch.float32
@@ -291,23 +291,21 @@ class MultimodalTransformerModel(nn.Module):
                     side = self._side_stream
                     side.wait_stream(main)
                 with torch.cuda.stream(side if side is not None else main):
+                    cw = self.contrastive_weight                     # :315-317, applied inside the loss kernels -> shape (1,)
                     if self.dp_group is not None:
                         from . import dist as mdist
-                        contrastive.append(mdist.sharded_infonce(e1, e2, con_labels, self.temperature, self.dp_group, fast=fast))
+                        contrastive.append(mdist.sharded_infonce(e1, e2, con_labels, self.temperature, self.dp_group, fast=fast,
+                                                                 weight=cw))
                     else:
-                        contrastive.append(ops.infonce(e1, e2, con_labels, self.temperature, fast=fast))
+                        contrastive.append(ops.infonce(e1, e2, con_labels, self.temperature, fast=fast, weight=cw))
                     if self.contract == "multitask":
-                        contrastive.append(ops.infonce(e2, e1, con_labels, self.temperature, fast=fast))
-                    contrastive = [self.contrastive_weight * c for c in contrastive]     # :315-317 -> shape (1,)
-                    weighted = True
+                        contrastive.append(ops.infonce(e2, e1, con_labels, self.temperature, fast=fast, weight=cw))
         arousal, valence = self._tail(raw_a, raw_b, slots, *((f0_lp, fv_lp) if self.wiring == "bidirectional" else ()))
         if side is not None:                                         # join the contrastive branch
             cur = torch.cuda.current_stream(arousal.device)
             cur.wait_stream(side)
             for c in contrastive:
                 c.record_stream(cur)
-        if not weighted:
-            contrastive = [self.contrastive_weight * c for c in contrastive]     # :315-317 -> shape (1,)
         if self.contract == "single":
             if labels is None:
                 return arousal                                       # Tester.py:53

@@ -998,7 +998,10 @@ class ContrastiveFn(Function):
     ~2^-16 relative, fp32 accumulation); otherwise they run on the exact-fp32 CUDA-core GEMM (1e-5 parity mode)."""
 
     @staticmethod
-    def forward(ctx, f1, f2, labels_r, labels_c, temperature, temperature_const, kind, row_offset, denom, same, fast):
+    def forward(ctx, f1, f2, labels_r, labels_c, temperature, temperature_const, kind, row_offset, denom, same, fast,
+                weight):
+        # weight (a learnable fp32 scalar or None): returns weight * loss, shape (1,) -- `self.contrastive_weight * loss`
+        # (MultimodalModel.py:315-317) from the loss kernels themselves instead of a multiply and its three backward launches
         a = K.cast(_c(f1.detach()), torch.float32)
         n1, norm1 = K.l2norm_fwd(a)
         if same:
@@ -1013,18 +1016,20 @@ class ContrastiveFn(Function):
         else:
             sim = K.linear_fwd(n1, n2, None, out_dtype=torch.float32)
         tptr = None if temperature is None else temperature.detach().float().view(1)
-        loss, stats = K.contrastive_fwd(kind, sim, labels_r, labels_c, tptr, temperature_const, row_offset, denom)
-        ctx.save_for_backward(n1, norm1, n2, norm2, sim, stats, labels_r, labels_c, tptr, n1_row, n2_row)
+        wptr = None if weight is None else weight.detach().float().view(1)
+        loss, stats, raw = K.contrastive_fwd(kind, sim, labels_r, labels_c, tptr, temperature_const, row_offset, denom, wptr)
+        ctx.save_for_backward(n1, norm1, n2, norm2, sim, stats, labels_r, labels_c, tptr, n1_row, n2_row, wptr, raw)
         ctx.cfg = (temperature_const, kind, row_offset, denom, same, f1.dtype, f2.dtype, fast)
-        return loss.view(())
+        return loss.view(()) if weight is None else loss.view(weight.shape if weight.dim() else (1,))
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dloss):
-        n1, norm1, n2, norm2, sim, stats, labels_r, labels_c, tptr, n1_row, n2_row = ctx.saved_tensors
+        n1, norm1, n2, norm2, sim, stats, labels_r, labels_c, tptr, n1_row, n2_row, wptr, raw = ctx.saved_tensors
         tconst, kind, row_offset, denom, same, d1, d2, fast = ctx.cfg
-        G, dtemp = K.contrastive_bwd(kind, sim, labels_r, labels_c, tptr, tconst, row_offset, denom, stats,
-                                     _c(dloss.float()).view(1), torch.float32)
+        G, dtemp, dweight = K.contrastive_bwd(kind, sim, labels_r, labels_c, tptr, tconst, row_offset, denom, stats,
+                                              _c(dloss.float()).view(1), torch.float32, weight=wptr, loss_raw=raw,
+                                              want_dweight=wptr is not None and ctx.needs_input_grad[11])
         if fast:
             g_col, g_row = K.split3(G, col_side="a", row_side="a")
             dn1 = K.linear_dgrad(g_col, n2_row, out_dtype=torch.float32)
@@ -1039,31 +1044,34 @@ class ContrastiveFn(Function):
             df1 = K.cast(K.l2norm_bwd(n1, norm1, dn1, None), d1)
             df2 = K.cast(K.l2norm_bwd(n2, norm2, dn2, None), d2) if ctx.needs_input_grad[1] else None
         dT = dtemp.view(()) if (tptr is not None and ctx.needs_input_grad[4]) else None
-        return df1, df2, None, None, dT, None, None, None, None, None, None
+        return df1, df2, None, None, dT, None, None, None, None, None, None, dweight
 
 
 def infonce(f1: Tensor, f2: Tensor, labels: Tensor, temperature, labels_cols: Optional[Tensor] = None,
-            row_offset: int = 0, fast: bool = False) -> Tensor:
+            row_offset: int = 0, fast: bool = False, weight: Optional[Tensor] = None) -> Tensor:
     """MultimodalTransformerModel.compute_contrastive_loss (MultimodalModel.py:232-260).
-    `labels_cols`/`row_offset` describe a row block of a batch-sharded similarity matrix."""
+    `labels_cols`/`row_offset` describe a row block of a batch-sharded similarity matrix.
+    weight (one-element fp32 tensor, e.g. the model's learnable contrastive_weight): returns weight * loss with the
+    weight's shape (MultimodalModel.py:315-317), computed and differentiated inside the loss kernels."""
     same = f1 is f2
     lc = labels if labels_cols is None else labels_cols
     t_tensor = temperature if isinstance(temperature, Tensor) else None
     t_const = 0.0 if t_tensor is not None else float(temperature)
-    return ContrastiveFn.apply(f1, f2, labels, lc, t_tensor, t_const, LOSS_INFONCE, row_offset, f1.shape[0], same, fast)
+    return ContrastiveFn.apply(f1, f2, labels, lc, t_tensor, t_const, LOSS_INFONCE, row_offset, f1.shape[0], same, fast,
+                               weight)
 
 
 def supcon(z1: Tensor, z2: Tensor, labels: Tensor, temperature: float = 0.1) -> Tensor:
     """train.py:16-40 contrastive_loss: SupCon over the 2B stacked views."""
     z = _StackFn.apply(z1, z2)
     lab = torch.cat([labels.view(-1), labels.view(-1)])
-    return ContrastiveFn.apply(z, z, lab, lab, None, float(temperature), LOSS_SUPCON, 0, z.shape[0], True, False)
+    return ContrastiveFn.apply(z, z, lab, lab, None, float(temperature), LOSS_SUPCON, 0, z.shape[0], True, False, None)
 
 
 def ntxent(z1: Tensor, z2: Tensor, temperature: float = 0.5) -> Tensor:
     """ME-MHACL/train.py:47-66 contrastive_loss: NT-Xent over the 2N stacked views."""
     z = _StackFn.apply(z1, z2)
-    return ContrastiveFn.apply(z, z, None, None, None, float(temperature), LOSS_NTXENT, 0, z.shape[0], True, False)
+    return ContrastiveFn.apply(z, z, None, None, None, float(temperature), LOSS_NTXENT, 0, z.shape[0], True, False, None)
 
 
 class _StackFn(Function):

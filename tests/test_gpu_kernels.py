@@ -467,6 +467,38 @@ def test_infonce_op(cuda_device, B, E, same, T):
     check_close(name, "d temperature", tg.grad, tt.grad, 1e-5, t32.grad)
 
 
+@pytest.mark.parametrize("fast", [False, True])
+def test_infonce_weight_folded_into_the_loss_kernels(cuda_device, fast):
+    """ops.infonce(..., weight=w) == w * ops.infonce(...) (`self.contrastive_weight * loss`, MultimodalModel.py:315-317):
+    value with the weight's shape, and the gradients w.r.t. both feature sets, the temperature and the weight."""
+    from mmsa import ops
+    B, E, T = 48, 256, 0.07
+    g = torch.Generator().manual_seed(11)
+    f1 = torch.randn(B, E, generator=g)
+    f2 = f1 * 0.7 + 0.3 * torch.randn(B, E, generator=g)
+    labels = torch.randint(0, 3, (B,), generator=g).to(cuda_device)
+    outs = []
+    for folded in (False, True):
+        x, y = f1.clone().to(cuda_device).requires_grad_(True), f2.clone().to(cuda_device).requires_grad_(True)
+        tg = torch.tensor(T, device=cuda_device, requires_grad=True)
+        w = torch.tensor([1.75], device=cuda_device, requires_grad=True)
+        if folded:
+            out = ops.infonce(x, y, labels, tg, fast=fast, weight=w)
+        else:
+            out = w * ops.infonce(x, y, labels, tg, fast=fast)
+        assert out.shape == (1,)
+        (3.0 * out.sum()).backward()
+        outs.append((out.detach(), x.grad, y.grad, tg.grad, w.grad))
+    for a, b, what in zip(outs[0], outs[1], ("loss", "d feat1", "d feat2", "d temperature", "d weight")):
+        assert b is not None and b.shape == a.shape, what
+        assert rel_err(b, a) <= 1e-6, what
+    # a weight that does not require a gradient gets none
+    x = f1.clone().to(cuda_device).requires_grad_(True)
+    w = torch.tensor([0.5], device=cuda_device)
+    ops.infonce(x, x, labels, T, weight=w).sum().backward()
+    assert x.grad is not None and w.grad is None
+
+
 @pytest.mark.parametrize("B,Bg,E,T", [(64, 64, 768, 0.01), (256, 256, 768, 0.07), (128, 512, 768, 0.01), (40, 40, 128, 0.2)])
 def test_infonce_split_bf16_tensor_core(cuda_device, B, Bg, E, T):
     """bf16-mode InfoNCE: the three GEMMs run on tcgen05 with split-bf16 operands (hi.hi + hi.lo + lo.hi,
@@ -733,8 +765,8 @@ def test_sharded_supcon_ntxent_rows(cuda_device):
         for r in range(world):
             sl = slice(r * B, (r + 1) * B)
             lr = lab[sl] if name == "supcon" else None
-            la = ops.ContrastiveFn.apply(x[sl], z_all, lr, lab_cols, None, T, kind, r * B, 2 * B, False, False)
-            lb = ops.ContrastiveFn.apply(y[sl], z_all, lr, lab_cols, None, T, kind, Bg + r * B, 2 * B, False, False)
+            la = ops.ContrastiveFn.apply(x[sl], z_all, lr, lab_cols, None, T, kind, r * B, 2 * B, False, False, None)
+            lb = ops.ContrastiveFn.apply(y[sl], z_all, lr, lab_cols, None, T, kind, Bg + r * B, 2 * B, False, False, None)
             total = total + (la + lb) / world
         total.backward()
         assert rel_err(total, ref) <= 1e-5, name
