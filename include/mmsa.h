@@ -257,6 +257,20 @@ int mmsa_bn_act_fwd(int dtype, int64_t B, int64_t N, int order, const void* x,
                     int64_t* num_batches_tracked, float momentum, float eps, int training,
                     float dropout_p, uint8_t* keep_mask, int mask_given, uint64_t seed, uint64_t offset,
                     const uint64_t* rng_state, void* y, void* y_lp, float* save_mean, float* save_rstd, void* stream);
+/* Linear + BatchNorm1d block in ONE launch (bf16 operands, fp32 accumulation): z = x W^T + bias is written in fp32 (what
+ * mmsa_bn_act_bwd and the Linear's backward need), then y = dropout(act(BN(z))) exactly as mmsa_bn_act_fwd would compute
+ * it from z (same statistics, running-stat update, num_batches_tracked, Philox indexing, keep_mask, y / y_lp outputs).
+ * x:[M,K] bf16 (row stride ldx), w:[N,K] bf16 (row stride ldw), bias:[N] fp32 or NULL, z:[M,N] fp32, y:[M,N] out_dtype.
+ * One CTA owns all M rows of 16 columns, so M <= 256; also N % 8 == 0, K % 8 == 0, 16-byte aligned operands:
+ * mmsa_linear_bn_act_supported(...) != 0 says whether a shape qualifies (host-only check); other shapes take
+ * mmsa_linear_fwd + mmsa_bn_act_fwd.  (MultimodalModel.py:179-199, ME-MHACL/model.py:82-97.) */
+int mmsa_linear_bn_act_supported(int64_t M, int64_t N, int64_t K, int64_t ldx, int64_t ldw);
+int mmsa_linear_bn_act_fwd(int64_t M, int64_t N, int64_t K, const void* x, int64_t ldx, const void* w, int64_t ldw,
+                           const float* bias, const float* gamma, const float* beta, float* running_mean,
+                           float* running_var, int64_t* num_batches_tracked, float momentum, float eps, int training,
+                           int order, float dropout_p, uint8_t* keep_mask, int mask_given, uint64_t seed, uint64_t offset,
+                           const uint64_t* rng_state, float* z, int out_dtype, void* y, void* y_lp, float* save_mean,
+                           float* save_rstd, void* stream);
 int mmsa_bn_act_bwd(int dtype, int64_t B, int64_t N, int order, const void* x, const void* dy,
                     const float* gamma, const float* beta, const float* save_mean, const float* save_rstd, int training,
                     float dropout_p, const uint8_t* keep_mask,

@@ -60,6 +60,8 @@ _PROTOS = {
     "mmsa_modal_head_bwd": (I, [I, L, L, I, L, P, P, P, P, P, P, P, P, P]),
     "mmsa_act_fwd": (I, [I, L, P, I, P, P]),
     "mmsa_act_bwd": (I, [I, L, P, P, I, P, P]),
+    "mmsa_linear_bn_act_supported": (I, [L, L, L, L, L]),
+    "mmsa_linear_bn_act_fwd": (I, [L, L, L, P, L, P, L, P, P, P, P, P, P, F, F, I, I, F, P, I, U, U, P, P, I, P, P, P, P, P]),
     "mmsa_bn_act_fwd": (I, [I, L, L, I, P, P, P, P, P, P, F, F, I, F, P, I, U, U, P, P, P, P, P, P]),
     "mmsa_bn_act_bwd": (I, [I, L, L, I, P, P, P, P, P, P, I, F, P, P, P, P, P, P]),
     "mmsa_dropout": (I, [I, L, P, F, P, I, U, U, P, P, P]),

@@ -419,6 +419,43 @@ def bn_act_fwd(x: Tensor, gamma, beta, running_mean, running_var, momentum: floa
     return y, save_mean, save_rstd, keep_mask
 
 
+def linear_bn_act_ok(x: Tensor, w: Tensor) -> bool:
+    """whether mmsa_linear_bn_act_fwd takes this Linear (bf16 operands, batch <= 256, N % 8 == 0, K % 8 == 0, aligned)"""
+    if x.dtype != torch.bfloat16 or w.dtype != torch.bfloat16 or x.dim() != 2 or w.dim() != 2:
+        return False
+    if x.stride(1) != 1 or w.stride(1) != 1 or x.data_ptr() % 16 or w.data_ptr() % 16:
+        return False
+    return bool(_lib.load().mmsa_linear_bn_act_supported(x.shape[0], w.shape[0], x.shape[1], x.stride(0), w.stride(0)))
+
+
+def linear_bn_act_fwd(x: Tensor, w: Tensor, bias: Optional[Tensor], gamma, beta, running_mean, running_var, momentum: float,
+                      eps: float, training: bool, order: int, dropout_p: float, keep_mask: Optional[Tensor], seed: int,
+                      offset: int, out_dtype: torch.dtype, rng_state: Optional[Tensor] = None, want_lp: bool = False,
+                      num_batches_tracked: Optional[Tensor] = None):
+    """Linear + BatchNorm block in one launch (mmsa_linear_bn_act_fwd): -> z [M,N] fp32 (= x w^T + bias), then exactly what
+    bn_act_fwd(z, ...) returns: y, save_mean, save_rstd, keep_mask[, y_lp]."""
+    _check(x, w, bias, gamma, beta, num_batches_tracked)
+    assert w.shape[1] == x.shape[1]
+    assert num_batches_tracked is None or num_batches_tracked.dtype == torch.int64
+    M, Kd = x.shape
+    N = w.shape[0]
+    z = torch.empty((M, N), device=x.device, dtype=torch.float32)
+    y = torch.empty((M, N), device=x.device, dtype=out_dtype)
+    y_lp = torch.empty((M, N), device=x.device, dtype=torch.bfloat16) if (want_lp and out_dtype == torch.float32) else None
+    save_mean = torch.empty((N,), device=x.device, dtype=torch.float32)
+    save_rstd = torch.empty((N,), device=x.device, dtype=torch.float32)
+    mask_given = keep_mask is not None
+    if training and dropout_p > 0 and keep_mask is None:
+        keep_mask = torch.empty((M, N), device=x.device, dtype=torch.uint8)
+    call("mmsa_linear_bn_act_fwd", M, N, Kd, x.data_ptr(), x.stride(0), w.data_ptr(), w.stride(0), _p(bias), gamma.data_ptr(),
+         beta.data_ptr(), _p(running_mean), _p(running_var), _p(num_batches_tracked), float(momentum), float(eps),
+         int(training), order, float(dropout_p), _p(keep_mask), int(mask_given), seed, offset, _p(rng_state), z.data_ptr(),
+         dt(out_dtype), y.data_ptr(), _p(y_lp), save_mean.data_ptr(), save_rstd.data_ptr(), _stream())
+    if want_lp:
+        return z, y, save_mean, save_rstd, keep_mask, y_lp
+    return z, y, save_mean, save_rstd, keep_mask
+
+
 def bn_act_bwd(x, dy, gamma, beta, save_mean, save_rstd, training: bool, order: int, dropout_p: float, keep_mask,
                out_dtype: torch.dtype):
     _check(x, dy)

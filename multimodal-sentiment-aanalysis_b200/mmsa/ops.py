@@ -97,6 +97,11 @@ OVERLAP_BLOCKS = os.environ.get("MMSA_OVERLAP_BLOCKS", "0") == "1"     # forward
 OVERLAP_TAIL = True       # tail weight gradients (SeqFn.backward) and the contrastive branch (model.forward) on a second stream
 
 
+# Linear + BatchNorm1d(+act+dropout) blocks of the [B,*] tail as one launch when the batch fits one CTA (<= 256 rows);
+# MMSA_LINEAR_BN=0 keeps the two-kernel form (GEMM, then mmsa_bn_act_fwd) for A/B timing
+FUSE_LINEAR_BN = os.environ.get("MMSA_LINEAR_BN", "1") != "0"
+
+
 def set_overlap(on: bool) -> None:
     """Switch every second-stream overlap on or off.  Off = one kernel at a time on the caller's stream: what
     bench.py's per-launch profiling pass needs (a kernel timed while another one shares the SMs is not a kernel time)."""
@@ -792,7 +797,11 @@ class SeqFn(Function):
                                       else K.cast(K.cast(_c(x2), torch.float32), cd))
         out_lp = None
         n = len(steps)
+        fused_next = False
         for si, st in enumerate(steps):
+            if fused_next:                   # this BatchNorm step ran inside the previous Linear's launch
+                fused_next = False
+                continue
             last = si == n - 1
             nxt_is_linear = (not last) and steps[si + 1][0] == "linear"
             out_dt = cd if nxt_is_linear else torch.float32
@@ -805,6 +814,33 @@ class SeqFn(Function):
                 if a is None:
                     a = K.cast(cur, cd)
                 wc = _w(w, cd)
+                if (FUSE_LINEAR_BN and not last and steps[si + 1][0] == "bn_act" and a2 is None and K.linear_bn_act_ok(a, wc)):
+                    # Linear + BatchNorm(+act+dropout) in ONE launch: a CTA owns all batch rows of its output columns, so the
+                    # column statistics never leave it (mmsa_linear_bn_act_fwd); the tape is the two-kernel path's
+                    bn, order, dmod, didx = steps[si + 1][1:5]
+                    gamma, beta = params[pi], params[pi + 1]
+                    bn_pidx = pi
+                    pi += 2
+                    last2 = si + 1 == n - 1
+                    nxt2_is_linear = (not last2) and steps[si + 2][0] == "linear"
+                    out_dt2 = cd if nxt2_is_linear else torch.float32
+                    p = dmod.p if (dmod is not None and training) else 0.0
+                    mask, seed, off = drop.next(f"{name}.{didx}", (a.shape[0], wc.shape[0])) if p > 0 else (None, 0, 0)
+                    nbt = bn.num_batches_tracked if (training and bn.track_running_stats) else None
+                    lp_here = want_lp and last2 and out_dt2 == torch.float32 and cd == torch.bfloat16
+                    res = K.linear_bn_act_fwd(a, wc, None if b is None else b.detach(), gamma.detach(), beta.detach(),
+                                              bn.running_mean, bn.running_var, 0.1 if bn.momentum is None else bn.momentum,
+                                              bn.eps, training, order, p, mask, seed, off, out_dt2,
+                                              rng_state=(drop.state(a.device) if (p > 0 and mask is None) else None),
+                                              want_lp=lp_here, num_batches_tracked=nbt)
+                    z, y, mean, rstd, mask = res[:5]
+                    if lp_here:
+                        out_lp = res[5]
+                    tape.append(("linear", a, None, wc, pidx, lin.bias is not None))
+                    tape.append(("bn_act", z, gamma.detach(), beta.detach(), mean, rstd, training, order, p, mask, bn_pidx))
+                    cur, a, a2 = (None, y, None) if nxt2_is_linear else (y, None, None)
+                    fused_next = True
+                    continue
                 z = K.linear_fwd(a, wc, None if b is None else b.detach(), x2=a2, out_dtype=torch.float32)
                 tape.append(("linear", a, a2, wc, pidx, lin.bias is not None))
                 cur, a, a2 = z, (K.cast(z, cd) if nxt_is_linear else None), None

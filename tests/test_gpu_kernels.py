@@ -360,6 +360,89 @@ def test_bn_act(cuda_device, dtype, order, training):
     assert float((dbp.double() - xr.grad.sum(0)).abs().max()) <= 1e-5 * float(xr.grad.abs().max()) * B
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 256, 2304), (256, 128, 256), (256, 128, 128), (6, 128, 128), (200, 64, 136),
+                                   (33, 24, 64), (1, 16, 8), (256, 256, 4096)])
+@pytest.mark.parametrize("order", [0, 1, 2])
+@pytest.mark.parametrize("training", [True, False])
+def test_linear_bn_act_one_launch(cuda_device, M, N, K, order, training):
+    """mmsa_linear_bn_act_fwd (Linear + BatchNorm1d + act + dropout in one launch, MultimodalModel.py:179-199) against the
+    two-launch form it replaces (mmsa_linear_fwd, then mmsa_bn_act_fwd) AND against float64 torch: z, y (fp32 with a bf16
+    copy, and bf16), batch statistics, running statistics, num_batches_tracked, the Philox keep mask (identical bits: same
+    indexing) and an injected mask.  Shapes: the tail's layers at B = 256 (K = 2304 splits the reduction over a cluster of 6,
+    K = 4096 over 8), a tiny batch, ragged K (136: zero-filled tail block), N not a multiple of the 16-column CTA tile, M = 1."""
+    k = _k()
+    if not training and order == 2:
+        pytest.skip("same code path as order 0 in eval mode")
+    p = 0.3
+    x = _rand((M, K), torch.bfloat16, cuda_device, 1)
+    w = _rand((N, K), torch.bfloat16, cuda_device, 2, 1 / math.sqrt(K))
+    bias = _rand((N,), torch.float32, cuda_device, 3, 0.2)
+    gamma = _rand((N,), torch.float32, cuda_device, 4) * 0.1 + 1
+    beta = _rand((N,), torch.float32, cuda_device, 5) * 0.1
+    rm = _rand((N,), torch.float32, cuda_device, 6) * 0.1
+    rv = _rand((N,), torch.float32, cuda_device, 7).abs() + 0.5
+    assert k.linear_bn_act_ok(x, w)
+    state = torch.tensor([1234, 1000], dtype=torch.int64, device=cuda_device)
+    # two-launch form
+    rm_a, rv_a, nbt_a = rm.clone(), rv.clone(), torch.zeros((), dtype=torch.int64, device=cuda_device)
+    z_a = k.linear_fwd(x, w, bias, out_dtype=torch.float32)
+    y_a, mean_a, rstd_a, mask_a, ylp_a = k.bn_act_fwd(z_a, gamma, beta, rm_a, rv_a, 0.1, 1e-5, training, order,
+                                                     p if training else 0.0, None, 0, 7, torch.float32, rng_state=state,
+                                                     want_lp=True, num_batches_tracked=nbt_a)
+    # one launch
+    rm_b, rv_b, nbt_b = rm.clone(), rv.clone(), torch.zeros((), dtype=torch.int64, device=cuda_device)
+    z_b, y_b, mean_b, rstd_b, mask_b, ylp_b = k.linear_bn_act_fwd(x, w, bias, gamma, beta, rm_b, rv_b, 0.1, 1e-5, training, order,
+                                                                 p if training else 0.0, None, 0, 7, torch.float32,
+                                                                 rng_state=state, want_lp=True, num_batches_tracked=nbt_b)
+    torch.cuda.synchronize()
+    assert rel_err(z_b, z_a) <= 1e-5
+    if training:
+        assert mask_b is not None and torch.equal(mask_b, mask_a)
+        assert rel_err(rm_b, rm_a) <= 1e-5 and rel_err(rv_b, rv_a) <= 1e-5
+        assert int(nbt_a) == 1 and int(nbt_b) == 1
+    else:
+        assert int(nbt_b) == 0 and torch.equal(rm_b, rm) and torch.equal(rv_b, rv)
+    # float64 statement of the block on the same bf16 operands
+    zr = x.double() @ w.double().t() + bias.double()
+    rm_r, rv_r = rm.double().clone(), rv.double().clone()
+    h = F.relu(zr) if order == 1 else zr
+    if training and M == 1:
+        h = (h - h) * gamma.double() + beta.double()          # one sample: batch variance 0 (torch refuses this case)
+    else:
+        h = F.batch_norm(h, rm_r, rv_r, gamma.double(), beta.double(), training, 0.1, 1e-5)
+    if order == 0:
+        h = F.gelu(h)
+    if training:
+        h = h * mask_b.double() / (1 - p)
+    tol = 1e-5 if M > 8 else 1e-4                             # tiny batches: 1/sqrt(var) amplifies the fp32 rounding of z
+    assert rel_err(z_b, zr) <= 1e-5
+    assert rel_err(y_b, h) <= tol, (rel_err(y_b, h), rel_err(y_a, h))
+    assert rel_err(mean_b, mean_a) <= 1e-5 and rel_err(rstd_b, rstd_a) <= (1e-5 if M > 8 else 1e-3)
+    assert ylp_b.dtype == torch.bfloat16 and torch.equal(ylp_b, y_b.to(torch.bfloat16))
+    # bf16 output + an injected keep mask
+    if training:
+        keep = (torch.rand(M, N, generator=torch.Generator().manual_seed(8)) >= p).to(torch.uint8).to(cuda_device)
+        res = k.linear_bn_act_fwd(x, w, bias, gamma, beta, rm.clone(), rv.clone(), 0.1, 1e-5, True, order, p, keep, 0, 0,
+                                  torch.bfloat16)
+        ref = k.bn_act_fwd(z_a, gamma, beta, rm.clone(), rv.clone(), 0.1, 1e-5, True, order, p, keep, 0, 0, torch.bfloat16)
+        assert res[1].dtype == torch.bfloat16 and rel_err(res[1], ref[0]) <= 2e-2
+        assert res[4] is keep
+    # no bias
+    z_n, y_n = k.linear_bn_act_fwd(x, w, None, gamma, beta, rm.clone(), rv.clone(), 0.1, 1e-5, training, order, 0.0, None, 0, 0,
+                                   torch.float32)[:2]
+    assert rel_err(z_n, zr - bias.double()) <= 1e-5
+
+
+def test_linear_bn_act_shapes_outside_the_one_launch_form(cuda_device):
+    k = _k()
+    x = _rand((300, 128), torch.bfloat16, cuda_device, 1)
+    w = _rand((64, 128), torch.bfloat16, cuda_device, 2)
+    assert not k.linear_bn_act_ok(x, w)                                        # batch > 256 rows
+    assert not k.linear_bn_act_ok(x[:64], _rand((12, 128), torch.bfloat16, cuda_device, 3))       # N % 8 != 0
+    assert not k.linear_bn_act_ok(x[:64].float(), w.float())                   # fp32 parity mode keeps the exact kernels
+    assert k.linear_bn_act_ok(x[:256], w)
+
+
 def test_dropout_rng(cuda_device):
     """in-kernel Philox: keep rate ~ 1-p, deterministic for a fixed (seed, offset), scaled by 1/(1-p)."""
     k = _k()
