@@ -94,6 +94,161 @@ bn_act_fwd_kernel(int64_t B, int N, int order, const float* __restrict__ x, cons
   }
 }
 
+// Register-resident forms for B <= kBnRegRows * kBnRows (= 256, every batch of the tail on the benchmarked path): each
+// thread loads its (at most) four rows ONCE, all loads in flight together, and the later passes run from registers.  The
+// loops of the general kernels above / below re-read x per pass, four dependent L2 round trips each: at these sizes the
+// kernels are nothing but that latency (8-9 us; ~3 us in this form).  Same arithmetic in the same order: bit-identical.
+constexpr int kBnRegRows = 4;
+template <typename T>
+__global__ void __launch_bounds__(kBnCols * kBnRows)
+bn_act_fwd_small_kernel(int B, int N, int order, const float* __restrict__ x, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, float* __restrict__ running_mean,
+                        float* __restrict__ running_var, int64_t* __restrict__ num_batches_tracked, float momentum,
+                        float eps, int training, float dropout_p, uint8_t* __restrict__ keep_mask, int mask_given,
+                        uint64_t seed, uint64_t offset, const uint64_t* __restrict__ rng_state, T* __restrict__ y,
+                        bf16* __restrict__ y_lp, float* __restrict__ save_mean, float* __restrict__ save_rstd) {
+  __shared__ float red[kBnRows][kBnCols + 1];
+  if (rng_state != nullptr) { seed = rng_state[0]; offset += rng_state[1]; }
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int col = blockIdx.x * kBnCols + tx;
+  const bool ok = col < N;
+  const bool pre_relu = (order == MMSA_RELU_THEN_BN);
+  const bool drop = training && dropout_p > 0.f;
+  float v[kBnRegRows];
+  uint8_t keep[kBnRegRows];
+  bool live[kBnRegRows];
+#pragma unroll
+  for (int i = 0; i < kBnRegRows; ++i) {
+    const int r = ty + i * kBnRows;
+    live[i] = ok && r < B;
+    v[i] = live[i] ? x[(int64_t)r * N + col] : 0.f;
+    keep[i] = (live[i] && drop && mask_given) ? keep_mask[(int64_t)r * N + col] : (uint8_t)1;
+    if (pre_relu) v[i] = fmaxf(v[i], 0.f);
+  }
+  float mean = 0.f, var = 1.f;
+  if (training) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kBnRegRows; ++i) if (live[i]) s += v[i];
+    red[ty][tx] = s;
+    __syncthreads();
+    s = 0.f;
+#pragma unroll
+    for (int k = 0; k < kBnRows; ++k) s += red[k][tx];
+    mean = s / (float)B;
+    __syncthreads();
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kBnRegRows; ++i) if (live[i]) { const float d = v[i] - mean; q += d * d; }
+    red[ty][tx] = q;
+    __syncthreads();
+    q = 0.f;
+#pragma unroll
+    for (int k = 0; k < kBnRows; ++k) q += red[k][tx];
+    var = q / (float)B;
+    if (num_batches_tracked != nullptr && blockIdx.x == 0 && tx == 0 && ty == 0) *num_batches_tracked += 1;
+    if (ok && ty == 0 && running_mean != nullptr) {
+      float unbiased = B > 1 ? q / (float)(B - 1) : var;
+      running_mean[col] = (1.f - momentum) * running_mean[col] + momentum * mean;
+      running_var[col] = (1.f - momentum) * running_var[col] + momentum * unbiased;
+    }
+  } else if (ok) {
+    mean = running_mean[col];
+    var = running_var[col];
+  }
+  const float rstd = 1.f / sqrtf(var + eps);
+  if (ok && ty == 0) { save_mean[col] = mean; save_rstd[col] = rstd; }
+  if (!ok) return;
+  const float gm = gamma[col], bt = beta[col];
+  const float keep_scale = drop ? 1.f / (1.f - dropout_p) : 1.f;
+#pragma unroll
+  for (int i = 0; i < kBnRegRows; ++i) {
+    if (!live[i]) continue;
+    const int64_t idx = (int64_t)(ty + i * kBnRows) * N + col;
+    float z = (v[i] - mean) * rstd * gm + bt;
+    if (order == MMSA_BN_THEN_GELU) z = gelu_erf(z);
+    if (drop) {
+      uint8_t kp = keep[i];
+      if (!mask_given) {
+        uint32_t rnd = philox_first(seed, offset + (uint64_t)idx);
+        kp = ((float)(rnd >> 8) * (1.f / 16777216.f)) >= dropout_p ? 1 : 0;
+        keep_mask[idx] = kp;
+      }
+      z = kp ? z * keep_scale : 0.f;
+    }
+    y[idx] = from_f<T>(z);
+    if (y_lp != nullptr) y_lp[idx] = __float2bfloat16_rn(z);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBnCols * kBnRows)
+bn_act_bwd_small_kernel(int B, int N, int order, const float* __restrict__ x, const float* __restrict__ dy,
+                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                        const float* __restrict__ save_mean, const float* __restrict__ save_rstd, int training,
+                        float dropout_p, const uint8_t* __restrict__ keep_mask, T* __restrict__ dx,
+                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias_prev) {
+  __shared__ float red[2][kBnRows][kBnCols + 1];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int col = blockIdx.x * kBnCols + tx;
+  const bool ok = col < N;
+  const bool pre_relu = (order == MMSA_RELU_THEN_BN);
+  const bool drop = training && dropout_p > 0.f;
+  const float keep_scale = drop ? 1.f / (1.f - dropout_p) : 1.f;
+  float raw[kBnRegRows], d[kBnRegRows];
+  uint8_t keep[kBnRegRows];
+  bool live[kBnRegRows];
+#pragma unroll
+  for (int i = 0; i < kBnRegRows; ++i) {                       // every load of the kernel, in flight together
+    const int r = ty + i * kBnRows;
+    live[i] = ok && r < B;
+    const int64_t idx = (int64_t)r * N + col;
+    raw[i] = live[i] ? x[idx] : 0.f;
+    d[i] = live[i] ? dy[idx] : 0.f;
+    keep[i] = (live[i] && drop) ? keep_mask[idx] : (uint8_t)1;
+  }
+  const float mean = ok ? save_mean[col] : 0.f, rstd = ok ? save_rstd[col] : 0.f;
+  const float gm = ok ? gamma[col] : 0.f, bt = ok ? beta[col] : 0.f;
+  float xh[kBnRegRows];
+  float sdz = 0.f, sdzx = 0.f;
+#pragma unroll
+  for (int i = 0; i < kBnRegRows; ++i) {
+    if (!live[i]) { xh[i] = 0.f; continue; }
+    const float v = pre_relu ? fmaxf(raw[i], 0.f) : raw[i];
+    xh[i] = (v - mean) * rstd;
+    if (drop) d[i] = keep[i] ? d[i] * keep_scale : 0.f;
+    if (order == MMSA_BN_THEN_GELU) d[i] *= gelu_erf_grad(xh[i] * gm + bt);
+    sdz += d[i];
+    sdzx += d[i] * xh[i];
+  }
+  red[0][ty][tx] = sdz;
+  red[1][ty][tx] = sdzx;
+  __syncthreads();
+  sdz = 0.f; sdzx = 0.f;
+#pragma unroll
+  for (int k = 0; k < kBnRows; ++k) { sdz += red[0][k][tx]; sdzx += red[1][k][tx]; }
+  if (ok && ty == 0) { dgamma[col] = sdzx; dbeta[col] = sdz; }
+  const float invB = 1.f / (float)B;
+  float sdx = 0.f;
+#pragma unroll
+  for (int i = 0; i < kBnRegRows; ++i) {
+    if (!live[i]) continue;
+    float dv = training ? gm * rstd * (d[i] - sdz * invB - xh[i] * sdzx * invB) : gm * rstd * d[i];
+    if (pre_relu && raw[i] <= 0.f) dv = 0.f;
+    sdx += dv;
+    dx[(int64_t)(ty + i * kBnRows) * N + col] = from_f<T>(dv);
+  }
+  __syncthreads();
+  red[0][ty][tx] = sdx;
+  __syncthreads();
+  if (ok && ty == 0 && dbias_prev != nullptr) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < kBnRows; ++k) t += red[0][k][tx];
+    dbias_prev[col] = t;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kBnCols * kBnRows)
 bn_act_bwd_kernel(int64_t B, int N, int order, const float* __restrict__ x, const float* __restrict__ dy,
@@ -467,6 +622,14 @@ int mmsa_bn_act_fwd(int dtype, int64_t B, int64_t N, int order, const void* x, c
   cudaStream_t s = (cudaStream_t)stream;
   ProfScope prof("bn_act_fwd", s, (double)B * N * 2.0 * (dtype == MMSA_F32 ? 4 : 2));
   dim3 block(kBnCols, kBnRows);
+  if (B <= kBnRegRows * kBnRows) {
+    MMSA_DISPATCH_DTYPE(dtype, T, (bn_act_fwd_small_kernel<T><<<(unsigned)ceil_div(N, kBnCols), block, 0, s>>>(
+        (int)B, (int)N, order, (const float*)x, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps,
+        training, dropout_p, keep_mask, mask_given, seed, offset, rng_state, (T*)y,
+        (bf16*)(dtype == MMSA_F32 ? y_lp : nullptr), save_mean, save_rstd)));
+    MMSA_LAUNCH_CHECK("bn_act_fwd_small_kernel");
+    return MMSA_OK;
+  }
   MMSA_DISPATCH_DTYPE(dtype, T, (bn_act_fwd_kernel<T><<<(unsigned)ceil_div(N, kBnCols), block, 0, s>>>(
       B, (int)N, order, (const float*)x, gamma, beta, running_mean, running_var, num_batches_tracked, momentum, eps,
       training, dropout_p,
@@ -484,6 +647,13 @@ int mmsa_bn_act_bwd(int dtype, int64_t B, int64_t N, int order, const void* x, c
   cudaStream_t s = (cudaStream_t)stream;
   ProfScope prof("bn_act_bwd", s, (double)B * N * 3.0 * (dtype == MMSA_F32 ? 4 : 2));
   dim3 block(kBnCols, kBnRows);
+  if (B <= kBnRegRows * kBnRows) {
+    MMSA_DISPATCH_DTYPE(dtype, T, (bn_act_bwd_small_kernel<T><<<(unsigned)ceil_div(N, kBnCols), block, 0, s>>>(
+        (int)B, (int)N, order, (const float*)x, (const float*)dy, gamma, beta, save_mean, save_rstd, training, dropout_p,
+        keep_mask, (T*)dx, dgamma, dbeta, dbias_prev)));
+    MMSA_LAUNCH_CHECK("bn_act_bwd_small_kernel");
+    return MMSA_OK;
+  }
   MMSA_DISPATCH_DTYPE(dtype, T, (bn_act_bwd_kernel<T><<<(unsigned)ceil_div(N, kBnCols), block, 0, s>>>(
       B, (int)N, order, (const float*)x, (const float*)dy, gamma, beta, save_mean, save_rstd, training, dropout_p, keep_mask,
       (T*)dx, dgamma, dbeta, dbias_prev)));

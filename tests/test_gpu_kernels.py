@@ -326,9 +326,10 @@ def test_modal_concat(cuda_device, dtype):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("order", [0, 1])
 @pytest.mark.parametrize("training", [True, False])
-def test_bn_act(cuda_device, dtype, order, training):
+@pytest.mark.parametrize("B", [48, 256, 300])       # <= 256 rows: register-resident kernels; above: the looping ones
+def test_bn_act(cuda_device, dtype, order, training, B):
     k = _k()
-    B, N, p = 48, 200, 0.3
+    N, p = 200, 0.3
     x = _rand((B, N), torch.float32, cuda_device, 1)               # fp32 in (GEMM output), `dtype` out
     gamma = _rand((N,), torch.float32, cuda_device, 2) * 0.1 + 1
     beta = _rand((N,), torch.float32, cuda_device, 3) * 0.1
