@@ -191,7 +191,8 @@ skinny_fwd_kernel(int64_t M, int N, int K, const bf16* __restrict__ x, int64_t l
   float acc[kSkinnyMaxN];
 #pragma unroll
   for (int c = 0; c < kSkinnyMaxN; ++c) acc[c] = 0.f;
-  for (int k = lane; k < K; k += 32) {
+#pragma unroll 4
+  for (int k = lane; k < K; k += 32) {                 // unrolled: the loads of four k-steps are in flight together
     const float xv = to_f(x[m * ldx + k]);
 #pragma unroll
     for (int c = 0; c < kSkinnyMaxN; ++c) if (c < N) acc[c] += xv * to_f(w[(int64_t)c * ldw + k]);
@@ -222,33 +223,35 @@ skinny_dgrad_kernel(int64_t M, int N, int K, const bf16* __restrict__ dy, int64_
   }
 }
 
-// block = 32 columns (k) x 8 row lanes; block x covers columns [32 x, 32 x + 32); block 0 also forms db
-__global__ void __launch_bounds__(256)
+// block = 32 columns (k) x 32 row lanes; block x covers columns [32 x, 32 x + 32); block 0 also forms db.  The kernel is a
+// pure latency chain (a [256, 3]^T x [256, 64..128] product): 32 row lanes and a 4-way unrolled row walk leave each thread
+// two rounds of loads at B = 256 instead of the 32 dependent L2 round trips of an 8-lane, one-row-at-a-time walk.
+constexpr int kSkinnyWgRows = 32;
+__global__ void __launch_bounds__(32 * kSkinnyWgRows)
 skinny_wgrad_kernel(int64_t M, int N, int K, const bf16* __restrict__ dy, int64_t lddy, const bf16* __restrict__ x, int64_t ldx,
                     float* __restrict__ dw, int64_t lddw, float* __restrict__ db) {
-  __shared__ float red[8][kSkinnyMaxN][33];
+  __shared__ float red[kSkinnyWgRows][kSkinnyMaxN][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int k = blockIdx.x * 32 + tx;
+  const bool want_b = db != nullptr && blockIdx.x == 0 && tx < N;
   float acc[kSkinnyMaxN], bsum = 0.f;
 #pragma unroll
   for (int c = 0; c < kSkinnyMaxN; ++c) acc[c] = 0.f;
-  for (int64_t m = ty; m < M; m += 8) {
+#pragma unroll 4
+  for (int64_t m = ty; m < M; m += kSkinnyWgRows) {
     const float xv = k < K ? to_f(x[m * ldx + k]) : 0.f;
 #pragma unroll
     for (int c = 0; c < kSkinnyMaxN; ++c) if (c < N) acc[c] += to_f(dy[m * lddy + c]) * xv;
-    if (db != nullptr && blockIdx.x == 0 && tx < N) bsum += to_f(dy[m * lddy + tx]);
+    if (want_b) bsum += to_f(dy[m * lddy + tx]);
   }
 #pragma unroll
   for (int c = 0; c < kSkinnyMaxN; ++c) red[ty][c][tx] = acc[c];
   __syncthreads();
-  if (ty == 0 && k < K && dw != nullptr) {
+  if (ty < kSkinnyMaxN && ty < N && k < K && dw != nullptr) {      // warp c sums output row c in row-lane order
+    float t = 0.f;
 #pragma unroll
-    for (int c = 0; c < kSkinnyMaxN; ++c) if (c < N) {
-      float t = 0.f;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) t += red[r][c][tx];
-      dw[(int64_t)c * lddw + k] = t;
-    }
+    for (int r = 0; r < kSkinnyWgRows; ++r) t += red[r][ty][tx];
+    dw[(int64_t)ty * lddw + k] = t;
   }
   if (db != nullptr && blockIdx.x == 0) {
     __syncthreads();
@@ -257,7 +260,7 @@ skinny_wgrad_kernel(int64_t M, int N, int K, const bf16* __restrict__ dy, int64_
     if (ty == 0 && tx < N) {
       float t = 0.f;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) t += red[r][0][tx];
+      for (int r = 0; r < kSkinnyWgRows; ++r) t += red[r][0][tx];
       db[tx] = t;
     }
   }
@@ -395,7 +398,7 @@ int mmsa_linear_wgrad(int dtype, int64_t M, int64_t N, int64_t K, const void* dy
   if (skinny_ok(dtype, N)) {
     if (dw == nullptr && db == nullptr) return MMSA_OK;
     ProfScope prof("skinny_wgrad", s, 2.0 * (double)M * N * K);
-    skinny_wgrad_kernel<<<(unsigned)ceil_div(K, 32), 256, 0, s>>>(M, (int)N, (int)K, (const bf16*)dy, lddy, (const bf16*)x, ldx, dw, lddw, db);
+    skinny_wgrad_kernel<<<(unsigned)ceil_div(K, 32), 32 * kSkinnyWgRows, 0, s>>>(M, (int)N, (int)K, (const bf16*)dy, lddy, (const bf16*)x, ldx, dw, lddw, db);
     MMSA_LAUNCH_CHECK("skinny_wgrad_kernel");
     return MMSA_OK;
   }
