@@ -127,51 +127,6 @@ def _side_stream(device) -> "torch.cuda.Stream":
     return st
 
 
-# ---- deferred join of the helper stream ------------------------------------------------------------------------------------
-# The tail's weight gradients are LEAVES of the backward chain: nothing on the main stream reads them before the backward pass
-# is over.  Joining the helper stream at the end of every Function.backward makes the main chain wait for them anyway (the
-# modality-weight head: 25 us of weight-gradient launches against 10 us of input gradients).  When the parameters' gradients
-# are not observed during the pass -- leaf parameters, no gradient yet (so AccumulateGrad only stores the tensor), no hooks --
-# the join is queued as an autograd-engine callback that runs once, when the pass ends; the tensors the helper stream still
-# reads are kept alive until then.  Otherwise (or with MMSA_DEFER_JOIN=0) the join happens on the spot.
-DEFER_JOIN = os.environ.get("MMSA_DEFER_JOIN", "1") != "0"
-_DEFERRED: Dict[Tuple[int, int], dict] = {}
-
-
-def _can_defer_join(params) -> bool:
-    if not DEFER_JOIN:
-        return False
-    for p in params:
-        if not isinstance(p, Tensor) or not p.requires_grad:
-            continue
-        if not p.is_leaf or p.grad is not None or p._backward_hooks or getattr(p, "_post_accumulate_grad_hooks", None):
-            return False
-    return True
-
-
-def _join_helper_stream(main, side, keep: list, params) -> None:
-    """main.wait_stream(side), now or -- when nothing can look at the parameter gradients earlier -- at the end of the
-    running backward pass; `keep`: tensors the helper stream's kernels read or write."""
-    if not _can_defer_join(params):
-        main.wait_stream(side)
-        keep.clear()
-        return
-    key = (main.cuda_stream, side.cuda_stream)
-    ent = _DEFERRED.get(key)
-    if ent is None:
-        ent = _DEFERRED[key] = {"keep": [], "armed": False}
-    ent["keep"].extend(keep)
-    keep.clear()
-    if not ent["armed"]:
-        ent["armed"] = True
-
-        def _join(ent=ent, main=main, side=side):
-            ent["armed"] = False
-            main.wait_stream(side)
-            ent["keep"].clear()
-        torch.autograd.Variable._execution_engine.queue_callback(_join)
-
-
 def _c(t: Tensor) -> Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
@@ -682,7 +637,6 @@ class ModalHeadFn(Function):
         hg, w, fused, fused_lp = K.modal_head_fwd(h_pre, _c(w2c), None if b2 is None else b2.detach(), slots32, cd)
         ctx.save_for_backward(xa, xb, w1c, w2c, h_pre, hg, w, *slots32)
         ctx.cfg = (cd, raw_a.shape, None if raw_b is None else raw_b.shape, b1 is not None, b2 is not None)
-        ctx.param_objs = (w1, b1, w2, b2)
         ctx.set_materialize_grads(False)     # fused_lp / w never have a gradient: no zero fills for them
         ctx.mark_non_differentiable(w)
         if fused_lp is not None:
@@ -695,7 +649,6 @@ class ModalHeadFn(Function):
         xa, xb, w1c, w2c, h_pre, hg, w, *slots32 = ctx.saved_tensors
         cd, shp_a, shp_b, has_b1, has_b2 = ctx.cfg
         if dfused is None:
-            ctx.param_objs = None
             return (None,) * (9 + len(slots32))
         need_slots = list(ctx.needs_input_grad[9:])
         dslots, dlogits, dh = K.modal_head_bwd(K.cast(_c(dfused), torch.float32), w, slots32, need_slots, h_pre, _c(w2c), cd)
@@ -722,9 +675,8 @@ class ModalHeadFn(Function):
             da = K.linear_dgrad(dh, w1c[:, :Ka], out_dtype=torch.float32).view(shp_a)
         if xb is not None and ctx.needs_input_grad[1]:
             db = K.linear_dgrad(dh, w1c[:, Ka:], out_dtype=torch.float32).view(shp_b)
-        if side is not None:
-            _join_helper_stream(main, side, [dlogits, hg, dh, xa, xb, dw1, db1, dw2, db2], ctx.param_objs)
-        ctx.param_objs = None
+        if side is not None:          # (deferring this join to the end of the backward pass was tried: no gain, and a tensor
+            main.wait_stream(side)    #  kept alive for the helper stream makes AccumulateGrad clone it on the main stream)
         return (da, db, None, None, dw1, db1, dw2, db2, None) + tuple(dslots)
 
 
@@ -927,7 +879,6 @@ class SeqFn(Function):
                     a, cur = K.cast(cur, cd), None
         ctx.tape = tape
         ctx.cd = cd
-        ctx.param_objs = params              # the Parameter objects (whether their gradients are observed mid-pass)
         ctx.set_materialize_grads(False)     # the compute-dtype copy never has a gradient: no zero fill for it
         ctx.n_params = len(params)
         ctx.has_x2 = x2 is not None
@@ -947,7 +898,6 @@ class SeqFn(Function):
         tape, cd = ctx.tape, ctx.cd
         ctx.tape = None
         if dy is None:
-            ctx.param_objs = None
             return (None,) * (10 + ctx.n_params)
         grads: List[Optional[Tensor]] = [None] * ctx.n_params
         need = ctx.needs_input_grad[10:]
@@ -1013,8 +963,8 @@ class SeqFn(Function):
             elif kind == "dropout":
                 d, _ = K.dropout(K.cast(d, torch.float32), op[1], op[2], True, 0, 0, out_dt)
         if used_side:
-            _join_helper_stream(main, side, keep, ctx.param_objs)
-        ctx.param_objs = None
+            main.wait_stream(side)
+            keep.clear()
         if tape and tape[0][0] != "linear" and ctx.needs_input_grad[0]:
             dx = K.cast(d, torch.float32)
         if dx is not None:
