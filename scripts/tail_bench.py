@@ -21,6 +21,7 @@ def main() -> None:
     ap.add_argument("--embed", type=int, default=768)
     ap.add_argument("--contract", default="single")
     ap.add_argument("--iters", type=int, default=300)
+    ap.add_argument("--eager-passes", type=int, default=0, help="only run this many eager passes (for an ncu launch list)")
     args = ap.parse_args()
     import mmsa
     from mmsa import _lib, ops
@@ -76,6 +77,11 @@ def main() -> None:
             best = min(best, e0.elapsed_time(e1) / args.iters * 1e3)
         return best, launches
 
+    if args.eager_passes:
+        for _ in range(args.eager_passes):
+            body(True)
+        torch.cuda.synchronize()
+        return
     with torch.no_grad():
         fwd_us, fwd_l = timed(False)
     both_us, both_l = timed(True)
