@@ -27,6 +27,8 @@ constexpr int LB_A_BYTES = LB_ROWS * LB_PITCH * 2;
 constexpr int LB_B_BYTES = LB_COLS * LB_PITCH * 2;
 constexpr int LB_STAGE_BYTES = LB_A_BYTES + LB_B_BYTES;
 constexpr int LB_SMEM = LB_STAGES * LB_STAGE_BYTES;
+constexpr int LB_ZP = LB_COLS + 1;                  // pitch (floats) of the epilogue's z tile
+static_assert(LB_ROWS * LB_ZP * 4 <= LB_SMEM, "the z tile aliases the operand ring");
 static_assert(LB_THREADS * 16 * 4 <= LB_SMEM, "the partial tile of the cluster sum aliases the operand ring");
 
 struct LbParams {
@@ -59,18 +61,10 @@ __device__ __forceinline__ int lb_clamp16(int elems) { return elems <= 0 ? 0 : (
 __device__ __forceinline__ void lb_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// sum over the 8 lanes that hold the same column pair (lane & 3 fixed): the row index g = lane >> 2 varies
-__device__ __forceinline__ float lb_rows_sum(float v) {
-  v += __shfl_xor_sync(0xffffffffu, v, 4);
-  v += __shfl_xor_sync(0xffffffffu, v, 8);
-  v += __shfl_xor_sync(0xffffffffu, v, 16);
-  return v;
-}
-
 __global__ void __launch_bounds__(LB_THREADS, 1)
 linear_bn_act_kernel(const LbParams p) {
   extern __shared__ __align__(16) uint8_t lb_smem[];
-  __shared__ float red[LB_THREADS / 32][LB_COLS];
+  __shared__ float red[LB_THREADS / 16][LB_COLS];
   __shared__ float stat[2][LB_COLS];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.x * LB_COLS;
@@ -172,151 +166,120 @@ linear_bn_act_kernel(const LbParams p) {
     if (slice != 0) return;
   }
 
-  // ---- epilogue (rank 0): thread owns rows wm + mi*16 + g (+8) and the column pairs n0 + nt*8 + q (+1) ----
-  const int g = lane >> 2, q = (lane & 3) * 2;
-  const bool pre_relu = p.order == MMSA_RELU_THEN_BN;
-  const float m_f = (float)p.M;
-  float v[2][2][4];
+  // ---- epilogue (rank 0).  The accumulators go through a shared-memory tile (over the drained ring) so that the statistics
+  //      and the element-wise tail are short ROLLED loops: unrolled over the 32 values a thread holds, the Philox + erf code
+  //      alone was 118 KB of straight-line SASS executed once per warp -- the kernel spent its time on instruction fetch.
+  __syncthreads();                                           // every warp is done with the operand ring
+  float* zt = reinterpret_cast<float*>(lb_smem);             // [LB_ROWS][LB_ZP] fp32: z = x w^T + bias
+  {
+    const int g = lane >> 2, q = (lane & 3) * 2;
 #pragma unroll
-  for (int nt = 0; nt < 2; ++nt) {
-    const int col = n0 + nt * 8 + q;                         // N % 8 == 0: the pair (col, col + 1) is inside or outside together
-    const bool cok = col < p.N;
-    const float b0 = (cok && p.bias) ? __ldg(p.bias + col) : 0.f, b1 = (cok && p.bias) ? __ldg(p.bias + col + 1) : 0.f;
+    for (int nt = 0; nt < 2; ++nt) {
+      const int cl = nt * 8 + q, col = n0 + cl;
+      const bool cok = col < p.N;                            // N % 8 == 0: the pair (col, col + 1) is inside or outside together
+      const float b0 = (cok && p.bias) ? __ldg(p.bias + col) : 0.f, b1 = (cok && p.bias) ? __ldg(p.bias + col + 1) : 0.f;
 #pragma unroll
-    for (int mi = 0; mi < 2; ++mi) {
+      for (int mi = 0; mi < 2; ++mi) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int row = wm + mi * 16 + g + h * 8;
-        const float z0 = acc[mi][nt][h * 2] + b0, z1 = acc[mi][nt][h * 2 + 1] + b1;
-        if (cok && row < p.M) *reinterpret_cast<float2*>(p.z + (long long)row * p.N + col) = make_float2(z0, z1);
-        v[mi][nt][h * 2] = pre_relu ? fmaxf(z0, 0.f) : z0;
-        v[mi][nt][h * 2 + 1] = pre_relu ? fmaxf(z1, 0.f) : z1;
+        for (int h = 0; h < 2; ++h) {
+          const int row = wm + mi * 16 + g + h * 8;
+          zt[row * LB_ZP + cl] = acc[mi][nt][h * 2] + b0;
+          zt[row * LB_ZP + cl + 1] = acc[mi][nt][h * 2 + 1] + b1;
+        }
       }
     }
   }
-  float mean_c[2][2], rstd_c[2][2];
+  __syncthreads();
+  const bool pre_relu = p.order == MMSA_RELU_THEN_BN;
+  const int sc = tid & (LB_COLS - 1), sg = tid >> 4;         // statistics: column sc, rows [16 sg, 16 sg + 16)
   if (p.training) {
-    // pass 1: column means over the batch rows (lanes -> warps in warp order: fixed summation order)
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt) {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        float s = 0.f;
-#pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-            if (wm + mi * 16 + g + h * 8 < p.M) s += v[mi][nt][h * 2 + e];
-        s = lb_rows_sum(s);
-        if (lane < 4) red[warp][nt * 8 + q + e] = s;
-      }
-    }
+    const float m_f = (float)p.M;
+    const int r_lo = sg * 16, r_hi = min(r_lo + 16, p.M);
+    float s = 0.f;
+    for (int r = r_lo; r < r_hi; ++r) { const float z = zt[r * LB_ZP + sc]; s += pre_relu ? fmaxf(z, 0.f) : z; }
+    red[sg][sc] = s;
     __syncthreads();
     if (tid < LB_COLS) {
       float t = 0.f;
 #pragma unroll
-      for (int w = 0; w < LB_THREADS / 32; ++w) t += red[w][tid];
+      for (int w = 0; w < LB_THREADS / 16; ++w) t += red[w][tid];
       stat[0][tid] = t / m_f;
     }
     __syncthreads();
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) mean_c[nt][e] = stat[0][nt * 8 + q + e];
-    // pass 2: biased variance around that mean
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt) {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        float s = 0.f;
-#pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-            if (wm + mi * 16 + g + h * 8 < p.M) { const float d = v[mi][nt][h * 2 + e] - mean_c[nt][e]; s += d * d; }
-        s = lb_rows_sum(s);
-        if (lane < 4) red[warp][nt * 8 + q + e] = s;         // pass 1's reads of `red` finished before the last barrier
-      }
+    const float mean = stat[0][sc];
+    s = 0.f;
+    for (int r = r_lo; r < r_hi; ++r) {
+      const float z = zt[r * LB_ZP + sc];
+      const float d = (pre_relu ? fmaxf(z, 0.f) : z) - mean;
+      s += d * d;
     }
+    red[sg][sc] = s;                                         // pass 1's reads of `red` finished before the last barrier
     __syncthreads();
     if (tid < LB_COLS) {
       float t = 0.f;
 #pragma unroll
-      for (int w = 0; w < LB_THREADS / 32; ++w) t += red[w][tid];
+      for (int w = 0; w < LB_THREADS / 16; ++w) t += red[w][tid];
       const float var = t / m_f;
       const float rstd = 1.f / sqrtf(var + p.eps);
       stat[1][tid] = rstd;
       const int col = n0 + tid;
       if (col < p.N) {
-        const float mean = stat[0][tid];
-        p.save_mean[col] = mean;
+        const float mu = stat[0][tid];
+        p.save_mean[col] = mu;
         p.save_rstd[col] = rstd;
         if (p.running_mean != nullptr) {
           const float unbiased = p.M > 1 ? t / (float)(p.M - 1) : var;
-          p.running_mean[col] = (1.f - p.momentum) * p.running_mean[col] + p.momentum * mean;
+          p.running_mean[col] = (1.f - p.momentum) * p.running_mean[col] + p.momentum * mu;
           p.running_var[col] = (1.f - p.momentum) * p.running_var[col] + p.momentum * unbiased;
         }
       }
     }
     if (p.nbt != nullptr && blockIdx.x == 0 && tid == 0) *p.nbt += 1;
-    __syncthreads();
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) rstd_c[nt][e] = stat[1][nt * 8 + q + e];
-  } else {
-#pragma unroll
-    for (int nt = 0; nt < 2; ++nt) {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int col = n0 + nt * 8 + q + e;
-        const bool cok = col < p.N;
-        mean_c[nt][e] = cok ? p.running_mean[col] : 0.f;
-        rstd_c[nt][e] = cok ? 1.f / sqrtf(p.running_var[col] + p.eps) : 0.f;
-        if (cok && warp == 0 && g == 0) { p.save_mean[col] = mean_c[nt][e]; p.save_rstd[col] = rstd_c[nt][e]; }
-      }
-    }
+  } else if (tid < LB_COLS) {
+    const int col = n0 + tid;
+    const bool cok = col < p.N;
+    const float mu = cok ? p.running_mean[col] : 0.f;
+    const float rstd = cok ? 1.f / sqrtf(p.running_var[col] + p.eps) : 0.f;
+    stat[0][tid] = mu;
+    stat[1][tid] = rstd;
+    if (cok) { p.save_mean[col] = mu; p.save_rstd[col] = rstd; }
   }
+  __syncthreads();
 
-  // affine, activation, dropout, stores
+  // affine, activation, dropout, stores: one column pair per thread and iteration (8 threads cover a row's 16 columns)
   uint64_t seed = p.seed, offset = p.offset;
   if (p.rng_state != nullptr) { seed = p.rng_state[0]; offset += p.rng_state[1]; }     // device-resident stream position
   const bool drop = p.training && p.dropout_p > 0.f;
   const float keep_scale = drop ? 1.f / (1.f - p.dropout_p) : 1.f;
-#pragma unroll
-  for (int nt = 0; nt < 2; ++nt) {
-    const int col = n0 + nt * 8 + q;
-    if (col >= p.N) continue;
-    const float g0 = __ldg(p.gamma + col), g1 = __ldg(p.gamma + col + 1);
-    const float t0 = __ldg(p.beta + col), t1 = __ldg(p.beta + col + 1);
-#pragma unroll
-    for (int mi = 0; mi < 2; ++mi) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int row = wm + mi * 16 + g + h * 8;
-        if (row >= p.M) continue;
-        float y0 = (v[mi][nt][h * 2] - mean_c[nt][0]) * rstd_c[nt][0] * g0 + t0;
-        float y1 = (v[mi][nt][h * 2 + 1] - mean_c[nt][1]) * rstd_c[nt][1] * g1 + t1;
-        if (p.order == MMSA_BN_THEN_GELU) { y0 = gelu_erf(y0); y1 = gelu_erf(y1); }
-        const long long idx = (long long)row * p.N + col;
-        if (drop) {
-          uint8_t k0, k1;
-          if (p.mask_given) { k0 = p.keep_mask[idx]; k1 = p.keep_mask[idx + 1]; }
-          else {
-            const uint32_t r0 = philox_first(seed, offset + (uint64_t)idx);
-            const uint32_t r1 = philox_first(seed, offset + (uint64_t)idx + 1u);
-            k0 = ((float)(r0 >> 8) * (1.f / 16777216.f)) >= p.dropout_p ? 1 : 0;
-            k1 = ((float)(r1 >> 8) * (1.f / 16777216.f)) >= p.dropout_p ? 1 : 0;
-            p.keep_mask[idx] = k0; p.keep_mask[idx + 1] = k1;
-          }
-          y0 = k0 ? y0 * keep_scale : 0.f;
-          y1 = k1 ? y1 * keep_scale : 0.f;
-        }
-        if (p.y_is_f32) *reinterpret_cast<float2*>(reinterpret_cast<float*>(p.y) + idx) = make_float2(y0, y1);
-        else *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<bf16*>(p.y) + idx) = __floats2bfloat162_rn(y0, y1);
-        if (p.y_lp != nullptr) *reinterpret_cast<__nv_bfloat162*>(p.y_lp + idx) = __floats2bfloat162_rn(y0, y1);
+  const int cl = (tid & 7) * 2, col = n0 + cl;
+  if (col >= p.N) return;
+  const float mean0 = stat[0][cl], mean1 = stat[0][cl + 1], rstd0 = stat[1][cl], rstd1 = stat[1][cl + 1];
+  const float g0 = __ldg(p.gamma + col), g1 = __ldg(p.gamma + col + 1);
+  const float t0 = __ldg(p.beta + col), t1 = __ldg(p.beta + col + 1);
+#pragma unroll 1
+  for (int row = tid >> 3; row < p.M; row += LB_THREADS / 8) {
+    const float z0 = zt[row * LB_ZP + cl], z1 = zt[row * LB_ZP + cl + 1];
+    const long long idx = (long long)row * p.N + col;
+    *reinterpret_cast<float2*>(p.z + idx) = make_float2(z0, z1);
+    float y0 = ((pre_relu ? fmaxf(z0, 0.f) : z0) - mean0) * rstd0 * g0 + t0;
+    float y1 = ((pre_relu ? fmaxf(z1, 0.f) : z1) - mean1) * rstd1 * g1 + t1;
+    if (p.order == MMSA_BN_THEN_GELU) { y0 = gelu_erf(y0); y1 = gelu_erf(y1); }
+    if (drop) {
+      uint8_t k0, k1;
+      if (p.mask_given) { k0 = p.keep_mask[idx]; k1 = p.keep_mask[idx + 1]; }
+      else {
+        const uint32_t r0 = philox_first(seed, offset + (uint64_t)idx);
+        const uint32_t r1 = philox_first(seed, offset + (uint64_t)idx + 1u);
+        k0 = ((float)(r0 >> 8) * (1.f / 16777216.f)) >= p.dropout_p ? 1 : 0;
+        k1 = ((float)(r1 >> 8) * (1.f / 16777216.f)) >= p.dropout_p ? 1 : 0;
+        p.keep_mask[idx] = k0; p.keep_mask[idx + 1] = k1;
       }
+      y0 = k0 ? y0 * keep_scale : 0.f;
+      y1 = k1 ? y1 * keep_scale : 0.f;
     }
+    if (p.y_is_f32) *reinterpret_cast<float2*>(reinterpret_cast<float*>(p.y) + idx) = make_float2(y0, y1);
+    else *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<bf16*>(p.y) + idx) = __floats2bfloat162_rn(y0, y1);
+    if (p.y_lp != nullptr) *reinterpret_cast<__nv_bfloat162*>(p.y_lp + idx) = __floats2bfloat162_rn(y0, y1);
   }
 }
 
