@@ -46,7 +46,9 @@ def launches():
     with open(os.path.join(PROF, f"{tag}_launches.md"), "w") as f:
         f.write(f"# {tag}: kernel launch list of `python bench.py --steps 2 --warmup 1 --no-graph` (ncu, "
                 f"`--metrics gpu__time_duration.sum --clock-control none`)\n\n")
-        f.write(f"{len(rows)} consecutive launches captured after the warm-up (about 3 steps of configs[1]: B=256, L=128, bf16). "
+        nsteps = sum(1 for r in rows if "ce_fwd" in r["Kernel Name"])
+        f.write(f"{len(rows)} consecutive launches captured from the start of the run ({nsteps} cross-entropy launches = steps of "
+                f"configs[1]: B=256, L=128, bf16; the two giant bf16 fills are the input slots' one-time torch.zeros). "
                 f"Times are cold-cache and serialised: compare SHARES.  Total {tot:.0f} us, of which {ours:.0f} us "
                 f"({100 * ours / tot:.1f} %) in this repo's kernels (the rest are torch fill/add plumbing kernels of the autograd tape).\n\n")
         f.write("| kernel | grid | block | launches | avg us | total us | share |\n|---|---|---|---:|---:|---:|---:|\n")
