@@ -1056,7 +1056,8 @@ class ContrastiveFn(Function):
         loss, stats, raw = K.contrastive_fwd(kind, sim, labels_r, labels_c, tptr, temperature_const, row_offset, denom, wptr)
         ctx.save_for_backward(n1, norm1, n2, norm2, sim, stats, labels_r, labels_c, tptr, n1_row, n2_row, wptr, raw)
         ctx.cfg = (temperature_const, kind, row_offset, denom, same, f1.dtype, f2.dtype, fast)
-        return loss.view(()) if weight is None else loss.view(weight.shape if weight.dim() else (1,))
+        ctx.wshape = None if weight is None else weight.shape
+        return loss.view(()) if weight is None else loss.view(weight.shape)
 
     @staticmethod
     @once_differentiable
@@ -1080,6 +1081,8 @@ class ContrastiveFn(Function):
             df1 = K.cast(K.l2norm_bwd(n1, norm1, dn1, None), d1)
             df2 = K.cast(K.l2norm_bwd(n2, norm2, dn2, None), d2) if ctx.needs_input_grad[1] else None
         dT = dtemp.view(()) if (tptr is not None and ctx.needs_input_grad[4]) else None
+        if dweight is not None:
+            dweight = dweight.view(ctx.wshape)
         return df1, df2, None, None, dT, None, None, None, None, None, None, dweight
 
 
